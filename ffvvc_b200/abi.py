@@ -1,0 +1,132 @@
+"""ctypes mirror of include/vvcdsp_cuda.h (the C ABI of libvvcdsp_cuda.so).
+
+The same plain-old-data descriptors are consumed by the CPU oracle (tests only), so the
+structures live here once.  Nothing in this module touches the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+EDGE_LEFT, EDGE_TOP, EDGE_RIGHT, EDGE_BOTTOM = 1, 2, 4, 8
+
+
+class VVCCudaFrame(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p * 3),
+        ("stride", C.c_ssize_t * 3),
+        ("batch_stride", C.c_ssize_t * 3),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("hshift", C.c_int32), ("vshift", C.c_int32),
+        ("bit_depth", C.c_int32), ("ctb_log2", C.c_int32),
+        ("batch", C.c_int32), ("chroma_format_idc", C.c_int32),
+    ]
+
+
+class VVCCudaALFCtb(C.Structure):
+    _fields_ = [
+        ("ctb_flag", C.c_uint8 * 3),
+        ("filt_set_idx_y", C.c_uint8),
+        ("chroma_alt_idx", C.c_uint8 * 2),
+        ("cc_idc", C.c_uint8 * 2),
+        ("edges", C.c_uint8),
+        ("reserved", C.c_uint8 * 3),
+    ]
+
+
+class VVCCudaALFSets(C.Structure):
+    _fields_ = [
+        ("luma_coeff", C.c_int16 * 12 * 25 * 8),
+        ("luma_clip_idx", C.c_uint8 * 12 * 25 * 8),
+        ("chroma_coeff", C.c_int16 * 6 * 8),
+        ("chroma_clip_idx", C.c_uint8 * 6 * 8),
+        ("cc_coeff", C.c_int16 * 7 * 5 * 2),
+    ]
+
+
+ALF_CTB_DTYPE = np.dtype([
+    ("ctb_flag", np.uint8, (3,)), ("filt_set_idx_y", np.uint8), ("chroma_alt_idx", np.uint8, (2,)),
+    ("cc_idc", np.uint8, (2,)), ("edges", np.uint8), ("reserved", np.uint8, (3,))])
+ALF_SETS_DTYPE = np.dtype([
+    ("luma_coeff", np.int16, (8, 25, 12)), ("luma_clip_idx", np.uint8, (8, 25, 12)),
+    ("chroma_coeff", np.int16, (8, 6)), ("chroma_clip_idx", np.uint8, (8, 6)),
+    ("cc_coeff", np.int16, (2, 5, 7))])
+assert ALF_CTB_DTYPE.itemsize == C.sizeof(VVCCudaALFCtb)
+assert ALF_SETS_DTYPE.itemsize == C.sizeof(VVCCudaALFSets)
+
+
+class FrameGeom:
+    """Geometry of a 4:2:0 (default) high-bit-depth picture ring."""
+
+    def __init__(self, width, height, bit_depth=10, ctb_log2=7, hshift=1, vshift=1, batch=1,
+                 chroma_format_idc=1, pitch_align=128):
+        self.width, self.height, self.bit_depth, self.ctb_log2 = width, height, bit_depth, ctb_log2
+        self.hshift, self.vshift, self.batch = hshift, vshift, batch
+        self.chroma_format_idc = chroma_format_idc
+        self.pitch_align = pitch_align
+
+    @property
+    def ctb_size(self):
+        return 1 << self.ctb_log2
+
+    @property
+    def ctb_cols(self):
+        return (self.width + self.ctb_size - 1) >> self.ctb_log2
+
+    @property
+    def ctb_rows(self):
+        return (self.height + self.ctb_size - 1) >> self.ctb_log2
+
+    @property
+    def ctb_count(self):
+        return self.ctb_cols * self.ctb_rows
+
+    def plane_wh(self, c):
+        if c == 0:
+            return self.width, self.height
+        return self.width >> self.hshift, self.height >> self.vshift
+
+    def plane_pitch(self, c):
+        """Row pitch in samples: a multiple of pitch_align (128 samples = 256 bytes)."""
+        w, _ = self.plane_wh(c)
+        a = self.pitch_align
+        return (w + a - 1) // a * a
+
+    def plane_shape(self, c):
+        return (self.batch, self.plane_wh(c)[1], self.plane_pitch(c))
+
+    @property
+    def luma_pixels(self):
+        return self.width * self.height * self.batch
+
+
+def frame_desc(geom, ptrs, pitches_bytes, batch_strides_bytes):
+    """Build a VVCCudaFrame from raw plane base addresses (host or device)."""
+    f = VVCCudaFrame()
+    for c in range(3):
+        f.data[c] = ptrs[c]
+        f.stride[c] = pitches_bytes[c]
+        f.batch_stride[c] = batch_strides_bytes[c]
+    f.width, f.height = geom.width, geom.height
+    f.hshift, f.vshift = geom.hshift, geom.vshift
+    f.bit_depth, f.ctb_log2 = geom.bit_depth, geom.ctb_log2
+    f.batch, f.chroma_format_idc = geom.batch, geom.chroma_format_idc
+    return f
+
+
+def frame_from_numpy(geom, planes):
+    """planes: three C-contiguous uint16 arrays of shape geom.plane_shape(c)."""
+    ptrs, pitches, bstr = [], [], []
+    for c, p in enumerate(planes):
+        assert p.dtype == np.uint16 and p.flags.c_contiguous and p.shape == geom.plane_shape(c), (c, p.shape)
+        ptrs.append(p.ctypes.data)
+        pitches.append(p.strides[1])
+        bstr.append(p.strides[0])
+    return frame_desc(geom, ptrs, pitches, bstr)
+
+
+def alloc_planes(geom, fill=None):
+    planes = [np.zeros(geom.plane_shape(c), dtype=np.uint16) for c in range(3)]
+    if fill is not None:
+        for p in planes:
+            p[...] = fill
+    return planes
