@@ -1,0 +1,422 @@
+// ALF stage for sm_100a: one fused launch per picture ring.
+//
+// Replaces the reference's per-CTB walk ff_vvc_alf_filter (libavcodec/vvc/vvc_filter.c:1254-1319)
+// and the table entries it calls (libavcodec/vvc/vvc_filter_template.c):
+//   alf_classify + alf_get_idx :270-381, alf_recon_coeff_and_clip :383-408,
+//   alf_filter_luma :43-135, alf_filter_chroma :137-221, alf_filter_cc :223-263.
+//
+// B200 design: a CTA owns a TWxTH luma tile and the co-located 4:2:0 chroma tiles of both
+// chroma planes.  It stages luma (+3 halo) and chroma (+2 halo) once into shared memory with
+// 128-bit loads, derives the Laplacian lattice, per-4x4 class/transpose and the 12 (coeff, clip)
+// pairs in shared memory, then filters luma 7x7, chroma 5x5 and adds the CC-ALF correction taken
+// from the staged pre-ALF luma - each plane is read once and written once (6 B per luma pixel).
+// Halo samples across a flagged CTB edge are a coordinate clamp, which is what the reference's
+// alf_prepare_buffer (:1105-1137) materialises in its padded scratch copy.
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace {
+
+struct AlfK {
+    const pel *src[3];
+    pel       *dst[3];
+    int        sp[3], dp[3];          // row pitch in samples
+    long long  sb[3], db[3];          // picture-to-picture stride in samples
+    int        w, h, bd, ctb_log2, ctb_cols, ctb_rows, planes;
+    const VVCCudaALFCtb  *ctbs;
+    const VVCCudaALFSets *sets;
+    int        sets_per_frame;
+};
+
+constexpr int kThreads = 256;
+
+template <int TW, int TH>
+struct AlfSmem {
+    static constexpr int LP = TW + 16;           // luma row pitch (samples), 8-sample aligned halo
+    static constexpr int CP = TW / 2 + 16;
+    alignas(16) pel     luma[TH + 6][LP];
+    alignas(16) pel     chroma[2][TH / 2 + 4][CP];
+    alignas(16) ushort4 cell[TH / 2 + 2][TW / 2 + 2];
+    alignas(16) short   coef[(TH / 4) * (TW / 4)][24];   // 12 coefficients then 12 clip values
+};
+
+struct ClampWin { int xlo, xhi, ylo, yhi; };
+
+__device__ __forceinline__ ClampWin make_win(int x0, int y0, int w, int h, int pw, int ph, unsigned edges)
+{
+    ClampWin c;
+    c.xlo = (edges & VVC_CUDA_EDGE_LEFT)   ? x0         : 0;
+    c.xhi = (edges & VVC_CUDA_EDGE_RIGHT)  ? x0 + w - 1 : pw - 1;
+    c.ylo = (edges & VVC_CUDA_EDGE_TOP)    ? y0         : 0;
+    c.yhi = (edges & VVC_CUDA_EDGE_BOTTOM) ? y0 + h - 1 : ph - 1;
+    return c;
+}
+
+// Stage rows [ry0, ry0+rows) x columns [rx0, rx0 + 8*chunks) of a plane into shared memory,
+// clamping coordinates to the CTB's window.
+template <int PITCH>
+__device__ __forceinline__ void stage_tile(pel *sm, const pel *__restrict__ plane, int pitch,
+                                           int rx0, int ry0, int rows, int chunks, ClampWin cw)
+{
+    for (int idx = threadIdx.x; idx < rows * chunks; idx += kThreads) {
+        const int i = idx / chunks, q = idx - i * chunks;
+        const int y = d_clip3(ry0 + i, cw.ylo, cw.yhi);
+        const int xs = rx0 + 8 * q;
+        const pel *row = plane + (long long)y * pitch;
+        pel *out = sm + i * PITCH + 8 * q;
+        if (xs >= cw.xlo && xs + 7 <= cw.xhi) {
+            *reinterpret_cast<uint4 *>(out) = __ldg(reinterpret_cast<const uint4 *>(row + xs));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                out[e] = __ldg(row + d_clip3(xs + e, cw.xlo, cw.xhi));
+        }
+    }
+}
+
+// vertical reach of k rows next to the virtual boundary (t = row - vb_pos), :80-96
+__device__ __forceinline__ int vb_reach(int k, int t, int span)
+{
+    if (t < 0 && t >= -span) return min(k, -t - 1);
+    if (t >= 0 && t < span)  return min(k, t);
+    return k;
+}
+
+__device__ __forceinline__ int pair_clip(int cur, int a, int b, int c)
+{
+    return d_clip3(a - cur, -c, c) + d_clip3(b - cur, -c, c);
+}
+
+__constant__ uint8_t c_perm[4][12] = {
+    { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 },
+    { 9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6 },
+    { 0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11 },
+    { 9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6 },
+};
+__constant__ uint8_t c_act[16] = { 0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4 };
+__constant__ uint8_t c_clip_shift[4] = { 0, 3, 5, 7 };
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
+{
+    using SM = AlfSmem<TW, TH>;
+    __shared__ SM sm;
+    constexpr int LP = SM::LP, CP = SM::CP;
+    constexpr int CW = TW / 2, CH = TH / 2;
+    constexpr int BX = TW / 4, BY = TH / 4;
+
+    const int tid = threadIdx.x;
+    const int k = blockIdx.z;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int ctb = 1 << p.ctb_log2;
+    const int cx = tx0 >> p.ctb_log2, cy = ty0 >> p.ctb_log2;
+    const VVCCudaALFCtb a = p.ctbs[((long long)k * p.ctb_rows + cy) * p.ctb_cols + cx];
+    const VVCCudaALFSets *sets = p.sets + (p.sets_per_frame ? k : 0);
+    const int bd = p.bd;
+
+    unsigned edges = a.edges;
+    if (cx == 0)              edges |= VVC_CUDA_EDGE_LEFT;
+    if (cy == 0)              edges |= VVC_CUDA_EDGE_TOP;
+    if (cx == p.ctb_cols - 1) edges |= VVC_CUDA_EDGE_RIGHT;
+    if (cy == p.ctb_rows - 1) edges |= VVC_CUDA_EDGE_BOTTOM;
+    const int x0 = cx << p.ctb_log2, y0 = cy << p.ctb_log2;
+    const int lw = min(ctb, p.w - x0), lh = min(ctb, p.h - y0);
+
+    // ---- stage the tiles ------------------------------------------------------------------
+    {
+        const ClampWin cw = make_win(x0, y0, lw, lh, p.w, p.h, edges);
+        stage_tile<LP>(&sm.luma[0][0], p.src[0] + k * p.sb[0], p.sp[0], tx0 - 8, ty0 - 3, TH + 6, LP / 8, cw);
+    }
+    if (p.planes == 3) {
+        const ClampWin cw = make_win(x0 >> 1, y0 >> 1, lw >> 1, lh >> 1, p.w >> 1, p.h >> 1, edges);
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+            stage_tile<CP>(&sm.chroma[c][0][0], p.src[c + 1] + k * p.sb[c + 1], p.sp[c + 1],
+                           (tx0 >> 1) - 8, (ty0 >> 1) - 2, CH + 4, CP / 8, cw);
+    }
+    __syncthreads();
+
+    const int vb = ctb - 4;               // luma virtual boundary, CTB relative (:1304)
+    const int trow = ty0 - y0;            // tile row inside the CTB
+
+    if (a.ctb_flag[0]) {
+        // ---- Laplacian lattice, one cell per 2x2 luma positions (:315-344) -----------------
+        for (int idx = tid; idx < (TH / 2 + 2) * (TW / 2 + 2); idx += kThreads) {
+            const int ci = idx / (TW / 2 + 2), cj = idx - ci * (TW / 2 + 2);
+            const int yy = trow + 2 * ci;                 // the reference's loop variable y
+            int r0 = 2 * ci, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3;   // shared-memory rows
+            if (yy == vb)          r3 = r2;
+            else if (yy == vb + 2) r0 = r1;
+            const int ca = 2 * cj + 6;                    // column of the first sample point
+            const pel *R0 = sm.luma[r0], *R1 = sm.luma[r1], *R2 = sm.luma[r2], *R3 = sm.luma[r3];
+            const int c0 = 2 * R1[ca], c1 = 2 * R2[ca + 1];
+            ushort4 g;
+            g.x = abs(c0 - R0[ca] - R2[ca])         + abs(c1 - R1[ca + 1] - R3[ca + 1]);   // vertical
+            g.y = abs(c0 - R1[ca - 1] - R1[ca + 1]) + abs(c1 - R2[ca] - R2[ca + 2]);       // horizontal
+            g.z = abs(c0 - R0[ca - 1] - R2[ca + 1]) + abs(c1 - R1[ca] - R3[ca + 2]);       // diagonal 0
+            g.w = abs(c0 - R0[ca + 1] - R2[ca - 1]) + abs(c1 - R1[ca + 2] - R3[ca]);       // diagonal 1
+            sm.cell[ci][cj] = g;
+        }
+        __syncthreads();
+
+        // ---- class / transpose per 4x4 block and its 12 (coeff, clip) pairs (:270-297,:346-408)
+        for (int b = tid; b < BX * BY; b += kThreads) {
+            const int bi = b / BX, bj = b - bi * BX;
+            const int by = trow + 4 * bi;
+            int first = 0, last = 4, scale = 2;
+            if (by + 4 == vb)  { last = 3;  scale = 3; }
+            else if (by == vb) { first = 1; scale = 3; }
+            int sv = 0, sh = 0, sd0 = 0, sd1 = 0;
+            for (int i = first; i < last; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const ushort4 g = sm.cell[2 * bi + i][2 * bj + j];
+                    sv += g.x; sh += g.y; sd0 += g.z; sd1 += g.w;
+                }
+            const int v_le_h = sv <= sh, d0_le_d1 = sd0 <= sd1;
+            const int hv_hi = max(sv, sh), hv_lo = min(sv, sh);
+            const int d_hi = max(sd0, sd1), d_lo = min(sd0, sd1);
+            const int hv_wins = (unsigned long long)d_hi * (unsigned)hv_lo <= (unsigned long long)hv_hi * (unsigned)d_lo;
+            const int hi = hv_wins ? hv_hi : d_hi, lo = hv_wins ? hv_lo : d_lo;
+            int cls = c_act[d_clip_ubits(((sh + sv) * scale) >> (bd - 1), 4)];
+            if (hi * 2 > 9 * lo)  cls += (2 * hv_wins + 2) * 5;
+            else if (hi > 2 * lo) cls += (2 * hv_wins + 1) * 5;
+            const int tr = d0_le_d1 * 2 + v_le_h;
+
+            short *out = sm.coef[b];
+            const int set = a.filt_set_idx_y;
+            if (set < 16) {
+                const int16_t *f = vvct_alf_fix_filt_coeff[vvct_alf_class_to_filt_map[set][cls]];
+#pragma unroll
+                for (int j = 0; j < 12; j++) {
+                    out[j]      = f[c_perm[tr][j]];
+                    out[12 + j] = (short)(1 << bd);
+                }
+            } else {
+                const int16_t *f  = sets->luma_coeff[set - 16][vvct_alf_aps_class_to_filt_map[cls]];
+                const uint8_t *ci = sets->luma_clip_idx[set - 16][cls];   // indexed by class (:400)
+#pragma unroll
+                for (int j = 0; j < 12; j++) {
+                    const int s = c_perm[tr][j];
+                    out[j]      = f[s];
+                    out[12 + j] = (short)(1 << (bd - c_clip_shift[ci[s]]));
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- luma 7x7 diamond (:43-135), 4x1 strips ------------------------------------------------
+    {
+        pel *dplane = p.dst[0] + k * p.db[0];
+        for (int s = tid; s < BX * TH; s += kThreads) {
+            const int r = s / BX, c4 = s - r * BX;
+            const int y = ty0 + r, x = tx0 + 4 * c4;
+            if (y >= p.h || x >= p.w)
+                continue;
+            const pel *p0 = &sm.luma[r + 3][8 + 4 * c4];
+            uint2 o;
+            if (!a.ctb_flag[0]) {
+                o = *reinterpret_cast<const uint2 *>(p0);
+            } else {
+                const int t = (y - y0) - vb;
+                const int d1 = vb_reach(1, t, 4) * LP, d2 = vb_reach(2, t, 4) * LP, d3 = vb_reach(3, t, 4) * LP;
+                const bool near_vb = (t == -1 || t == 0);
+                const short *cf = sm.coef[(r >> 2) * BX + c4];
+                int f[12], c[12];
+                {
+                    const uint4 *cv = reinterpret_cast<const uint4 *>(cf);
+                    const uint4 v0 = cv[0], v1 = cv[1], v2 = cv[2];
+                    const unsigned raw[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        f[2 * j]     = (short)(raw[j] & 0xffff);
+                        f[2 * j + 1] = (short)(raw[j] >> 16);
+                        c[2 * j]     = (short)(raw[6 + j] & 0xffff);
+                        c[2 * j + 1] = (short)(raw[6 + j] >> 16);
+                    }
+                }
+                unsigned short res[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const pel *q = p0 + j;
+                    const int cur = q[0];
+                    int sum = 0;
+                    sum += f[0]  * pair_clip(cur, q[d3],      q[-d3],     c[0]);
+                    sum += f[1]  * pair_clip(cur, q[d2 + 1],  q[-d2 - 1], c[1]);
+                    sum += f[2]  * pair_clip(cur, q[d2],      q[-d2],     c[2]);
+                    sum += f[3]  * pair_clip(cur, q[d2 - 1],  q[-d2 + 1], c[3]);
+                    sum += f[4]  * pair_clip(cur, q[d1 + 2],  q[-d1 - 2], c[4]);
+                    sum += f[5]  * pair_clip(cur, q[d1 + 1],  q[-d1 - 1], c[5]);
+                    sum += f[6]  * pair_clip(cur, q[d1],      q[-d1],     c[6]);
+                    sum += f[7]  * pair_clip(cur, q[d1 - 1],  q[-d1 + 1], c[7]);
+                    sum += f[8]  * pair_clip(cur, q[d1 - 2],  q[-d1 + 2], c[8]);
+                    sum += f[9]  * pair_clip(cur, q[3],       q[-3],      c[9]);
+                    sum += f[10] * pair_clip(cur, q[2],       q[-2],      c[10]);
+                    sum += f[11] * pair_clip(cur, q[1],       q[-1],      c[11]);
+                    sum = near_vb ? (sum + 512) >> 10 : (sum + 64) >> 7;
+                    res[j] = (unsigned short)d_clip_pel(cur + sum, bd);
+                }
+                o.x = res[0] | ((unsigned)res[1] << 16);
+                o.y = res[2] | ((unsigned)res[3] << 16);
+            }
+            *reinterpret_cast<uint2 *>(dplane + (long long)y * p.dp[0] + x) = o;
+        }
+    }
+
+    // ---- chroma 5x5 diamond (:137-221) + CC-ALF from the staged pre-ALF luma (:223-263) --------
+    if (p.planes == 3) {
+        const int cvb = (ctb >> 1) - 2;
+        const int pw = p.w >> 1, ph = p.h >> 1;
+        constexpr int SX = CW / 4;                      // strips per chroma row
+        for (int s = tid; s < 2 * SX * CH; s += kThreads) {
+            const int pc = s / (SX * CH);               // 0 = Cb, 1 = Cr
+            const int rem = s - pc * (SX * CH);
+            const int r = rem / SX, c4 = rem - r * SX;
+            const int y = (ty0 >> 1) + r, x = (tx0 >> 1) + 4 * c4;
+            if (y >= ph || x >= pw)
+                continue;
+            const pel *p0 = &sm.chroma[pc][r + 2][8 + 4 * c4];
+            int val[4];
+            if (!a.ctb_flag[pc + 1]) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    val[j] = p0[j];
+            } else {
+                const int t = (y - (y0 >> 1)) - cvb;
+                const int d1 = vb_reach(1, t, 2) * CP, d2 = vb_reach(2, t, 2) * CP;
+                const bool near_vb = (t == -1 || t == 0);
+                const int alt = a.chroma_alt_idx[pc];
+                int f[6], c[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    f[j] = sets->chroma_coeff[alt][j];
+                    c[j] = 1 << (bd - c_clip_shift[sets->chroma_clip_idx[alt][j]]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const pel *q = p0 + j;
+                    const int cur = q[0];
+                    int sum = 0;
+                    sum += f[0] * pair_clip(cur, q[d2],     q[-d2],     c[0]);
+                    sum += f[1] * pair_clip(cur, q[d1 + 1], q[-d1 - 1], c[1]);
+                    sum += f[2] * pair_clip(cur, q[d1],     q[-d1],     c[2]);
+                    sum += f[3] * pair_clip(cur, q[d1 - 1], q[-d1 + 1], c[3]);
+                    sum += f[4] * pair_clip(cur, q[2],      q[-2],      c[4]);
+                    sum += f[5] * pair_clip(cur, q[1],      q[-1],      c[5]);
+                    sum = near_vb ? (sum + 512) >> 10 : (sum + 64) >> 7;
+                    val[j] = d_clip_pel(cur + sum, bd);
+                }
+            }
+            if (a.cc_idc[pc]) {
+                const int t = (((y - (y0 >> 1)) << 1)) - vb;     // luma row relative to the VB
+                int up = -LP, dn = LP, dn2 = 2 * LP;
+                if (t == -2 || t == 1)       dn2 = LP;
+                else if (t == -1 || t == 0)  up = dn = dn2 = 0;
+                const int16_t *f = sets->cc_coeff[pc][a.cc_idc[pc] - 1];
+                const pel *l0 = &sm.luma[2 * r + 3][8 + 8 * c4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const pel *l = l0 + 2 * j;
+                    const int cur = l[0];
+                    int sum = 0;
+                    sum += f[0] * (l[up]      - cur);
+                    sum += f[1] * (l[-1]      - cur);
+                    sum += f[2] * (l[1]       - cur);
+                    sum += f[3] * (l[dn - 1]  - cur);
+                    sum += f[4] * (l[dn]      - cur);
+                    sum += f[5] * (l[dn + 1]  - cur);
+                    sum += f[6] * (l[dn2]     - cur);
+                    sum = d_clip3((sum + 64) >> 7, -(1 << (bd - 1)), (1 << (bd - 1)) - 1);
+                    val[j] = d_clip_pel(val[j] + sum, bd);
+                }
+            }
+            uint2 o;
+            o.x = (unsigned)val[0] | ((unsigned)val[1] << 16);
+            o.y = (unsigned)val[2] | ((unsigned)val[3] << 16);
+            *reinterpret_cast<uint2 *>(p.dst[pc + 1] + k * p.db[pc + 1] + (long long)y * p.dp[pc + 1] + x) = o;
+        }
+    }
+}
+
+int check_frames(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src)
+{
+    if (!dst || !src)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "alf: null frame");
+    if (src->bit_depth != 10 && src->bit_depth != 12)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "alf: bit depth %d not accelerated (10/12 only)", src->bit_depth);
+    if (src->ctb_log2 < 5 || src->ctb_log2 > 7 || src->batch < 1 || src->width < 8 || src->height < 8 ||
+        (src->width & 7) || (src->height & 7))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "alf: unsupported geometry %dx%d ctb %d", src->width, src->height, 1 << src->ctb_log2);
+    if (src->chroma_format_idc && (src->hshift != 1 || src->vshift != 1))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "alf: only 4:0:0 and 4:2:0 are accelerated");
+    if (dst->width != src->width || dst->height != src->height || dst->batch != src->batch ||
+        dst->bit_depth != src->bit_depth || dst->chroma_format_idc != src->chroma_format_idc)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "alf: dst/src geometry differs");
+    if (!frame_vec_ok(dst) || !frame_vec_ok(src))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "alf: planes and strides must be 16-byte aligned");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int vvc_cuda_alf_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                                  const VVCCudaALFCtb *ctbs, const VVCCudaALFSets *sets, int sets_per_frame)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (check_frames(ctx, dst, src))
+        return ctx->err;
+    AlfK p;
+    p.planes = src->chroma_format_idc ? 3 : 1;
+    for (int c = 0; c < 3; c++) {
+        p.src[c] = (const pel *)src->data[c];
+        p.dst[c] = (pel *)dst->data[c];
+        p.sp[c] = (int)(src->stride[c] / 2);  p.dp[c] = (int)(dst->stride[c] / 2);
+        p.sb[c] = src->batch_stride[c] / 2;   p.db[c] = dst->batch_stride[c] / 2;
+    }
+    p.w = src->width; p.h = src->height; p.bd = src->bit_depth; p.ctb_log2 = src->ctb_log2;
+    p.ctb_cols = ceil_div(p.w, 1 << p.ctb_log2);
+    p.ctb_rows = ceil_div(p.h, 1 << p.ctb_log2);
+    p.ctbs = ctbs; p.sets = sets; p.sets_per_frame = sets_per_frame;
+
+    if (p.ctb_log2 >= 6) {
+        dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, 32), src->batch);
+        alf_frame_kernel<64, 32><<<grid, kThreads, 0, ctx->stream>>>(p);
+    } else {
+        dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 32), src->batch);
+        alf_frame_kernel<32, 32><<<grid, kThreads, 0, ctx->stream>>>(p);
+    }
+    VVC_LAUNCHED(ctx);
+    return VVC_CUDA_OK;
+}
+
+extern "C" int vvc_cuda_alf_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                                       const VVCCudaALFCtb *ctbs, const VVCCudaALFSets *sets, int sets_per_frame)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!dst || !src || !ctbs || !sets)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "alf_host: null argument");
+    const int n_ctb = ceil_div(src->width, 1 << src->ctb_log2) * ceil_div(src->height, 1 << src->ctb_log2) * src->batch;
+    const size_t fsz = align_up(vvc_stage_frame_size(src), 256);
+    const size_t csz = align_up((size_t)n_ctb * sizeof(VVCCudaALFCtb), 256);
+    const size_t ssz = align_up(sizeof(VVCCudaALFSets) * (sets_per_frame ? src->batch : 1), 256);
+    uint8_t *base = (uint8_t *)vvc_ctx_dev_stage(ctx, 2 * fsz + csz + ssz);
+    if (!base)
+        return ctx->err;
+    VVCCudaFrame dsrc, ddst;
+    vvc_stage_frame_layout(src, base, &dsrc);
+    vvc_stage_frame_layout(dst, base + fsz, &ddst);
+    VVCCudaALFCtb  *dctb  = (VVCCudaALFCtb *)(base + 2 * fsz);
+    VVCCudaALFSets *dsets = (VVCCudaALFSets *)(base + 2 * fsz + csz);
+    if (vvc_stage_frame_h2d(ctx, &dsrc, src))
+        return ctx->err;
+    VVC_TRY(ctx, cudaMemcpyAsync(dctb, ctbs, (size_t)n_ctb * sizeof(VVCCudaALFCtb), cudaMemcpyHostToDevice, ctx->stream));
+    VVC_TRY(ctx, cudaMemcpyAsync(dsets, sets, sizeof(VVCCudaALFSets) * (sets_per_frame ? src->batch : 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (vvc_cuda_alf_frame(ctx, &ddst, &dsrc, dctb, dsets, sets_per_frame))
+        return ctx->err;
+    if (vvc_stage_frame_d2h(ctx, dst, &ddst))
+        return ctx->err;
+    return vvc_cuda_sync(ctx);
+}

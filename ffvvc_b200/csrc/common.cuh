@@ -1,0 +1,59 @@
+// Shared declarations of libvvcdsp_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "vvcdsp_cuda.h"
+
+typedef uint16_t pel;   // high-bit-depth sample, as in the reference's 10/12-bit templates
+
+struct VVCCudaCtx {
+    int           device;
+    cudaStream_t  stream;
+    bool          own_stream;
+    int           err;                  // sticky VVC_CUDA_ERR_*
+    char          msg[256];
+    uint64_t      launches;
+    // staging for the *_host entries and the per-call table shims
+    void         *d_stage;  size_t d_stage_size;
+    void         *h_stage;  size_t h_stage_size;    // pinned
+};
+
+int  vvc_ctx_fail(VVCCudaCtx *ctx, int code, const char *fmt, ...);
+int  vvc_ctx_check(VVCCudaCtx *ctx, cudaError_t e, const char *what);
+// Grow-only staging buffers; contents are not preserved across a grow.
+void *vvc_ctx_dev_stage(VVCCudaCtx *ctx, size_t bytes);
+void *vvc_ctx_host_stage(VVCCudaCtx *ctx, size_t bytes);
+
+#define VVC_TRY(ctx, call)  do { if (vvc_ctx_check((ctx), (call), #call)) return (ctx)->err; } while (0)
+#define VVC_LAUNCHED(ctx)   do { (ctx)->launches++; if (vvc_ctx_check((ctx), cudaGetLastError(), "kernel launch")) return (ctx)->err; } while (0)
+
+// ---- integer helpers with the reference's semantics (libavutil/common.h:174-280) ----
+__device__ __forceinline__ int d_clip3(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int d_clip_pel(int v, int bd) { return min(max(v, 0), (1 << bd) - 1); }
+__device__ __forceinline__ int d_clip_sbits(int v, int bits) { return min(max(v, -(1 << bits)), (1 << bits) - 1); }
+__device__ __forceinline__ int d_clip_ubits(int v, int bits) { return min(max(v, 0), (1 << bits) - 1); }
+__device__ __forceinline__ int d_ilog2(unsigned v) { return v ? 31 - __clz(v) : 0; }   // av_log2
+__device__ __forceinline__ int d_sign(int v) { return (v > 0) - (v < 0); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Geometry checks shared by the frame-level entries.
+static inline bool frame_vec_ok(const VVCCudaFrame *f)
+{
+    const int planes = f->chroma_format_idc ? 3 : 1;
+    for (int c = 0; c < planes; c++)
+        if (((uintptr_t)f->data[c] & 15) || (f->stride[c] & 15) || (f->batch_stride[c] & 15))
+            return false;
+    return true;
+}
+
+// ---- host<->device staging of pictures for the *_host entries (host_stage.cu) ----
+size_t vvc_stage_frame_size(const VVCCudaFrame *f);
+// Lay a device picture ring of the same geometry as `host` out at `dbase` (256-byte pitch).
+void   vvc_stage_frame_layout(const VVCCudaFrame *host, void *dbase, VVCCudaFrame *dev);
+int    vvc_stage_frame_h2d(VVCCudaCtx *ctx, const VVCCudaFrame *dev, const VVCCudaFrame *host);
+int    vvc_stage_frame_d2h(VVCCudaCtx *ctx, const VVCCudaFrame *host, const VVCCudaFrame *dev);
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

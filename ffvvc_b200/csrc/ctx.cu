@@ -1,0 +1,121 @@
+// Context management of libvvcdsp_cuda.so: stream ownership, sticky error latch, staging.
+// Error model follows SURVEY.md 8(b): the reference's DSP entries return void, so CUDA failures
+// are latched here and surface from vvc_cuda_sync()/vvc_cuda_last_error().
+#include <stdarg.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+int vvc_ctx_fail(VVCCudaCtx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx->err == VVC_CUDA_OK) {
+        va_list ap;
+        ctx->err = code;
+        va_start(ap, fmt);
+        vsnprintf(ctx->msg, sizeof(ctx->msg), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int vvc_ctx_check(VVCCudaCtx *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess)
+        return 0;
+    vvc_ctx_fail(ctx, VVC_CUDA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return 1;
+}
+
+void *vvc_ctx_dev_stage(VVCCudaCtx *ctx, size_t bytes)
+{
+    if (bytes > ctx->d_stage_size) {
+        if (ctx->d_stage) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->d_stage);
+        }
+        ctx->d_stage = NULL; ctx->d_stage_size = 0;
+        size_t want = bytes + bytes / 4 + (1 << 20);
+        if (vvc_ctx_check(ctx, cudaMalloc(&ctx->d_stage, want), "cudaMalloc(stage)"))
+            return NULL;
+        ctx->d_stage_size = want;
+    }
+    return ctx->d_stage;
+}
+
+void *vvc_ctx_host_stage(VVCCudaCtx *ctx, size_t bytes)
+{
+    if (bytes > ctx->h_stage_size) {
+        if (ctx->h_stage) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFreeHost(ctx->h_stage);
+        }
+        ctx->h_stage = NULL; ctx->h_stage_size = 0;
+        size_t want = bytes + bytes / 4 + (1 << 20);
+        if (vvc_ctx_check(ctx, cudaMallocHost(&ctx->h_stage, want), "cudaMallocHost(stage)"))
+            return NULL;
+        ctx->h_stage_size = want;
+    }
+    return ctx->h_stage;
+}
+
+extern "C" {
+
+const char *vvc_cuda_version(void) { return "vvcdsp-b200 0.1 (sm_100a)"; }
+
+int vvc_cuda_ctx_create(VVCCudaCtx **out, int device, void *stream)
+{
+    if (!out)
+        return VVC_CUDA_ERR_ARG;
+    *out = NULL;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n)
+        return VVC_CUDA_ERR_CUDA;          // no usable device: fail loudly, never fall back
+    VVCCudaCtx *ctx = (VVCCudaCtx *)calloc(1, sizeof(*ctx));
+    if (!ctx)
+        return VVC_CUDA_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return VVC_CUDA_ERR_CUDA; }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return VVC_CUDA_ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return VVC_CUDA_OK;
+}
+
+void vvc_cuda_ctx_destroy(VVCCudaCtx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+int vvc_cuda_sync(VVCCudaCtx *ctx)
+{
+    vvc_ctx_check(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    return ctx->err;
+}
+
+int         vvc_cuda_last_error(const VVCCudaCtx *ctx)   { return ctx->err; }
+const char *vvc_cuda_error_string(const VVCCudaCtx *ctx) { return ctx->err ? ctx->msg : "ok"; }
+void       *vvc_cuda_stream(const VVCCudaCtx *ctx)       { return (void *)ctx->stream; }
+uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx) { return ctx->launches; }
+
+}  // extern "C"
+
+// sizeof() of the descriptor PODs as compiled here, so bindings can verify their mirrors.
+extern "C" size_t vvc_cuda_abi_sizeof(int which)
+{
+    switch (which) {
+    case 0: return sizeof(VVCCudaFrame);
+    case 1: return sizeof(VVCCudaALFCtb);
+    case 2: return sizeof(VVCCudaALFSets);
+    default: return 0;
+    }
+}

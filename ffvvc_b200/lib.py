@@ -1,0 +1,98 @@
+"""Loader and thin Python face of libvvcdsp_cuda.so (the product's C ABI, include/vvcdsp_cuda.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no device is usable,
+importing callers get an exception.  PyTorch is used only to own device memory and streams.
+"""
+import ctypes as C
+import os
+import re
+
+from . import abi
+from .dsp_tables import VVCDSPContext
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvvcdsp_cuda.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vvcdsp_cuda.h")
+
+FP = C.POINTER(abi.VVCCudaFrame)
+CTX = C.c_void_p
+
+_lib = None
+
+
+class VVCCudaError(RuntimeError):
+    pass
+
+
+def declared_symbols():
+    """Every function name include/vvcdsp_cuda.h declares (used by the export test)."""
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:vvc_cuda|ff_vvc)_[a-z0-9_]+)\s*\(", src)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VVCCudaError("%s not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.vvc_cuda_version.restype = C.c_char_p
+    lib.vvc_cuda_ctx_create.argtypes = [C.POINTER(CTX), C.c_int, C.c_void_p]
+    lib.vvc_cuda_ctx_destroy.argtypes = [CTX]
+    lib.vvc_cuda_ctx_destroy.restype = None
+    lib.vvc_cuda_sync.argtypes = [CTX]
+    lib.vvc_cuda_last_error.argtypes = [CTX]
+    lib.vvc_cuda_error_string.argtypes = [CTX]
+    lib.vvc_cuda_error_string.restype = C.c_char_p
+    lib.vvc_cuda_stream.argtypes = [CTX]
+    lib.vvc_cuda_stream.restype = C.c_void_p
+    lib.vvc_cuda_launch_count.argtypes = [CTX]
+    lib.vvc_cuda_launch_count.restype = C.c_uint64
+    for name in ("vvc_cuda_alf_frame", "vvc_cuda_alf_frame_host"):
+        fn = getattr(lib, name)
+        fn.argtypes = [CTX, FP, FP, C.c_void_p, C.c_void_p, C.c_int]
+    _lib = lib
+    return lib
+
+
+class Context:
+    """One decoder stream's CUDA context (vvc_cuda_ctx_create / _destroy)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        self.handle = CTX()
+        rc = self.lib.vvc_cuda_ctx_create(C.byref(self.handle), device, stream)
+        if rc != 0:
+            raise VVCCudaError("vvc_cuda_ctx_create(device=%d) failed with %d: no usable CUDA device" % (device, rc))
+
+    def close(self):
+        if self.handle:
+            self.lib.vvc_cuda_ctx_destroy(self.handle)
+            self.handle = CTX()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise VVCCudaError("libvvcdsp_cuda error %d: %s" % (rc, self.lib.vvc_cuda_error_string(self.handle).decode()))
+
+    def sync(self):
+        self.check(self.lib.vvc_cuda_sync(self.handle))
+
+    @property
+    def launches(self):
+        return int(self.lib.vvc_cuda_launch_count(self.handle))
+
+    # ---- stages -------------------------------------------------------------------------
+    def alf_frame(self, dst, src, ctbs_ptr, sets_ptr, sets_per_frame=0):
+        self.check(self.lib.vvc_cuda_alf_frame(self.handle, C.byref(dst), C.byref(src), ctbs_ptr, sets_ptr, sets_per_frame))
+
+    def alf_frame_host(self, dst, src, ctbs_ptr, sets_ptr, sets_per_frame=0):
+        self.check(self.lib.vvc_cuda_alf_frame_host(self.handle, C.byref(dst), C.byref(src), ctbs_ptr, sets_ptr, sets_per_frame))

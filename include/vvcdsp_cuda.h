@@ -57,6 +57,9 @@ void       *vvc_cuda_stream(const VVCCudaCtx *ctx);    /* the cudaStream_t in us
 /* number of kernel launches issued through this context since creation (bench bookkeeping) */
 uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx);
 const char *vvc_cuda_version(void);
+/* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
+ * 2 VVCCudaALFSets, ...): lets foreign-language bindings verify their struct mirrors. */
+size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
  * Pictures
