@@ -130,3 +130,75 @@ def alloc_planes(geom, fill=None):
         for p in planes:
             p[...] = fill
     return planes
+
+
+# ---- deblocking / SAO descriptors (include/vvcdsp_cuda.h) ----------------------------------
+class VVCCudaDbkEdge(C.Structure):
+    _fields_ = [("tc", C.c_uint16), ("beta", C.c_uint8), ("max_len", C.c_uint8)]
+
+
+class VVCCudaDeblockMaps(C.Structure):
+    _fields_ = [
+        ("edge", C.c_void_p * 3 * 2),
+        ("pitch", C.c_int32 * 3 * 2),
+        ("rows", C.c_int32 * 3 * 2),
+        ("size", C.c_int64 * 3 * 2),
+    ]
+
+
+class VVCCudaSAOCtb(C.Structure):
+    _fields_ = [
+        ("type_idx", C.c_uint8 * 3), ("band_position", C.c_uint8 * 3), ("eo_class", C.c_uint8 * 3),
+        ("restore", C.c_uint8), ("no_filter", C.c_uint8), ("reserved", C.c_uint8),
+        ("offset_val", C.c_int16 * 5 * 3),
+    ]
+
+
+DBK_EDGE_DTYPE = np.dtype([("tc", np.uint16), ("beta", np.uint8), ("max_len", np.uint8)])
+SAO_CTB_DTYPE = np.dtype([
+    ("type_idx", np.uint8, (3,)), ("band_position", np.uint8, (3,)), ("eo_class", np.uint8, (3,)),
+    ("restore", np.uint8), ("no_filter", np.uint8), ("reserved", np.uint8), ("offset_val", np.int16, (3, 5))])
+assert DBK_EDGE_DTYPE.itemsize == C.sizeof(VVCCudaDbkEdge) == 4
+assert SAO_CTB_DTYPE.itemsize == C.sizeof(VVCCudaSAOCtb) == 42
+
+
+def deblock_map_shape(geom, direction, c):
+    """(rows, pitch) of the edge map for plane c; direction 1 = vertical edges, 0 = horizontal."""
+    w, h = geom.plane_wh(c)
+    grid = 8 if c else 4
+    seg = (4 >> (geom.vshift if direction else geom.hshift)) if c else 4
+    if direction:
+        return (h + seg - 1) // seg, (w + grid - 1) // grid
+    return (h + grid - 1) // grid, (w + seg - 1) // seg
+
+
+def deblock_maps_desc(geom, arrays, ptr_of=lambda a: a.ctypes.data):
+    """arrays[dir][c]: DBK_EDGE_DTYPE arrays of shape (batch, rows, pitch) -> VVCCudaDeblockMaps."""
+    m = VVCCudaDeblockMaps()
+    for d in range(2):
+        for c in range(3):
+            a = arrays[d][c]
+            rows, pitch = deblock_map_shape(geom, d, c)
+            assert a.shape == (geom.batch, rows, pitch), (a.shape, rows, pitch)
+            m.edge[d][c] = ptr_of(a)
+            m.pitch[d][c] = pitch
+            m.rows[d][c] = rows
+            m.size[d][c] = rows * pitch
+    return m
+
+
+class VVCCudaInloopDesc(C.Structure):
+    _fields_ = [
+        ("deblock", C.POINTER(VVCCudaDeblockMaps)),
+        ("sao", C.c_void_p), ("alf", C.c_void_p), ("alf_sets", C.c_void_p),
+        ("alf_sets_per_frame", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+def inloop_desc(maps_desc, sao_ptr, alf_ptr, sets_ptr, sets_per_frame=0):
+    d = VVCCudaInloopDesc()
+    d.deblock = C.pointer(maps_desc)
+    d.sao, d.alf, d.alf_sets = sao_ptr, alf_ptr, sets_ptr
+    d.alf_sets_per_frame = sets_per_frame
+    d._keep = maps_desc
+    return d

@@ -19,6 +19,9 @@ struct VVCCudaCtx {
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;
     void         *h_stage;  size_t h_stage_size;    // pinned
+    void         *d_scratch[2]; size_t d_scratch_size[2];   // intermediate pictures of chained stages
+    cudaStream_t  copy_in, copy_out;                 // lazily created, *_host pipelines
+    cudaEvent_t   ev[8];
 };
 
 int  vvc_ctx_fail(VVCCudaCtx *ctx, int code, const char *fmt, ...);
@@ -26,6 +29,7 @@ int  vvc_ctx_check(VVCCudaCtx *ctx, cudaError_t e, const char *what);
 // Grow-only staging buffers; contents are not preserved across a grow.
 void *vvc_ctx_dev_stage(VVCCudaCtx *ctx, size_t bytes);
 void *vvc_ctx_host_stage(VVCCudaCtx *ctx, size_t bytes);
+void *vvc_ctx_scratch(VVCCudaCtx *ctx, int slot, size_t bytes);
 
 #define VVC_TRY(ctx, call)  do { if (vvc_ctx_check((ctx), (call), #call)) return (ctx)->err; } while (0)
 #define VVC_LAUNCHED(ctx)   do { (ctx)->launches++; if (vvc_ctx_check((ctx), cudaGetLastError(), "kernel launch")) return (ctx)->err; } while (0)

@@ -57,6 +57,21 @@ void *vvc_ctx_host_stage(VVCCudaCtx *ctx, size_t bytes)
     return ctx->h_stage;
 }
 
+void *vvc_ctx_scratch(VVCCudaCtx *ctx, int slot, size_t bytes)
+{
+    if (bytes > ctx->d_scratch_size[slot]) {
+        if (ctx->d_scratch[slot]) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->d_scratch[slot]);
+        }
+        ctx->d_scratch[slot] = NULL; ctx->d_scratch_size[slot] = 0;
+        if (vvc_ctx_check(ctx, cudaMalloc(&ctx->d_scratch[slot], bytes), "cudaMalloc(scratch)"))
+            return NULL;
+        ctx->d_scratch_size[slot] = bytes;
+    }
+    return ctx->d_scratch[slot];
+}
+
 extern "C" {
 
 const char *vvc_cuda_version(void) { return "vvcdsp-b200 0.1 (sm_100a)"; }
@@ -92,6 +107,10 @@ void vvc_cuda_ctx_destroy(VVCCudaCtx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 2; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -116,6 +135,10 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 0: return sizeof(VVCCudaFrame);
     case 1: return sizeof(VVCCudaALFCtb);
     case 2: return sizeof(VVCCudaALFSets);
+    case 3: return sizeof(VVCCudaDbkEdge);
+    case 4: return sizeof(VVCCudaDeblockMaps);
+    case 5: return sizeof(VVCCudaSAOCtb);
+    case 6: return sizeof(VVCCudaInloopDesc);
     default: return 0;
     }
 }

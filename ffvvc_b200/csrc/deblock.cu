@@ -1,0 +1,423 @@
+// Deblocking stage for sm_100a: one launch per direction per picture ring.
+//
+// Replaces the pixel work of ff_vvc_deblock_vertical / _horizontal (libavcodec/vvc/vvc_filter.c:861-1003):
+//   vvc_loop_filter_luma              libavcodec/vvc/vvc_filter_template.c:546-631
+//   loop_filter_luma_large            libavcodec/vvc/vvc_filter_template.c:466-544
+//   loop_filter_luma_strong / _weak   libavcodec/h26x/h2656_deblock_template.c:25-81
+//   vvc_loop_filter_chroma            libavcodec/vvc/vvc_filter_template.c:681-754
+//   loop_filter_chroma_strong(_one_side) :633-679, loop_filter_chroma_weak h2656_deblock_template.c:83-99
+//
+// B200 design: a CTA owns a TWxTH tile of one plane.  It stages the tile plus an 8-sample apron
+// across the edge direction into shared memory with 128-bit loads, then one thread per
+// (edge, line) evaluates the segment decision and filters its line from the *unfiltered* copy into
+// a second shared copy; the tile's own samples are written back with 128-bit stores.  Each sample
+// is written exactly once by its owning CTA (edges on both tile borders are evaluated by both
+// neighbours), so the pass is deterministic, out of place, and for edge sets that obey the
+// reference's filter-length rules identical to the reference's in-place sequential walk
+// (same-direction edges never read each other's output).
+#include "common.cuh"
+
+namespace {
+
+struct DbkK {
+    const pel *src[3];
+    pel       *dst[3];
+    int        sp[3], dp[3];
+    long long  sb[3], db[3];
+    int        pw[3], ph[3];              // plane sizes
+    int        vs[3], hs[3];
+    const VVCCudaDbkEdge *map[3];
+    int        mpitch[3];
+    long long  msize[3];
+    int        bd, ctb_log2, planes;
+    int        tiles_x[3], tiles_y[3], tile_base[3];   // flattened tile index ranges per plane
+};
+
+constexpr int kThreads = 256;
+
+#define AT(base, k) ((base)[(k) * xs])
+
+__device__ __forceinline__ int curv(const pel *l, int xs, int a, int b, int c)
+{
+    return abs((int)AT(l, a) - 2 * (int)AT(l, b) + (int)AT(l, c));
+}
+
+// One line of a luma segment.  seg_in points at Q0 of line 0 of the segment in the unfiltered tile,
+// seg_out at the same sample of the output tile.
+__device__ __forceinline__ void luma_line(const pel *seg_in, pel *seg_out, int xs, int ys, int line,
+                                          int tc_in, int beta_in, int lp, int lq, int hor_ctu_edge, int bd)
+{
+    const int tc = tc_in << (bd - 10), beta = beta_in << (bd - 8);
+    if (!tc)
+        return;
+    const pel *l0 = seg_in, *l3 = seg_in + 3 * ys;
+    const pel *in = seg_in + line * ys;
+    pel *out = seg_out + line * ys;
+
+    const int dp0 = curv(l0, xs, -3, -2, -1), dq0 = curv(l0, xs, 2, 1, 0);
+    const int dp3 = curv(l3, xs, -3, -2, -1), dq3 = curv(l3, xs, 2, 1, 0);
+    const int d0 = dp0 + dq0, d3 = dp3 + dq3;
+    const int tc25 = (tc * 5 + 1) >> 1;
+    const bool big_p = lp > 3 && !hor_ctu_edge, big_q = lq > 3;
+
+    if (big_p || big_q) {
+        const int dp0l = big_p ? (dp0 + curv(l0, xs, -6, -5, -4) + 1) >> 1 : dp0;
+        const int dq0l = big_q ? (dq0 + curv(l0, xs, 5, 4, 3) + 1) >> 1 : dq0;
+        const int dp3l = big_p ? (dp3 + curv(l3, xs, -6, -5, -4) + 1) >> 1 : dp3;
+        const int dq3l = big_q ? (dq3 + curv(l3, xs, 5, 4, 3) + 1) >> 1 : dq3;
+        const int d0l = dp0l + dq0l, d3l = dp3l + dq3l;
+        lp = big_p ? lp : 3;          // sticky for the normal decision below (:591-592)
+        lq = big_q ? lq : 3;
+        if (d0l + d3l < beta) {
+            const int b53 = (beta * 3) >> 5, b4 = beta >> 4;
+            int sp0 = abs(AT(l0, -4) - AT(l0, -1)) + (lp == 7 ? abs(AT(l0, -8) - AT(l0, -7) - AT(l0, -6) + AT(l0, -5)) : 0);
+            int sq0 = abs(AT(l0, 0) - AT(l0, 3))   + (lq == 7 ? abs(AT(l0, 4) - AT(l0, 5) - AT(l0, 6) + AT(l0, 7)) : 0);
+            int sp3 = abs(AT(l3, -4) - AT(l3, -1)) + (lp == 7 ? abs(AT(l3, -8) - AT(l3, -7) - AT(l3, -6) + AT(l3, -5)) : 0);
+            int sq3 = abs(AT(l3, 0) - AT(l3, 3))   + (lq == 7 ? abs(AT(l3, 4) - AT(l3, 5) - AT(l3, 6) + AT(l3, 7)) : 0);
+            if (big_p) {
+                sp0 = (sp0 + abs(AT(l0, -4) - AT(l0, -1 - lp)) + 1) >> 1;
+                sp3 = (sp3 + abs(AT(l3, -4) - AT(l3, -1 - lp)) + 1) >> 1;
+            }
+            if (big_q) {
+                sq0 = (sq0 + abs(AT(l0, 3) - AT(l0, lq)) + 1) >> 1;
+                sq3 = (sq3 + abs(AT(l3, 3) - AT(l3, lq)) + 1) >> 1;
+            }
+            if (sp0 + sq0 < b53 && abs(AT(l0, -1) - AT(l0, 0)) < tc25 &&
+                sp3 + sq3 < b53 && abs(AT(l3, -1) - AT(l3, 0)) < tc25 &&
+                (d0l << 1) < b4 && (d3l << 1) < b4) {
+                // ---- long filter (:466-544): bilinear pull towards the middle value m ----
+                int p[8], q[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) { p[i] = AT(in, -1 - i); q[i] = AT(in, i); }
+                int m;
+                if (lp == 5 && lq == 5)
+                    m = (p[4] + p[3] + 2 * (p[2] + p[1] + p[0] + q[0] + q[1] + q[2]) + q[3] + q[4] + 8) >> 4;
+                else if (lp == lq)
+                    m = (p[6] + p[5] + p[4] + p[3] + p[2] + p[1] + 2 * (p[0] + q[0]) + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + 8) >> 4;
+                else if (lp + lq == 12)
+                    m = (p[5] + p[4] + p[3] + p[2] + 2 * (p[1] + p[0] + q[0] + q[1]) + q[2] + q[3] + q[4] + q[5] + 8) >> 4;
+                else if (lp + lq == 8)
+                    m = (p[3] + p[2] + p[1] + p[0] + q[0] + q[1] + q[2] + q[3] + 4) >> 3;
+                else if (lq == 7)
+                    m = (2 * (p[2] + p[1] + p[0] + q[0]) + p[0] + p[1] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + 8) >> 4;
+                else
+                    m = (p[6] + p[5] + p[4] + p[3] + p[2] + p[1] + 2 * (q[2] + q[1] + q[0] + p[0]) + q[0] + q[1] + 8) >> 4;
+                // tap weights 3:{53,32,11} 5:{58,45,32,19,6} 7:{59,50,41,32,23,14,5}; tc scale 6,(5),4,(3),2,(1,1)
+                {
+                    const int w0 = lp == 3 ? 53 : lp == 5 ? 58 : 59, ws = lp == 3 ? 21 : lp == 5 ? 13 : 9, ks = lp == 3 ? 2 : 1;
+                    const int ref = (p[lp] + p[lp - 1] + 1) >> 1;
+#pragma unroll
+                    for (int i = 0; i < 7; i++)
+                        if (i < lp) {
+                            const int w = w0 - ws * i, lim = (tc * max(6 - ks * i, 1)) >> 1;
+                            AT(out, -1 - i) = (pel)(p[i] + d_clip3(((m * w + ref * (64 - w) + 32) >> 6) - p[i], -lim, lim));
+                        }
+                }
+                {
+                    const int w0 = lq == 3 ? 53 : lq == 5 ? 58 : 59, ws = lq == 3 ? 21 : lq == 5 ? 13 : 9, ks = lq == 3 ? 2 : 1;
+                    const int ref = (q[lq] + q[lq - 1] + 1) >> 1;
+#pragma unroll
+                    for (int i = 0; i < 7; i++)
+                        if (i < lq) {
+                            const int w = w0 - ws * i, lim = (tc * max(6 - ks * i, 1)) >> 1;
+                            AT(out, i) = (pel)(q[i] + d_clip3(((m * w + ref * (64 - w) + 32) >> 6) - q[i], -lim, lim));
+                        }
+                }
+                return;
+            }
+        }
+    }
+    if (d0 + d3 >= beta)
+        return;
+    const int p3 = AT(in, -4), p2 = AT(in, -3), p1 = AT(in, -2), p0 = AT(in, -1);
+    const int q0 = AT(in, 0), q1 = AT(in, 1), q2 = AT(in, 2), q3 = AT(in, 3);
+    if (lp > 2 && lq > 2 &&
+        abs(AT(l0, -4) - AT(l0, -1)) + abs(AT(l0, 3) - AT(l0, 0)) < (beta >> 3) && abs(AT(l0, -1) - AT(l0, 0)) < tc25 &&
+        abs(AT(l3, -4) - AT(l3, -1)) + abs(AT(l3, 3) - AT(l3, 0)) < (beta >> 3) && abs(AT(l3, -1) - AT(l3, 0)) < tc25 &&
+        (d0 << 1) < (beta >> 2) && (d3 << 1) < (beta >> 2)) {
+        AT(out, -1) = (pel)(p0 + d_clip3(((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3) - p0, -3 * tc, 3 * tc));
+        AT(out, -2) = (pel)(p1 + d_clip3(((p2 + p1 + p0 + q0 + 2) >> 2) - p1, -2 * tc, 2 * tc));
+        AT(out, -3) = (pel)(p2 + d_clip3(((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3) - p2, -tc, tc));
+        AT(out, 0)  = (pel)(q0 + d_clip3(((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3) - q0, -3 * tc, 3 * tc));
+        AT(out, 1)  = (pel)(q1 + d_clip3(((p0 + q0 + q1 + q2 + 2) >> 2) - q1, -2 * tc, 2 * tc));
+        AT(out, 2)  = (pel)(q2 + d_clip3(((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3) - q2, -tc, tc));
+    } else {
+        int np = 1, nq = 1;
+        if (lp > 1 && lq > 1) {
+            const int side = (beta + (beta >> 1)) >> 3;
+            if (dp0 + dp3 < side) np = 2;
+            if (dq0 + dq3 < side) nq = 2;
+        }
+        int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+        if (abs(delta) < 10 * tc) {
+            const int half = tc >> 1;
+            delta = d_clip3(delta, -tc, tc);
+            AT(out, -1) = (pel)d_clip_pel(p0 + delta, bd);
+            AT(out, 0)  = (pel)d_clip_pel(q0 - delta, bd);
+            if (np > 1)
+                AT(out, -2) = (pel)d_clip_pel(p1 + d_clip3((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -half, half), bd);
+            if (nq > 1)
+                AT(out, 1)  = (pel)d_clip_pel(q1 + d_clip3((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -half, half), bd);
+        }
+    }
+}
+
+// One line of a chroma segment of `lines` lines (2 when the edge direction is subsampled, else 4).
+__device__ __forceinline__ void chroma_line(const pel *seg_in, pel *seg_out, int xs, int ys, int line, int lines,
+                                            int tc_in, int beta_in, int lp, int lq, int bd)
+{
+    const int tc = tc_in << (bd - 10), beta = beta_in << (bd - 8);
+    if (!tc || !lp || !lq)
+        return;
+    if (lq == 3) {
+        const pel *l0 = seg_in, *l1 = seg_in + (lines == 2 ? 1 : 3) * ys;
+        const int tc25 = (tc * 5 + 1) >> 1;
+        const bool one = lp == 1;
+        const int p0 = AT(l0, -1), p1 = AT(l0, -2), p2 = one ? p1 : AT(l0, -3), p3 = one ? p1 : AT(l0, -4);
+        const int n0 = AT(l1, -1), n1 = AT(l1, -2), n2 = one ? n1 : AT(l1, -3), n3 = one ? n1 : AT(l1, -4);
+        const int d0 = abs(p2 - 2 * p1 + p0) + curv(l0, xs, 2, 1, 0);
+        const int d1 = abs(n2 - 2 * n1 + n0) + curv(l1, xs, 2, 1, 0);
+        bool strong = false;
+        if (d0 + d1 < beta) {
+            const bool ok0 = (d0 << 1) < (beta >> 2) && abs(p3 - p0) + abs(AT(l0, 0) - AT(l0, 3)) < (beta >> 3) && abs(p0 - AT(l0, 0)) < tc25;
+            const bool ok1 = (d1 << 1) < (beta >> 2) && abs(n3 - n0) + abs(AT(l1, 0) - AT(l1, 3)) < (beta >> 3) && abs(n0 - AT(l1, 0)) < tc25;
+            strong = ok0 && ok1;
+        }
+        if (!strong)
+            lp = lq = 1;
+    }
+    const pel *in = seg_in + line * ys;
+    pel *out = seg_out + line * ys;
+    const int p3 = AT(in, -4), p2 = AT(in, -3), p1 = AT(in, -2), p0 = AT(in, -1);
+    const int q0 = AT(in, 0), q1 = AT(in, 1), q2 = AT(in, 2), q3 = AT(in, 3);
+    if (lq == 3) {
+        if (lp == 3) {
+            AT(out, -1) = (pel)d_clip3((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3, p0 - tc, p0 + tc);
+            AT(out, -2) = (pel)d_clip3((2 * p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3, p1 - tc, p1 + tc);
+            AT(out, -3) = (pel)d_clip3((3 * p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3, p2 - tc, p2 + tc);
+            AT(out, 0)  = (pel)d_clip3((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3, q0 - tc, q0 + tc);
+        } else {
+            AT(out, -1) = (pel)d_clip3((3 * p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3, p0 - tc, p0 + tc);
+            AT(out, 0)  = (pel)d_clip3((2 * p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3, q0 - tc, q0 + tc);
+        }
+        AT(out, 1) = (pel)d_clip3((p1 + p0 + q0 + 2 * q1 + q2 + 2 * q3 + 4) >> 3, q1 - tc, q1 + tc);
+        AT(out, 2) = (pel)d_clip3((p0 + q0 + q1 + 2 * q2 + 3 * q3 + 4) >> 3, q2 - tc, q2 + tc);
+    } else {
+        const int delta = d_clip3((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
+        AT(out, -1) = (pel)d_clip_pel(p0 + delta, bd);
+        AT(out, 0)  = (pel)d_clip_pel(q0 - delta, bd);
+    }
+}
+
+#undef AT
+
+// VERT: vertical edges (filtering runs along rows).  Tile geometry:
+//   VERT : TW = 64, TH = 32, apron of 8 columns left and right, row pitch TW + 16 + 2 (odd word count
+//          so the 32 lanes of a warp, which walk consecutive rows of one edge, hit distinct banks)
+//   !VERT: TW = 128, TH = 16, apron of 8 rows above and below, lanes walk consecutive columns
+template <bool VERT>
+struct DbkTile {
+    static constexpr int TW = VERT ? 64 : 128, TH = VERT ? 32 : 16;
+    static constexpr int AX = VERT ? 8 : 0, AY = VERT ? 0 : 8;
+    static constexpr int PITCH = TW + 2 * AX + (VERT ? 2 : 0);
+    static constexpr int ROWS = TH + 2 * AY;
+};
+
+template <bool VERT>
+__global__ void __launch_bounds__(kThreads) deblock_kernel(const DbkK p)
+{
+    using T = DbkTile<VERT>;
+    constexpr int TW = T::TW, TH = T::TH, AX = T::AX, AY = T::AY, PITCH = T::PITCH, ROWS = T::ROWS;
+    __shared__ alignas(16) pel s_in[ROWS * PITCH];
+    __shared__ alignas(16) pel s_out[ROWS * PITCH];
+
+    // which plane / tile
+    int c = 0, t = blockIdx.x;
+    if (p.planes == 3) {
+        if (t >= p.tile_base[2])      c = 2;
+        else if (t >= p.tile_base[1]) c = 1;
+    }
+    t -= p.tile_base[c];
+    const int k = blockIdx.y;
+    const int tx0 = (t % p.tiles_x[c]) * TW, ty0 = (t / p.tiles_x[c]) * TH;
+    const int pw = p.pw[c], ph = p.ph[c];
+    const pel *src = p.src[c] + k * p.sb[c];
+    pel *dst = p.dst[c] + k * p.db[c];
+    const int tid = threadIdx.x;
+
+    // ---- stage tile + apron (coordinates clamped to the picture) ----
+    constexpr int CHUNKS = (TW + 2 * AX) / 8;
+    for (int idx = tid; idx < ROWS * CHUNKS; idx += kThreads) {
+        const int i = idx / CHUNKS, q = idx - i * CHUNKS;
+        const int y = min(max(ty0 - AY + i, 0), ph - 1);
+        const int xs0 = tx0 - AX + 8 * q;
+        const pel *row = src + (long long)y * p.sp[c];
+        unsigned v[4];
+        if (xs0 >= 0 && xs0 + 7 < pw) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(row + xs0));
+            v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const unsigned lo = __ldg(row + min(max(xs0 + 2 * e, 0), pw - 1));
+                const unsigned hi = __ldg(row + min(max(xs0 + 2 * e + 1, 0), pw - 1));
+                v[e] = lo | (hi << 16);
+            }
+        }
+        unsigned *o_in  = reinterpret_cast<unsigned *>(&s_in[i * PITCH + 8 * q]);
+        unsigned *o_out = reinterpret_cast<unsigned *>(&s_out[i * PITCH + 8 * q]);
+#pragma unroll
+        for (int e = 0; e < 4; e++) { o_in[e] = v[e]; o_out[e] = v[e]; }
+    }
+    __syncthreads();
+
+    // ---- filter: one thread per (edge, line) ----
+    const bool chroma = c != 0;
+    const int grid = chroma ? 8 : 4;
+    const int shift = chroma ? (VERT ? p.vs[c] : p.hs[c]) : 0;
+    const int seg = chroma ? 4 >> shift : 4;                 // lines per segment
+    constexpr int ALONG = VERT ? TH : TW;                    // tile extent along the edges
+    constexpr int ACROSS = VERT ? TW : TH;
+    const int n_edges = ACROSS / grid + 1;                   // both tile borders included
+    const VVCCudaDbkEdge *map = p.map[c] + k * p.msize[c];
+    const int ctb_mask = (1 << p.ctb_log2) - 1;
+    constexpr int xs = VERT ? 1 : PITCH, ys = VERT ? PITCH : 1;
+
+    for (int it = tid; it < n_edges * ALONG; it += kThreads) {
+        const int e = it / ALONG, a = it - e * ALONG;        // a: position along the edge inside the tile
+        const int pos = (VERT ? tx0 : ty0) + e * grid;       // edge coordinate in the plane
+        const int along = (VERT ? ty0 : tx0) + a;
+        if (pos == 0 || pos >= (VERT ? pw : ph) || along >= (VERT ? ph : pw))
+            continue;
+        const int sidx = along / seg, line = along - sidx * seg;
+        const VVCCudaDbkEdge ed = VERT ? map[(long long)sidx * p.mpitch[c] + pos / grid]
+                                       : map[(long long)(pos / grid) * p.mpitch[c] + sidx];
+        if (!ed.tc)
+            continue;
+        // Q0 of line 0 of this segment inside the tile
+        const int a0 = a - line;
+        const int off = VERT ? (a0 + AY) * PITCH + (e * grid + AX) : (e * grid + AY) * PITCH + (a0 + AX);
+        if (!chroma) {
+            const int ctu_edge = !VERT && !(pos & ctb_mask);
+            luma_line(s_in + off, s_out + off, xs, ys, line, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, ctu_edge, p.bd);
+        } else {
+            chroma_line(s_in + off, s_out + off, xs, ys, line, seg, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, p.bd);
+        }
+    }
+    __syncthreads();
+
+    // ---- write the tile's own samples ----
+    constexpr int OCH = TW / 8;
+    for (int idx = tid; idx < TH * OCH; idx += kThreads) {
+        const int i = idx / OCH, q = idx - i * OCH;
+        const int y = ty0 + i, x = tx0 + 8 * q;
+        if (y >= ph || x >= pw)
+            continue;
+        const pel *sp = &s_out[(i + AY) * PITCH + AX + 8 * q];
+        pel *drow = dst + (long long)y * p.dp[c] + x;
+        if (x + 7 < pw) {
+            const unsigned *s32 = reinterpret_cast<const unsigned *>(sp);
+            *reinterpret_cast<uint4 *>(drow) = make_uint4(s32[0], s32[1], s32[2], s32[3]);
+        } else {
+            for (int e2 = 0; x + e2 < pw; e2++)
+                drow[e2] = sp[e2];
+        }
+    }
+}
+
+int check_pair(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src, const char *who)
+{
+    if (!dst || !src)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "%s: null frame", who);
+    if (src->bit_depth != 10 && src->bit_depth != 12)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "%s: bit depth %d not accelerated (10/12 only)", who, src->bit_depth);
+    if (src->ctb_log2 < 5 || src->ctb_log2 > 7 || src->batch < 1 || src->width < 8 || src->height < 8 ||
+        (src->width & 7) || (src->height & 7))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "%s: unsupported geometry %dx%d", who, src->width, src->height);
+    if (src->chroma_format_idc && (src->hshift != 1 || src->vshift != 1))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "%s: only 4:0:0 and 4:2:0 are accelerated", who);
+    if (dst->width != src->width || dst->height != src->height || dst->batch != src->batch ||
+        dst->bit_depth != src->bit_depth || dst->chroma_format_idc != src->chroma_format_idc)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "%s: dst/src geometry differs", who);
+    if (!frame_vec_ok(dst) || !frame_vec_ok(src))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "%s: planes and strides must be 16-byte aligned", who);
+    if (dst->data[0] == src->data[0])
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "%s: dst must not alias src", who);
+    return 0;
+}
+
+template <bool VERT>
+int launch(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src, const VVCCudaDeblockMaps *maps, int dir)
+{
+    using T = DbkTile<VERT>;
+    DbkK p;
+    p.planes = src->chroma_format_idc ? 3 : 1;
+    int total = 0;
+    for (int c = 0; c < 3; c++) {
+        p.src[c] = (const pel *)src->data[c];  p.dst[c] = (pel *)dst->data[c];
+        p.sp[c] = (int)(src->stride[c] / 2);   p.dp[c] = (int)(dst->stride[c] / 2);
+        p.sb[c] = src->batch_stride[c] / 2;    p.db[c] = dst->batch_stride[c] / 2;
+        p.hs[c] = c ? src->hshift : 0;         p.vs[c] = c ? src->vshift : 0;
+        p.pw[c] = src->width >> p.hs[c];       p.ph[c] = src->height >> p.vs[c];
+        p.map[c] = maps->edge[dir][c];         p.mpitch[c] = maps->pitch[dir][c];  p.msize[c] = maps->size[dir][c];
+        p.tiles_x[c] = ceil_div(p.pw[c], T::TW);  p.tiles_y[c] = ceil_div(p.ph[c], T::TH);
+        p.tile_base[c] = total;
+        if (c < p.planes)
+            total += p.tiles_x[c] * p.tiles_y[c];
+    }
+    p.bd = src->bit_depth; p.ctb_log2 = src->ctb_log2;
+    deblock_kernel<VERT><<<dim3(total, src->batch), kThreads, 0, ctx->stream>>>(p);
+    VVC_LAUNCHED(ctx);
+    return VVC_CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" int vvc_cuda_deblock_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                                      const VVCCudaDeblockMaps *maps, int dir)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!maps)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "deblock: null maps");
+    if (check_pair(ctx, dst, src, "deblock"))
+        return ctx->err;
+    return dir ? launch<true>(ctx, dst, src, maps, 1) : launch<false>(ctx, dst, src, maps, 0);
+}
+
+extern "C" int vvc_cuda_deblock_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                                           const VVCCudaDeblockMaps *maps)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!dst || !src || !maps)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "deblock_host: null argument");
+    const int planes = src->chroma_format_idc ? 3 : 1;
+    const size_t fsz = align_up(vvc_stage_frame_size(src), 256);
+    size_t msz = 0;
+    for (int d = 0; d < 2; d++)
+        for (int c = 0; c < planes; c++)
+            msz += align_up((size_t)maps->size[d][c] * src->batch * sizeof(VVCCudaDbkEdge), 256);
+    uint8_t *base = (uint8_t *)vvc_ctx_dev_stage(ctx, 2 * fsz + msz);
+    if (!base)
+        return ctx->err;
+    VVCCudaFrame a, b;
+    vvc_stage_frame_layout(src, base, &a);
+    vvc_stage_frame_layout(src, base + fsz, &b);
+    VVCCudaDeblockMaps dm = *maps;
+    uint8_t *at = base + 2 * fsz;
+    for (int d = 0; d < 2; d++)
+        for (int c = 0; c < planes; c++) {
+            const size_t bytes = (size_t)maps->size[d][c] * src->batch * sizeof(VVCCudaDbkEdge);
+            VVC_TRY(ctx, cudaMemcpyAsync(at, maps->edge[d][c], bytes, cudaMemcpyHostToDevice, ctx->stream));
+            dm.edge[d][c] = (const VVCCudaDbkEdge *)at;
+            at += align_up(bytes, 256);
+        }
+    if (vvc_stage_frame_h2d(ctx, &a, src))
+        return ctx->err;
+    if (vvc_cuda_deblock_frame(ctx, &b, &a, &dm, 1) || vvc_cuda_deblock_frame(ctx, &a, &b, &dm, 0))
+        return ctx->err;
+    if (vvc_stage_frame_d2h(ctx, dst, &a))
+        return ctx->err;
+    return vvc_cuda_sync(ctx);
+}

@@ -54,6 +54,14 @@ def load():
     for name in ("vvc_cuda_alf_frame", "vvc_cuda_alf_frame_host"):
         fn = getattr(lib, name)
         fn.argtypes = [CTX, FP, FP, C.c_void_p, C.c_void_p, C.c_int]
+    MP = C.POINTER(abi.VVCCudaDeblockMaps)
+    lib.vvc_cuda_deblock_frame.argtypes = [CTX, FP, FP, MP, C.c_int]
+    lib.vvc_cuda_deblock_frame_host.argtypes = [CTX, FP, FP, MP]
+    lib.vvc_cuda_sao_frame.argtypes = [CTX, FP, FP, C.c_void_p]
+    lib.vvc_cuda_sao_frame_host.argtypes = [CTX, FP, FP, C.c_void_p]
+    IP = C.POINTER(abi.VVCCudaInloopDesc)
+    lib.vvc_cuda_inloop_frame.argtypes = [CTX, FP, FP, IP]
+    lib.vvc_cuda_inloop_frame_host.argtypes = [CTX, FP, FP, IP]
     _lib = lib
     return lib
 
@@ -96,3 +104,23 @@ class Context:
 
     def alf_frame_host(self, dst, src, ctbs_ptr, sets_ptr, sets_per_frame=0):
         self.check(self.lib.vvc_cuda_alf_frame_host(self.handle, C.byref(dst), C.byref(src), ctbs_ptr, sets_ptr, sets_per_frame))
+
+    def deblock_frame(self, dst, src, maps, direction):
+        """direction 1 = vertical edges (DEBLOCK_V), 0 = horizontal edges (DEBLOCK_H)."""
+        self.check(self.lib.vvc_cuda_deblock_frame(self.handle, C.byref(dst), C.byref(src), C.byref(maps), direction))
+
+    def deblock_frame_host(self, dst, src, maps):
+        self.check(self.lib.vvc_cuda_deblock_frame_host(self.handle, C.byref(dst), C.byref(src), C.byref(maps)))
+
+    def sao_frame(self, dst, src, ctbs_ptr):
+        self.check(self.lib.vvc_cuda_sao_frame(self.handle, C.byref(dst), C.byref(src), ctbs_ptr))
+
+    def sao_frame_host(self, dst, src, ctbs_ptr):
+        self.check(self.lib.vvc_cuda_sao_frame_host(self.handle, C.byref(dst), C.byref(src), ctbs_ptr))
+
+    def inloop_frame(self, dst, src, desc):
+        """DEBLOCK_V -> DEBLOCK_H -> SAO -> ALF on device-resident pictures and descriptors."""
+        self.check(self.lib.vvc_cuda_inloop_frame(self.handle, C.byref(dst), C.byref(src), C.byref(desc)))
+
+    def inloop_frame_host(self, dst, src, desc):
+        self.check(self.lib.vvc_cuda_inloop_frame_host(self.handle, C.byref(dst), C.byref(src), C.byref(desc)))

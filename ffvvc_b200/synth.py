@@ -105,3 +105,140 @@ def alf_params(geom, seed=777, all_on=True):
     cc = np.where(mag == 0, 0, sgn * (1 << np.maximum(mag - 1, 0)))
     sets["cc_coeff"][0] = cc.reshape(2, 5, 7)
     return ctbs, sets
+
+
+# ---------------------------------------------------------------------------------------------
+# Deblocking inputs: a random transform-block partition, and from it the per-segment
+# (tc, beta, max lengths) the reference driver derives (vvc_filter.c:374-397, 795-826, 861-1003).
+# ---------------------------------------------------------------------------------------------
+TC_TABLE = np.array([0] * 18 + [3, 4, 4, 4, 4, 5, 5, 5, 5, 7, 7, 8, 9, 10, 10, 11, 13, 14, 15, 17, 19, 21, 24, 25, 29, 33,
+                                36, 41, 45, 51, 57, 64, 71, 80, 89, 100, 112, 125, 141, 157, 177, 198, 222, 250, 280, 314,
+                                352, 395], dtype=np.int64)          # Table 43, vvc_filter.c:38-44
+BETA_TABLE = np.array([0] * 16 + list(range(6, 19)) + list(range(20, 90, 2)), dtype=np.int64)   # vvc_filter.c:47-52
+assert len(TC_TABLE) == 66 and len(BETA_TABLE) == 64
+
+
+def tb_partition(geom, rng, stop_p=0.35):
+    """Random aligned TB partition per 4x4 luma unit: returns (log2 tb width, log2 tb height).
+
+    Blocks start at 64x64 and are halved alternately in width and height (order chosen per
+    64x64 block) until a random stop, so sizes 4..64 and 1:2 / 2:1 shapes occur.
+    """
+    uh, uw = (geom.height + 3) // 4, (geom.width + 3) // 4
+    uy, ux = np.mgrid[0:uh, 0:uw]
+    lw = np.full((uh, uw), 6, dtype=np.int64)
+    lh = np.full((uh, uw), 6, dtype=np.int64)
+    alive = np.ones((uh, uw), dtype=bool)
+    g64h, g64w = (uh + 15) // 16, (uw + 15) // 16
+    width_first = rng.below(g64h * g64w, 2).reshape(g64h, g64w)[uy >> 4, ux >> 4].astype(bool)
+    for stage in range(8):
+        # block id of every unit at its current shape
+        by, bx = uy >> (lh - 2), ux >> (lw - 2)
+        gh, gw = int(by.max()) + 1, int(bx.max()) + 1
+        dec = (rng.below(gh * gw, 1000) >= int(stop_p * 1000)).reshape(gh, gw)
+        split = alive & dec[by, bx]
+        halve_w = (stage % 2 == 0) == width_first
+        lw = np.where(split & halve_w, lw - 1, lw)
+        lh = np.where(split & ~halve_w, lh - 1, lh)
+        alive = split
+    return lw, lh
+
+
+def _edge_records(bs, qp_edge, len_p, len_q):
+    rec = np.zeros(bs.shape, dtype=abi.DBK_EDGE_DTYPE)
+    tc = TC_TABLE[np.clip(qp_edge + 2 * (bs - 1), 0, 65)]
+    rec["tc"] = np.where(bs > 0, tc, 0)
+    rec["beta"] = np.where(bs > 0, BETA_TABLE[np.clip(qp_edge, 0, 63)], 0)
+    rec["max_len"] = np.where(bs > 0, len_p | (len_q << 4), 0)
+    return rec
+
+
+def deblock_maps(geom, seed=4242, qp_base=22, qp_span=21):
+    """Edge maps [dir][c] (batch, rows, pitch) following SURVEY.md 8(d) config 2:
+    bs in {0,1,2} with p = {.45,.35,.20} on the 8x8 grid and {.85,.10,.05} on off-grid 4-lines,
+    qp = qp_base + rnd % qp_span per 16x16, luma max lengths from the TB sizes
+    (derive_max_filter_length_luma), chroma lengths from chroma TB sizes and bs."""
+    rng = LCG(seed)
+    uh, uw = (geom.height + 3) // 4, (geom.width + 3) // 4
+    out = [[None] * 3, [None] * 3]
+    for d in range(2):
+        for c in range(3):
+            rows, pitch = abi.deblock_map_shape(geom, d, c)
+            out[d][c] = np.zeros((geom.batch, rows, pitch), dtype=abi.DBK_EDGE_DTYPE)
+    ctb4 = geom.ctb_size // 4
+    for k in range(geom.batch):
+        lw, lh = tb_partition(geom, rng)
+        uy, ux = np.mgrid[0:uh, 0:uw]
+        qp16 = qp_base + rng.below(((uh + 3) // 4) * ((uw + 3) // 4), qp_span).reshape((uh + 3) // 4, (uw + 3) // 4)
+        qp = qp16[uy >> 2, ux >> 2]
+        for d in (1, 0):
+            size = (1 << lw) if d else (1 << lh)          # TB size across the edge
+            pos = ux if d else uy
+            is_edge = ((pos * 4) % size == 0) & (pos > 0)
+            size_q = size
+            size_p = np.roll(size, 1, axis=1 if d else 0)
+            qp_p = np.roll(qp, 1, axis=1 if d else 0)
+            on8 = (pos % 2 == 0)
+            r = rng.below(uh * uw, 100).reshape(uh, uw)
+            bs = np.where(on8, (r >= 45).astype(np.int64) + (r >= 80), (r >= 85).astype(np.int64) + (r >= 95))
+            bs = np.where(is_edge, bs, 0)
+            # ---- luma (vvc_filter.c:374-397) ----
+            small = (size_p <= 4) | (size_q <= 4)
+            lp = np.where(small, 1, np.where(size_p >= 32, 7, 3))
+            lq = np.where(small, 1, np.where(size_q >= 32, 7, 3))
+            # sub-block (affine/sbTMVP) CUs cap the q side, merge-subblock/intra-affine neighbours the p side (:392-396)
+            cap = rng.below(uh * uw, 10).reshape(uh, uw)
+            lq = np.where(cap == 0, np.minimum(lq, 5), lq)
+            lp = np.where(cap == 1, np.minimum(lp, 5), lp)
+            qe = (qp + qp_p + 1) >> 1
+            rec = _edge_records(bs, qe, lp, lq)
+            # luma map rows/cols are exactly the 4x4 units
+            out[d][0][k] = rec
+            # ---- chroma 4:2:0: edges on the 8-sample chroma grid = 16 luma, i.e. every 4th unit ----
+            if geom.chroma_format_idc:
+                csize_p, csize_q = size_p >> 1, size_q >> 1
+                ctu_edge = (uy % ctb4 == 0) if d == 0 else np.zeros_like(on8)
+                big = (csize_p >= 8) & (csize_q >= 8)
+                clp = np.where(big, np.where(ctu_edge, 1, 3), (bs == 2).astype(np.int64))
+                clq = np.where(big, 3, (bs == 2).astype(np.int64))
+                for c in (1, 2):
+                    cqe = qe + (1 if c == 1 else -1)     # distinct Cb/Cr qp, as separate qp tables give
+                    crec = _edge_records(bs, cqe, clp, clq)
+                    rows, pitch = abi.deblock_map_shape(geom, d, c)
+                    if d:   # vertical: x every 16 luma = 4 units; segment = 2 chroma lines = 1 unit row
+                        out[d][c][k] = crec[:rows, ::4][:, :pitch]
+                    else:   # horizontal: y every 4 units; segment = 2 chroma columns = 1 unit column
+                        out[d][c][k] = crec[::4, :pitch][:rows]
+    return out
+
+
+def sao_params(geom, seed=99, with_restore=False):
+    """Per-CTB SAO parameters, SURVEY.md 8(d) config 2: type rnd%3, band position rnd%32,
+    eo rnd%4, offsets rnd % (1 << (bd-5)) with the edge-class signs (+,+,-,-) the parser applies
+    (vvc_ctu.c:2202-2211)."""
+    rng = LCG(seed)
+    n = geom.ctb_count * geom.batch
+    p = np.zeros(n, dtype=abi.SAO_CTB_DTYPE)
+    p["type_idx"][:] = rng.below(n * 3, 3).reshape(n, 3)
+    p["band_position"][:] = rng.below(n * 3, 32).reshape(n, 3)
+    p["eo_class"][:] = rng.below(n * 3, 4).reshape(n, 3)
+    mag = rng.below(n * 3 * 4, 1 << (geom.bit_depth - 5)).reshape(n, 3, 4)
+    sign_band = rng.below(n * 3 * 4, 2).reshape(n, 3, 4) * 2 - 1
+    edge_sign = np.array([1, 1, -1, -1])
+    is_edge = (p["type_idx"] == 2)[:, :, None]
+    p["offset_val"][:, :, 1:] = np.where(is_edge, mag * edge_sign, mag * sign_band)
+    if with_restore:
+        p["restore"] = 1
+        flags = rng.below(n, 256).astype(np.uint8)
+        cols, rows = geom.ctb_cols, geom.ctb_rows
+        idx = np.arange(n) % (cols * rows)
+        cx, cy = idx % cols, idx // cols
+        # flags are only ever set towards neighbours that exist (vvc_filter.c:181-212)
+        left, top, right, bottom = cx == 0, cy == 0, cx == cols - 1, cy == rows - 1
+        clear = np.zeros(n, dtype=np.uint8)
+        clear |= np.where(left, 0x01 | 0x10 | 0x80, 0).astype(np.uint8)
+        clear |= np.where(right, 0x02 | 0x20 | 0x40, 0).astype(np.uint8)
+        clear |= np.where(top, 0x04 | 0x10 | 0x20, 0).astype(np.uint8)
+        clear |= np.where(bottom, 0x08 | 0x40 | 0x80, 0).astype(np.uint8)
+        p["no_filter"] = flags & ~clear
+    return p

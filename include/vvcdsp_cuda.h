@@ -58,7 +58,7 @@ void       *vvc_cuda_stream(const VVCCudaCtx *ctx);    /* the cudaStream_t in us
 uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx);
 const char *vvc_cuda_version(void);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, ...): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, ...): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -121,6 +121,96 @@ int vvc_cuda_alf_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFr
                        const VVCCudaALFCtb *ctbs, const VVCCudaALFSets *sets, int sets_per_frame);
 int vvc_cuda_alf_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
                             const VVCCudaALFCtb *ctbs, const VVCCudaALFSets *sets, int sets_per_frame);
+
+/* ------------------------------------------------------------------------------------------
+ * Deblocking stage (replaces the pixel work of ff_vvc_deblock_vertical / _horizontal,
+ * libavcodec/vvc/vvc_filter.c:861-1003, i.e. the table entries lf.filter_luma[2] /
+ * lf.filter_chroma[2], libavcodec/vvc/vvc_filter_template.c:466-754 and
+ * libavcodec/h26x/h2656_deblock_template.c:25-99)
+ * ---------------------------------------------------------------------------------------- */
+/* One 4-sample (luma) / (4 >> subsampling)-sample (chroma) segment of one edge: exactly the
+ * per-segment inputs the reference hands to lf.filter_luma / lf.filter_chroma
+ * (_tc[i], _beta[i], _max_len_p[i], _max_len_q[i]; no_p/no_q are always 0 in the reference,
+ * vvc_filter.c:870-871).  tc == 0 marks "not filtered" (bs == 0).  tc and beta are the values
+ * of the reference's tctable/betatable lookups, BEFORE the bit-depth shift the DSP applies. */
+typedef struct VVCCudaDbkEdge {
+    uint16_t tc;
+    uint8_t  beta;
+    uint8_t  max_len;          /* max_len_p | max_len_q << 4 */
+} VVCCudaDbkEdge;
+
+/* Edge maps of one picture.  Index [dir][c]: dir 0 = horizontal edges (lf.filter_*[0]),
+ * dir 1 = vertical edges (lf.filter_*[1]), c = plane.  In plane c's own sample units, with
+ * G = 4 (luma) or 8 (chroma) the edge grid and L = 4 (luma) or 4 >> shift (chroma) the segment
+ * length along the edge:
+ *   vertical   entry (ex, sy): edge at x = ex * G, lines   [sy * L, sy * L + L)
+ *   horizontal entry (sx, ey): edge at y = ey * G, columns [sx * L, sx * L + L)
+ * stored row-major with `pitch[dir][c]` entries per row; picture k of a ring starts
+ * `size[dir][c]` entries after picture k-1.  Entries with ex == 0 / ey == 0 (picture border)
+ * are ignored, as in the reference (vvc_filter.c:897,965). */
+typedef struct VVCCudaDeblockMaps {
+    const VVCCudaDbkEdge *edge[2][3];
+    int32_t pitch[2][3];
+    int32_t rows[2][3];
+    int64_t size[2][3];
+} VVCCudaDeblockMaps;
+
+/* dir: 1 = all vertical edges of the picture (DEBLOCK_V), 0 = all horizontal edges (DEBLOCK_H);
+ * the reference's task graph requires V before H (vvc_thread.c:159-167).  Out of place
+ * (dst != src): every edge reads unfiltered samples of `src`; for edge sets that obey the
+ * reference's filter-length rules (vvc_filter.c:374-397) this equals the reference's in-place
+ * sequential walk.  The maps struct is passed by value semantics (host memory), the arrays it
+ * points to are device memory (or host memory for the _host entry). */
+int vvc_cuda_deblock_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                           const VVCCudaDeblockMaps *maps, int dir);
+/* both passes: src -> tmp (vertical) -> dst (horizontal) */
+int vvc_cuda_deblock_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                                const VVCCudaDeblockMaps *maps);
+
+/* ------------------------------------------------------------------------------------------
+ * SAO stage (replaces ff_vvc_sao_filter, libavcodec/vvc/vvc_filter.c:154-298, and the table
+ * entries sao.band_filter[9] / edge_filter[9] / edge_restore[2],
+ * libavcodec/h26x/h2656_sao_template.c:24-215)
+ * ---------------------------------------------------------------------------------------- */
+/* per-CTB parameters; mirrors SAOParams (libavcodec/vvc/vvc_ctu.h:440-451) plus the
+ * "unfilterable edge" flags ff_vvc_sao_filter derives per CTB (vvc_filter.c:163-213). */
+typedef struct VVCCudaSAOCtb {
+    uint8_t type_idx[3];       /* 0 off, 1 band, 2 edge                                   */
+    uint8_t band_position[3];
+    uint8_t eo_class[3];       /* 0 horizontal, 1 vertical, 2 135 degrees, 3 45 degrees   */
+    uint8_t restore;           /* 1: use the edge_restore[1] rules with the flags below   */
+    uint8_t no_filter;         /* bit0-1 vert_edge[0..1], bit2-3 horiz_edge[0..1], bit4-7 diag_edge[0..3] */
+    uint8_t reserved;
+    int16_t offset_val[3][5];  /* SaoOffsetVal, [0] is 0 in a conforming stream            */
+} VVCCudaSAOCtb;
+
+/* dst != src; ctbs: ctb_count entries per picture of the ring, raster order. */
+int vvc_cuda_sao_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                       const VVCCudaSAOCtb *ctbs);
+int vvc_cuda_sao_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                            const VVCCudaSAOCtb *ctbs);
+
+/* ------------------------------------------------------------------------------------------
+ * In-loop chain: DEBLOCK_V -> DEBLOCK_H -> SAO -> ALF in one call (the tail of the reference's
+ * per-CTU stage list, libavcodec/vvc/vvc_thread.c:41-51, run stage by stage over the picture,
+ * which its dependency scores allow - SURVEY.md 3.3).  Intermediate pictures live in the
+ * context's scratch area.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct VVCCudaInloopDesc {
+    const VVCCudaDeblockMaps *deblock;        /* host struct; its arrays follow the entry's memory space */
+    const VVCCudaSAOCtb      *sao;
+    const VVCCudaALFCtb      *alf;
+    const VVCCudaALFSets     *alf_sets;
+    int32_t                   alf_sets_per_frame;
+    int32_t                   reserved;
+} VVCCudaInloopDesc;
+
+int vvc_cuda_inloop_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                          const VVCCudaInloopDesc *desc);
+/* host pictures and descriptors: copies in (pictures + all maps), runs the four stages, copies the
+ * finished pictures out.  With batch > 1 the copies of picture k+1 overlap the kernels of picture k. */
+int vvc_cuda_inloop_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
+                               const VVCCudaInloopDesc *desc);
 
 #ifdef __cplusplus
 }

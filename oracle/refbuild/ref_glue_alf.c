@@ -47,10 +47,10 @@ void vvcref_alf_frame(const VVCCudaFrame *dstf, const VVCCudaFrame *srcf,
     const int cols = (srcf->width + ctb - 1) >> srcf->ctb_log2;
     const int rows = (srcf->height + ctb - 1) >> srcf->ctb_log2;
     const int planes = srcf->chroma_format_idc ? 3 : 1;
-    static pixel pad_luma[PAD_STRIDE * (128 + 16)], pad_chroma[PAD_STRIDE * (128 + 16)];
-    static int16_t coeff[1024 * 12], clip[1024 * 12];
-    static int class_idx[1024], transpose_idx[1024];
-    static int gradient_tmp[66 * 66 * 4];
+    static _Thread_local pixel pad_luma[PAD_STRIDE * (128 + 16)], pad_chroma[PAD_STRIDE * (128 + 16)];
+    static _Thread_local int16_t coeff[1024 * 12], clip[1024 * 12];
+    static _Thread_local int class_idx[1024], transpose_idx[1024];
+    static _Thread_local int gradient_tmp[66 * 66 * 4];
     const int clip_shift[4] = { 0, 3, 5, 7 };
 
     for (int k = 0; k < srcf->batch; k++) {

@@ -40,6 +40,11 @@ def oracle():
         lib = C.CDLL(ORACLE_SO)
         lib.vvco_alf_frame.argtypes = [FP, FP, C.c_void_p, C.c_void_p, C.c_int]
         lib.vvco_alf_frame.restype = None
+        MP = C.POINTER(abi.VVCCudaDeblockMaps)
+        lib.vvco_deblock_frame.argtypes = [FP, FP, MP, C.c_int]
+        lib.vvco_deblock_frame.restype = None
+        lib.vvco_sao_frame.argtypes = [FP, FP, C.c_void_p]
+        lib.vvco_sao_frame.restype = None
         _oracle = lib
     return _oracle
 
@@ -59,6 +64,11 @@ def ref():
         lib.vvcref_dsp.argtypes = [C.c_int]
         lib.vvcref_alf_frame.argtypes = [FP, FP, C.c_void_p, C.c_void_p, C.c_int]
         lib.vvcref_alf_frame.restype = None
+        MP = C.POINTER(abi.VVCCudaDeblockMaps)
+        lib.vvcref_deblock_frame.argtypes = [FP, FP, MP, C.c_int]
+        lib.vvcref_deblock_frame.restype = None
+        lib.vvcref_sao_frame.argtypes = [FP, FP, C.c_void_p]
+        lib.vvcref_sao_frame.restype = None
         _ref = lib
     return _ref
 
