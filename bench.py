@@ -229,7 +229,9 @@ def main():
     inp = Inputs(args.width, args.height, frames, seed=12345 + rank)
     geom = inp.geom
     ggeom = abi.FrameGeom(args.width, args.height, batch=group)
-    ctx = lib.Context(local_rank, torch.cuda.current_stream().cuda_stream)
+    ctx = lib.Context(local_rank)
+    stream = ctx.torch_stream()
+    torch.cuda.set_stream(stream)      # uploads, events and kernels all on the context's stream
 
     # ---- device-resident ring -------------------------------------------------------------
     src = device.DeviceFrames(geom, device=dev, planes=inp.planes)

@@ -70,8 +70,12 @@ class Context:
     """One decoder stream's CUDA context (vvc_cuda_ctx_create / _destroy)."""
 
     def __init__(self, device=0, stream=None):
+        """stream: a cudaStream_t handle (int) all work is queued on.  None/0 lets the library
+        create its own non-blocking stream - callers that also queue torch work (uploads, events)
+        must then do so on `torch_stream()`, the legacy default stream does not order with it."""
         self.lib = load()
         self.handle = CTX()
+        self.device = device
         rc = self.lib.vvc_cuda_ctx_create(C.byref(self.handle), device, stream)
         if rc != 0:
             raise VVCCudaError("vvc_cuda_ctx_create(device=%d) failed with %d: no usable CUDA device" % (device, rc))
@@ -93,6 +97,15 @@ class Context:
 
     def sync(self):
         self.check(self.lib.vvc_cuda_sync(self.handle))
+
+    @property
+    def stream_ptr(self):
+        return int(self.lib.vvc_cuda_stream(self.handle) or 0)
+
+    def torch_stream(self):
+        """The context's stream as a torch stream object (for events / `with torch.cuda.stream`)."""
+        import torch
+        return torch.cuda.ExternalStream(self.stream_ptr, device="cuda:%d" % self.device)
 
     @property
     def launches(self):

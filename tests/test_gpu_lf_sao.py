@@ -17,8 +17,9 @@ def ctx():
     import torch
     from ffvvc_b200 import lib
     assert torch.cuda.is_available()
-    c = lib.Context(0, torch.cuda.current_stream().cuda_stream)
-    yield c
+    c = lib.Context(0)                          # library-owned stream
+    with torch.cuda.stream(c.torch_stream()):   # torch uploads/downloads are ordered on the same stream
+        yield c
     c.close()
 
 
