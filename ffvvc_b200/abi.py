@@ -202,3 +202,37 @@ def inloop_desc(maps_desc, sao_ptr, alf_ptr, sets_ptr, sets_per_frame=0):
     d.alf_sets_per_frame = sets_per_frame
     d._keep = maps_desc
     return d
+
+
+# ---- residual stage (include/vvcdsp_cuda.h) ---------------------------------------------------
+TB_TS, TB_BDPCM, TB_BDPCM_VERT, TB_JOINT, TB_STORE_RESIDUAL = 1, 2, 4, 8, 16
+
+
+class VVCCudaTB(C.Structure):
+    _fields_ = [
+        ("coeff_offset", C.c_uint32), ("x0", C.c_uint16), ("y0", C.c_uint16),
+        ("log2_w", C.c_uint8), ("log2_h", C.c_uint8), ("c_idx", C.c_uint8),
+        ("trh", C.c_uint8), ("trv", C.c_uint8), ("nzw", C.c_uint8), ("nzh", C.c_uint8),
+        ("flags", C.c_uint8), ("lfnst", C.c_uint8), ("joint_sign", C.c_int8),
+        ("joint_shift", C.c_uint8), ("joint_c_idx", C.c_uint8), ("pic", C.c_uint8),
+        ("reserved", C.c_uint8), ("chroma_scale", C.c_uint16),
+    ]
+
+
+TB_DTYPE = np.dtype([
+    ("coeff_offset", np.uint32), ("x0", np.uint16), ("y0", np.uint16),
+    ("log2_w", np.uint8), ("log2_h", np.uint8), ("c_idx", np.uint8), ("trh", np.uint8), ("trv", np.uint8),
+    ("nzw", np.uint8), ("nzh", np.uint8), ("flags", np.uint8), ("lfnst", np.uint8), ("joint_sign", np.int8),
+    ("joint_shift", np.uint8), ("joint_c_idx", np.uint8), ("pic", np.uint8),
+    ("reserved", np.uint8), ("chroma_scale", np.uint16)], align=True)
+assert TB_DTYPE.itemsize == C.sizeof(VVCCudaTB) == 24, (TB_DTYPE.itemsize, C.sizeof(VVCCudaTB))
+
+
+class VVCCudaRect(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("w", C.c_uint16), ("h", C.c_uint16),
+                ("pic", C.c_uint16), ("reserved", C.c_uint16)]
+
+
+RECT_DTYPE = np.dtype([("x", np.uint16), ("y", np.uint16), ("w", np.uint16), ("h", np.uint16),
+                       ("pic", np.uint16), ("reserved", np.uint16)])
+assert RECT_DTYPE.itemsize == C.sizeof(VVCCudaRect) == 12

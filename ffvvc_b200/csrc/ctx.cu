@@ -139,6 +139,7 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 4: return sizeof(VVCCudaDeblockMaps);
     case 5: return sizeof(VVCCudaSAOCtb);
     case 6: return sizeof(VVCCudaInloopDesc);
+    case 7: return sizeof(VVCCudaTB);
     default: return 0;
     }
 }

@@ -62,6 +62,11 @@ def load():
     IP = C.POINTER(abi.VVCCudaInloopDesc)
     lib.vvc_cuda_inloop_frame.argtypes = [CTX, FP, FP, IP]
     lib.vvc_cuda_inloop_frame_host.argtypes = [CTX, FP, FP, IP]
+    lib.vvc_cuda_itx_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.vvc_cuda_itx_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+    lib.vvc_cuda_lmcs_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
+    lib.vvc_cuda_lmcs_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
+    lib.vvc_cuda_lmcs_rects.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, C.c_int]
     _lib = lib
     return lib
 
@@ -137,3 +142,19 @@ class Context:
 
     def inloop_frame_host(self, dst, src, desc):
         self.check(self.lib.vvc_cuda_inloop_frame_host(self.handle, C.byref(dst), C.byref(src), C.byref(desc)))
+
+    def itx_frame(self, frame, coeffs_ptr, tbs_ptr, n_tbs, log2_transform_range=15):
+        """Inverse LFNST/transform + add_residual for a TB list; frame holds the prediction (in place)."""
+        self.check(self.lib.vvc_cuda_itx_frame(self.handle, C.byref(frame), coeffs_ptr, tbs_ptr, n_tbs, log2_transform_range))
+
+    def itx_frame_host(self, frame, coeffs_ptr, n_coeffs, tbs_ptr, n_tbs, log2_transform_range=15):
+        self.check(self.lib.vvc_cuda_itx_frame_host(self.handle, C.byref(frame), coeffs_ptr, n_coeffs, tbs_ptr, n_tbs, log2_transform_range))
+
+    def lmcs_frame(self, frame, lut_ptr, ctb_enable_ptr=None):
+        self.check(self.lib.vvc_cuda_lmcs_frame(self.handle, C.byref(frame), lut_ptr, ctb_enable_ptr))
+
+    def lmcs_frame_host(self, frame, lut_ptr, ctb_enable_ptr=None):
+        self.check(self.lib.vvc_cuda_lmcs_frame_host(self.handle, C.byref(frame), lut_ptr, ctb_enable_ptr))
+
+    def lmcs_rects(self, frame, lut_ptr, rects_ptr, n):
+        self.check(self.lib.vvc_cuda_lmcs_rects(self.handle, C.byref(frame), lut_ptr, rects_ptr, n))

@@ -242,3 +242,146 @@ def sao_params(geom, seed=99, with_restore=False):
         clear |= np.where(bottom, 0x08 | 0x40 | 0x80, 0).astype(np.uint8)
         p["no_filter"] = flags & ~clear
     return p
+
+
+# ---------------------------------------------------------------------------------------------
+# Residual stage inputs (coefficient/nz distributions of
+# tests/checkasm/vvc_itx.c:25-75)
+# ---------------------------------------------------------------------------------------------
+def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True):
+    """Tile every picture of the ring with transform blocks (luma + both chroma planes).
+
+    Returns (tbs, coeffs): TB_DTYPE records and the dense int32 coefficient buffer.
+    lfnst_set_of: callable predModeIntra -> transform set (the oracle's table accessor); when None no
+    TB uses LFNST.  extras: append 1-D and STORE_RESIDUAL blocks (do not touch the picture).
+    """
+    rng = LCG(seed)
+    recs = []
+    for k in range(geom.batch):
+        lw, lh = tb_partition(geom, rng, stop_p=0.45)
+        uh, uw = lw.shape
+        uy, ux = np.mgrid[0:uh, 0:uw]
+        origin = ((ux * 4) % (1 << lw) == 0) & ((uy * 4) % (1 << lh) == 0)
+        # blocks must lie inside the picture (partition blocks are aligned, pictures are multiples of 8:
+        # clip oversize blocks by re-splitting them into 8x8)
+        x0, y0 = ux[origin] * 4, uy[origin] * 4
+        l2w, l2h = lw[origin], lh[origin]
+        inside = (x0 + (1 << l2w) <= geom.width) & (y0 + (1 << l2h) <= geom.height)
+        x0, y0, l2w, l2h = x0[inside], y0[inside], l2w[inside], l2h[inside]
+        n = len(x0)
+        for c in range(3 if geom.chroma_format_idc else 1):
+            r = np.zeros(n, dtype=abi.TB_DTYPE)
+            sh = 1 if c else 0
+            r["x0"], r["y0"] = x0 >> sh, y0 >> sh
+            r["log2_w"], r["log2_h"] = l2w - sh, l2h - sh
+            r["c_idx"], r["pic"] = c, k
+            recs.append(r)
+    tbs = np.concatenate(recs)
+    n = len(tbs)
+    w, h = 1 << tbs["log2_w"].astype(np.int64), 1 << tbs["log2_h"].astype(np.int64)
+    luma = tbs["c_idx"] == 0
+    # transform types: luma TBs <= 32 draw from {DCT2, DST7, DCT8}^2, others DCT2
+    mts_ok_w = luma & (w >= 4) & (w <= 32) & (h <= 32) & (h >= 4)
+    trh = np.where(mts_ok_w, rng.below(n, 3), 0)
+    trv = np.where(mts_ok_w, rng.below(n, 3), 0)
+    tbs["trh"], tbs["trv"] = trh, trv
+    tbs["nzw"] = rng.below(n, 1 << 16) % np.minimum(np.where(trh == 0, 32, 16), w) + 1
+    tbs["nzh"] = rng.below(n, 1 << 16) % np.minimum(np.where(trv == 0, 32, 16), h) + 1
+    # transform skip / BDPCM on 3 % of the blocks up to 32x32
+    r = rng.below(n, 100)
+    ts = (r < 3) & (w <= 32) & (h <= 32) & (w >= 4) & (h >= 4)
+    bd = rng.below(n, 4)
+    tbs["flags"] = np.where(ts, abi.TB_TS | np.where(bd == 0, abi.TB_BDPCM, np.where(bd == 1, abi.TB_BDPCM_VERT, 0)), 0)
+    tbs["trh"] = np.where(ts, 0, tbs["trh"])
+    tbs["trv"] = np.where(ts, 0, tbs["trv"])
+    # LFNST on 10 % of the non-skipped blocks >= 4x4 (forces DCT2 x DCT2)
+    if lfnst_set_of is not None:
+        r = rng.below(n, 100)
+        lf = (r >= 90) & ~ts & (w >= 4) & (h >= 4)
+        mode = rng.below(n, 95 + 14) - 14                      # predModeIntra incl. wide angles -14..-1, 67..80
+        sets = np.array([lfnst_set_of(int(m)) for m in range(-14, 95)])[mode + 14]
+        idx = rng.below(n, 2) + 1
+        small_in = ((w == 8) & (h == 8)) | ((w == 4) & (h == 4))
+        code = idx | (sets << 2) | ((mode > 34).astype(np.int64) << 4) | (small_in.astype(np.int64) << 5)
+        tbs["lfnst"] = np.where(lf, code, 0)
+        tbs["trh"] = np.where(lf, 0, tbs["trh"])
+        tbs["trv"] = np.where(lf, 0, tbs["trv"])
+    # joint CbCr on 10 % of the Cb blocks: the co-located Cr block is dropped
+    if geom.chroma_format_idc:
+        cb = np.nonzero(tbs["c_idx"] == 1)[0]
+        cr = np.nonzero(tbs["c_idx"] == 2)[0]
+        assert len(cb) == len(cr)
+        j = rng.below(len(cb), 10) == 0
+        tbs["flags"][cb[j]] |= abi.TB_JOINT
+        tbs["joint_c_idx"][cb[j]] = 2
+        tbs["joint_sign"][cb[j]] = rng.below(int(j.sum()), 2) * 2 - 1
+        tbs["joint_shift"][cb[j]] = rng.below(int(j.sum()), 2)
+        keep = np.ones(n, dtype=bool)
+        keep[cr[j]] = False
+        tbs = tbs[keep]
+    if extras:
+        # 1-D cells (16, 32, 64 long) and blocks that return their residual instead of adding it
+        ex = np.zeros(24, dtype=abi.TB_DTYPE)
+        for i in range(24):
+            size = (4, 5, 6)[i % 3]
+            horiz = (i // 3) % 2
+            tr = 0 if size == 6 else (i // 6) % 3
+            ex[i]["log2_w"], ex[i]["log2_h"] = (size, 0) if horiz else (0, size)
+            ex[i]["trh"], ex[i]["trv"] = (tr, 0) if horiz else (0, tr)
+            lim = min(32 if tr == 0 else 16, 1 << size)
+            ex[i]["nzw"] = (int(rng.below(1, lim)[0]) + 1) if horiz else 1
+            ex[i]["nzh"] = 1 if horiz else (int(rng.below(1, lim)[0]) + 1)
+            ex[i]["flags"] = abi.TB_STORE_RESIDUAL
+        pick = rng.below(64, len(tbs))
+        more = tbs[pick].copy()
+        more["flags"] = (more["flags"] & (255 - abi.TB_JOINT)) | abi.TB_STORE_RESIDUAL
+        tbs = np.concatenate([tbs, ex, more])
+    n = len(tbs)
+    w, h = 1 << tbs["log2_w"].astype(np.int64), 1 << tbs["log2_h"].astype(np.int64)
+    area = w * h
+    off = np.concatenate([[0], np.cumsum(area)])
+    tbs["coeff_offset"] = off[:-1]
+    total = int(off[-1])
+    # coefficients: clip_intp2(rnd, 15) inside the nz window, zero outside (decoder invariant, vvc_cabac.c:2392)
+    tb_of = np.repeat(np.arange(n), area)
+    local = np.arange(total) - off[tb_of]
+    cx, cy = local % w[tb_of], local // w[tb_of]
+    full = ((tbs["flags"] & abi.TB_TS) != 0) | (tbs["lfnst"] != 0)
+    lf_in = np.where((tbs["lfnst"] >> 5) & 1, 8, 16)
+    inside = (cx < tbs["nzw"][tb_of]) & (cy < tbs["nzh"][tb_of])
+    inside = np.where(full[tb_of], True, inside)
+    raw = rng.take(total).astype(np.int64)
+    wide = ((raw << 8) ^ (raw >> 3)) & 0xFFFFFFFF
+    wide = np.where(wide >= 1 << 31, wide - (1 << 32), wide)
+    sat = np.clip(wide, -32768, 32767)                       # checkasm style: mostly saturated
+    mild = (raw % 1025) - 512
+    use_sat = (rng.below(n, 2) == 0)[tb_of] if saturate else np.zeros(total, dtype=bool)
+    val = np.where(use_sat, sat, mild)
+    # LFNST blocks carry only their first 8/16 diagonal-scan coefficients
+    diag_x = np.array([0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 1, 2, 3, 2, 3, 3])
+    diag_y = np.array([0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 3, 2, 1, 3, 2, 3])
+    rank = np.full((4, 4), 99)
+    rank[diag_y, diag_x] = np.arange(16)
+    in_44 = (cx < 4) & (cy < 4)
+    lf_rank = np.where(in_44, rank[np.minimum(cy, 3), np.minimum(cx, 3)], 99)
+    is_lf = (tbs["lfnst"] != 0)[tb_of]
+    inside = np.where(is_lf, lf_rank < lf_in[tb_of], inside)
+    coeffs = np.where(inside, val, 0).astype(np.int32)
+    return tbs, coeffs
+
+
+def lmcs_luts(bit_depth=10, seed=5):
+    """A forward/inverse LMCS look-up pair shaped like the ones vvc_ps.c:592-672 derives: 16 bins,
+    piecewise linear, monotone; the inverse LUT is the numeric inverse of the forward one."""
+    rng = LCG(seed)
+    n = 1 << bit_depth
+    org = n // 16
+    cw = org // 2 + rng.below(16, org)                  # bin code words, each in [org/2, 3*org/2)
+    cw[0] = cw[15] = 0                                    # lmcs_min_bin_idx = 1, max = 14
+    cw = (cw * (n - 1) // max(int(cw.sum()), 1)).astype(np.int64)
+    pivot = np.concatenate([[0], np.cumsum(cw)])
+    x = np.arange(n)
+    b = np.minimum(x // org, 15)
+    fwd = np.clip(pivot[b] + ((x - b * org) * cw[b] + org // 2) // org, 0, n - 1)
+    inv = np.clip(np.searchsorted(fwd, x, side="left"), 0, n - 1)
+    return fwd.astype(np.uint16), inv.astype(np.uint16)

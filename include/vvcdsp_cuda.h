@@ -212,6 +212,68 @@ int vvc_cuda_inloop_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCud
 int vvc_cuda_inloop_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
                                const VVCCudaInloopDesc *desc);
 
+/* ------------------------------------------------------------------------------------------
+ * Residual stage: inverse LFNST + inverse transform + add_residual for a list of transform
+ * blocks (replaces the per-TB tail of itransform(), libavcodec/vvc/vvc_intra.c:432-478, i.e.
+ * ilfnst_transform :65-127 / ff_vvc_inv_lfnst_1d vvc_itx_1d.c:708-721, the table entries
+ * itx.itx[trh][trv][log2w][log2h] (vvcdsp.c:94-195, vvc_itx_1d.c:70-706), itx.transform_bdpcm,
+ * itx.add_residual, itx.add_residual_joint (vvcdsp_template.c:32-95)).
+ * Dequantisation stays on the host, so coefficients arrive as the
+ * reference stores them after dequant(): one dense row-major int32[h][w] per TB.
+ * ---------------------------------------------------------------------------------------- */
+#define VVC_CUDA_TB_TS              1   /* transform skip: no LFNST / transform (tb->ts)                 */
+#define VVC_CUDA_TB_BDPCM           2   /* run itx.transform_bdpcm first (horizontal accumulate)         */
+#define VVC_CUDA_TB_BDPCM_VERT      4   /* ... vertical accumulate                                       */
+#define VVC_CUDA_TB_JOINT           8   /* joint CbCr: also add (res * joint_sign) >> joint_shift to plane joint_c_idx */
+#define VVC_CUDA_TB_STORE_RESIDUAL 16   /* write the residual back over the coefficients (what the reference's
+                                           in-place itx leaves in tb->coeffs) instead of adding it to the picture */
+
+typedef struct VVCCudaTB {
+    uint32_t coeff_offset;   /* first coefficient of this TB, in int32 units from the buffer start     */
+    uint16_t x0, y0;         /* top-left sample in plane c_idx (that plane's own sample units)          */
+    uint8_t  log2_w, log2_h; /* 0..6 (1 x N and N x 1 blocks as in the reference's 1-D cells)           */
+    uint8_t  c_idx;
+    uint8_t  trh, trv;       /* enum TxType (vvcdsp.h:30-35): 0 DCT2, 1 DST7, 2 DCT8                    */
+    uint8_t  nzw, nzh;       /* max_scan_x + 1, max_scan_y + 1, as passed to itx.itx[]                  */
+    uint8_t  flags;          /* VVC_CUDA_TB_*                                                           */
+    uint8_t  lfnst;          /* 0 off; else bits0-1 lfnst_idx (1|2), bits2-3 transform set
+                                (ff_vvc_lfnst_tr_set_index[predModeIntra], 1 for wide-angle < 0),
+                                bit4 transpose (predModeIntra > 34), bit5 nonZeroSize == 8             */
+    int8_t   joint_sign;
+    uint8_t  joint_shift;
+    uint8_t  joint_c_idx;
+    uint8_t  pic;            /* picture of the ring this TB belongs to                                  */
+    uint8_t  reserved;
+    uint16_t chroma_scale;   /* reserved for LMCS chroma residual scaling (0 = off)                     */
+} VVCCudaTB;                 /* 24 bytes */
+
+/* frame: prediction in, reconstruction out (in place - TBs are disjoint).  coeffs: dequantised
+ * coefficients; only written when a TB has VVC_CUDA_TB_STORE_RESIDUAL. */
+int vvc_cuda_itx_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs,
+                       const VVCCudaTB *tbs, int n_tbs, int log2_transform_range);
+int vvc_cuda_itx_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs, size_t n_coeffs,
+                            const VVCCudaTB *tbs, int n_tbs, int log2_transform_range);
+
+/* ------------------------------------------------------------------------------------------
+ * LMCS stage (replaces lmcs.filter, libavcodec/vvc/vvc_filter_template.c:25-36, as driven by
+ * ff_vvc_lmcs_filter, vvc_filter.c:1322-1332 (inverse LUT per CTU) and by predict_inter,
+ * vvc_inter.c:888-891 (forward LUT on the luma of inter CUs))
+ * ---------------------------------------------------------------------------------------- */
+typedef struct VVCCudaRect {
+    uint16_t x, y, w, h;     /* luma samples */
+    uint16_t pic;            /* picture of the ring */
+    uint16_t reserved;
+} VVCCudaRect;
+
+/* luma[x] = lut[luma[x]] in place on every CTB whose ctb_enable byte is non-zero (NULL = all CTBs;
+ * ctb_count bytes per picture of the ring).  lut: (1 << bit_depth) uint16 entries
+ * (VVCLMCS.inv_lut / fwd_lut, libavcodec/vvc/vvc_ps.h:192-199). */
+int vvc_cuda_lmcs_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const uint16_t *lut, const uint8_t *ctb_enable);
+/* same mapping on a list of luma rectangles (the inter CUs of a picture) */
+int vvc_cuda_lmcs_rects(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const uint16_t *lut,
+                        const VVCCudaRect *rects, int n_rects);
+int vvc_cuda_lmcs_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const uint16_t *lut, const uint8_t *ctb_enable);
+
 #ifdef __cplusplus
 }
 #endif

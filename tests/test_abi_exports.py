@@ -18,7 +18,7 @@ def test_descriptor_sizes_match_the_header():
     handle.vvc_cuda_abi_sizeof.restype = C.c_size_t
     handle.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
     want = {0: C.sizeof(abi.VVCCudaFrame), 1: C.sizeof(abi.VVCCudaALFCtb), 2: C.sizeof(abi.VVCCudaALFSets),
-            3: C.sizeof(abi.VVCCudaDbkEdge), 4: C.sizeof(abi.VVCCudaDeblockMaps), 5: C.sizeof(abi.VVCCudaSAOCtb), 6: C.sizeof(abi.VVCCudaInloopDesc)}
+            3: C.sizeof(abi.VVCCudaDbkEdge), 4: C.sizeof(abi.VVCCudaDeblockMaps), 5: C.sizeof(abi.VVCCudaSAOCtb), 6: C.sizeof(abi.VVCCudaInloopDesc), 7: C.sizeof(abi.VVCCudaTB)}
     for which, size in want.items():
         assert handle.vvc_cuda_abi_sizeof(which) == size, which
 

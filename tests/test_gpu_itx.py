@@ -1,0 +1,100 @@
+"""GPU parity: residual stage (LFNST + inverse transforms + BDPCM + add_residual / joint CbCr) vs the oracle."""
+import numpy as np
+import pytest
+
+from ffvvc_b200 import abi, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from ffvvc_b200 import lib
+    c = lib.Context(0)
+    with torch.cuda.stream(c.torch_stream()):
+        yield c
+    c.close()
+
+
+def cuda_itx(ctx, geom, tbs, coeffs, pred):
+    from ffvvc_b200 import device
+    fr = device.DeviceFrames(geom, planes=pred)
+    t1, p1 = device.to_device(coeffs)
+    t2, p2 = device.to_device(tbs)
+    ctx.itx_frame(fr.desc, p1, p2, len(tbs), 15)
+    ctx.sync()
+    return fr.to_numpy(), t1.cpu().numpy().view(np.int32)
+
+
+def oracle_itx(geom, tbs, coeffs, pred):
+    planes = [p.copy() for p in pred]
+    co = coeffs.copy()
+    util.oracle().vvco_itx_frame(abi.frame_from_numpy(geom, planes), co.ctypes.data, tbs.ctypes.data, len(tbs), 15)
+    return planes, co
+
+
+@pytest.mark.parametrize("w,h,batch,seed", [(416, 240, 1, 1), (256, 128, 2, 2), (832, 480, 1, 3), (1920, 1080, 1, 4)])
+def test_residual_stage_bit_exact(ctx, w, h, batch, seed):
+    geom = abi.FrameGeom(w, h, batch=batch)
+    tbs, coeffs = synth.tb_list(geom, seed=seed, lfnst_set_of=util.oracle().vvco_lfnst_tr_set)
+    pred = synth.uniform_planes(geom, seed=seed + 10)
+    gp, gc = cuda_itx(ctx, geom, tbs, coeffs, pred)
+    op, oc = oracle_itx(geom, tbs, coeffs, pred)
+    util.assert_planes_equal(geom, gp, op, "cuda vs oracle")
+    assert np.array_equal(gc, oc), "stored residuals differ"
+
+
+def test_every_table_cell(ctx):
+    from tests.test_oracle_vs_ref_itx import test_every_table_cell_like_checkasm as _unused  # noqa: F401
+    rng = synth.LCG(5)
+    recs = []
+    sizes = [1, 2, 4, 8, 16, 32, 64]
+    for trh in range(3):
+        for trv in range(3):
+            for lw, w in enumerate(sizes):
+                for lh, h in enumerate(sizes):
+                    if (w == 1 and h == 1) or ((w == 1 or h == 1) and max(w, h) < 16):
+                        continue
+                    if (trh and not 4 <= w <= 32) or (trv and not 4 <= h <= 32):
+                        continue
+                    for rep in range(4):
+                        r = np.zeros(1, dtype=abi.TB_DTYPE)
+                        r["log2_w"], r["log2_h"], r["trh"], r["trv"] = lw, lh, trh, trv
+                        r["nzw"] = int(rng.below(1, min(32 if trh == 0 else 16, w))[0]) + 1
+                        r["nzh"] = int(rng.below(1, min(32 if trv == 0 else 16, h))[0]) + 1
+                        r["flags"] = abi.TB_STORE_RESIDUAL
+                        recs.append(r)
+    tbs = np.concatenate(recs)
+    area = (1 << tbs["log2_w"].astype(np.int64)) * (1 << tbs["log2_h"].astype(np.int64))
+    off = np.concatenate([[0], np.cumsum(area)])
+    tbs["coeff_offset"] = off[:-1]
+    raw = rng.take(int(off[-1])).astype(np.int64)
+    coeffs = np.clip(((raw << 9) & 0xFFFFFFFF) - (1 << 31), -32768, 32767).astype(np.int32)
+    geom = abi.FrameGeom(64, 64)
+    pred = abi.alloc_planes(geom)
+    gp, gc = cuda_itx(ctx, geom, tbs, coeffs, pred)
+    op, oc = oracle_itx(geom, tbs, coeffs, pred)
+    bad = np.nonzero(gc != oc)[0]
+    if len(bad):
+        i = np.searchsorted(tbs["coeff_offset"], bad[0], side="right") - 1
+        raise AssertionError("%d residual mismatches, first in TB %s" % (len(bad), tbs[i]))
+
+
+def test_host_entry_and_4k_linearity(ctx):
+    geom = abi.FrameGeom(416, 240)
+    tbs, coeffs = synth.tb_list(geom, seed=9, lfnst_set_of=util.oracle().vvco_lfnst_tr_set)
+    pred = synth.uniform_planes(geom, seed=19)
+    planes = [p.copy() for p in pred]
+    co = coeffs.copy()
+    ctx.itx_frame_host(abi.frame_from_numpy(geom, planes), co.ctypes.data, co.size, tbs.ctypes.data, len(tbs), 15)
+    op, oc = oracle_itx(geom, tbs, coeffs, pred)
+    util.assert_planes_equal(geom, planes, op, "host entry vs oracle")
+    assert np.array_equal(co, oc)
+    # 4K property: zero coefficients leave the prediction untouched; DC-only blocks add a constant
+    g4 = abi.FrameGeom(3840, 2160)
+    tbs4, co4 = synth.tb_list(g4, seed=11, extras=False)
+    pred4 = synth.uniform_planes(g4, seed=12)
+    gp, _ = cuda_itx(ctx, g4, tbs4, np.zeros_like(co4), pred4)
+    util.assert_planes_equal(g4, gp, pred4, "zero residual must be the identity")

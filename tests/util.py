@@ -45,6 +45,13 @@ def oracle():
         lib.vvco_deblock_frame.restype = None
         lib.vvco_sao_frame.argtypes = [FP, FP, C.c_void_p]
         lib.vvco_sao_frame.restype = None
+        lib.vvco_itx_frame.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.vvco_itx_frame.restype = None
+        lib.vvco_lfnst_tr_set.argtypes = [C.c_int]
+        lib.vvco_lmcs_frame.argtypes = [FP, C.c_void_p, C.c_void_p]
+        lib.vvco_lmcs_frame.restype = None
+        lib.vvco_lmcs_rects.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int]
+        lib.vvco_lmcs_rects.restype = None
         _oracle = lib
     return _oracle
 
@@ -69,6 +76,12 @@ def ref():
         lib.vvcref_deblock_frame.restype = None
         lib.vvcref_sao_frame.argtypes = [FP, FP, C.c_void_p]
         lib.vvcref_sao_frame.restype = None
+        lib.vvcref_itx_frame.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.vvcref_itx_frame.restype = None
+        lib.vvcref_lmcs_frame.argtypes = [FP, C.c_void_p, C.c_void_p]
+        lib.vvcref_lmcs_frame.restype = None
+        lib.vvcref_lmcs_rects.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int]
+        lib.vvcref_lmcs_rects.restype = None
         _ref = lib
     return _ref
 
