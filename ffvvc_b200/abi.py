@@ -236,3 +236,21 @@ class VVCCudaRect(C.Structure):
 RECT_DTYPE = np.dtype([("x", np.uint16), ("y", np.uint16), ("w", np.uint16), ("h", np.uint16),
                        ("pic", np.uint16), ("reserved", np.uint16)])
 assert RECT_DTYPE.itemsize == C.sizeof(VVCCudaRect) == 12
+
+
+# ---- inter prediction stage (include/vvcdsp_cuda.h) -------------------------------------------
+PB_LUMA, PB_CHROMA = 1, 2
+PB_DMVR, PB_BDOF, PB_PROF0, PB_PROF1, PB_GPM, PB_WEIGHTED = 1, 2, 4, 8, 16, 32
+PF_L0, PF_L1, PF_BI = 1, 2, 3
+
+PB_DTYPE = np.dtype([
+    ("x0", np.uint16), ("y0", np.uint16), ("w", np.uint8), ("h", np.uint8), ("planes", np.uint8),
+    ("pred_flag", np.uint8), ("ref", np.uint8, (2,)), ("pic", np.uint8), ("flags", np.uint8),
+    ("mv", np.int32, (2, 2)), ("filt", np.uint8), ("bcw_idx", np.uint8), ("wp", np.uint16),
+    ("prof", np.uint16), ("gpm_step_x", np.int16), ("gpm_step_y", np.int16), ("reserved", np.uint16),
+    ("gpm_weights", np.int32)], align=True)
+WP_DTYPE = np.dtype([("weight", np.int16, (2, 3)), ("offset", np.int16, (2, 3)),
+                     ("log2_denom", np.uint8, (2,)), ("reserved", np.uint8, (2,))], align=True)
+PROF_DTYPE = np.dtype([("diff_mv_x", np.int16, (2, 16)), ("diff_mv_y", np.int16, (2, 16))])
+DMVR_OUT_DTYPE = np.dtype([("mv", np.int32, (2, 2)), ("min_sad", np.int32), ("bdof_applied", np.int32)])
+assert PB_DTYPE.itemsize == 44 and WP_DTYPE.itemsize == 28 and PROF_DTYPE.itemsize == 128 and DMVR_OUT_DTYPE.itemsize == 24

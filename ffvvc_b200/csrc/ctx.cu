@@ -140,6 +140,11 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 5: return sizeof(VVCCudaSAOCtb);
     case 6: return sizeof(VVCCudaInloopDesc);
     case 7: return sizeof(VVCCudaTB);
+    case 8: return sizeof(VVCCudaPB);
+    case 9: return sizeof(VVCCudaWP);
+    case 10: return sizeof(VVCCudaProf);
+    case 11: return sizeof(VVCCudaDmvrOut);
+    case 12: return sizeof(VVCCudaRect);
     default: return 0;
     }
 }

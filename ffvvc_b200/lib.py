@@ -67,6 +67,10 @@ def load():
     lib.vvc_cuda_lmcs_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_lmcs_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_lmcs_rects.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, C.c_int]
+    lib.vvc_cuda_inter_frame.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vvc_cuda_inter_frame_host.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
+    lib.vvc_cuda_abi_sizeof.restype = C.c_size_t
     _lib = lib
     return lib
 
@@ -155,6 +159,14 @@ class Context:
 
     def lmcs_frame_host(self, frame, lut_ptr, ctb_enable_ptr=None):
         self.check(self.lib.vvc_cuda_lmcs_frame_host(self.handle, C.byref(frame), lut_ptr, ctb_enable_ptr))
+
+    def inter_frame(self, dst, refs, pbs_ptr, n_pbs, wp_ptr, prof_ptr, dmvr_out_ptr=None):
+        """Motion compensation (+ DMVR / BDOF / PROF / GPM / weighted prediction) of a record list."""
+        self.check(self.lib.vvc_cuda_inter_frame(self.handle, C.byref(dst), C.byref(refs), pbs_ptr, n_pbs, wp_ptr, prof_ptr, dmvr_out_ptr))
+
+    def inter_frame_host(self, dst, refs, pbs_ptr, n_pbs, wp_ptr, n_wp, prof_ptr, n_prof, dmvr_out_ptr=None):
+        self.check(self.lib.vvc_cuda_inter_frame_host(self.handle, C.byref(dst), C.byref(refs), pbs_ptr, n_pbs,
+                                                      wp_ptr, n_wp, prof_ptr, n_prof, dmvr_out_ptr))
 
     def lmcs_rects(self, frame, lut_ptr, rects_ptr, n):
         self.check(self.lib.vvc_cuda_lmcs_rects(self.handle, C.byref(frame), lut_ptr, rects_ptr, n))

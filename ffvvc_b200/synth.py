@@ -385,3 +385,179 @@ def lmcs_luts(bit_depth=10, seed=5):
     fwd = np.clip(pivot[b] + ((x - b * org) * cw[b] + org // 2) // org, 0, n - 1)
     inv = np.clip(np.searchsorted(fwd, x, side="left"), 0, n - 1)
     return fwd.astype(np.uint16), inv.astype(np.uint16)
+
+
+# ---------------------------------------------------------------------------------------------
+# Inter prediction inputs: a random-access-like motion field
+# ---------------------------------------------------------------------------------------------
+_TABLES = {}
+
+
+def spec_table(name):
+    """One table of ffvvc_b200/csrc/vvc_tables.inc (generated H.266 constants) as a numpy array."""
+    if not _TABLES:
+        import os
+        import re
+        src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "vvc_tables.inc")).read()
+        for m in re.finditer(r"VVCT_TABLE\((\w+), vvct_(\w+), ((?:\[\d+\])+)\) = \{([^}]*)\}", src):
+            dims = [int(d) for d in re.findall(r"\[(\d+)\]", m.group(3))]
+            vals = np.array([int(v) for v in m.group(4).replace("\n", " ").split(",") if v.strip()], dtype=np.int64)
+            _TABLES[m.group(2)] = vals.reshape(dims)
+    return _TABLES[name]
+
+
+def pb_list(geom, n_refs=2, seed=2024, dst_pics=None, mix=None):
+    """Prediction-block records for every picture of the destination ring.
+
+    The picture is tiled by CUs of 4..64 samples per side (one shape per 64x64 region); each CU draws a
+    mode: uni / bi (avg), DMVR+BDOF, BDOF only, BCW, explicit weights, affine (+PROF) or GPM, and a
+    motion vector = smooth field (up to +-48 px) + jitter; 5 % of the CUs get vectors far outside the
+    picture so the reference-window clamps are exercised.  CUs are cut into records of at most 16x16
+    (4x4 + one chroma record per 8x8 for affine CUs), which is how the reference itself walks DMVR/BDOF
+    and affine sub-blocks (vvc_inter.c:782-873).
+    Returns (pbs, wp, prof).
+    """
+    rng = LCG(seed)
+    mix = mix or dict(bi=70, dmvr=50, bdof_only=5, bcw=10, wp=5, affine=5, gpm=3)
+    pics = range(geom.batch) if dst_pics is None else dst_pics
+    n_wp = 8
+    wp = np.zeros(n_wp, dtype=abi.WP_DTYPE)
+    wp["weight"][:] = (rng.below(n_wp * 6, 256) - 128).reshape(n_wp, 2, 3)
+    wp["offset"][:] = (rng.below(n_wp * 6, 256) - 128).reshape(n_wp, 2, 3)
+    wp["log2_denom"][:] = rng.below(n_wp * 2, 8).reshape(n_wp, 2)
+    ang_idx, ang_w, ang_mirror = spec_table("gpm_angle_idx"), spec_table("gpm_angle_to_weights_idx"), spec_table("gpm_angle_to_mirror")
+    offx, offy = spec_table("gpm_weights_offset_x"), spec_table("gpm_weights_offset_y")
+    recs, profs = [], []
+    n_prof = 0
+    W, H = geom.width, geom.height
+    for k in pics:
+        g64h, g64w = (H + 63) // 64, (W + 63) // 64
+        shape_w = np.array([2, 3, 3, 4, 4, 4, 5, 5, 6, 6])[rng.below(g64h * g64w, 10)].reshape(g64h, g64w)
+        shape_h = np.array([2, 3, 3, 4, 4, 4, 5, 5, 6, 6])[rng.below(g64h * g64w, 10)].reshape(g64h, g64w)
+        shape_h = np.where((shape_w == 2) & (shape_h == 2), 3, shape_h)        # no 4x4 inter CUs
+        for lw in range(2, 7):
+            for lh in range(2, 7):
+                ry, rx = np.nonzero((shape_w == lw) & (shape_h == lh))
+                if not len(ry):
+                    continue
+                cw, ch = 1 << lw, 1 << lh
+                # every CU of these 64x64 regions
+                iy, ix = np.mgrid[0:64 // ch, 0:64 // cw]
+                cx = (rx[:, None] * 64 + ix.reshape(-1)[None, :] * cw).reshape(-1)
+                cy = (ry[:, None] * 64 + iy.reshape(-1)[None, :] * ch).reshape(-1)
+                ok = (cx + cw <= W) & (cy + ch <= H)
+                cx, cy = cx[ok], cy[ok]
+                n = len(cx)
+                if not n:
+                    continue
+                r = rng.below(n, 100)
+                small = cw == 4 or ch == 4
+                bi = (r < mix["bi"]) & (not small)
+                r2 = rng.below(n, 100)
+                eligible = bi & (cw >= 8) & (ch >= 8) & (cw * ch >= 128)
+                e0 = mix["dmvr"]; e1 = e0 + mix["bdof_only"]; e2 = e1 + mix["bcw"]; e3 = e2 + mix["wp"]
+                dmvr = eligible & (r2 < e0)
+                bdof = eligible & (r2 < e1)
+                bcw = bi & (r2 >= e1) & (r2 < e2)
+                wpf = (r2 >= e2) & (r2 < e3)                                   # uni or bi
+                r3 = rng.below(n, 100)
+                affine = (r3 < mix["affine"]) & ~dmvr & ~bdof & (cw >= 16) & (ch >= 16)
+                gpm = (r3 >= mix["affine"]) & (r3 < mix["affine"] + mix["gpm"]) & (cw >= 8) & (ch >= 8) & ~affine
+                dmvr &= ~gpm; bdof &= ~gpm; bcw &= ~gpm; wpf &= ~gpm
+                pred = np.where(bi | gpm, abi.PF_BI, np.where(rng.below(n, 2) == 0, abi.PF_L0, abi.PF_L1))
+                # motion: smooth field + jitter, 1/16 sample units
+                ph = 0.37 * k
+                fx = 768 * np.sin(0.0021 * cx + 0.0013 * cy + ph) + (rng.below(n, 129) - 64)
+                fy = 512 * np.cos(0.0017 * cx - 0.0029 * cy + ph) + (rng.below(n, 129) - 64)
+                mv = np.zeros((n, 2, 2), dtype=np.int64)
+                mv[:, 0, 0], mv[:, 0, 1] = fx, fy
+                mv[:, 1, 0] = -fx + (rng.below(n, 65) - 32)                     # roughly mirrored second list
+                mv[:, 1, 1] = -fy + (rng.below(n, 65) - 32)
+                ints = rng.below(n, 8) == 0                                      # some integer / half-pel vectors
+                mv[ints] &= ~15
+                far = rng.below(n, 20) == 0
+                mv[far] += (rng.below(int(far.sum()) * 4, 2).reshape(-1, 2, 2) * 2 - 1) * (16 * max(W, H))
+                refs = rng.below(n * 2, n_refs).reshape(n, 2)
+                filt = np.where(affine, 2, (rng.below(n, 10) == 0).astype(np.int64))
+                bcw_idx = np.where(bcw, rng.below(n, 4) + 1, 0)
+                wp_idx = rng.below(n, n_wp)
+                # GPM geometry (pred_gpm_blk, vvc_inter.c:466-505)
+                part = rng.below(n, 64)
+                ang = ang_idx[part]
+                mirror = ang_mirror[ang]
+                ox_ = offx[part, max(lh - 3, 0), max(lw - 3, 0)]
+                oy_ = offy[part, max(lh - 3, 0), max(lw - 3, 0)]
+                gsx = np.where(mirror == 1, -1, 1)
+                gsy = np.where(mirror == 2, -112, 112)
+                gbase = ang_w[ang] * 112 * 112 + np.where(mirror == 0, oy_ * 112 + ox_,
+                                                          np.where(mirror == 1, oy_ * 112 + 111 - ox_, (111 - oy_) * 112 + ox_))
+                # PROF tables for the affine CUs
+                aff_ids = np.nonzero(affine)[0]
+                prof_idx = np.zeros(n, dtype=np.int64)
+                prof_idx[aff_ids] = n_prof + np.arange(len(aff_ids))
+                if len(aff_ids):
+                    pr = np.zeros(len(aff_ids), dtype=abi.PROF_DTYPE)
+                    pr["diff_mv_x"][:] = (rng.below(len(aff_ids) * 32, 63) - 31).reshape(-1, 2, 16)
+                    pr["diff_mv_y"][:] = (rng.below(len(aff_ids) * 32, 63) - 31).reshape(-1, 2, 16)
+                    profs.append(pr)
+                    n_prof += len(aff_ids)
+                prof_flags = np.where(affine, rng.below(n, 4), 0)                # cb_prof_flag[0] | cb_prof_flag[1] << 1
+                flags = (dmvr * abi.PB_DMVR) | (bdof * abi.PB_BDOF) | (gpm * abi.PB_GPM) | (wpf * abi.PB_WEIGHTED) \
+                    | ((prof_flags & 1) * abi.PB_PROF0) | ((prof_flags >> 1) * abi.PB_PROF1)
+
+                def expand(sel, tw, th, planes, mvs=None, sub=None):
+                    ids = np.nonzero(sel)[0]
+                    if not len(ids):
+                        return
+                    ty, tx = np.mgrid[0:ch // th, 0:cw // tw]
+                    tx, ty = tx.reshape(-1) * tw, ty.reshape(-1) * th
+                    m = len(tx)
+                    rec = np.zeros(len(ids) * m, dtype=abi.PB_DTYPE)
+                    rid = np.repeat(ids, m)
+                    px, py = np.tile(tx, len(ids)), np.tile(ty, len(ids))
+                    rec["x0"], rec["y0"] = cx[rid] + px, cy[rid] + py
+                    rec["w"], rec["h"], rec["planes"], rec["pic"] = tw, th, planes, k
+                    rec["pred_flag"], rec["ref"], rec["flags"] = pred[rid], refs[rid], flags[rid]
+                    rec["filt"], rec["bcw_idx"], rec["wp"], rec["prof"] = filt[rid], bcw_idx[rid], wp_idx[rid], prof_idx[rid]
+                    rec["gpm_step_x"], rec["gpm_step_y"] = gsx[rid], gsy[rid]
+                    rec["gpm_weights"] = gbase[rid] + py * gsy[rid] + px * gsx[rid]
+                    base_mv = mv[rid]
+                    if sub is not None:     # affine: per sub-block vectors = CU vector + a linear field
+                        gxx, gxy, gyx, gyy = sub
+                        d = np.zeros_like(base_mv)
+                        d[:, :, 0] = (gxx[rid] * px + gxy[rid] * py)[:, None] >> 4
+                        d[:, :, 1] = (gyx[rid] * px + gyy[rid] * py)[:, None] >> 4
+                        base_mv = base_mv + d
+                    rec["mv"] = base_mv if mvs is None else mvs(base_mv, rid, px, py)
+                    recs.append(rec)
+
+                both = abi.PB_LUMA | abi.PB_CHROMA if geom.chroma_format_idc else abi.PB_LUMA
+                expand(~affine, min(cw, 16), min(ch, 16), both)
+                if affine.any():
+                    sub = tuple(rng.below(n, 33) - 16 for _ in range(4))
+                    expand(affine, 4, 4, abi.PB_LUMA, sub=sub)
+                    if geom.chroma_format_idc:
+                        def mvc(base, rid, px, py):
+                            # derive_affine_mvc (vvc_inter.c:813-826): mv(x, y) + mv(x + 4, y + 4), rounded by 1
+                            gxx, gxy, gyx, gyy = sub
+                            d2 = np.zeros_like(base)
+                            d2[:, :, 0] = (gxx[rid] * (px + 4) + gxy[rid] * (py + 4))[:, None] >> 4
+                            d2[:, :, 1] = (gyx[rid] * (px + 4) + gyy[rid] * (py + 4))[:, None] >> 4
+                            d1 = np.zeros_like(base)
+                            d1[:, :, 0] = (gxx[rid] * px + gxy[rid] * py)[:, None] >> 4
+                            d1[:, :, 1] = (gyx[rid] * px + gyy[rid] * py)[:, None] >> 4
+                            s = (base + d1) + (base + d2)
+                            return (s + 1 - (s >= 0)) >> 1
+                        # chroma of affine CUs: one record per 8x8 luma, no PROF / weights from the luma flags kept
+                        saved = flags.copy()
+                        flags &= ~(abi.PB_PROF0 | abi.PB_PROF1)
+                        ids_before = len(recs)
+                        expand(affine, 8, 8, abi.PB_CHROMA, mvs=mvc)
+                        flags[:] = saved
+                        del ids_before
+    pbs = np.concatenate(recs) if recs else np.zeros(0, dtype=abi.PB_DTYPE)
+    prof = np.concatenate(profs) if profs else np.zeros(1, dtype=abi.PROF_DTYPE)
+    # uni records carry no bi-only tools
+    uni = pbs["pred_flag"] != abi.PF_BI
+    pbs["bcw_idx"][uni] = 0
+    return pbs, wp, prof

@@ -58,7 +58,7 @@ void       *vvc_cuda_stream(const VVCCudaCtx *ctx);    /* the cudaStream_t in us
 uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx);
 const char *vvc_cuda_version(void);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, ...): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -273,6 +273,86 @@ int vvc_cuda_lmcs_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const uint16
 int vvc_cuda_lmcs_rects(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const uint16_t *lut,
                         const VVCCudaRect *rects, int n_rects);
 int vvc_cuda_lmcs_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const uint16_t *lut, const uint8_t *ctb_enable);
+
+/* ------------------------------------------------------------------------------------------
+ * Inter prediction stage (replaces the pixel work of ff_vvc_predict_inter, libavcodec/vvc/
+ * vvc_inter.c:899-913: pred_regular_blk :782-811 incl. dmvr_mv_refine :685-748, pred_affine_blk
+ * :828-873, pred_gpm_blk :466-521, and the table entries inter.put / put_uni / put_uni_w / avg /
+ * w_avg / put_gpm / bdof_fetch_samples / fetch_samples / prof_grad_filter / apply_prof* /
+ * apply_bdof / sad / dmvr, libavcodec/h26x/h2656_inter_template.c:29-577,
+ * libavcodec/vvc/vvc_inter_template.c:25-436, libavcodec/vvc/vvcdsp.c:29-65).
+ *
+ * The host (CABAC + MV derivation) emits one prediction-block record per motion-compensated block
+ * of at most 16x16 luma samples: DMVR/BDOF sub-blocks are 16x16 by construction
+ * (vvc_inter.c:796-797), larger plain CUs are simply cut into 16x16 pieces (MC is per-sample),
+ * affine CUs give one luma record per 4x4 sub-block plus one chroma record per 2x2 group
+ * (:862-868).  Reference pictures live in one ring (the DPB); ref[] is the ring slot.
+ * ---------------------------------------------------------------------------------------- */
+#define VVC_CUDA_PB_LUMA        1    /* planes: predict luma                                      */
+#define VVC_CUDA_PB_CHROMA      2    /* planes: predict Cb and Cr (4:2:0: (w/2) x (h/2) at (x0/2, y0/2)) */
+
+#define VVC_CUDA_PB_DMVR        1    /* flags: pu->dmvr_flag (bi-pred only, w*h >= 128)             */
+#define VVC_CUDA_PB_BDOF        2    /* pu->bdof_flag (bi-pred only)                                */
+#define VVC_CUDA_PB_PROF0       4    /* pu->cb_prof_flag[0] (4x4 affine luma blocks)                */
+#define VVC_CUDA_PB_PROF1       8    /* pu->cb_prof_flag[1]                                         */
+#define VVC_CUDA_PB_GPM        16    /* geometric partition blend of two uni predictions (mv[0], mv[1]) */
+#define VVC_CUDA_PB_WEIGHTED   32    /* the reference's weight_flag is set (derive_weight(_uni), vvc_inter.c:129-177): wp valid */
+
+typedef struct VVCCudaPB {
+    uint16_t x0, y0;          /* luma position of the block                                         */
+    uint8_t  w, h;            /* luma size: 4, 8 or 16 each                                         */
+    uint8_t  planes;          /* VVC_CUDA_PB_LUMA | VVC_CUDA_PB_CHROMA                              */
+    uint8_t  pred_flag;       /* PF_L0 = 1, PF_L1 = 2, PF_BI = 3 (vvc_ctu.h:215-220).  Entry i of mv[] / ref[]
+                                 is list i as in MvField; a GPM block uses both entries (gpm_mv[0], gpm_mv[1]) */
+    uint8_t  ref[2];          /* DPB ring slot of the reference picture of each used entry          */
+    uint8_t  pic;             /* destination picture slot                                           */
+    uint8_t  flags;           /* VVC_CUDA_PB_*                                                      */
+    int32_t  mv[2][2];        /* [entry][x,y] in 1/16 luma sample                                   */
+    uint8_t  filt;            /* luma filter set: 0 regular, 1 alternative half-pel (hpel_if_idx), 2 affine */
+    uint8_t  bcw_idx;         /* 0 = off, else w1 = {4,5,3,10,-2}[bcw_idx], denom 2 (vvc_inter.c:31,161-165) */
+    uint16_t wp;              /* index into the weighted-prediction table (VVC_CUDA_PB_WEIGHTED)     */
+    uint16_t prof;            /* index into the PROF table: diff_mv of the CU                        */
+    int16_t  gpm_step_x;      /* GPM: weight pointer steps for luma (+-1, +-112), vvc_inter.c:491-502; */
+    int16_t  gpm_step_y;      /*      chroma uses twice these steps from the same first weight        */
+    uint16_t reserved;
+    int32_t  gpm_weights;     /* GPM: index of this block's first weight in the 6 x 112 x 112 table   */
+} VVCCudaPB;                  /* 44 bytes */
+
+/* explicit weights resolved per (ref_idx_l0, ref_idx_l1) pair, mirrors PredWeightTable
+ * (libavcodec/vvc/vvc_ps.h:135-143) as read by derive_weight(_uni), vvc_inter.c:129-177 */
+typedef struct VVCCudaWP {
+    int16_t weight[2][3];     /* [list][plane] */
+    int16_t offset[2][3];
+    uint8_t log2_denom[2];    /* luma, chroma */
+    uint8_t reserved[2];
+} VVCCudaWP;                  /* 28 bytes */
+
+/* PROF displacement of one affine CU, mirrors pu->diff_mv_x/y (vvc_ctu.h:268-270) */
+typedef struct VVCCudaProf {
+    int16_t diff_mv_x[2][16];
+    int16_t diff_mv_y[2][16];
+} VVCCudaProf;                /* 128 bytes */
+
+/* per block outputs of DMVR, what set_dmvr_info() stores for later pictures (vvc_inter.c:750-762) */
+typedef struct VVCCudaDmvrOut {
+    int32_t mv[2][2];         /* refined motion vectors */
+    int32_t min_sad;
+    int32_t bdof_applied;     /* sb_bdof_flag after the min_sad < 2wh test (:745) */
+} VVCCudaDmvrOut;             /* 24 bytes */
+
+/* dst: picture ring being predicted (record i writes slot pbs[i].pic); refs: the DPB ring (must not
+ * alias the written slots).  dmvr_out: optional, n_pbs entries (only DMVR records are written).
+ * CIIP blocks are not part of this entry: their inter half needs the intra predictor and is blended
+ * by inter.put_ciip in the RECON stage (vvc_intra.c:515-516).  The forward LMCS mapping of inter CUs
+ * (vvc_inter.c:888-891) is vvc_cuda_lmcs_rects().  All arrays device memory. */
+int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *refs,
+                         const VVCCudaPB *pbs, int n_pbs, const VVCCudaWP *wp, const VVCCudaProf *prof,
+                         VVCCudaDmvrOut *dmvr_out);
+/* host arrays and pictures: copies refs + descriptors in, runs, copies the predicted pictures and
+ * dmvr_out back */
+int vvc_cuda_inter_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *refs,
+                              const VVCCudaPB *pbs, int n_pbs, const VVCCudaWP *wp, int n_wp,
+                              const VVCCudaProf *prof, int n_prof, VVCCudaDmvrOut *dmvr_out);
 
 #ifdef __cplusplus
 }

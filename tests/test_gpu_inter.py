@@ -1,0 +1,94 @@
+"""GPU parity: inter prediction stage (8/4-tap MC, bi-pred avg / w_avg / BCW, DMVR, BDOF, PROF, GPM,
+picture-border and DMVR-window clamps) vs the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from ffvvc_b200 import abi, synth
+from tests import util
+from tests.test_oracle_vs_ref_inter import STRESS_MIX, make_case, run_inter
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from ffvvc_b200 import lib
+    c = lib.Context(0)
+    with torch.cuda.stream(c.torch_stream()):
+        yield c
+    c.close()
+
+
+def cuda_inter(ctx, gd, gr, refs, pbs, wp, prof):
+    from ffvvc_b200 import device
+    dst = device.DeviceFrames(gd, planes=abi.alloc_planes(gd, fill=77))
+    ref = device.DeviceFrames(gr, planes=refs)
+    t1, p1 = device.to_device(pbs)
+    t2, p2 = device.to_device(wp)
+    t3, p3 = device.to_device(prof)
+    t4, p4 = device.to_device(np.zeros(len(pbs), dtype=abi.DMVR_OUT_DTYPE))
+    ctx.inter_frame(dst.desc, ref.desc, p1, len(pbs), p2, p3, p4)
+    ctx.sync()
+    return dst.to_numpy(), t4.cpu().numpy().view(abi.DMVR_OUT_DTYPE)
+
+
+@pytest.mark.parametrize("w,h,seed,uniform,bd", [(416, 240, 1, False, 10), (416, 240, 2, True, 10), (256, 192, 3, False, 10),
+                                                  (832, 480, 4, False, 10), (136, 72, 5, True, 10), (256, 128, 9, False, 12),
+                                                  (1920, 1080, 6, False, 10)])
+def test_inter_stage_bit_exact(ctx, w, h, seed, uniform, bd):
+    gd, gr, refs, pbs, wp, prof = make_case(w, h, seed, mix=STRESS_MIX if seed != 6 else None, uniform=uniform, bit_depth=bd)
+    gp, go = cuda_inter(ctx, gd, gr, refs, pbs, wp, prof)
+    od, oo = run_inter(util.oracle().vvco_inter_frame, gd, gr, refs, pbs, wp, prof)
+    util.assert_planes_equal(gd, gp, od, "cuda vs oracle")
+    dm = (pbs["flags"] & abi.PB_DMVR) != 0
+    assert np.array_equal(go[dm], oo[dm]), "DMVR outputs (refined vectors, min SAD, BDOF decision) differ"
+
+
+def test_inter_ring_and_host_entry(ctx):
+    """Two destination pictures predicted from a 3-picture DPB ring; the *_host entry gives the same result."""
+    gd, gr, refs, pbs, wp, prof = make_case(256, 128, 21, mix=STRESS_MIX, batch=2)
+    gp, go = cuda_inter(ctx, gd, gr, refs, pbs, wp, prof)
+    od, oo = run_inter(util.oracle().vvco_inter_frame, gd, gr, refs, pbs, wp, prof)
+    util.assert_planes_equal(gd, gp, od, "cuda vs oracle (ring)")
+    hd = abi.alloc_planes(gd, fill=77)
+    ho = np.zeros(len(pbs), dtype=abi.DMVR_OUT_DTYPE)
+    ctx.inter_frame_host(abi.frame_from_numpy(gd, hd), abi.frame_from_numpy(gr, refs), pbs.ctypes.data, len(pbs),
+                         wp.ctypes.data, len(wp), prof.ctypes.data, len(prof), ho.ctypes.data)
+    util.assert_planes_equal(gd, hd, od, "host entry vs oracle")
+    dm = (pbs["flags"] & abi.PB_DMVR) != 0
+    assert np.array_equal(ho[dm], oo[dm])
+
+
+def test_inter_4k_properties(ctx):
+    """BASELINE config 4 size: properties that need no CPU pass over the whole picture.
+    (a) integer-pel uni prediction with a zero vector copies the reference; (b) the full 4K mix equals the
+    oracle on a sample of records re-run in isolation."""
+    gd = abi.FrameGeom(3840, 2160)
+    gr = abi.FrameGeom(3840, 2160, batch=2)
+    refs = synth.struct_planes(abi.FrameGeom(3840, 2160, batch=1), seed=3)
+    refs = [np.ascontiguousarray(np.concatenate([p, p[:, ::-1]])) for p in refs]
+    pbs, wp, prof = synth.pb_list(gd, n_refs=2, seed=8)
+    # (a)
+    ys, xs = np.mgrid[0:2160 // 16, 0:3840 // 16]
+    cp = np.zeros(ys.size, dtype=abi.PB_DTYPE)
+    cp["x0"], cp["y0"], cp["w"], cp["h"] = xs.reshape(-1) * 16, ys.reshape(-1) * 16, 16, 16
+    cp["planes"], cp["pred_flag"] = 3, abi.PF_L0
+    gp, _ = cuda_inter(ctx, gd, gr, refs, cp, wp, prof)
+    for c in range(3):
+        wv = gd.plane_wh(c)[0]
+        assert np.array_equal(gp[c][0, :, :wv], refs[c][0, :, :wv])
+    # (b)
+    gp, go = cuda_inter(ctx, gd, gr, refs, pbs, wp, prof)
+    pick = synth.LCG(4).below(4000, len(pbs))
+    sub = pbs[pick]
+    od, oo = run_inter(util.oracle().vvco_inter_frame, gd, gr, refs, sub, wp, prof)
+    for r in sub:
+        for c in range(3):
+            if not (r["planes"] & (2 if c else 1)):
+                continue
+            sh = 1 if c else 0
+            x0, y0, bw, bh = r["x0"] >> sh, r["y0"] >> sh, r["w"] >> sh, r["h"] >> sh
+            assert np.array_equal(gp[c][0, y0:y0 + bh, x0:x0 + bw], od[c][0, y0:y0 + bh, x0:x0 + bw]), (r, c)
+    dm = (sub["flags"] & abi.PB_DMVR) != 0
+    assert np.array_equal(go[pick][dm], oo[dm])

@@ -52,6 +52,8 @@ def oracle():
         lib.vvco_lmcs_frame.restype = None
         lib.vvco_lmcs_rects.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int]
         lib.vvco_lmcs_rects.restype = None
+        lib.vvco_inter_frame.argtypes = [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vvco_inter_frame.restype = None
         _oracle = lib
     return _oracle
 
@@ -82,6 +84,8 @@ def ref():
         lib.vvcref_lmcs_frame.restype = None
         lib.vvcref_lmcs_rects.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int]
         lib.vvcref_lmcs_rects.restype = None
+        lib.vvcref_inter_frame.argtypes = [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vvcref_inter_frame.restype = None
         _ref = lib
     return _ref
 
