@@ -3,12 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over a ring of distinct synthetic 4K 10-bit 4:2:0 pictures
-that is larger than the 126 MB L2.  Ours: every stage is a CUDA kernel of libvvcdsp_cuda.so called
-through the C ABI; `value` has pictures and descriptors resident in HBM, `e2e` goes through the
-*_host entry with pinned host buffers (H2D + kernels + D2H inside the timed region).
-Reference arm (--impl reference): the reference's own C table entries (oracle/_ref, else the
-oracle port) on the host cores, bounded sample, same metric.
+Workload (BASELINE.json config 5): every picture of a ring of distinct synthetic
+3840x2160 10-bit 4:2:0 pictures goes through the whole hot path in the reference's stage order
+    INTER (MC, bi-pred, DMVR, BDOF, PROF, GPM) -> residual (LFNST + inverse transforms + add_residual)
+    -> inverse LMCS -> deblock V -> deblock H -> SAO -> ALF / CC-ALF.
+One "step" = one pass over the ring.  The ring (pictures, reference pictures, coefficients) is several
+times larger than the 126 MB L2.
+
+Ours: every stage is a CUDA kernel of libvvcdsp_cuda.so called through the C ABI.  `value` has pictures
+and descriptors resident in HBM; `e2e` goes through vvc_cuda_recon_frame_host with pinned HOST buffers
+(H2D of references, records and coefficients + kernels + D2H of the pictures inside the timed region).
+Reference arm (--impl reference) and the cpu_baseline leg: the reference's own C table entries
+(oracle/_ref/libvvcref.so, else the oracle port) on the host cores, one picture per thread.
 Multi-GPU: independent streams, one process per GPU, no data-path collective.
 """
 import argparse
@@ -28,7 +34,11 @@ from ffvvc_b200 import abi, synth  # noqa: E402
 
 METRIC = "vvc_4k10_recon_loopfilter_mpix_per_s"
 UNIT = "Mpix/s"
-L2_BYTES = 126 * 1024 * 1024
+STAGES = ["inter", "residual", "lmcs", "deblock_v", "deblock_h", "sao", "alf"]
+# algorithmic bytes per luma pixel moved by ONE launch of each stage (SURVEY.md 8(d), 4:2:0 10 bit):
+# inter all-bi 9; residual 8 B/sample x 1.5; LMCS luma r+w; each filter pass reads + writes 3 planes
+ALGO_BYTES_PER_LUMA_PX = {"inter": 9.0, "residual": 12.0, "lmcs": 4.0, "deblock_v": 6.0, "deblock_h": 6.0, "sao": 6.0, "alf": 6.0}
+CHAIN_ALGO_BYTES_PER_LUMA_PX = 43.0     # 9 + 12 + 4 + 18 (deblock V+H counted once), SURVEY.md config 5
 
 
 def load_peaks():
@@ -40,38 +50,39 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# Synthetic workload (SURVEY.md 8(d) config 2 distributions on 4K pictures)
+# Synthetic workload
 # ---------------------------------------------------------------------------------------------
 class Inputs:
-    """Host-side synthetic inputs for a ring of `frames` pictures (distinct seeds per picture)."""
+    """Host-side inputs for `distinct` different pictures; ring slot k reuses content k % distinct at
+    its own addresses (so the ring still defeats L2)."""
 
-    def __init__(self, width, height, frames, seed=12345, distinct=4):
-        self.geom = abi.FrameGeom(width, height, batch=frames)
-        distinct = min(distinct, frames)
-        g1 = abi.FrameGeom(width, height, batch=distinct)
-        base = synth.struct_planes(g1, seed=seed)
-        reps = (frames + distinct - 1) // distinct
-        # ring slots beyond `distinct` repeat content at different addresses (still defeats L2)
-        self.planes = [np.ascontiguousarray(np.concatenate([p] * reps)[:frames]) for p in base]
-        m1 = synth.deblock_maps(g1, seed=seed + 1, qp_base=27, qp_span=16)
-        self.maps = [[np.ascontiguousarray(np.concatenate([m1[d][c]] * reps)[:frames]) for c in range(3)] for d in range(2)]
-        sao1 = synth.sao_params(g1, seed=seed + 2)
-        alf1, self.sets = synth.alf_params(g1, seed=seed + 3)
-        n1 = g1.ctb_count
-        self.sao = np.ascontiguousarray(np.concatenate([sao1] * reps)[:frames * n1])
-        self.alf = np.ascontiguousarray(np.concatenate([alf1] * reps)[:frames * n1])
+    def __init__(self, width, height, seed=12345, distinct=2, lfnst_set_of=None):
+        self.w, self.h, self.distinct = width, height, distinct
+        self.g1 = abi.FrameGeom(width, height)
+        gd = abi.FrameGeom(width, height, batch=distinct)
+        self.ref_planes = synth.struct_planes(gd, seed=seed)          # reference pictures (distinct contents)
+        self.pbs, self.tbs, self.coeffs, self.maps, self.sao, self.alf = [], [], [], [], [], []
+        for i in range(distinct):
+            pbs, self.wp, self.prof = synth.pb_list(self.g1, n_refs=2, seed=seed + 10 * i + 1)
+            self.pbs.append(pbs)
+            tbs, co = synth.tb_list(self.g1, seed=seed + 10 * i + 2, lfnst_set_of=lfnst_set_of, extras=False, saturate=False)
+            self.tbs.append(tbs)
+            self.coeffs.append(co)
+            self.maps.append(synth.deblock_maps(self.g1, seed=seed + 10 * i + 3, qp_base=27, qp_span=16))
+            self.sao.append(synth.sao_params(self.g1, seed=seed + 10 * i + 4))
+            alf, self.sets = synth.alf_params(self.g1, seed=seed + 10 * i + 5)
+            self.alf.append(alf)
+        _, self.inv_lut = synth.lmcs_luts(10, seed=seed + 7)
 
-    def desc_bytes(self):
-        return sum(m.nbytes for d in self.maps for m in d) + self.sao.nbytes + self.alf.nbytes + self.sets.nbytes
+    def records(self, k, n_ref_slots, pic):
+        """Prediction records of ring picture k: reference slots (2k, 2k+1) mod ring, destination `pic`."""
+        pbs = self.pbs[k % self.distinct].copy()
+        pbs["ref"] = (2 * k + pbs["ref"]) % n_ref_slots
+        pbs["pic"] = pic
+        return pbs
 
     def frame_bytes(self):
-        g = self.geom
-        return sum(g.plane_wh(c)[0] * g.plane_wh(c)[1] * 2 for c in range(3)) * g.batch
-
-
-# algorithmic bytes per luma pixel (SURVEY.md 8(d)): one read + one write of all planes per sweep
-ALGO_BYTES_PER_LUMA_PX = {"deblock_v": 6.0, "deblock_h": 6.0, "sao": 6.0, "alf": 6.0}
-CHAIN_ALGO_BYTES_PER_LUMA_PX = 18.0    # deblock (V+H counted once) + SAO + ALF
+        return sum(self.g1.plane_wh(c)[0] * self.g1.plane_wh(c)[1] * 2 for c in range(3))
 
 
 class ClockSampler(threading.Thread):
@@ -109,7 +120,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.01)
 
     def result(self):
         self.stop_flag = True
@@ -119,47 +130,53 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU reference arm
+# CPU arm: the reference's C (or the oracle port) on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_chain_lib():
-    """Returns (kind, chain(frame_in_planes, maps, sao, alf, sets, geom) -> planes)."""
-    FP = C.POINTER(abi.VVCCudaFrame)
-    MP = C.POINTER(abi.VVCCudaDeblockMaps)
+def cpu_lib():
+    FP, MP = C.POINTER(abi.VVCCudaFrame), C.POINTER(abi.VVCCudaDeblockMaps)
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libvvcref.so")
     if os.path.exists(ref_so):
         lib, kind, pre = C.CDLL(ref_so), "reference", "vvcref_"
     else:
         lib, kind, pre = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so")), "port", "vvco_"
-    dbk = getattr(lib, pre + "deblock_frame")
-    sao = getattr(lib, pre + "sao_frame")
-    alf = getattr(lib, pre + "alf_frame")
-    dbk.argtypes, dbk.restype = [FP, FP, MP, C.c_int], None
-    sao.argtypes, sao.restype = [FP, FP, C.c_void_p], None
-    alf.argtypes, alf.restype = [FP, FP, C.c_void_p, C.c_void_p, C.c_int], None
-
-    def chain(geom, planes, maps, sao_p, alf_p, sets):
-        md = abi.deblock_maps_desc(geom, maps)
-        a, b = abi.alloc_planes(geom), abi.alloc_planes(geom)
-        fa, fb = abi.frame_from_numpy(geom, a), abi.frame_from_numpy(geom, b)
-        dbk(fa, abi.frame_from_numpy(geom, planes), C.byref(md), 1)
-        dbk(fb, fa, C.byref(md), 0)
-        sao(fa, fb, sao_p.ctypes.data)
-        alf(fb, fa, alf_p.ctypes.data, sets.ctypes.data, 0)
-        return b
-
-    return kind, chain
+    fns = {}
+    sig = {"inter_frame": [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
+           "itx_frame": [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int],
+           "lmcs_frame": [FP, C.c_void_p, C.c_void_p],
+           "deblock_frame": [FP, FP, MP, C.c_int], "sao_frame": [FP, FP, C.c_void_p],
+           "alf_frame": [FP, FP, C.c_void_p, C.c_void_p, C.c_int]}
+    for name, args in sig.items():
+        f = getattr(lib, pre + name)
+        f.argtypes, f.restype = args, None
+        fns[name] = f
+    return kind, fns
 
 
-def run_cpu_reference(width, height, steps, warmup, threads):
-    """Each step: `threads` host threads each push one picture through the reference C chain."""
-    kind, chain = cpu_chain_lib()
-    inp = Inputs(width, height, frames=1)
-    g1 = abi.FrameGeom(width, height)
-    work = [(g1, [p.copy() for p in inp.planes], [[m.copy() for m in d] for d in inp.maps], inp.sao.copy(), inp.alf.copy(), inp.sets.copy())
-            for _ in range(threads)]
+def cpu_reconstruct(fns, inp, i, refs, scratch):
+    """One picture (content i) through the reference C stage by stage; returns the output planes."""
+    g, gr = inp.g1, abi.FrameGeom(inp.w, inp.h, batch=inp.distinct)
+    cur, a, b = scratch
+    pbs = inp.pbs[i]
+    fns["inter_frame"](abi.frame_from_numpy(g, cur), abi.frame_from_numpy(gr, refs), pbs.ctypes.data, len(pbs),
+                       inp.wp.ctypes.data, inp.prof.ctypes.data, None)
+    fns["itx_frame"](abi.frame_from_numpy(g, cur), inp.coeffs[i].ctypes.data, inp.tbs[i].ctypes.data, len(inp.tbs[i]), 15)
+    fns["lmcs_frame"](abi.frame_from_numpy(g, cur), inp.inv_lut.ctypes.data, None)
+    md = abi.deblock_maps_desc(g, inp.maps[i])
+    fns["deblock_frame"](abi.frame_from_numpy(g, a), abi.frame_from_numpy(g, cur), C.byref(md), 1)
+    fns["deblock_frame"](abi.frame_from_numpy(g, b), abi.frame_from_numpy(g, a), C.byref(md), 0)
+    fns["sao_frame"](abi.frame_from_numpy(g, a), abi.frame_from_numpy(g, b), inp.sao[i].ctypes.data)
+    fns["alf_frame"](abi.frame_from_numpy(g, b), abi.frame_from_numpy(g, a), inp.alf[i].ctypes.data, inp.sets.ctypes.data, 0)
+    return b
+
+
+def run_cpu(inp, steps, warmup, threads):
+    """Each step: `threads` host threads each reconstruct one 4K picture with the reference C."""
+    kind, fns = cpu_lib()
+    scratch = [[abi.alloc_planes(inp.g1) for _ in range(3)] for _ in range(threads)]
 
     def one_step():
-        ts = [threading.Thread(target=chain, args=w) for w in work]
+        ts = [threading.Thread(target=cpu_reconstruct, args=(fns, inp, t % inp.distinct, inp.ref_planes, scratch[t]))
+              for t in range(threads)]
         t0 = time.perf_counter()
         for t in ts:
             t.start()
@@ -169,10 +186,8 @@ def run_cpu_reference(width, height, steps, warmup, threads):
 
     for _ in range(warmup):
         one_step()
-    times = [one_step() for _ in range(steps)]
-    total = sum(times)
-    mpix = width * height * threads * steps / total / 1e6
-    return kind, mpix, total / steps * 1e3
+    total = sum(one_step() for _ in range(steps))
+    return kind, inp.w * inp.h * threads * steps / total / 1e6, total / steps * 1e3
 
 
 # ---------------------------------------------------------------------------------------------
@@ -184,8 +199,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--frames", type=int, default=16, help="pictures in the ring = pictures per step")
-    ap.add_argument("--group", type=int, default=1, help="pictures per launch (stage kernels run group by group)")
+    ap.add_argument("--frames", type=int, default=8, help="pictures in the ring = pictures per step")
+    ap.add_argument("--group", type=int, default=8, help="pictures per launch (independent streams batched into one launch per stage)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -195,13 +210,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = args.cpu_threads or (os.cpu_count() or 1)
-    workload = "inloop_4k: deblock V+H -> SAO -> ALF/CC-ALF on %dx%d 10-bit 4:2:0 (MC, itx, LMCS stages not yet in the timed chain)" % (args.width, args.height)
+    workload = ("recon_4k: INTER (MC/bi/DMVR/BDOF/PROF/GPM) -> residual (LFNST+itx+add) -> inverse LMCS -> deblock V+H -> SAO -> "
+                "ALF/CC-ALF on %dx%d 10-bit 4:2:0, 100%% inter area, coded fraction 1.0") % (args.width, args.height)
+
+    oracle_so = os.path.join(ROOT, "oracle", "liboracle.so")
+    lfnst_set_of = None
+    if os.path.exists(oracle_so):                 # table accessor only (which LFNST set a mode maps to), not compute
+        olib = C.CDLL(oracle_so)
+        olib.vvco_lfnst_tr_set.argtypes = [C.c_int]
+        lfnst_set_of = olib.vvco_lfnst_tr_set
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        kind, mpix, ms = run_cpu_reference(args.width, args.height, args.steps, max(args.warmup, 1), threads)
-        sample = "%d pictures per step (one per host thread) of the same synthetic workload" % threads
+        inp = Inputs(args.width, args.height, seed=12345, distinct=2, lfnst_set_of=lfnst_set_of)
+        kind, mpix, ms = run_cpu(inp, args.steps, max(args.warmup, 1), threads)
+        sample = "%d pictures per step (one %dx%d picture per host thread) of the same synthetic workload" % (threads, args.width, args.height)
         line = {
             "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -226,28 +250,31 @@ def main():
     frames, group = args.frames, max(1, min(args.group, args.frames))
     while frames % group:
         group -= 1
-    inp = Inputs(args.width, args.height, frames, seed=12345 + rank)
-    geom = inp.geom
-    ggeom = abi.FrameGeom(args.width, args.height, batch=group)
+    inp = Inputs(args.width, args.height, seed=12345 + rank, distinct=2, lfnst_set_of=lfnst_set_of)
+    g1 = inp.g1
+    gring = abi.FrameGeom(args.width, args.height, batch=frames)
+    ggrp = abi.FrameGeom(args.width, args.height, batch=group)
     ctx = lib.Context(local_rank)
     stream = ctx.torch_stream()
     torch.cuda.set_stream(stream)      # uploads, events and kernels all on the context's stream
 
-    # ---- device-resident ring -------------------------------------------------------------
-    src = device.DeviceFrames(geom, device=dev, planes=inp.planes)
-    dst = device.DeviceFrames(geom, device=dev)
-    tmp_a = device.DeviceFrames(ggeom, device=dev)
-    tmp_b = device.DeviceFrames(ggeom, device=dev)
+    # ---- device-resident rings --------------------------------------------------------------------
+    reps = frames // inp.distinct + 1
+    ring_planes = [np.ascontiguousarray(np.concatenate([p] * reps)[:frames]) for p in inp.ref_planes]
+    refs = device.DeviceFrames(gring, device=dev, planes=ring_planes)       # DPB ring (frames pictures > L2)
+    cur = device.DeviceFrames(gring, device=dev)
+    out = device.DeviceFrames(gring, device=dev)
+    tmp_a = device.DeviceFrames(ggrp, device=dev)
+    tmp_b = device.DeviceFrames(ggrp, device=dev)
     keep = []
-    map_ptr = [[None] * 3, [None] * 3]
-    for d in range(2):
-        for c in range(3):
-            t, ptr = device.to_device(inp.maps[d][c], dev)
-            keep.append(t)
-            map_ptr[d][c] = ptr
-    t_sao, p_sao = device.to_device(inp.sao, dev)
-    t_alf, p_alf = device.to_device(inp.alf, dev)
-    t_set, p_set = device.to_device(inp.sets, dev)
+
+    def up(a):
+        t, p = device.to_device(a, dev)
+        keep.append(t)
+        return p
+
+    p_wp, p_prof, p_sets, p_lut = up(inp.wp), up(inp.prof), up(inp.sets), up(inp.inv_lut)
+    n_ctb = g1.ctb_count
 
     def sub_frame(df, k0):
         f = abi.VVCCudaFrame()
@@ -258,32 +285,49 @@ def main():
         return f
 
     groups = []
-    n_ctb = geom.ctb_count
     for k0 in range(0, frames, group):
+        ks = list(range(k0, k0 + group))
+        pbs = np.concatenate([inp.records(k, frames, j) for j, k in enumerate(ks)])
+        tb_parts, co_parts, off = [], [], 0
+        for j, k in enumerate(ks):
+            t = inp.tbs[k % inp.distinct].copy()
+            t["pic"] = j
+            t["coeff_offset"] += off
+            off += len(inp.coeffs[k % inp.distinct])
+            tb_parts.append(t)
+            co_parts.append(inp.coeffs[k % inp.distinct])
+        tbs, coeffs = np.concatenate(tb_parts), np.concatenate(co_parts)
         md = abi.VVCCudaDeblockMaps()
         for d in range(2):
             for c in range(3):
-                rows, pitch = abi.deblock_map_shape(geom, d, c)
-                md.edge[d][c] = map_ptr[d][c] + k0 * rows * pitch * 4
+                rows, pitch = abi.deblock_map_shape(g1, d, c)
+                arr = np.concatenate([inp.maps[k % inp.distinct][d][c] for k in ks])
+                md.edge[d][c] = up(arr)
                 md.pitch[d][c], md.rows[d][c], md.size[d][c] = pitch, rows, rows * pitch
-        groups.append((sub_frame(src, k0), sub_frame(dst, k0), md,
-                       p_sao + k0 * n_ctb * abi.SAO_CTB_DTYPE.itemsize, p_alf + k0 * n_ctb * abi.ALF_CTB_DTYPE.itemsize))
-
-    stage_names = ["deblock_v", "deblock_h", "sao", "alf"]
-    launches_per_step = len(groups) * 4
+        groups.append(dict(
+            cur=sub_frame(cur, k0), out=sub_frame(out, k0), pbs=up(pbs), n_pbs=len(pbs), tbs=up(tbs), n_tbs=len(tbs),
+            coeffs=up(coeffs), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
+            alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
+    launches_per_step = len(groups) * len(STAGES)
 
     def step(events=None):
-        for gi, (fs, fd, md, ps, pa) in enumerate(groups):
+        for gi, g in enumerate(groups):
             ev = events[gi] if events is not None else None
             if ev: ev[0].record()
-            ctx.deblock_frame(tmp_a.desc, fs, md, 1)
+            ctx.inter_frame(g["cur"], refs.desc, g["pbs"], g["n_pbs"], p_wp, p_prof, None)
             if ev: ev[1].record()
-            ctx.deblock_frame(tmp_b.desc, tmp_a.desc, md, 0)
+            ctx.itx_frame(g["cur"], g["coeffs"], g["tbs"], g["n_tbs"], 15)
             if ev: ev[2].record()
-            ctx.sao_frame(tmp_a.desc, tmp_b.desc, ps)
+            ctx.lmcs_frame(g["cur"], p_lut, None)
             if ev: ev[3].record()
-            ctx.alf_frame(fd, tmp_a.desc, pa, p_set, 0)
+            ctx.deblock_frame(tmp_a.desc, g["cur"], g["md"], 1)
             if ev: ev[4].record()
+            ctx.deblock_frame(tmp_b.desc, tmp_a.desc, g["md"], 0)
+            if ev: ev[5].record()
+            ctx.sao_frame(tmp_a.desc, tmp_b.desc, g["sao"])
+            if ev: ev[6].record()
+            ctx.alf_frame(g["out"], tmp_a.desc, g["alf"], p_sets, 0)
+            if ev: ev[7].record()
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,11 +340,12 @@ def main():
         step()
     barrier()
 
-    # ---- timed region: K steps, device events; per-kernel events ride along --------------------
+    # ---- timed region: K steps, device events; per-kernel events ride along --------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launches
-    evs = [[[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in groups] for _ in range(args.steps)]
+    nst = len(STAGES)
+    evs = [[[torch.cuda.Event(enable_timing=True) for _ in range(nst + 1)] for _ in groups] for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
@@ -312,11 +357,12 @@ def main():
     elapsed_ms = t_start.elapsed_time(t_end)
     gpu_launches = ctx.launches - l0
     ctx.sync()
+    assert gpu_launches == launches_per_step * args.steps, (gpu_launches, launches_per_step)
 
-    stage_ms = np.zeros(4)
+    stage_ms = np.zeros(nst)
     for s in range(args.steps):
         for g in evs[s]:
-            for i in range(4):
+            for i in range(nst):
                 stage_ms[i] += g[i].elapsed_time(g[i + 1])
     stage_ms /= args.steps * len(groups)          # average duration of one launch of each stage
 
@@ -329,78 +375,107 @@ def main():
     luma_px_per_step = args.width * args.height * frames
     value = luma_px_per_step * args.steps * world / (elapsed_ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel --------------------------------------------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = load_peaks()
     dom = int(np.argmax(stage_ms))
     px_per_launch = args.width * args.height * group
-    algo_bytes = ALGO_BYTES_PER_LUMA_PX[stage_names[dom]] * px_per_launch
+    algo_bytes = ALGO_BYTES_PER_LUMA_PX[STAGES[dom]] * px_per_launch
     achieved = algo_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    per_stage = {n: {"ms_per_launch": float(v), "achieved_gbs": ALGO_BYTES_PER_LUMA_PX[n] * px_per_launch / (v * 1e-3) / 1e9,
+                     "frac": ALGO_BYTES_PER_LUMA_PX[n] * px_per_launch / (v * 1e-3) / 1e9 / peak}
+                 for n, v in zip(STAGES, stage_ms)}
+    chain_gbs = CHAIN_ALGO_BYTES_PER_LUMA_PX * luma_px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9 * (1.0 if world == 1 else 1.0)
     roofline = {
-        "bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": STAGES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": algo_bytes,
-        "stage_ms_per_launch": {n: float(v) for n, v in zip(stage_names, stage_ms)},
-        "chain": {"algorithmic_bytes_per_luma_px": CHAIN_ALGO_BYTES_PER_LUMA_PX,
-                  "achieved_gbs": CHAIN_ALGO_BYTES_PER_LUMA_PX * luma_px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9 / 1.0,
-                  "frac": CHAIN_ALGO_BYTES_PER_LUMA_PX * luma_px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9 / peak},
+        "algorithmic_bytes_per_launch": algo_bytes, "stages": per_stage,
+        "chain": {"algorithmic_bytes_per_luma_px": CHAIN_ALGO_BYTES_PER_LUMA_PX, "achieved_gbs": chain_gbs, "frac": chain_gbs / peak},
     }
 
-    # ---- e2e: pinned host pictures through the *_host entry -------------------------------------
+    # ---- e2e: pinned host buffers through vvc_cuda_recon_frame_host -----------------------------------
     e2e = None
     if not args.no_e2e:
-        hp_in = [torch.from_numpy(p.view(np.int16)).pin_memory() for p in inp.planes]
-        hp_out = [torch.empty_like(t).pin_memory() for t in hp_in]
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
-        h_maps = [[pin(inp.maps[d][c]) for c in range(3)] for d in range(2)]
-        h_sao, h_alf, h_set = pin(inp.sao), pin(inp.alf), pin(inp.sets)
-        f_in = abi.frame_desc(geom, [t.data_ptr() for t in hp_in], [t.stride(1) * 2 for t in hp_in], [t.stride(0) * 2 for t in hp_in])
-        f_out = abi.frame_desc(geom, [t.data_ptr() for t in hp_out], [t.stride(1) * 2 for t in hp_out], [t.stride(0) * 2 for t in hp_out])
-        hmd = abi.VVCCudaDeblockMaps()
-        for d in range(2):
-            for c in range(3):
-                rows, pitch = abi.deblock_map_shape(geom, d, c)
-                hmd.edge[d][c] = h_maps[d][c].data_ptr()
-                hmd.pitch[d][c], hmd.rows[d][c], hmd.size[d][c] = pitch, rows, rows * pitch
-        hdesc = abi.inloop_desc(hmd, h_sao.data_ptr(), h_alf.data_ptr(), h_set.data_ptr())
-        e_steps = max(2, min(args.steps, 5))
-        for _ in range(2):
-            ctx.inloop_frame_host(f_out, f_in, hdesc)
+        pin_keep = []
+
+        def pin(a):
+            t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+            pin_keep.append(t)
+            return t.data_ptr(), t.numel()
+
+        h_refs = [torch.from_numpy(p.view(np.int16)).pin_memory() for p in ring_planes]
+        h_out = [torch.empty_like(t).pin_memory() for t in h_refs]
+        f_refs = abi.frame_desc(gring, [t.data_ptr() for t in h_refs], [t.stride(1) * 2 for t in h_refs], [t.stride(0) * 2 for t in h_refs])
+        f_out = abi.frame_desc(gring, [t.data_ptr() for t in h_out], [t.stride(1) * 2 for t in h_out], [t.stride(0) * 2 for t in h_out])
+        (hp_wp, b_wp), (hp_prof, b_prof), (hp_sets, b_sets), (hp_lut, b_lut) = pin(inp.wp), pin(inp.prof), pin(inp.sets), pin(inp.inv_lut)
+        per_content = []
+        for i in range(inp.distinct):
+            hmd = abi.VVCCudaDeblockMaps()
+            nb = 0
+            for d in range(2):
+                for c in range(3):
+                    rows, pitch = abi.deblock_map_shape(g1, d, c)
+                    hmd.edge[d][c], n = pin(inp.maps[i][d][c])
+                    nb += n
+                    hmd.pitch[d][c], hmd.rows[d][c], hmd.size[d][c] = pitch, rows, rows * pitch
+            (p_co, b_co), (p_tb, b_tb), (p_sa, b_sa), (p_al, b_al) = pin(inp.coeffs[i]), pin(inp.tbs[i]), pin(inp.sao[i]), pin(inp.alf[i])
+            per_content.append(dict(md=hmd, co=p_co, n_co=len(inp.coeffs[i]), tb=p_tb, n_tb=len(inp.tbs[i]), sao=p_sa, alf=p_al,
+                                    bytes=nb + b_co + b_tb + b_sa + b_al))
+        descs = (abi.VVCCudaReconDesc * frames)()
+        h2d = sum(t.numel() * 2 for t in h_refs)
+        d2h = sum(t.numel() * 2 for t in h_out)
+        for k in range(frames):
+            pc = per_content[k % inp.distinct]
+            p_pb, b_pb = pin(inp.records(k, frames, 0))
+            d = descs[k]
+            d.pbs, d.n_pbs, d.wp, d.n_wp, d.prof, d.n_prof = p_pb, len(inp.pbs[k % inp.distinct]), hp_wp, len(inp.wp), hp_prof, len(inp.prof)
+            d.log2_transform_range = 15
+            d.coeffs, d.n_coeffs, d.tbs, d.n_tbs = pc["co"], pc["n_co"], pc["tb"], pc["n_tb"]
+            d.lmcs_inv_lut = hp_lut
+            d.inloop.deblock = C.pointer(pc["md"])
+            d.inloop.sao, d.inloop.alf, d.inloop.alf_sets = pc["sao"], pc["alf"], hp_sets
+            h2d += b_pb + b_wp + b_prof + b_lut + b_sets + pc["bytes"]
+        e_steps = max(2, min(args.steps, 4))
+        ctx.recon_frame_host(f_out, f_refs, descs)
         barrier()
-        t0 = time.perf_counter()
         es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         es.record()
         for _ in range(e_steps):
-            ctx.inloop_frame_host(f_out, f_in, hdesc)      # returns after the D2H copy finished
+            ctx.recon_frame_host(f_out, f_refs, descs)      # returns after the last D2H copy finished
         ee.record()
         barrier()
-        e_ms = max(es.elapsed_time(ee), (time.perf_counter() - t0) * 1e3 * 0.0)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = max(es.elapsed_time(ee), wall_ms)            # the call is synchronous: wall clock is the honest bound
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
         e2e = {"value": luma_px_per_step * e_steps * world / (e_ms * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": int(inp.frame_bytes() + inp.desc_bytes()), "d2h_bytes_per_step": int(inp.frame_bytes()),
-               "steps": e_steps, "api": "vvc_cuda_inloop_frame_host (pinned host pictures + descriptors)"}
-        # sanity: the host path produced the same pictures as the device path
-        got = dst.to_numpy()
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
+               "api": "vvc_cuda_recon_frame_host (pinned host reference pictures, records, coefficients; output pictures copied back)"}
+        # sanity: the host path produced the same pictures as the device-resident path
+        got = out.to_numpy()
         for c in range(3):
-            assert np.array_equal(hp_out[c].numpy().view(np.uint16), got[c]), "e2e result differs from device-resident result"
+            wv = g1.plane_wh(c)[0]
+            assert np.array_equal(h_out[c].numpy().view(np.uint16)[:, :, :wv], got[c][:, :, :wv]), "e2e result differs from device-resident result"
 
-    # ---- CPU baseline beside it (rank 0, N == 1 only) --------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        kind, mpix, ms = run_cpu_reference(args.width, args.height, steps=2, warmup=1, threads=threads)
+        kind, mpix, ms = run_cpu(inp, steps=1, warmup=1, threads=threads)
         cpu_baseline = {"value": mpix, "unit": UNIT, "cores": threads, "kind": kind,
-                        "sample": "2 timed steps x %d pictures (one %dx%d picture per host thread), same synthetic workload" % (threads, args.width, args.height)}
+                        "sample": "1 warm-up + 1 timed step x %d pictures (one %dx%d picture per host thread, all stages), same synthetic workload, %.0f ms" % (
+                            threads, args.width, args.height, ms)}
 
     if rank == 0:
+        ring_mb = (3 * inp.frame_bytes() * frames + sum(len(c) for c in inp.coeffs) * 4 / inp.distinct * frames) / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16", "data": "synthetic",
             "config": {"workload": workload, "pictures_per_step": frames, "pictures_per_launch": group,
-                       "l2": "inputs larger than L2: ring of %d pictures = %.0f MB per plane set (> 126 MB), no flush needed" % (frames, inp.frame_bytes() / 1e6),
+                       "l2": "inputs larger than L2: per step %d reference + %d reconstructed + %d output pictures and their coefficients = %.0f MB (> 126 MB), no flush needed" % (frames, frames, frames, ring_mb),
                        "parallelism": "independent streams x%d, no collective" % world},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
             "clocks": clocks,

@@ -254,3 +254,15 @@ WP_DTYPE = np.dtype([("weight", np.int16, (2, 3)), ("offset", np.int16, (2, 3)),
 PROF_DTYPE = np.dtype([("diff_mv_x", np.int16, (2, 16)), ("diff_mv_y", np.int16, (2, 16))])
 DMVR_OUT_DTYPE = np.dtype([("mv", np.int32, (2, 2)), ("min_sad", np.int32), ("bdof_applied", np.int32)])
 assert PB_DTYPE.itemsize == 44 and WP_DTYPE.itemsize == 28 and PROF_DTYPE.itemsize == 128 and DMVR_OUT_DTYPE.itemsize == 24
+
+
+class VVCCudaReconDesc(C.Structure):
+    _fields_ = [
+        ("pbs", C.c_void_p), ("wp", C.c_void_p), ("prof", C.c_void_p), ("dmvr_out", C.c_void_p),
+        ("n_pbs", C.c_int32), ("n_wp", C.c_int32), ("n_prof", C.c_int32), ("log2_transform_range", C.c_int32),
+        ("lmcs_fwd_lut", C.c_void_p), ("lmcs_rects", C.c_void_p),
+        ("n_lmcs_rects", C.c_int32), ("n_tbs", C.c_int32),
+        ("coeffs", C.c_void_p), ("n_coeffs", C.c_size_t), ("tbs", C.c_void_p),
+        ("lmcs_inv_lut", C.c_void_p), ("lmcs_ctb_enable", C.c_void_p),
+        ("inloop", VVCCudaInloopDesc),
+    ]

@@ -145,6 +145,7 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 10: return sizeof(VVCCudaProf);
     case 11: return sizeof(VVCCudaDmvrOut);
     case 12: return sizeof(VVCCudaRect);
+    case 13: return sizeof(VVCCudaReconDesc);
     default: return 0;
     }
 }

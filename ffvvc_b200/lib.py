@@ -69,6 +69,9 @@ def load():
     lib.vvc_cuda_lmcs_rects.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, C.c_int]
     lib.vvc_cuda_inter_frame.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_inter_frame_host.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    RP = C.POINTER(abi.VVCCudaReconDesc)
+    lib.vvc_cuda_recon_frame.argtypes = [CTX, FP, FP, FP, RP]
+    lib.vvc_cuda_recon_frame_host.argtypes = [CTX, FP, FP, RP]
     lib.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
     lib.vvc_cuda_abi_sizeof.restype = C.c_size_t
     _lib = lib
@@ -167,6 +170,14 @@ class Context:
     def inter_frame_host(self, dst, refs, pbs_ptr, n_pbs, wp_ptr, n_wp, prof_ptr, n_prof, dmvr_out_ptr=None):
         self.check(self.lib.vvc_cuda_inter_frame_host(self.handle, C.byref(dst), C.byref(refs), pbs_ptr, n_pbs,
                                                       wp_ptr, n_wp, prof_ptr, n_prof, dmvr_out_ptr))
+
+    def recon_frame(self, out, cur, refs, desc):
+        """INTER -> residual -> LMCS -> deblock V/H -> SAO -> ALF on device-resident pictures and descriptors."""
+        self.check(self.lib.vvc_cuda_recon_frame(self.handle, C.byref(out), C.byref(cur), C.byref(refs), C.byref(desc)))
+
+    def recon_frame_host(self, out, refs, descs):
+        """descs: ctypes array of VVCCudaReconDesc, one per picture of `out` (host pointers everywhere)."""
+        self.check(self.lib.vvc_cuda_recon_frame_host(self.handle, C.byref(out), C.byref(refs), descs))
 
     def lmcs_rects(self, frame, lut_ptr, rects_ptr, n):
         self.check(self.lib.vvc_cuda_lmcs_rects(self.handle, C.byref(frame), lut_ptr, rects_ptr, n))

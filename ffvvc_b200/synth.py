@@ -434,6 +434,15 @@ def pb_list(geom, n_refs=2, seed=2024, dst_pics=None, mix=None):
         g64h, g64w = (H + 63) // 64, (W + 63) // 64
         shape_w = np.array([2, 3, 3, 4, 4, 4, 5, 5, 6, 6])[rng.below(g64h * g64w, 10)].reshape(g64h, g64w)
         shape_h = np.array([2, 3, 3, 4, 4, 4, 5, 5, 6, 6])[rng.below(g64h * g64w, 10)].reshape(g64h, g64w)
+        # partial 64x64 regions at the right / bottom picture border: cap the CU size so the region's
+        # visible part is tiled completely (every sample of the picture is predicted)
+        def cap(rem):
+            low = int(rem) & -int(rem)
+            return 6 if rem >= 64 else max(2, low.bit_length() - 1)
+        cap_w = np.array([cap(min(64, W - x * 64)) for x in range(g64w)])
+        cap_h = np.array([cap(min(64, H - y * 64)) for y in range(g64h)])
+        shape_w = np.minimum(shape_w, cap_w[None, :])
+        shape_h = np.minimum(shape_h, cap_h[:, None])
         shape_h = np.where((shape_w == 2) & (shape_h == 2), 3, shape_h)        # no 4x4 inter CUs
         for lw in range(2, 7):
             for lh in range(2, 7):

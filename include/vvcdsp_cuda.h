@@ -58,7 +58,7 @@ void       *vvc_cuda_stream(const VVCCudaCtx *ctx);    /* the cudaStream_t in us
 uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx);
 const char *vvc_cuda_version(void);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -353,6 +353,47 @@ int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCuda
 int vvc_cuda_inter_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *refs,
                               const VVCCudaPB *pbs, int n_pbs, const VVCCudaWP *wp, int n_wp,
                               const VVCCudaProf *prof, int n_prof, VVCCudaDmvrOut *dmvr_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-picture reconstruction: INTER -> RECON (residual) -> LMCS -> DEBLOCK_V -> DEBLOCK_H -> SAO ->
+ * ALF, the reference's per-CTU stage list (libavcodec/vvc/vvc_thread.c:41-51) run stage by stage
+ * over the picture (7 launches, + 1 when forward-LMCS rectangles are given).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct VVCCudaReconDesc {
+    /* INTER */
+    const VVCCudaPB   *pbs;
+    const VVCCudaWP   *wp;
+    const VVCCudaProf *prof;
+    VVCCudaDmvrOut    *dmvr_out;          /* optional */
+    int32_t            n_pbs, n_wp, n_prof;
+    int32_t            log2_transform_range;
+    /* forward LMCS on the luma of inter CUs (vvc_inter.c:888-891); optional */
+    const uint16_t    *lmcs_fwd_lut;
+    const VVCCudaRect *lmcs_rects;
+    int32_t            n_lmcs_rects;
+    /* RECON: residual of every TB */
+    int32_t            n_tbs;
+    int32_t           *coeffs;
+    size_t             n_coeffs;          /* only read by the _host entry (bytes to copy = 4 * n_coeffs) */
+    const VVCCudaTB   *tbs;
+    /* LMCS inverse mapping per CTU; NULL lut = stage skipped (sh_lmcs_used_flag == 0) */
+    const uint16_t    *lmcs_inv_lut;
+    const uint8_t     *lmcs_ctb_enable;
+    /* DEBLOCK_V, DEBLOCK_H, SAO, ALF */
+    VVCCudaInloopDesc  inloop;
+} VVCCudaReconDesc;
+
+/* Device memory everywhere.  cur: the picture (ring) being reconstructed: prediction, residual and
+ * LMCS happen in place in it; out: the filtered output picture (ring); refs: the DPB ring.
+ * The record lists of `desc` cover the whole ring (their `pic` fields select the picture). */
+int vvc_cuda_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *cur,
+                         const VVCCudaFrame *refs, const VVCCudaReconDesc *desc);
+/* Host memory everywhere.  descs: one entry per picture of the `out` ring, its records use pic == 0.
+ * Picture k's descriptors and coefficients are copied in on a copy stream while picture k-1 is being
+ * reconstructed and picture k-2 is copied out; refs are copied in once.  Returns when all output
+ * pictures (and dmvr_out arrays) are in host memory. */
+int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
+                              const VVCCudaReconDesc *descs);
 
 #ifdef __cplusplus
 }

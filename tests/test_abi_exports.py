@@ -18,7 +18,9 @@ def test_descriptor_sizes_match_the_header():
     handle.vvc_cuda_abi_sizeof.restype = C.c_size_t
     handle.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
     want = {0: C.sizeof(abi.VVCCudaFrame), 1: C.sizeof(abi.VVCCudaALFCtb), 2: C.sizeof(abi.VVCCudaALFSets),
-            3: C.sizeof(abi.VVCCudaDbkEdge), 4: C.sizeof(abi.VVCCudaDeblockMaps), 5: C.sizeof(abi.VVCCudaSAOCtb), 6: C.sizeof(abi.VVCCudaInloopDesc), 7: C.sizeof(abi.VVCCudaTB)}
+            3: C.sizeof(abi.VVCCudaDbkEdge), 4: C.sizeof(abi.VVCCudaDeblockMaps), 5: C.sizeof(abi.VVCCudaSAOCtb), 6: C.sizeof(abi.VVCCudaInloopDesc), 7: C.sizeof(abi.VVCCudaTB),
+            8: abi.PB_DTYPE.itemsize, 9: abi.WP_DTYPE.itemsize, 10: abi.PROF_DTYPE.itemsize, 11: abi.DMVR_OUT_DTYPE.itemsize,
+            12: C.sizeof(abi.VVCCudaRect), 13: C.sizeof(abi.VVCCudaReconDesc)}
     for which, size in want.items():
         assert handle.vvc_cuda_abi_sizeof(which) == size, which
 
