@@ -174,14 +174,23 @@ def run_cpu(inp, steps, warmup, threads):
     kind, fns = cpu_lib()
     scratch = [[abi.alloc_planes(inp.g1) for _ in range(3)] for _ in range(threads)]
 
+    errors = []
+
+    def work(t):
+        try:
+            cpu_reconstruct(fns, inp, t % inp.distinct, inp.ref_planes, scratch[t])
+        except Exception as e:          # a silent thread death would fake a fast CPU
+            errors.append(e)
+
     def one_step():
-        ts = [threading.Thread(target=cpu_reconstruct, args=(fns, inp, t % inp.distinct, inp.ref_planes, scratch[t]))
-              for t in range(threads)]
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
         t0 = time.perf_counter()
         for t in ts:
             t.start()
         for t in ts:
             t.join()
+        if errors:
+            raise errors[0]
         return time.perf_counter() - t0
 
     for _ in range(warmup):
