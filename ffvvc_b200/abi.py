@@ -10,6 +10,9 @@ import numpy as np
 EDGE_LEFT, EDGE_TOP, EDGE_RIGHT, EDGE_BOTTOM = 1, 2, 4, 8
 
 
+OPT_GENERIC_KERNELS = 1      # vvc_cuda_ctx_set_option()
+
+
 class VVCCudaFrame(C.Structure):
     _fields_ = [
         ("data", C.c_void_p * 3),

@@ -16,6 +16,7 @@ struct VVCCudaCtx {
     int           err;                  // sticky VVC_CUDA_ERR_*
     char          msg[256];
     uint64_t      launches;
+    int           force_generic;        // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_GENERIC_KERNELS)
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;
     void         *h_stage;  size_t h_stage_size;    // pinned

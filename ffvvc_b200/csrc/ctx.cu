@@ -126,6 +126,16 @@ const char *vvc_cuda_error_string(const VVCCudaCtx *ctx) { return ctx->err ? ctx
 void       *vvc_cuda_stream(const VVCCudaCtx *ctx)       { return (void *)ctx->stream; }
 uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx) { return ctx->launches; }
 
+int vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value)
+{
+    if (!ctx)
+        return VVC_CUDA_ERR_ARG;
+    switch (option) {
+    case VVC_CUDA_OPT_GENERIC_KERNELS: ctx->force_generic = value != 0; return VVC_CUDA_OK;
+    default: return VVC_CUDA_ERR_ARG;
+    }
+}
+
 }  // extern "C"
 
 // sizeof() of the descriptor PODs as compiled here, so bindings can verify their mirrors.

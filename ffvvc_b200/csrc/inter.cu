@@ -18,7 +18,7 @@
 // 25 SADs + refinement), BDOF and PROF work entirely out of shared memory, so DRAM traffic is the
 // reference window in and the predicted block out.  The whole DMVR decision stays on the device;
 // refined vectors are written to dmvr_out for the host's later motion-vector prediction.
-#include "common.cuh"
+#include "inter_common.cuh"
 #include "tables.cuh"
 
 namespace {
@@ -29,18 +29,6 @@ constexpr int GP = 18;                 // BDOF_PADDED_SIZE
 constexpr int WIN_LUMA = 23 * 24;      // (16 + 7) rows, pitch 24
 constexpr int WIN_CHROMA = 11 * 12;
 
-struct InterK {
-    const pel *ref[3];
-    pel       *dst[3];
-    int        rp[3], dp[3];
-    long long  rb[3], db[3];
-    int        w, h, bd, planes;
-    const VVCCudaPB   *pbs;
-    int                n;
-    const VVCCudaWP   *wp;
-    const VVCCudaProf *prof;
-    VVCCudaDmvrOut    *dmvr_out;
-};
 
 // one reference fetch unit: a list (luma) or a (plane, list) pair (chroma)
 struct Unit {
@@ -619,6 +607,8 @@ extern "C" int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, co
     }
     p.w = dst->width; p.h = dst->height; p.bd = dst->bit_depth;
     p.pbs = pbs; p.n = n_pbs; p.wp = wp; p.prof = prof; p.dmvr_out = dmvr_out;
+    if (p.bd == 10 && frame_vec_ok(dst) && frame_vec_ok(refs) && !ctx->force_generic)
+        return vvc_inter_launch_warp(ctx, p);
     const int grid = n_pbs < 148 * 12 ? n_pbs : 148 * 12;
     inter_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);

@@ -1,0 +1,773 @@
+// Inter prediction for 10-bit pictures, warp-per-record kernel (sm_100a).
+//
+// Same contract as inter.cu (the generic kernel): replaces the pixel work of ff_vvc_predict_inter
+// (libavcodec/vvc/vvc_inter.c:899-913) -- pred_regular_blk :782-811, dmvr_mv_refine :685-748,
+// parametric_mv_refine :642-681, pred_affine_blk :828-873 with luma_prof_uni/bi :368-446, pred_gpm_blk
+// :466-521, the edge emulation :33-110 -- and the table entries they call: put / put_uni / put_uni_w
+// (libavcodec/h26x/h2656_inter_template.c:29-577), avg, w_avg, put_gpm, bdof_fetch_samples,
+// fetch_samples, prof_grad_filter, apply_prof*, apply_bdof, dmvr* (libavcodec/vvc/vvc_inter_template.c
+// :25-436), sad and pad_int16 (libavcodec/vvc/vvcdsp.c:29-65).
+//
+// B200 design
+//  * One warp owns one record (<= 16x16 luma + its chroma); warps of a CTA are independent, so the very
+//    different record kinds (plain uni 4x4 ... DMVR+BDOF 16x16) never wait on each other and the only
+//    synchronisation is __syncwarp().
+//  * Reference windows are staged with aligned 32-bit loads (two samples) when they lie inside the
+//    picture, otherwise sample by sample with the clamp ff_emulated_edge_mc materialises.  For DMVR
+//    records the window of the UNREFINED block is staged once with a 2-sample replicated apron: that is
+//    exactly emulated_edge_dmvr's clamp window (vvc_inter.c:60-89), and it serves the bilinear search, the
+//    final motion compensation at the refined vector and the BDOF ring.
+//  * The separable 8/4-tap filters run on sample PAIRS: IDP.2A (two 16-bit samples x two 8-bit taps, exact
+//    32-bit accumulate) does an 8-tap sum in 4 instructions.  A lane filters 8 outputs of one row from 16
+//    samples it holds in registers and stores them transposed, so the vertical pass reads its column as
+//    two 128-bit shared loads and runs the same 8-outputs-per-lane code.
+//  * The bilinear DMVR prediction and the 25 SADs use 16x2 packed arithmetic (VIMNMX.U16x2, IDP.2A).
+#include "inter_common.cuh"
+#include "tables.cuh"
+
+namespace {
+
+constexpr int kWarps = 4, kThreads = kWarps * 32;
+constexpr int PWL = 15, WUL = 27 * PWL + 1;   // luma window: 27 rows x 15 words (30 samples); unit stride 406 words
+constexpr int PWC = 9, WUC = 15 * PWC;        // chroma window: 15 rows x 9 words (18 samples)
+constexpr int HPL = 24, HUL = 16 * HPL;       // transposed first-pass output: [col][row], luma
+constexpr int HPC = 16, HUC = 8 * HPC;        //                                            chroma
+constexpr int TP = 32, TU = 18 * TP;          // int16 tile: sample (x, y) at (y + 1) * TP + 8 + x, ring around it
+constexpr int DP = 24, DU = 20 * DP;          // DMVR bilinear tiles
+constexpr int GU = 256;                       // BDOF gradients: [y * 16 + x]
+
+struct UnitMC {
+    int      woff, r0, c0;      // window of the unit: word offset, first row, first sample column
+    int      shh, shv;          // shifts after the two passes
+    uint32_t hf0, hf1, vf0, vf1;
+};
+
+struct __align__(16) WarpSmem {
+    union {
+        struct {
+            uint32_t win[2 * WUL];            // 3248 bytes
+            short    hbt[2 * HUL];            // 1536 bytes
+        } a;
+        struct {                              // BDOF, after the windows are dead
+            short grad[4][GU];                // [list * 2 + (0 horizontal, 1 vertical)]
+            int   csum[5][16][4];             // per row, per block column: sums over the 6 window columns
+        } b;
+    };
+    union {
+        short tile[2][TU];
+        short dm[2][DU];
+        short ctile[4][64];
+    };
+    UnitMC um[4];
+    int    sad[25];
+    int    vxy[16][2];
+};
+
+struct Rec {
+    int x0, y0, w, h, planes, pred, ref[2], pic, flags;
+    int mv[2][2];
+    int filt, bcw, wp, prof, gsx, gsy, gw;
+};
+
+__device__ __forceinline__ Rec load_rec(const VVCCudaPB *pb)
+{
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(pb);
+    uint32_t r[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++)
+        r[i] = __ldg(q + i);
+    Rec o;
+    o.x0 = r[0] & 0xffff;         o.y0 = r[0] >> 16;
+    o.w = r[1] & 0xff;            o.h = (r[1] >> 8) & 0xff;   o.planes = (r[1] >> 16) & 0xff;  o.pred = r[1] >> 24;
+    o.ref[0] = r[2] & 0xff;       o.ref[1] = (r[2] >> 8) & 0xff; o.pic = (r[2] >> 16) & 0xff;  o.flags = r[2] >> 24;
+    o.mv[0][0] = (int)r[3];       o.mv[0][1] = (int)r[4];     o.mv[1][0] = (int)r[5];          o.mv[1][1] = (int)r[6];
+    o.filt = r[7] & 0xff;         o.bcw = (r[7] >> 8) & 0xff; o.wp = r[7] >> 16;
+    o.prof = r[8] & 0xffff;       o.gsx = (short)(r[8] >> 16);
+    o.gsy = (short)(r[9] & 0xffff);
+    o.gw = (int)r[10];
+    return o;
+}
+
+__device__ __forceinline__ uint32_t frc(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_rc(lo, hi, sh); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (short)(v & 0xffff); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
+__device__ __forceinline__ uint32_t pack16(int a, int b) { return (uint32_t)(a & 0xffff) | ((uint32_t)b << 16); }
+// (t * inv_rows(d)) >> 16 == t / d for t < 128; d is a window row count: 23, 15, 11 (luma), 11, 7, 5 (chroma)
+__device__ __forceinline__ uint32_t inv_rows(int d) { return d == 23 ? 2850u : d == 15 ? 4370u : d == 11 ? 5958u : d == 7 ? 9363u : 13108u; }
+
+// ---- window staging ----------------------------------------------------------------------------------
+// Core of a window: samples [wx0, wx0 + cols) x [wy0, wy0 + rows) of a plane, picture-clamped, stored from
+// the even column bx = wx0 & ~1 at word (row + padr) * pw + padw.  Lane = (word of the row, row group): 16
+// words x 2 rows or 8 words x 4 rows per step, no index division.  One out-of-line copy serves every caller
+// (the kernel's code size matters: warps sit in different record kinds and share the instruction cache).
+__device__ __noinline__ void stage_core(uint32_t *win, int pw, int padw, int padr, const pel *plane, int pitch, int W, int H,
+                                        int wx0, int wy0, int cols, int rows, int lane)
+{
+    const int e = wx0 & 1, bx = wx0 - e, nw = (cols + e + 1) >> 1;
+    const int lk = nw > 8 ? 4 : 3;
+    const int k = lane & ((1 << lk) - 1), rsub = lane >> lk, rstep = 32 >> lk;
+    if (k >= nw)
+        return;
+    const bool inside = bx >= 0 && bx + 2 * nw <= W && wy0 >= 0 && wy0 + rows <= H;
+    uint32_t *dst = win + (padr + rsub) * pw + padw + k;
+    const int dstep = rstep * pw;
+    if (inside) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (long long)(wy0 + rsub) * pitch + bx) + k;
+        const int sstep = rstep * (pitch >> 1);
+#pragma unroll 4
+        for (int r = rsub; r < rows; r += rstep, src += sstep, dst += dstep)
+            *dst = __ldg(src);
+    } else {
+        const int xa = d_clip3(bx + 2 * k, 0, W - 1), xb = d_clip3(bx + 2 * k + 1, 0, W - 1);
+#pragma unroll 2
+        for (int r = rsub; r < rows; r += rstep, dst += dstep) {
+            const pel *row = plane + (long long)d_clip3(wy0 + r, 0, H - 1) * pitch;
+            *dst = (uint32_t)__ldg(row + xa) | ((uint32_t)__ldg(row + xb) << 16);
+        }
+    }
+}
+
+// Replicated apron of a DMVR window (core at rows 2.., sample column 2 + e..): 2 samples each side, 2 rows
+// above and below.  Equals clamping the coordinates to the unrefined block's window (emulated_edge_dmvr).
+__device__ __noinline__ void pad_window(uint32_t *win, int pw, int e, int cols0, int rows0, int lane)
+{
+    if (lane < rows0) {                                    // lane = core row
+        uint16_t *row = reinterpret_cast<uint16_t *>(win) + (lane + 2) * (2 * pw);
+        const int first = 2 + e, last = 2 + e + cols0 - 1;
+        const uint16_t a = row[first], b = row[last];
+        row[0] = a; row[1] = a;
+        if (e)
+            row[2] = a;
+        row[last + 1] = b; row[last + 2] = b;
+    }
+    __syncwarp();
+    if (lane < pw) {
+        const uint32_t top = win[2 * pw + lane], bot = win[(rows0 + 1) * pw + lane];
+        win[lane] = top; win[pw + lane] = top;
+        win[(rows0 + 2) * pw + lane] = bot; win[(rows0 + 3) * pw + lane] = bot;
+    }
+}
+
+// ---- separable interpolation -------------------------------------------------------------------------
+// First pass (put_*_h and the tmp_array loop of put_*_hv, h2656_inter_template.c:97-150, 342-395): a task is
+// (unit, 8-column half, window row).  Output stored transposed: hbt[unit][col][row].
+template <int TAPS>
+__device__ __forceinline__ void pass_h(WarpSmem &s, int lane, int n_units, int rows, int lhh)
+{
+    constexpr int NW = TAPS == 8 ? 8 : 6, PW = TAPS == 8 ? PWL : PWC, HP = TAPS == 8 ? HPL : HPC, HU = TAPS == 8 ? HUL : HUC;
+    const int ntask = (n_units << lhh) * rows;
+    const uint32_t inv = inv_rows(rows);
+    for (int t = lane; t < ntask; t += 32) {
+        const int q = (t * inv) >> 16, r = t - q * rows;
+        const int hh = q & ((1 << lhh) - 1), u = q >> lhh;
+        const UnitMC m = s.um[u];
+        const int c = m.c0 + 8 * hh, sh = (c & 1) << 4;
+        const uint32_t *wp = s.a.win + m.woff + (m.r0 + r) * PW + (c >> 1);
+        uint32_t wd[NW], A[2 * NW - 2];
+#pragma unroll
+        for (int k = 0; k < NW; k++)
+            wd[k] = wp[k];
+#pragma unroll
+        for (int i = 0; i < NW - 1; i++) {
+            A[2 * i] = frc(wd[i], wd[i + 1], sh);
+            A[2 * i + 1] = frc(wd[i], wd[i + 1], sh + 16);
+        }
+        short *hb = s.a.hbt + u * HU + (8 * hh) * HP + r;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int v;
+            if (TAPS == 8)
+                v = __dp2a_lo((int)A[j], (int)m.hf0, __dp2a_hi((int)A[j + 2], (int)m.hf0,
+                    __dp2a_lo((int)A[j + 4], (int)m.hf1, __dp2a_hi((int)A[j + 6], (int)m.hf1, 0))));
+            else
+                v = __dp2a_lo((int)A[j], (int)m.hf0, __dp2a_hi((int)A[j + 2], (int)m.hf0, 0));
+            hb[j * HP] = (short)(v >> m.shh);
+        }
+    }
+}
+
+// Second pass: a task is (unit, 8-row half, column); writes the int16 tile the reference's put() produces.
+template <int TAPS>
+__device__ __forceinline__ void pass_v(WarpSmem &s, int lane, int n_units, int lbw, int bh)
+{
+    constexpr int HP = TAPS == 8 ? HPL : HPC, HU = TAPS == 8 ? HUL : HUC;
+    const int lvh = bh > 8 ? 1 : 0;
+    const int ntask = (n_units << lvh) << lbw;
+    for (int t = lane; t < ntask; t += 32) {
+        const int x = t & ((1 << lbw) - 1), q = t >> lbw;
+        const int hv = q & ((1 << lvh) - 1), u = q >> lvh;
+        const UnitMC m = s.um[u];
+        const uint4 *cp = reinterpret_cast<const uint4 *>(s.a.hbt + u * HU + x * HP + 8 * hv);
+        const uint4 c0 = cp[0], c1 = cp[1];
+        const uint32_t wd[8] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w };
+        uint32_t A[14];
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            A[2 * i] = wd[i];
+            A[2 * i + 1] = __funnelshift_r(wd[i], wd[i + 1], 16);
+        }
+        short *out = TAPS == 8 ? &s.tile[u][(8 * hv + 1) * TP + 8 + x] : &s.ctile[u][x];
+        constexpr int OP = TAPS == 8 ? TP : 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int v;
+            if (TAPS == 8)
+                v = __dp2a_lo((int)A[j], (int)m.vf0, __dp2a_hi((int)A[j + 2], (int)m.vf0,
+                    __dp2a_lo((int)A[j + 4], (int)m.vf1, __dp2a_hi((int)A[j + 6], (int)m.vf1, 0))));
+            else
+                v = __dp2a_lo((int)A[j], (int)m.vf0, __dp2a_hi((int)A[j + 2], (int)m.vf0, 0));
+            if (8 * hv + j < bh)
+                out[j * OP] = (short)(v >> m.shv);
+        }
+    }
+}
+
+// ---- final roundings (avg / w_avg / put_uni / put_uni_w, vvc_inter_template.c:25-57, h2656_inter_template.c) ----
+struct Weights { int on, denom, w0, w1, o0, o1; };
+
+__device__ __forceinline__ Weights bi_weights(const Rec &pb, const VVCCudaWP *wp, int c)
+{
+    Weights w = { 0, 0, 0, 0, 0, 0 };
+    if (pb.bcw) {
+        const int w1 = pb.bcw == 1 ? 5 : pb.bcw == 2 ? 3 : pb.bcw == 3 ? 10 : -2;      // {4,5,3,10,-2}[bcw_idx]
+        w.on = 1; w.denom = 2; w.w1 = w1; w.w0 = 8 - w1;
+    } else if ((pb.flags & VVC_CUDA_PB_WEIGHTED) && !(pb.flags & VVC_CUDA_PB_DMVR)) {
+        const VVCCudaWP *e = wp + pb.wp;
+        w.on = 1; w.denom = e->log2_denom[c > 0];
+        w.w0 = e->weight[0][c]; w.w1 = e->weight[1][c]; w.o0 = e->offset[0][c]; w.o1 = e->offset[1][c];
+    }
+    return w;
+}
+
+__device__ __forceinline__ int combine_bi(int a, int b, const Weights &w)
+{
+    if (!w.on)
+        return d_clip_pel((a + b + 16) >> 5, 10);
+    const int shift = w.denom + 5;
+    const int offset = (((w.o0 + w.o1) << 2) + 1) << (shift - 1);
+    return d_clip_pel((a * w.w0 + b * w.w1 + offset) >> shift, 10);
+}
+
+struct UniW { int on, shift, wx, ox; };
+
+__device__ __forceinline__ UniW uni_weights(const Rec &pb, const VVCCudaWP *wp, int lx, int c)
+{
+    UniW w = { 0, 0, 0, 0 };
+    if (pb.flags & VVC_CUDA_PB_WEIGHTED) {
+        const VVCCudaWP *e = wp + pb.wp;
+        w.on = 1; w.shift = e->log2_denom[c > 0] + 4; w.wx = e->weight[lx][c]; w.ox = e->offset[lx][c] * 4;
+    }
+    return w;
+}
+
+__device__ __forceinline__ int finish_uni(int val, const UniW &w)
+{
+    if (w.on)
+        return d_clip_pel(((val * w.wx + (1 << (w.shift - 1))) >> w.shift) + w.ox, 10);
+    return d_clip_pel((val + 8) >> 4, 10);
+}
+
+__device__ __forceinline__ int vsign(int v) { return v < 0 ? -1 : (v != 0); }
+
+__device__ int parametric(const int *sd, int stride)      // parametric_mv_refine, vvc_inter.c:642-681
+{
+    const int sm = sd[-stride], sc = sd[0], sp = sd[stride];
+    int denom = ((sm + sp) - (sc << 1)) << 3;
+    if (!denom) return 0;
+    if (sm == sc) return -8;
+    if (sp == sc) return 8;
+    int num = (sm - sp) * 16, neg = 0, q = 0;
+    if (num < 0) { num = -num; neg = 1; }
+    for (int i = 0; i < 3; i++) {
+        q <<= 1;
+        if (num >= denom) { num -= denom; q++; }
+        denom >>= 1;
+    }
+    return neg ? -q : q;
+}
+
+// 4 luma samples of tile `ui` at (x, y)
+__device__ __forceinline__ void tile4(const WarpSmem &s, int ui, int x, int y, int v[4])
+{
+    const uint2 q = *reinterpret_cast<const uint2 *>(&s.tile[ui][(y + 1) * TP + 8 + x]);
+    v[0] = lo16(q.x); v[1] = hi16(q.x); v[2] = lo16(q.y); v[3] = hi16(q.y);
+}
+
+// ring of integer samples around a tile: bdof_fetch_samples / fetch_samples (vvc_inter_template.c:101-133)
+__device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, int mx, int my, int lane)
+{
+    const UnitMC m = s.um[ui];
+    const uint16_t *w16 = reinterpret_cast<const uint16_t *>(s.a.win + m.woff);
+    const int xo = m.c0 + (mx >> 3) + 3, yo = m.r0 + (my >> 3) + 3;
+    const int per = 2 * (bw + 2) + 2 * bh;
+    for (int idx = lane; idx < per; idx += 32) {
+        int tx, ty;
+        if (idx < bw + 2)                 { tx = idx - 1;            ty = -1; }
+        else if (idx < 2 * (bw + 2))      { tx = idx - (bw + 2) - 1; ty = bh; }
+        else if (idx < 2 * (bw + 2) + bh) { tx = -1;                 ty = idx - 2 * (bw + 2); }
+        else                              { tx = bw;                 ty = idx - 2 * (bw + 2) - bh; }
+        s.tile[ui][(ty + 1) * TP + 8 + tx] = (short)(w16[(ty + yo) * (2 * PWL) + tx + xo] << 4);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
+{
+    __shared__ WarpSmem sm[kWarps];
+    const int lane = threadIdx.x & 31;
+    WarpSmem &s = sm[threadIdx.x >> 5];
+    const int nwarps = gridDim.x * kWarps;
+    const uint2 *lumaf = reinterpret_cast<const uint2 *>(&vvct_luma_mc_filters[0][0][0]);
+    const uint32_t *chromaf = reinterpret_cast<const uint32_t *>(&vvct_chroma_mc_filters[0][0][0]);
+
+    for (int ri = blockIdx.x * kWarps + (threadIdx.x >> 5); ri < p.n; ri += nwarps) {
+        __syncwarp();
+        const Rec pb = load_rec(p.pbs + ri);
+        const int w = pb.w, h = pb.h, lw = 31 - __clz(w);
+        const bool gpm = pb.flags & VVC_CUDA_PB_GPM;
+        const bool bi = gpm || pb.pred == 3;
+        const bool dmvr = (pb.flags & VVC_CUDA_PB_DMVR) != 0;
+        const int lx = pb.pred - 1;                                  // the list of a uni record
+        int mvr[2][2] = { { pb.mv[0][0], pb.mv[0][1] }, { pb.mv[1][0], pb.mv[1][1] } };   // vectors used for MC
+        int bdof = (pb.flags & VVC_CUDA_PB_BDOF) ? 1 : 0;
+        const bool dmvr_luma = dmvr && (pb.planes & VVC_CUDA_PB_LUMA);
+#define MVR(l, c) ((l) ? mvr[1][c] : mvr[0][c])
+#define MV0(l, c) ((l) ? pb.mv[1][c] : pb.mv[0][c])
+#define REF(l)    ((l) ? pb.ref[1] : pb.ref[0])
+
+        // ---- DMVR: stage both unrefined windows, bilinear prediction, 25 SADs, refinement -------------
+        if (dmvr_luma) {
+#pragma unroll 1
+            for (int l = 0; l < 2; l++)
+                stage_core(s.a.win + l * WUL, PWL, 1, 2, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h,
+                           pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane);
+            __syncwarp();
+#pragma unroll 1
+            for (int l = 0; l < 2; l++)
+                pad_window(s.a.win + l * WUL, PWL, (pb.x0 + (MV0(l, 0) >> 4) - 3) & 1, w + 7, h + 7, lane);
+            __syncwarp();
+            // bilinear (dmvr / dmvr_h / dmvr_v / dmvr_hv, vvc_inter_template.c:324-409) on sample pairs; lane = row
+            const int nwo = (w + 4) >> 1;
+#pragma unroll 1
+            for (int l = 0; l < 2; l++) {
+                const int mx = MV0(l, 0) & 15, my = MV0(l, 1) & 15;
+                const int fx0 = vvct_dmvr_filters[mx][0], fx1 = vvct_dmvr_filters[mx][1];
+                const int fy0 = vvct_dmvr_filters[my][0], fy1 = vvct_dmvr_filters[my][1];
+                const int e = (pb.x0 + (MV0(l, 0) >> 4) - 3) & 1, c0 = 3 + e, sh = (c0 & 1) << 4;
+                const int y = min(lane, h + 4);
+                const uint32_t *wp = s.a.win + l * WUL + (3 + y) * PWL + (c0 >> 1);
+                uint32_t hrow[10];
+                uint32_t prev = wp[0];
+#pragma unroll
+                for (int i = 0; i < 10; i++) {
+                    hrow[i] = 0;
+                    if (i < nwo) {
+                        const uint32_t next = wp[i + 1];
+                        const uint32_t P = frc(prev, next, sh), Q = frc(prev, next, sh + 16);
+                        hrow[i] = ((fx0 * P + fx1 * Q + 0x00080008u) >> 4) & 0x0fff0fffu;
+                        prev = next;
+                    }
+                }
+                uint32_t *dst = reinterpret_cast<uint32_t *>(&s.dm[l][y * DP]);
+#pragma unroll
+                for (int i = 0; i < 10; i++) {
+                    const uint32_t below = __shfl_down_sync(0xffffffffu, hrow[i], 1);
+                    if (i < nwo && lane < h + 4)
+                        dst[i] = ((fy0 * hrow[i] + fy1 * below + 0x00080008u) >> 4) & 0x0fff0fffu;
+                }
+            }
+            __syncwarp();
+            // SAD on every other row (vvc_sad, vvcdsp.c:49-65): task = (dy, row), the 5 dx share the loaded rows
+            {
+                const int lhr = 31 - __clz(h >> 1), ntask = 5 << lhr, nwr = w >> 1;
+                for (int base = 0; base < ntask; base += 32) {
+                    const int t = base + lane;
+                    const bool act = t < ntask;
+                    const int dyi = act ? t >> lhr : 0, y = (t & ((1 << lhr) - 1)) << 1;
+                    const uint32_t *ra = reinterpret_cast<const uint32_t *>(&s.dm[0][(dyi + y) * DP]);
+                    const uint32_t *rb = reinterpret_cast<const uint32_t *>(&s.dm[1][(4 - dyi + y) * DP]);
+                    uint32_t A[10], B[10], A1[9], B1[9];
+#pragma unroll
+                    for (int k = 0; k < 10; k++) {
+                        A[k] = k < nwr + 2 ? ra[k] : 0;
+                        B[k] = k < nwr + 2 ? rb[k] : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 9; k++) {
+                        A1[k] = __funnelshift_r(A[k], A[k + 1], 16);
+                        B1[k] = __funnelshift_r(B[k], B[k + 1], 16);
+                    }
+                    int sd[5] = { 0, 0, 0, 0, 0 };
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (k < nwr) {
+#define SADW(a, b) __dp2a_lo((int)(__vmaxu2(a, b) - __vminu2(a, b)), 0x0101, 0)
+                            sd[0] += SADW(A[k], B[k + 2]);         // dx = -2: a at 0, b at 4
+                            sd[1] += SADW(A1[k], B1[k + 1]);       // dx = -1: a at 1, b at 3
+                            sd[2] += SADW(A[k + 1], B[k + 1]);     // dx =  0
+                            sd[3] += SADW(A1[k + 1], B1[k]);       // dx = +1: a at 3, b at 1
+                            sd[4] += SADW(A[k + 2], B[k]);         // dx = +2
+#undef SADW
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < 5; d++) {
+                        int v = act ? sd[d] : 0;
+                        for (int o = 1; o < (h >> 1); o <<= 1)
+                            v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (act && !(t & ((1 << lhr) - 1)))
+                            s.sad[dyi * 5 + d] = v;
+                    }
+                }
+            }
+            __syncwarp();
+            // decision (dmvr_mv_refine, vvc_inter.c:700-747), computed redundantly by every lane
+            {
+                const int mine = s.sad[lane < 25 ? lane : 0];
+                const int centre = __shfl_sync(0xffffffffu, mine, 12);
+                int min_sad = centre - (centre >> 2);
+                if (min_sad >= w * h) {
+                    __syncwarp();
+                    if (lane == 12)
+                        s.sad[12] = min_sad;
+                    // first strict minimum in scan order, the centre first (ties keep the earlier candidate)
+                    uint32_t key = lane == 12 ? (uint32_t)min_sad << 5 : lane < 25 ? ((uint32_t)mine << 5) | (lane + 1) : 0xffffffffu;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1)
+                        key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+                    const int pos = (key & 31) ? (int)(key & 31) - 1 : 12;
+                    min_sad = (int)(key >> 5);
+                    const int min_dx = pos % 5, min_dy = pos / 5;
+                    int dmv0 = (min_dx - 2) * 16, dmv1 = (min_dy - 2) * 16;
+                    __syncwarp();
+                    if (min_dx != 0 && min_dx != 4 && min_dy != 0 && min_dy != 4) {
+                        dmv0 += parametric(&s.sad[pos], 1);
+                        dmv1 += parametric(&s.sad[pos], 5);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        mvr[i][0] = d_clip3(mvr[i][0] + (1 - 2 * i) * dmv0, -(1 << 17), (1 << 17) - 1);
+                        mvr[i][1] = d_clip3(mvr[i][1] + (1 - 2 * i) * dmv1, -(1 << 17), (1 << 17) - 1);
+                    }
+                }
+                if (min_sad < 2 * w * h)
+                    bdof = 0;
+                if (p.dmvr_out && lane == 0) {
+                    VVCCudaDmvrOut o;
+                    o.mv[0][0] = mvr[0][0]; o.mv[0][1] = mvr[0][1]; o.mv[1][0] = mvr[1][0]; o.mv[1][1] = mvr[1][1];
+                    o.min_sad = min_sad; o.bdof_applied = bdof;
+                    p.dmvr_out[ri] = o;
+                }
+            }
+            __syncwarp();
+        }
+        const bool do_bdof = bdof && !gpm;
+        pel *dstp[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            dstp[c] = p.dst[c] + pb.pic * p.db[c];
+
+        // ---- luma ------------------------------------------------------------------------------------
+        if (pb.planes & VVC_CUDA_PB_LUMA) {
+            const int n_units = bi ? 2 : 1;
+            {   // unit descriptors; unit i is list i (bi / GPM) or the single list (uni)
+                const int u = lane & 1, list = bi ? u : lx;
+                const int mvx = MVR(list, 0), mvy = MVR(list, 1), m0x = MV0(list, 0), m0y = MV0(list, 1);
+                const int mx = mvx & 15, my = mvy & 15, filt = gpm ? 0 : pb.filt;
+                UnitMC m;
+                m.woff = u * WUL;
+                if (dmvr) {
+                    const int e = (pb.x0 + (m0x >> 4) - 3) & 1;
+                    m.c0 = 2 + e + d_clip3((mvx >> 4) - (m0x >> 4), -2, 2);
+                    m.r0 = 2 + d_clip3((mvy >> 4) - (m0y >> 4), -2, 2);
+                } else {
+                    m.c0 = (pb.x0 + (mvx >> 4) - 3) & 1;
+                    m.r0 = 0;
+                }
+                const uint2 fh = lumaf[filt * 16 + mx], fv = lumaf[filt * 16 + my];
+                m.hf0 = mx ? fh.x : 0x01000000u;  m.hf1 = mx ? fh.y : 0u;  m.shh = mx ? 2 : 0;
+                m.vf0 = my ? fv.x : (mx ? 0x01000000u : 0x10000000u);  m.vf1 = my ? fv.y : 0u;
+                m.shv = my ? (mx ? 6 : 2) : 0;
+                if (lane < n_units)
+                    s.um[lane] = m;
+                if (!dmvr_luma) {
+#pragma unroll 1
+                    for (int i = 0; i < 2; i++) {
+                        if (i < n_units) {
+                            const int li = bi ? i : lx;
+                            stage_core(s.a.win + i * WUL, PWL, 0, 0, p.ref[0] + REF(li) * p.rb[0], p.rp[0], p.w, p.h,
+                                            pb.x0 + (MVR(li, 0) >> 4) - 3, pb.y0 + (MVR(li, 1) >> 4) - 3, w + 7, h + 7, lane);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            pass_h<8>(s, lane, n_units, h + 7, w > 8 ? 1 : 0);
+            __syncwarp();
+            pass_v<8>(s, lane, n_units, lw, h);
+            __syncwarp();
+            pel *d = dstp[0] + (long long)pb.y0 * p.dp[0] + pb.x0;
+            const int ntask = h << (lw - 2);
+            if (!bi) {
+                const UniW uw = uni_weights(pb, p.wp, lx, 0);
+                const bool use_prof = pb.flags & (lx ? VVC_CUDA_PB_PROF1 : VVC_CUDA_PB_PROF0);
+                if (use_prof) {                             // luma_prof_uni, vvc_inter.c:368-408 (4x4 blocks)
+                    fetch_ring(s, 0, w, h, MVR(lx, 0) & 15, MVR(lx, 1) & 15, lane);
+                    __syncwarp();
+                    if (lane < 16) {
+                        const int x = lane & 3, y = lane >> 2;
+                        const VVCCudaProf *pr = p.prof + pb.prof;
+                        const short *q = &s.tile[0][(y + 1) * TP + 8 + x];
+                        const int gh = (short)((q[1] >> 6) - (q[-1] >> 6)), gv = (short)((q[TP] >> 6) - (q[-TP] >> 6));
+                        const int di = gh * pr->diff_mv_x[lx][lane] + gv * pr->diff_mv_y[lx][lane];
+                        d[(long long)y * p.dp[0] + x] = (pel)finish_uni(q[0] + d_clip3(di, -8192, 8191), uw);
+                    }
+                } else {
+                    for (int t = lane; t < ntask; t += 32) {
+                        const int x = (t & ((w >> 2) - 1)) << 2, y = t >> (lw - 2);
+                        int a[4];
+                        tile4(s, 0, x, y, a);
+                        uint2 o;
+                        o.x = pack16(finish_uni(a[0], uw), finish_uni(a[1], uw));
+                        o.y = pack16(finish_uni(a[2], uw), finish_uni(a[3], uw));
+                        *reinterpret_cast<uint2 *>(d + (long long)y * p.dp[0] + x) = o;
+                    }
+                }
+            } else {
+                const int prof_mask = gpm ? 0 : pb.flags & (VVC_CUDA_PB_PROF0 | VVC_CUDA_PB_PROF1);
+                if (do_bdof || prof_mask) {
+                    fetch_ring(s, 0, w, h, mvr[0][0] & 15, mvr[0][1] & 15, lane);
+                    fetch_ring(s, 1, w, h, mvr[1][0] & 15, mvr[1][1] & 15, lane);
+                    __syncwarp();
+                }
+                if (prof_mask) {                            // luma_prof_bi, vvc_inter.c:410-446 (4x4 blocks)
+                    const int ui = lane >> 4, e = lane & 15, x = e & 3, y = e >> 2;
+                    const bool act = prof_mask & (ui ? VVC_CUDA_PB_PROF1 : VVC_CUDA_PB_PROF0);
+                    int val = 0;
+                    if (act) {
+                        const VVCCudaProf *pr = p.prof + pb.prof;
+                        const short *q = &s.tile[ui][(y + 1) * TP + 8 + x];
+                        const int gh = (short)((q[1] >> 6) - (q[-1] >> 6)), gv = (short)((q[TP] >> 6) - (q[-TP] >> 6));
+                        const int di = gh * pr->diff_mv_x[ui][e] + gv * pr->diff_mv_y[ui][e];
+                        val = q[0] + d_clip3(di, -8192, 8191);
+                    }
+                    __syncwarp();
+                    if (act)
+                        s.tile[ui][(y + 1) * TP + 8 + x] = (short)val;
+                    __syncwarp();
+                }
+                if (gpm) {                                  // put_gpm, vvc_inter_template.c:78-98
+                    const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;
+                    for (int t = lane; t < ntask; t += 32) {
+                        const int x = (t & ((w >> 2) - 1)) << 2, y = t >> (lw - 2);
+                        int a[4], b[4], o[4];
+                        tile4(s, 0, x, y, a);
+                        tile4(s, 1, x, y, b);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int g = wt[y * pb.gsy + (x + i) * pb.gsx];
+                            o[i] = d_clip_pel((a[i] * g + b[i] * (8 - g) + 64) >> 7, 10);
+                        }
+                        *reinterpret_cast<uint2 *>(d + (long long)y * p.dp[0] + x) = make_uint2(pack16(o[0], o[1]), pack16(o[2], o[3]));
+                    }
+                } else if (do_bdof) {                       // apply_bdof, vvc_inter_template.c:237-317
+                    // gradients (prof_grad_filter :135-158) of both tiles; lane = (list, row), samples in pairs.
+                    // The padded borders the reference creates with pad_int16 equal clamped coordinates below.
+                    uint32_t gh[8], gv[8];
+                    {
+                        const int l = lane >= h, y = lane - l * h;
+                        const bool act = lane < 2 * h;
+                        const int yy = act ? y : 0;
+                        const uint32_t *up = reinterpret_cast<const uint32_t *>(&s.tile[l][yy * TP]);
+                        const uint32_t *mid = up + TP / 2, *dn = mid + TP / 2;
+                        const int nwr = w >> 1;
+                        uint32_t prevS = ((mid[3] ^ 0x80008000u) >> 6) & 0x03ff03ffu;
+                        uint32_t curS = ((mid[4] ^ 0x80008000u) >> 6) & 0x03ff03ffu;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            gh[k] = gv[k] = 0;
+                            if (k < nwr) {
+                                const uint32_t nextS = ((mid[5 + k] ^ 0x80008000u) >> 6) & 0x03ff03ffu;
+                                gh[k] = __vsub2(__funnelshift_r(curS, nextS, 16), __funnelshift_r(prevS, curS, 16));
+                                const uint32_t su = ((up[4 + k] ^ 0x80008000u) >> 6) & 0x03ff03ffu;
+                                const uint32_t sd = ((dn[4 + k] ^ 0x80008000u) >> 6) & 0x03ff03ffu;
+                                gv[k] = __vsub2(sd, su);
+                                prevS = curS; curS = nextS;
+                            }
+                        }
+                    }
+                    __syncwarp();                           // windows and first-pass rows are dead: reuse as gradient storage
+                    if (lane < 2 * h) {
+                        const int l = lane >= h, y = lane - l * h;
+                        uint32_t *g0 = reinterpret_cast<uint32_t *>(&s.b.grad[l * 2][y * 16]);
+                        uint32_t *g1 = reinterpret_cast<uint32_t *>(&s.b.grad[l * 2 + 1][y * 16]);
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (k < (w >> 1)) { g0[k] = gh[k]; g1[k] = gv[k]; }
+                    }
+                    __syncwarp();
+                    // derive_bdof_vx_vy :237-265: 6x6 window sums per 4x4 block, separable.  Column pass:
+                    const int lbx = lw - 2;
+                    for (int t = lane; t < (h << lbx); t += 32) {
+                        const int bxi = t & ((1 << lbx) - 1), y = t >> lbx;
+                        int sgx2 = 0, sgy2 = 0, sgxgy = 0, sgxdi = 0, sgydi = 0;
+#pragma unroll
+                        for (int dx = -1; dx < 5; dx++) {
+                            const int x = d_clip3(4 * bxi + dx, 0, w - 1);
+                            const int ti = (y + 1) * TP + 8 + x, gi = y * 16 + x;
+                            const int diff = (s.tile[0][ti] >> 4) - (s.tile[1][ti] >> 4);
+                            const int th = (s.b.grad[0][gi] + s.b.grad[2][gi]) >> 1;
+                            const int tv = (s.b.grad[1][gi] + s.b.grad[3][gi]) >> 1;
+                            sgx2 += abs(th); sgy2 += abs(tv);
+                            sgxgy += vsign(tv) * th;
+                            sgxdi -= vsign(th) * diff;
+                            sgydi -= vsign(tv) * diff;
+                        }
+                        s.b.csum[0][y][bxi] = sgx2; s.b.csum[1][y][bxi] = sgy2; s.b.csum[2][y][bxi] = sgxgy;
+                        s.b.csum[3][y][bxi] = sgxdi; s.b.csum[4][y][bxi] = sgydi;
+                    }
+                    __syncwarp();
+                    if (lane < ((h >> 2) << lbx)) {         // row pass + vx, vy; lane = 4x4 block
+                        const int bxi = lane & ((1 << lbx) - 1), byi = lane >> lbx;
+                        int sum[5] = { 0, 0, 0, 0, 0 };
+#pragma unroll
+                        for (int dy = -1; dy < 5; dy++) {
+                            const int y = d_clip3(4 * byi + dy, 0, h - 1);
+#pragma unroll
+                            for (int q = 0; q < 5; q++)
+                                sum[q] += s.b.csum[q][y][bxi];
+                        }
+                        const int vx = sum[0] > 0 ? d_clip3((sum[3] * 4) >> d_ilog2(sum[0]), -15, 15) : 0;
+                        const int vy = sum[1] > 0 ? d_clip3(((sum[4] * 4) - ((vx * sum[2]) >> 1)) >> d_ilog2(sum[1]), -15, 15) : 0;
+                        s.vxy[lane][0] = vx; s.vxy[lane][1] = vy;
+                    }
+                    __syncwarp();
+                    for (int t = lane; t < ntask; t += 32) {   // apply_bdof_min_block :267-286
+                        const int x4 = t & ((w >> 2) - 1), x = x4 << 2, y = t >> (lw - 2);
+                        const int vx = s.vxy[((y >> 2) << lbx) + x4][0], vy = s.vxy[((y >> 2) << lbx) + x4][1];
+                        int a[4], b[4], o[4];
+                        tile4(s, 0, x, y, a);
+                        tile4(s, 1, x, y, b);
+                        const uint2 g0h = *reinterpret_cast<const uint2 *>(&s.b.grad[0][y * 16 + x]);
+                        const uint2 g0v = *reinterpret_cast<const uint2 *>(&s.b.grad[1][y * 16 + x]);
+                        const uint2 g1h = *reinterpret_cast<const uint2 *>(&s.b.grad[2][y * 16 + x]);
+                        const uint2 g1v = *reinterpret_cast<const uint2 *>(&s.b.grad[3][y * 16 + x]);
+                        const int dh[4] = { lo16(g0h.x) - lo16(g1h.x), hi16(g0h.x) - hi16(g1h.x), lo16(g0h.y) - lo16(g1h.y), hi16(g0h.y) - hi16(g1h.y) };
+                        const int dv[4] = { lo16(g0v.x) - lo16(g1v.x), hi16(g0v.x) - hi16(g1v.x), lo16(g0v.y) - lo16(g1v.y), hi16(g0v.y) - hi16(g1v.y) };
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            o[i] = d_clip_pel((a[i] + 16 + b[i] + vx * dh[i] + vy * dv[i]) >> 5, 10);
+                        *reinterpret_cast<uint2 *>(d + (long long)y * p.dp[0] + x) = make_uint2(pack16(o[0], o[1]), pack16(o[2], o[3]));
+                    }
+                } else {
+                    const Weights wt = bi_weights(pb, p.wp, 0);
+                    for (int t = lane; t < ntask; t += 32) {
+                        const int x = (t & ((w >> 2) - 1)) << 2, y = t >> (lw - 2);
+                        int a[4], b[4];
+                        tile4(s, 0, x, y, a);
+                        tile4(s, 1, x, y, b);
+                        uint2 o;
+                        o.x = pack16(combine_bi(a[0], b[0], wt), combine_bi(a[1], b[1], wt));
+                        o.y = pack16(combine_bi(a[2], b[2], wt), combine_bi(a[3], b[3], wt));
+                        *reinterpret_cast<uint2 *>(d + (long long)y * p.dp[0] + x) = o;
+                    }
+                }
+            }
+        }
+
+        // ---- chroma (both planes, 4:2:0) -----------------------------------------------------------------
+        if ((pb.planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) {
+            __syncwarp();
+            const int bw = w >> 1, bh = h >> 1, lbw = lw - 1;
+            const int x0 = pb.x0 >> 1, y0 = pb.y0 >> 1, pw = p.w >> 1, ph = p.h >> 1;
+            const int n_units = bi ? 4 : 2;
+            {   // unit u: bi -> (plane u >> 1, list u & 1); uni -> (plane u, the single list)
+                const int u = lane & 3, list = bi ? (u & 1) : lx;
+                const int mvx = MVR(list, 0), mvy = MVR(list, 1), m0x = MV0(list, 0), m0y = MV0(list, 1);
+                const int mx = mvx & 31, my = mvy & 31;
+                UnitMC m;
+                m.woff = u * WUC;
+                if (dmvr) {
+                    const int e = (x0 + (m0x >> 5) - 1) & 1;
+                    m.c0 = 2 + e + d_clip3((mvx >> 5) - (m0x >> 5), -2, 2);
+                    m.r0 = 2 + d_clip3((mvy >> 5) - (m0y >> 5), -2, 2);
+                } else {
+                    m.c0 = (x0 + (mvx >> 5) - 1) & 1;
+                    m.r0 = 0;
+                }
+                m.hf0 = mx ? chromaf[mx] : 0x00000100u;  m.hf1 = 0;  m.shh = mx ? 2 : 0;
+                m.vf0 = my ? chromaf[my] : (mx ? 0x00000100u : 0x00001000u);  m.vf1 = 0;
+                m.shv = my ? (mx ? 6 : 2) : 0;
+                if (lane < n_units)
+                    s.um[lane] = m;
+            }
+#pragma unroll 1
+            for (int u = 0; u < 4; u++) {
+                if (u < n_units) {
+                    const int list = bi ? (u & 1) : lx, pc = bi ? (u >> 1) : u;
+                    const pel *plane = (pc ? p.ref[2] + REF(list) * p.rb[2] : p.ref[1] + REF(list) * p.rb[1]);
+                    const int rpitch = pc ? p.rp[2] : p.rp[1];
+                    if (dmvr)
+                        stage_core(s.a.win + u * WUC, PWC, 1, 2, plane, rpitch, pw, ph,
+                                        x0 + (MV0(list, 0) >> 5) - 1, y0 + (MV0(list, 1) >> 5) - 1, bw + 3, bh + 3, lane);
+                    else
+                        stage_core(s.a.win + u * WUC, PWC, 0, 0, plane, rpitch, pw, ph,
+                                        x0 + (MVR(list, 0) >> 5) - 1, y0 + (MVR(list, 1) >> 5) - 1, bw + 3, bh + 3, lane);
+                }
+            }
+            __syncwarp();
+            if (dmvr) {
+#pragma unroll 1
+                for (int u = 0; u < 4; u++)
+                    if (u < n_units) {
+                        const int list = bi ? (u & 1) : lx;
+                        pad_window(s.a.win + u * WUC, PWC, (x0 + (MV0(list, 0) >> 5) - 1) & 1, bw + 3, bh + 3, lane);
+                    }
+                __syncwarp();
+            }
+            pass_h<4>(s, lane, n_units, bh + 3, 0);
+            __syncwarp();
+            pass_v<4>(s, lane, n_units, lbw, bh);
+            __syncwarp();
+            // lane task = (plane, row, sample pair)
+            const int lpw = lbw - 1, ntask = (2 * bh) << lpw;
+            const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;
+            for (int t = lane; t < ntask; t += 32) {
+                const int x = (t & ((1 << lpw) - 1)) << 1, q = t >> lpw;
+                const int pc = q >= bh, y = q - pc * bh;
+                int o[2];
+                if (!bi) {
+                    const UniW uw = uni_weights(pb, p.wp, lx, pc + 1);
+                    const uint32_t a = *reinterpret_cast<const uint32_t *>(&s.ctile[pc][y * 8 + x]);
+                    o[0] = finish_uni(lo16(a), uw); o[1] = finish_uni(hi16(a), uw);
+                } else {
+                    const uint32_t a = *reinterpret_cast<const uint32_t *>(&s.ctile[pc * 2][y * 8 + x]);
+                    const uint32_t b = *reinterpret_cast<const uint32_t *>(&s.ctile[pc * 2 + 1][y * 8 + x]);
+                    if (gpm) {
+                        const int g0 = wt[y * 2 * pb.gsy + x * 2 * pb.gsx], g1 = wt[y * 2 * pb.gsy + (x + 1) * 2 * pb.gsx];
+                        o[0] = d_clip_pel((lo16(a) * g0 + lo16(b) * (8 - g0) + 64) >> 7, 10);
+                        o[1] = d_clip_pel((hi16(a) * g1 + hi16(b) * (8 - g1) + 64) >> 7, 10);
+                    } else {
+                        const Weights bw_ = bi_weights(pb, p.wp, pc + 1);
+                        o[0] = combine_bi(lo16(a), lo16(b), bw_); o[1] = combine_bi(hi16(a), hi16(b), bw_);
+                    }
+                }
+                pel *d = (pc ? dstp[2] + (long long)(y0 + y) * p.dp[2] : dstp[1] + (long long)(y0 + y) * p.dp[1]) + x0 + x;
+                *reinterpret_cast<uint32_t *>(d) = pack16(o[0], o[1]);
+            }
+        }
+#undef MVR
+#undef MV0
+#undef REF
+    }
+}
+
+}  // namespace
+
+int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p)
+{
+    const int ctas = ceil_div(p.n, kWarps);
+    const int grid = ctas < 148 * 16 ? ctas : 148 * 16;
+    inter_warp_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
+    VVC_LAUNCHED(ctx);
+    return VVC_CUDA_OK;
+}

@@ -72,6 +72,7 @@ def load():
     RP = C.POINTER(abi.VVCCudaReconDesc)
     lib.vvc_cuda_recon_frame.argtypes = [CTX, FP, FP, FP, RP]
     lib.vvc_cuda_recon_frame_host.argtypes = [CTX, FP, FP, RP]
+    lib.vvc_cuda_ctx_set_option.argtypes = [CTX, C.c_int, C.c_int]
     lib.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
     lib.vvc_cuda_abi_sizeof.restype = C.c_size_t
     _lib = lib
@@ -118,6 +119,9 @@ class Context:
         """The context's stream as a torch stream object (for events / `with torch.cuda.stream`)."""
         import torch
         return torch.cuda.ExternalStream(self.stream_ptr, device="cuda:%d" % self.device)
+
+    def set_option(self, option, value):
+        self.check(self.lib.vvc_cuda_ctx_set_option(self.handle, option, value))
 
     @property
     def launches(self):

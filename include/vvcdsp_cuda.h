@@ -57,6 +57,10 @@ void       *vvc_cuda_stream(const VVCCudaCtx *ctx);    /* the cudaStream_t in us
 /* number of kernel launches issued through this context since creation (bench bookkeeping) */
 uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx);
 const char *vvc_cuda_version(void);
+/* Options.  VVC_CUDA_OPT_GENERIC_KERNELS = 1 routes every stage through the generic kernels (any bit
+ * depth / alignment) even where a specialised 10-bit kernel exists; both are CUDA, results identical. */
+#define VVC_CUDA_OPT_GENERIC_KERNELS 1
+int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
  * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);

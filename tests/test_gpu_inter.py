@@ -45,6 +45,19 @@ def test_inter_stage_bit_exact(ctx, w, h, seed, uniform, bd):
     assert np.array_equal(go[dm], oo[dm]), "DMVR outputs (refined vectors, min SAD, BDOF decision) differ"
 
 
+def test_inter_generic_kernel_matches(ctx):
+    """The generic CTA-per-record kernel (any bit depth / alignment) and the 10-bit warp-per-record kernel agree."""
+    gd, gr, refs, pbs, wp, prof = make_case(416, 240, 11, mix=STRESS_MIX)
+    fast, fo = cuda_inter(ctx, gd, gr, refs, pbs, wp, prof)
+    ctx.set_option(abi.OPT_GENERIC_KERNELS, 1)
+    try:
+        gen, go = cuda_inter(ctx, gd, gr, refs, pbs, wp, prof)
+    finally:
+        ctx.set_option(abi.OPT_GENERIC_KERNELS, 0)
+    util.assert_planes_equal(gd, fast, gen, "warp kernel vs generic kernel")
+    assert np.array_equal(fo, go)
+
+
 def test_inter_ring_and_host_entry(ctx):
     """Two destination pictures predicted from a 3-picture DPB ring; the *_host entry gives the same result."""
     gd, gr, refs, pbs, wp, prof = make_case(256, 128, 21, mix=STRESS_MIX, batch=2)

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Per-source-line executed-instruction and stall-sample totals of one kernel in an .ncu-rep.
+Joins `ncu --page source --print-source sass` (per SASS address) with `nvdisasm --print-line-info`
+of the object the kernel was built from.  Usage: ncu_lines.py rep.ncu-rep build/x.o [top]"""
+import collections
+import csv
+import glob
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+
+def main(rep, obj, top=40):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    h = rows[hdr]
+    ia, ii, isamp, ino = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples"), h.index("stall_no_inst")
+    ilong, ishort, iwait = h.index("stall_long_sb"), h.index("stall_short_sb"), h.index("stall_wait")
+    per_addr = []
+    for r in rows[hdr + 1:]:
+        if len(r) <= ino or not r[ia]:
+            continue
+        per_addr.append((int(r[ii] or 0), int(r[isamp] or 0), int(r[ino] or 0), int(r[ilong] or 0), int(r[ishort] or 0), int(r[iwait] or 0), r[1]))
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=td, check=True, capture_output=True)
+        cubin = glob.glob(os.path.join(td, "*.cubin"))[0]
+        dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True, check=True).stdout
+    line_of, cur = [], 0
+    for ln in dis.splitlines():
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+\S", ln) and ".byte" not in ln and ".dword" not in ln and ".short" not in ln:
+            line_of.append(cur)
+    n = min(len(line_of), len(per_addr))
+    agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0, 0, 0])
+    for k in range(n):
+        a = agg[line_of[k]]
+        for j in range(6):
+            a[j] += per_addr[k][j]
+        a[6] += 1
+    tot = [sum(v[j] for v in agg.values()) for j in range(7)]
+    print("sass instrs %d (disasm %d), executed %d, samples %d (no_inst %d, long_sb %d, short_sb %d, wait %d)" % (
+        len(per_addr), len(line_of), tot[0], tot[1], tot[2], tot[3], tot[4], tot[5]))
+    print("%-28s %6s %12s %6s %8s %8s %8s %8s" % ("line", "sass", "executed", "%", "samples", "no_inst", "long_sb", "short_sb"))
+    for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(top)]:
+        print("%-28s %6d %12d %6.2f %8d %8d %8d %8d" % ("%s:%d" % key if key else "?", v[6], v[0], 100.0 * v[0] / max(tot[0], 1), v[1], v[2], v[3], v[4]))
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:])
