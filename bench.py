@@ -317,7 +317,9 @@ def main():
             cur=sub_frame(cur, k0), out=sub_frame(out, k0), pbs=up(pbs), n_pbs=len(pbs), tbs=up(tbs), n_tbs=len(tbs),
             coeffs=up(coeffs), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
             alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
-    launches_per_step = len(groups) * len(STAGES)
+    # kernels per picture group: inter = 6 (classify, four thread-per-patch class kernels, warp-per-record kernel),
+    # every other stage 1
+    launches_per_step = len(groups) * (len(STAGES) + 5)
 
     def step(events=None):
         for gi, g in enumerate(groups):

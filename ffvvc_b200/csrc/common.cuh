@@ -20,7 +20,7 @@ struct VVCCudaCtx {
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;
     void         *h_stage;  size_t h_stage_size;    // pinned
-    void         *d_scratch[2]; size_t d_scratch_size[2];   // intermediate pictures of chained stages
+    void         *d_scratch[3]; size_t d_scratch_size[3];   // [0],[1] intermediate pictures of chained stages, [2] inter task lists
     cudaStream_t  copy_in, copy_out;                 // lazily created, *_host pipelines
     cudaEvent_t   ev[8];
 };

@@ -107,7 +107,7 @@ void vvc_cuda_ctx_destroy(VVCCudaCtx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    for (int i = 0; i < 2; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+    for (int i = 0; i < 3; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -607,8 +607,12 @@ extern "C" int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, co
     }
     p.w = dst->width; p.h = dst->height; p.bd = dst->bit_depth;
     p.pbs = pbs; p.n = n_pbs; p.wp = wp; p.prof = prof; p.dmvr_out = dmvr_out;
-    if (p.bd == 10 && frame_vec_ok(dst) && frame_vec_ok(refs) && !ctx->force_generic)
-        return vvc_inter_launch_warp(ctx, p);
+    if (p.bd == 10 && frame_vec_ok(dst) && frame_vec_ok(refs) && !ctx->force_generic) {
+        InterLists lists;
+        if (vvc_inter_launch_patch(ctx, p, &lists))
+            return ctx->err;
+        return vvc_inter_launch_warp(ctx, p, lists);
+    }
     const int grid = n_pbs < 148 * 12 ? n_pbs : 148 * 12;
     inter_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);

@@ -1,0 +1,289 @@
+// Inter prediction for 10-bit pictures, thread-per-patch kernel (sm_100a): every record that needs no
+// cooperative tile -- plain uni / bi prediction, BCW and explicit weights, GPM -- which is most of a picture.
+//
+// Reference semantics: pred_regular_luma / pred_regular_chroma (libavcodec/vvc/vvc_inter.c:545-639),
+// pred_gpm_blk :466-521, the edge emulation :33-58, and the table entries put / put_uni / put_uni_w
+// (libavcodec/h26x/h2656_inter_template.c:29-577), avg, w_avg, put_gpm (libavcodec/vvc/vvc_inter_template.c
+// :25-98).
+//
+// B200 design: 8 lanes per record, one lane per patch of 4 columns x 8 rows.  A lane runs the whole separable
+// filter in registers: per window row six 32-bit loads (12 samples, L1/L2 resident: neighbouring patches
+// share them), the horizontal 8-tap sums as IDP.2A on sample pairs, and a streaming vertical pass that keeps
+// only the last 7 row-pairs per column.  No shared memory, no synchronisation, no per-record scalar work
+// replicated over a warp -- about 25 thread-instructions per predicted sample.
+#include "inter_common.cuh"
+#include "tables.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+
+// 8 samples x .. x + 7 of a row with the column clamped to the picture (the rare path: one out-of-line copy)
+__device__ __noinline__ uint4 load8_clamped(const pel *row, int x, int W)
+{
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        v[k] = __ldg(row + d_clip3(x + k, 0, W - 1));
+    return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+
+// One list of one patch, 4 columns x 8 rows: the 14-bit intermediate prediction put() produces, times the
+// list's weight, added to acc[4 * row + col].  (x, y) = integer position of the patch's first sample in the
+// reference plane; rows >= nrows are not computed.  gw != NULL: per-sample GPM weights (first sample's
+// address, steps gsx / gsy).
+template <int TAPS>
+__device__ __forceinline__ void mc_patch(const pel *plane, int pitch, int W, int H, int x, int y, int nrows,
+                                         uint32_t hf0, uint32_t hf1, uint32_t vf0, uint32_t vf1, int shh, int shv,
+                                         int acc[32], int wl, const uint8_t *gw, int gsx, int gsy, int cmax, bool second)
+{
+    constexpr int B = TAPS / 2 - 1, NW = TAPS == 8 ? 6 : 4, NR = 8 + TAPS - 1;
+    const int e = (x - B) & 1, bx = x - B - e, sh = e << 4, y0 = y - B;
+    const bool inside = bx >= 0 && bx + 2 * NW <= W && y0 >= 0 && y0 + nrows + TAPS - 1 <= H;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (long long)y0 * pitch + bx);
+    const int wpitch = pitch >> 1;
+    uint32_t P[NR - 1][4];
+    int prev[4] = { 0, 0, 0, 0 };
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        if (r < nrows + TAPS - 1) {
+            uint32_t wd[NW];
+            if (inside) {
+#pragma unroll
+                for (int k = 0; k < NW; k++)
+                    wd[k] = __ldg(src + r * wpitch + k);
+            } else {                                   // emulated_edge_mc: coordinates clamped to the picture
+                const pel *row = plane + (long long)d_clip3(y0 + r, 0, H - 1) * pitch;
+                const uint4 q0 = load8_clamped(row, bx, W);
+                wd[0] = q0.x; wd[1] = q0.y; wd[2] = q0.z; wd[3] = q0.w;
+                if (NW > 4) {
+                    const uint4 q1 = load8_clamped(row, bx + 8, W);
+                    wd[NW - 2] = q1.x; wd[NW - 1] = q1.y;
+                }
+            }
+            uint32_t A[2 * NW - 2];
+#pragma unroll
+            for (int i = 0; i < NW - 1; i++) {
+                A[2 * i] = __funnelshift_rc(wd[i], wd[i + 1], sh);
+                A[2 * i + 1] = __funnelshift_rc(wd[i], wd[i + 1], sh + 16);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int v;
+                if (TAPS == 8)
+                    v = __dp2a_lo((int)A[c], (int)hf0, __dp2a_hi((int)A[c + 2], (int)hf0,
+                        __dp2a_lo((int)A[c + 4], (int)hf1, __dp2a_hi((int)A[c + 6], (int)hf1, 0))));
+                else
+                    v = __dp2a_lo((int)A[c], (int)hf0, __dp2a_hi((int)A[c + 2], (int)hf0, 0));
+                v >>= shh;
+                if (r > 0)
+                    P[r - 1][c] = __byte_perm(prev[c], v, 0x5410);      // (row r - 1, row r) of column c
+                prev[c] = v;
+            }
+            if (r >= TAPS - 1) {
+                const int yo = r - (TAPS - 1);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int o;
+                    if (TAPS == 8)
+                        o = __dp2a_lo((int)P[yo][c], (int)vf0, __dp2a_hi((int)P[yo + 2][c], (int)vf0,
+                            __dp2a_lo((int)P[yo + 4][c], (int)vf1, __dp2a_hi((int)P[yo + 6][c], (int)vf1, 0)))) >> shv;
+                    else
+                        o = __dp2a_lo((int)P[yo][c], (int)vf0, __dp2a_hi((int)P[yo + 2][c], (int)vf0, 0)) >> shv;
+                    int wgt = wl;
+                    if (gw) {                              // put_gpm: weight of this sample, 8 - weight for the second list
+                        const int g = gw[yo * gsy + min(c, cmax) * gsx];
+                        wgt = second ? 8 - g : g;
+                    }
+                    acc[4 * yo + c] += (short)o * wgt;     // put() stores int16_t
+                }
+            }
+        }
+    }
+}
+
+struct Blend { int w0, w1, off, sh, ox; };
+
+// Final rounding of every record kind as ONE formula, clip(((a * w0 + b * w1 + off) >> sh) + ox):
+//   put_uni            w0 = 1,  off = 8, sh = 4                                  (h2656_inter_template.c:44-58)
+//   put_uni_w          w0 = wx, off = 1 << (sh - 1), sh = denom + 4, ox          (:60-78)
+//   avg                w0 = w1 = 1, off = 16, sh = 5                             (vvc_inter_template.c:25-40)
+//   w_avg (BCW / WP)   w0, w1, off = ((o0 + o1) * 4 + 1) << (sh - 1), sh = denom + 5   (:42-57)
+//   put_gpm            w0 = g, w1 = 8 - g per sample, off = 64, sh = 7           (:78-98)
+__device__ __forceinline__ Blend blend_of(const Rec &pb, const VVCCudaWP *wp, bool bi, int lx, int c)
+{
+    Blend k;
+    if (pb.flags & VVC_CUDA_PB_GPM) {
+        k.w0 = 0; k.w1 = 0; k.off = 64; k.sh = 7; k.ox = 0;
+    } else if (!bi) {
+        const UniW u = uni_weights(pb, wp, lx, c);
+        k.w0 = u.on ? u.wx : 1; k.w1 = 0; k.sh = u.on ? u.shift : 4; k.off = 1 << (k.sh - 1); k.ox = u.ox;
+    } else {
+        const Weights v = bi_weights(pb, wp, c);
+        k.w0 = v.on ? v.w0 : 1; k.w1 = v.on ? v.w1 : 1; k.sh = (v.on ? v.denom : 0) + 5;
+        k.off = v.on ? (((v.o0 + v.o1) << 2) + 1) << (k.sh - 1) : 16; k.ox = 0;
+    }
+    return k;
+}
+
+__device__ __forceinline__ uint2 finish4(const int *acc, const Blend &k)
+{
+    int o[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        o[c] = d_clip_pel(((acc[c] + k.off) >> k.sh) + k.ox, 10);
+    return make_uint2(pack16(o[0], o[1]), pack16(o[2], o[3]));
+}
+
+// ---- work lists -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, const InterLists ls)
+{
+    const int ri = blockIdx.x * 256 + threadIdx.x;
+    if (ri >= p.n)
+        return;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p.pbs + ri);
+    const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+    const int w = r1 & 0xff, h = (r1 >> 8) & 0xff, planes = (r1 >> 16) & 0xff, pred = r1 >> 24, flags = r2 >> 24;
+    if (flags & VVC_PB_COOPERATIVE) {
+        ls.coop[atomicAdd(ls.count + 4, 1u)] = ri;
+        return;
+    }
+    const int bi = (flags & VVC_CUDA_PB_GPM) || pred == 3;
+    if (planes & VVC_CUDA_PB_LUMA) {
+        const int n = (w >> 2) * ((h + 7) >> 3);
+        const int base = (int)atomicAdd(ls.count + bi, (unsigned)n);
+        for (int k = 0; k < n; k++)
+            ls.luma[bi ? ls.cap_luma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+    }
+    if ((planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) {
+        const int n = w > 8 ? 4 : 2;                             // 2 planes x patch columns of the (w / 2)-wide block
+        const int base = (int)atomicAdd(ls.count + 2 + bi, (unsigned)n);
+        for (int k = 0; k < n; k++)
+            ls.chroma[bi ? ls.cap_chroma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+    }
+}
+
+#define MV0(l, c) ((l) ? pb.mv[1][c] : pb.mv[0][c])
+#define REF(l)    ((l) ? pb.ref[1] : pb.ref[0])
+
+// ---- luma: patch pi of (w / 4) x ceil(h / 8) ---------------------------------------------------------------
+template <bool BI>
+__device__ __forceinline__ void luma_task(const InterK &p, const Rec &pb, int pi)
+{
+    const int w = pb.w, h = pb.h, lw = 31 - __clz(w);
+    const bool gpm = BI && (pb.flags & VVC_CUDA_PB_GPM);
+    const int lx = pb.pred - 1;
+    const uint2 *lumaf = reinterpret_cast<const uint2 *>(&vvct_luma_mc_filters[0][0][0]);
+    const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;
+    const int ox = (pi & ((w >> 2) - 1)) << 2, oy = (pi >> (lw - 2)) << 3, nrows = min(8, h - oy);
+    const Blend k = blend_of(pb, p.wp, BI, lx, 0);
+    int acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+        acc[i] = 0;
+#pragma unroll 1
+    for (int it = 0; it < (BI ? 2 : 1); it++) {
+        const int l = BI ? it : lx;
+        const int mvx = MV0(l, 0), mvy = MV0(l, 1), mx = mvx & 15, my = mvy & 15, filt = gpm ? 0 : pb.filt;
+        const uint2 fh = lumaf[filt * 16 + mx], fv = lumaf[filt * 16 + my];
+        mc_patch<8>(p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, pb.x0 + ox + (mvx >> 4), pb.y0 + oy + (mvy >> 4), nrows,
+                    mx ? fh.x : 0x01000000u, mx ? fh.y : 0u, my ? fv.x : (mx ? 0x01000000u : 0x10000000u), my ? fv.y : 0u,
+                    mx ? 2 : 0, my ? (mx ? 6 : 2) : 0, acc, (BI && l) ? k.w1 : k.w0,
+                    gpm ? wt + oy * pb.gsy + ox * pb.gsx : nullptr, pb.gsx, pb.gsy, 3, BI && l == 1);
+    }
+    pel *d = p.dst[0] + pb.pic * p.db[0] + (long long)(pb.y0 + oy) * p.dp[0] + pb.x0 + ox;
+#pragma unroll
+    for (int y = 0; y < 8; y++)
+        if (y < nrows)
+            *reinterpret_cast<uint2 *>(d + (long long)y * p.dp[0]) = finish4(&acc[4 * y], k);
+}
+
+// ---- chroma (4:2:0): task pi = (plane, patch column) ----------------------------------------------------------
+template <bool BI>
+__device__ __forceinline__ void chroma_task(const InterK &p, const Rec &pb, int pi)
+{
+    const bool gpm = BI && (pb.flags & VVC_CUDA_PB_GPM);
+    const int lx = pb.pred - 1;
+    const uint32_t *chromaf = reinterpret_cast<const uint32_t *>(&vvct_chroma_mc_filters[0][0][0]);
+    const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;
+    const int bw = pb.w >> 1, bh = pb.h >> 1, ncx = bw > 4 ? 2 : 1;
+    const int pc = pi >> (ncx >> 1), ox = (pi & (ncx - 1)) << 2;
+    const int x0 = pb.x0 >> 1, y0 = pb.y0 >> 1;
+    const pel *rplane = pc ? p.ref[2] : p.ref[1];
+    const long long rb = pc ? p.rb[2] : p.rb[1];
+    const int rp = pc ? p.rp[2] : p.rp[1];
+    const Blend k = blend_of(pb, p.wp, BI, lx, pc + 1);
+    int acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+        acc[i] = 0;
+#pragma unroll 1
+    for (int it = 0; it < (BI ? 2 : 1); it++) {
+        const int l = BI ? it : lx;
+        const int mvx = MV0(l, 0), mvy = MV0(l, 1), mx = mvx & 31, my = mvy & 31;
+        // GPM weights of chroma: every second luma weight; columns past a 2-wide block reuse its last weight
+        mc_patch<4>(rplane + REF(l) * rb, rp, p.w >> 1, p.h >> 1, x0 + ox + (mvx >> 5), y0 + (mvy >> 5), bh,
+                    mx ? chromaf[mx] : 0x00000100u, 0u, my ? chromaf[my] : (mx ? 0x00000100u : 0x00001000u), 0u,
+                    mx ? 2 : 0, my ? (mx ? 6 : 2) : 0, acc, (BI && l) ? k.w1 : k.w0,
+                    gpm ? wt + ox * 2 * pb.gsx : nullptr, 2 * pb.gsx, 2 * pb.gsy, bw - 1 - ox > 3 ? 3 : bw - 1 - ox, BI && l == 1);
+    }
+    const int dpitch = pc ? p.dp[2] : p.dp[1];
+    pel *d = (pc ? p.dst[2] + pb.pic * p.db[2] : p.dst[1] + pb.pic * p.db[1]) + (long long)y0 * dpitch + x0 + ox;
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        if (y < bh) {
+            const uint2 o = finish4(&acc[4 * y], k);
+            uint32_t *q = reinterpret_cast<uint32_t *>(d + (long long)y * dpitch);
+            q[0] = o.x;
+            if (bw > 2)
+                q[1] = o.y;
+        }
+    }
+}
+#undef MV0
+#undef REF
+
+// Persistent kernels, one per task class (own register budget each): a grid-stride loop over the class's
+// list, so every warp of the launch runs the same specialised code.
+template <bool LUMA, bool BI>
+__global__ void __launch_bounds__(kThreads, LUMA ? 3 : 4) inter_patch_kernel(const InterK p, const InterLists ls)
+{
+    const int n = (int)ls.count[(LUMA ? 0 : 2) + (BI ? 1 : 0)];
+    const uint32_t *list = LUMA ? ls.luma : ls.chroma;
+    const int cap = LUMA ? ls.cap_luma : ls.cap_chroma;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+        const uint32_t t = __ldg(list + (BI ? cap - 1 - i : i));
+        const Rec pb = load_rec(p.pbs + (t >> 3));
+        if (LUMA)
+            luma_task<BI>(p, pb, t & 7);
+        else
+            chroma_task<BI>(p, pb, t & 7);
+    }
+}
+
+}  // namespace
+
+int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
+{
+    // scratch: [count: 64 bytes][luma: 8 n][chroma: 4 n][coop: n] words
+    const size_t n = (size_t)p.n;
+    uint32_t *base = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + 13 * n * sizeof(uint32_t));
+    if (!base)
+        return ctx->err;
+    ls->count = base;
+    ls->luma = base + 16;            ls->cap_luma = (int)(8 * n);
+    ls->chroma = ls->luma + 8 * n;   ls->cap_chroma = (int)(4 * n);
+    ls->coop = ls->chroma + 4 * n;
+    VVC_TRY(ctx, cudaMemsetAsync(ls->count, 0, 64, ctx->stream));
+    inter_classify_kernel<<<ceil_div(p.n, 256), 256, 0, ctx->stream>>>(p, *ls);
+    VVC_LAUNCHED(ctx);
+    inter_patch_kernel<true, true><<<148 * 3, kThreads, 0, ctx->stream>>>(p, *ls);
+    VVC_LAUNCHED(ctx);
+    inter_patch_kernel<true, false><<<148 * 3, kThreads, 0, ctx->stream>>>(p, *ls);
+    VVC_LAUNCHED(ctx);
+    inter_patch_kernel<false, true><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
+    VVC_LAUNCHED(ctx);
+    inter_patch_kernel<false, false><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
+    VVC_LAUNCHED(ctx);
+    return VVC_CUDA_OK;
+}

@@ -63,35 +63,6 @@ struct __align__(16) WarpSmem {
     int    vxy[16][2];
 };
 
-struct Rec {
-    int x0, y0, w, h, planes, pred, ref[2], pic, flags;
-    int mv[2][2];
-    int filt, bcw, wp, prof, gsx, gsy, gw;
-};
-
-__device__ __forceinline__ Rec load_rec(const VVCCudaPB *pb)
-{
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(pb);
-    uint32_t r[11];
-#pragma unroll
-    for (int i = 0; i < 11; i++)
-        r[i] = __ldg(q + i);
-    Rec o;
-    o.x0 = r[0] & 0xffff;         o.y0 = r[0] >> 16;
-    o.w = r[1] & 0xff;            o.h = (r[1] >> 8) & 0xff;   o.planes = (r[1] >> 16) & 0xff;  o.pred = r[1] >> 24;
-    o.ref[0] = r[2] & 0xff;       o.ref[1] = (r[2] >> 8) & 0xff; o.pic = (r[2] >> 16) & 0xff;  o.flags = r[2] >> 24;
-    o.mv[0][0] = (int)r[3];       o.mv[0][1] = (int)r[4];     o.mv[1][0] = (int)r[5];          o.mv[1][1] = (int)r[6];
-    o.filt = r[7] & 0xff;         o.bcw = (r[7] >> 8) & 0xff; o.wp = r[7] >> 16;
-    o.prof = r[8] & 0xffff;       o.gsx = (short)(r[8] >> 16);
-    o.gsy = (short)(r[9] & 0xffff);
-    o.gw = (int)r[10];
-    return o;
-}
-
-__device__ __forceinline__ uint32_t frc(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_rc(lo, hi, sh); }
-__device__ __forceinline__ int lo16(uint32_t v) { return (short)(v & 0xffff); }
-__device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
-__device__ __forceinline__ uint32_t pack16(int a, int b) { return (uint32_t)(a & 0xffff) | ((uint32_t)b << 16); }
 // (t * inv_rows(d)) >> 16 == t / d for t < 128; d is a window row count: 23, 15, 11 (luma), 11, 7, 5 (chroma)
 __device__ __forceinline__ uint32_t inv_rows(int d) { return d == 23 ? 2850u : d == 15 ? 4370u : d == 11 ? 5958u : d == 7 ? 9363u : 13108u; }
 
@@ -100,7 +71,7 @@ __device__ __forceinline__ uint32_t inv_rows(int d) { return d == 23 ? 2850u : d
 // the even column bx = wx0 & ~1 at word (row + padr) * pw + padw.  Lane = (word of the row, row group): 16
 // words x 2 rows or 8 words x 4 rows per step, no index division.  One out-of-line copy serves every caller
 // (the kernel's code size matters: warps sit in different record kinds and share the instruction cache).
-__device__ __noinline__ void stage_core(uint32_t *win, int pw, int padw, int padr, const pel *plane, int pitch, int W, int H,
+__device__ __noinline__ void stage_core(uint32_t *win, int pw, int padw, int padr, const pel *plane, int pitch, int W, int H,   //@region stage_core
                                         int wx0, int wy0, int cols, int rows, int lane)
 {
     const int e = wx0 & 1, bx = wx0 - e, nw = (cols + e + 1) >> 1;
@@ -129,7 +100,7 @@ __device__ __noinline__ void stage_core(uint32_t *win, int pw, int padw, int pad
 
 // Replicated apron of a DMVR window (core at rows 2.., sample column 2 + e..): 2 samples each side, 2 rows
 // above and below.  Equals clamping the coordinates to the unrefined block's window (emulated_edge_dmvr).
-__device__ __noinline__ void pad_window(uint32_t *win, int pw, int e, int cols0, int rows0, int lane)
+__device__ __noinline__ void pad_window(uint32_t *win, int pw, int e, int cols0, int rows0, int lane)   //@region pad_window
 {
     if (lane < rows0) {                                    // lane = core row
         uint16_t *row = reinterpret_cast<uint16_t *>(win) + (lane + 2) * (2 * pw);
@@ -152,7 +123,7 @@ __device__ __noinline__ void pad_window(uint32_t *win, int pw, int e, int cols0,
 // First pass (put_*_h and the tmp_array loop of put_*_hv, h2656_inter_template.c:97-150, 342-395): a task is
 // (unit, 8-column half, window row).  Output stored transposed: hbt[unit][col][row].
 template <int TAPS>
-__device__ __forceinline__ void pass_h(WarpSmem &s, int lane, int n_units, int rows, int lhh)
+__device__ __forceinline__ void pass_h(WarpSmem &s, int lane, int n_units, int rows, int lhh)   //@region pass_h
 {
     constexpr int NW = TAPS == 8 ? 8 : 6, PW = TAPS == 8 ? PWL : PWC, HP = TAPS == 8 ? HPL : HPC, HU = TAPS == 8 ? HUL : HUC;
     const int ntask = (n_units << lhh) * rows;
@@ -188,7 +159,7 @@ __device__ __forceinline__ void pass_h(WarpSmem &s, int lane, int n_units, int r
 
 // Second pass: a task is (unit, 8-row half, column); writes the int16 tile the reference's put() produces.
 template <int TAPS>
-__device__ __forceinline__ void pass_v(WarpSmem &s, int lane, int n_units, int lbw, int bh)
+__device__ __forceinline__ void pass_v(WarpSmem &s, int lane, int n_units, int lbw, int bh)   //@region pass_v
 {
     constexpr int HP = TAPS == 8 ? HPL : HPC, HU = TAPS == 8 ? HUL : HUC;
     const int lvh = bh > 8 ? 1 : 0;
@@ -222,51 +193,6 @@ __device__ __forceinline__ void pass_v(WarpSmem &s, int lane, int n_units, int l
     }
 }
 
-// ---- final roundings (avg / w_avg / put_uni / put_uni_w, vvc_inter_template.c:25-57, h2656_inter_template.c) ----
-struct Weights { int on, denom, w0, w1, o0, o1; };
-
-__device__ __forceinline__ Weights bi_weights(const Rec &pb, const VVCCudaWP *wp, int c)
-{
-    Weights w = { 0, 0, 0, 0, 0, 0 };
-    if (pb.bcw) {
-        const int w1 = pb.bcw == 1 ? 5 : pb.bcw == 2 ? 3 : pb.bcw == 3 ? 10 : -2;      // {4,5,3,10,-2}[bcw_idx]
-        w.on = 1; w.denom = 2; w.w1 = w1; w.w0 = 8 - w1;
-    } else if ((pb.flags & VVC_CUDA_PB_WEIGHTED) && !(pb.flags & VVC_CUDA_PB_DMVR)) {
-        const VVCCudaWP *e = wp + pb.wp;
-        w.on = 1; w.denom = e->log2_denom[c > 0];
-        w.w0 = e->weight[0][c]; w.w1 = e->weight[1][c]; w.o0 = e->offset[0][c]; w.o1 = e->offset[1][c];
-    }
-    return w;
-}
-
-__device__ __forceinline__ int combine_bi(int a, int b, const Weights &w)
-{
-    if (!w.on)
-        return d_clip_pel((a + b + 16) >> 5, 10);
-    const int shift = w.denom + 5;
-    const int offset = (((w.o0 + w.o1) << 2) + 1) << (shift - 1);
-    return d_clip_pel((a * w.w0 + b * w.w1 + offset) >> shift, 10);
-}
-
-struct UniW { int on, shift, wx, ox; };
-
-__device__ __forceinline__ UniW uni_weights(const Rec &pb, const VVCCudaWP *wp, int lx, int c)
-{
-    UniW w = { 0, 0, 0, 0 };
-    if (pb.flags & VVC_CUDA_PB_WEIGHTED) {
-        const VVCCudaWP *e = wp + pb.wp;
-        w.on = 1; w.shift = e->log2_denom[c > 0] + 4; w.wx = e->weight[lx][c]; w.ox = e->offset[lx][c] * 4;
-    }
-    return w;
-}
-
-__device__ __forceinline__ int finish_uni(int val, const UniW &w)
-{
-    if (w.on)
-        return d_clip_pel(((val * w.wx + (1 << (w.shift - 1))) >> w.shift) + w.ox, 10);
-    return d_clip_pel((val + 8) >> 4, 10);
-}
-
 __device__ __forceinline__ int vsign(int v) { return v < 0 ? -1 : (v != 0); }
 
 __device__ int parametric(const int *sd, int stride)      // parametric_mv_refine, vvc_inter.c:642-681
@@ -294,7 +220,7 @@ __device__ __forceinline__ void tile4(const WarpSmem &s, int ui, int x, int y, i
 }
 
 // ring of integer samples around a tile: bdof_fetch_samples / fetch_samples (vvc_inter_template.c:101-133)
-__device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, int mx, int my, int lane)
+__device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, int mx, int my, int lane)   //@region fetch_ring
 {
     const UnitMC m = s.um[ui];
     const uint16_t *w16 = reinterpret_cast<const uint16_t *>(s.a.win + m.woff);
@@ -310,7 +236,7 @@ __device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, 
     }
 }
 
-__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
+__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, const uint32_t *__restrict__ count)   //@region rec_load
 {
     __shared__ WarpSmem sm[kWarps];
     const int lane = threadIdx.x & 31;
@@ -319,8 +245,10 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
     const uint2 *lumaf = reinterpret_cast<const uint2 *>(&vvct_luma_mc_filters[0][0][0]);
     const uint32_t *chromaf = reinterpret_cast<const uint32_t *>(&vvct_chroma_mc_filters[0][0][0]);
 
-    for (int ri = blockIdx.x * kWarps + (threadIdx.x >> 5); ri < p.n; ri += nwarps) {
+    const int n_coop = (int)count[4];
+    for (int ci = blockIdx.x * kWarps + (threadIdx.x >> 5); ci < n_coop; ci += nwarps) {
         __syncwarp();
+        const int ri = (int)__ldg(coop + ci);
         const Rec pb = load_rec(p.pbs + ri);
         const int w = pb.w, h = pb.h, lw = 31 - __clz(w);
         const bool gpm = pb.flags & VVC_CUDA_PB_GPM;
@@ -335,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
 #define REF(l)    ((l) ? pb.ref[1] : pb.ref[0])
 
         // ---- DMVR: stage both unrefined windows, bilinear prediction, 25 SADs, refinement -------------
-        if (dmvr_luma) {
+        if (dmvr_luma) {   //@region dmvr_stage
 #pragma unroll 1
             for (int l = 0; l < 2; l++)
                 stage_core(s.a.win + l * WUL, PWL, 1, 2, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h,
@@ -346,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                 pad_window(s.a.win + l * WUL, PWL, (pb.x0 + (MV0(l, 0) >> 4) - 3) & 1, w + 7, h + 7, lane);
             __syncwarp();
             // bilinear (dmvr / dmvr_h / dmvr_v / dmvr_hv, vvc_inter_template.c:324-409) on sample pairs; lane = row
-            const int nwo = (w + 4) >> 1;
+            const int nwo = (w + 4) >> 1;   //@region dmvr_bilinear
 #pragma unroll 1
             for (int l = 0; l < 2; l++) {
                 const int mx = MV0(l, 0) & 15, my = MV0(l, 1) & 15;
@@ -378,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
             __syncwarp();
             // SAD on every other row (vvc_sad, vvcdsp.c:49-65): task = (dy, row), the 5 dx share the loaded rows
             {
-                const int lhr = 31 - __clz(h >> 1), ntask = 5 << lhr, nwr = w >> 1;
+                const int lhr = 31 - __clz(h >> 1), ntask = 5 << lhr, nwr = w >> 1;   //@region dmvr_sad
                 for (int base = 0; base < ntask; base += 32) {
                     const int t = base + lane;
                     const bool act = t < ntask;
@@ -422,7 +350,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
             __syncwarp();
             // decision (dmvr_mv_refine, vvc_inter.c:700-747), computed redundantly by every lane
             {
-                const int mine = s.sad[lane < 25 ? lane : 0];
+                const int mine = s.sad[lane < 25 ? lane : 0];   //@region dmvr_decision
                 const int centre = __shfl_sync(0xffffffffu, mine, 12);
                 int min_sad = centre - (centre >> 2);
                 if (min_sad >= w * h) {
@@ -460,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
             }
             __syncwarp();
         }
-        const bool do_bdof = bdof && !gpm;
+        const bool do_bdof = bdof && !gpm;   //@region luma_setup
         pel *dstp[3];
 #pragma unroll
         for (int c = 0; c < 3; c++)
@@ -501,11 +429,11 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                 }
             }
             __syncwarp();
-            pass_h<8>(s, lane, n_units, h + 7, w > 8 ? 1 : 0);
+            pass_h<8>(s, lane, n_units, h + 7, w > 8 ? 1 : 0);   //@region luma_passes
             __syncwarp();
             pass_v<8>(s, lane, n_units, lw, h);
             __syncwarp();
-            pel *d = dstp[0] + (long long)pb.y0 * p.dp[0] + pb.x0;
+            pel *d = dstp[0] + (long long)pb.y0 * p.dp[0] + pb.x0;   //@region luma_final_uni
             const int ntask = h << (lw - 2);
             if (!bi) {
                 const UniW uw = uni_weights(pb, p.wp, lx, 0);
@@ -533,7 +461,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                     }
                 }
             } else {
-                const int prof_mask = gpm ? 0 : pb.flags & (VVC_CUDA_PB_PROF0 | VVC_CUDA_PB_PROF1);
+                const int prof_mask = gpm ? 0 : pb.flags & (VVC_CUDA_PB_PROF0 | VVC_CUDA_PB_PROF1);   //@region bi_ring_prof
                 if (do_bdof || prof_mask) {
                     fetch_ring(s, 0, w, h, mvr[0][0] & 15, mvr[0][1] & 15, lane);
                     fetch_ring(s, 1, w, h, mvr[1][0] & 15, mvr[1][1] & 15, lane);
@@ -556,7 +484,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                     __syncwarp();
                 }
                 if (gpm) {                                  // put_gpm, vvc_inter_template.c:78-98
-                    const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;
+                    const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;   //@region gpm
                     for (int t = lane; t < ntask; t += 32) {
                         const int x = (t & ((w >> 2) - 1)) << 2, y = t >> (lw - 2);
                         int a[4], b[4], o[4];
@@ -572,7 +500,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                 } else if (do_bdof) {                       // apply_bdof, vvc_inter_template.c:237-317
                     // gradients (prof_grad_filter :135-158) of both tiles; lane = (list, row), samples in pairs.
                     // The padded borders the reference creates with pad_int16 equal clamped coordinates below.
-                    uint32_t gh[8], gv[8];
+                    uint32_t gh[8], gv[8];   //@region bdof_grad
                     {
                         const int l = lane >= h, y = lane - l * h;
                         const bool act = lane < 2 * h;
@@ -606,7 +534,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                     }
                     __syncwarp();
                     // derive_bdof_vx_vy :237-265: 6x6 window sums per 4x4 block, separable.  Column pass:
-                    const int lbx = lw - 2;
+                    const int lbx = lw - 2;   //@region bdof_sums
                     for (int t = lane; t < (h << lbx); t += 32) {
                         const int bxi = t & ((1 << lbx) - 1), y = t >> lbx;
                         int sgx2 = 0, sgy2 = 0, sgxgy = 0, sgxdi = 0, sgydi = 0;
@@ -641,7 +569,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                         s.vxy[lane][0] = vx; s.vxy[lane][1] = vy;
                     }
                     __syncwarp();
-                    for (int t = lane; t < ntask; t += 32) {   // apply_bdof_min_block :267-286
+                    for (int t = lane; t < ntask; t += 32) {   // apply_bdof_min_block :267-286   //@region bdof_apply
                         const int x4 = t & ((w >> 2) - 1), x = x4 << 2, y = t >> (lw - 2);
                         const int vx = s.vxy[((y >> 2) << lbx) + x4][0], vy = s.vxy[((y >> 2) << lbx) + x4][1];
                         int a[4], b[4], o[4];
@@ -659,7 +587,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                         *reinterpret_cast<uint2 *>(d + (long long)y * p.dp[0] + x) = make_uint2(pack16(o[0], o[1]), pack16(o[2], o[3]));
                     }
                 } else {
-                    const Weights wt = bi_weights(pb, p.wp, 0);
+                    const Weights wt = bi_weights(pb, p.wp, 0);   //@region bi_avg
                     for (int t = lane; t < ntask; t += 32) {
                         const int x = (t & ((w >> 2) - 1)) << 2, y = t >> (lw - 2);
                         int a[4], b[4];
@@ -677,7 +605,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
         // ---- chroma (both planes, 4:2:0) -----------------------------------------------------------------
         if ((pb.planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) {
             __syncwarp();
-            const int bw = w >> 1, bh = h >> 1, lbw = lw - 1;
+            const int bw = w >> 1, bh = h >> 1, lbw = lw - 1;   //@region chroma_setup_stage
             const int x0 = pb.x0 >> 1, y0 = pb.y0 >> 1, pw = p.w >> 1, ph = p.h >> 1;
             const int n_units = bi ? 4 : 2;
             {   // unit u: bi -> (plane u >> 1, list u & 1); uni -> (plane u, the single list)
@@ -724,12 +652,12 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
                     }
                 __syncwarp();
             }
-            pass_h<4>(s, lane, n_units, bh + 3, 0);
+            pass_h<4>(s, lane, n_units, bh + 3, 0);   //@region chroma_passes
             __syncwarp();
             pass_v<4>(s, lane, n_units, lbw, bh);
             __syncwarp();
             // lane task = (plane, row, sample pair)
-            const int lpw = lbw - 1, ntask = (2 * bh) << lpw;
+            const int lpw = lbw - 1, ntask = (2 * bh) << lpw;   //@region chroma_final
             const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;
             for (int t = lane; t < ntask; t += 32) {
                 const int x = (t & ((1 << lpw) - 1)) << 1, q = t >> lpw;
@@ -763,11 +691,11 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p)
 
 }  // namespace
 
-int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p)
+int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists)
 {
     const int ctas = ceil_div(p.n, kWarps);
-    const int grid = ctas < 148 * 16 ? ctas : 148 * 16;
-    inter_warp_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
+    const int grid = ctas < 148 * 7 ? ctas : 148 * 7;            // persistent: 7 CTAs fit an SM (shared memory)
+    inter_warp_kernel<<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, lists.count);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

@@ -24,26 +24,33 @@ def main(rep, obj, top=40):
     for r in rows[hdr + 1:]:
         if len(r) <= ino or not r[ia]:
             continue
-        per_addr.append((int(r[ii] or 0), int(r[isamp] or 0), int(r[ino] or 0), int(r[ilong] or 0), int(r[ishort] or 0), int(r[iwait] or 0), r[1]))
+        per_addr.append((int(r[ii] or 0), int(r[isamp] or 0), int(r[ino] or 0), int(r[ilong] or 0), int(r[ishort] or 0), int(r[iwait] or 0), r[1], int(r[ia], 16)))
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=td, check=True, capture_output=True)
         cubin = glob.glob(os.path.join(td, "*.cubin"))[0]
         dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True, check=True).stdout
-    line_of, cur = [], 0
+    line_at, cur, in_text = {}, None, False
     for ln in dis.splitlines():
+        if ln.lstrip().startswith(".section"):
+            in_text = ".text." in ln
+            continue
+        if not in_text:
+            continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+\S", ln) and ".byte" not in ln and ".dword" not in ln and ".short" not in ln:
-            line_of.append(cur)
-    n = min(len(line_of), len(per_addr))
+        m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+\S", ln)
+        if m and ".byte" not in ln and ".dword" not in ln and ".short" not in ln:
+            line_at[int(m.group(1), 16)] = cur
     agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0, 0, 0])
-    for k in range(n):
-        a = agg[line_of[k]]
+    base = per_addr[0][7]
+    for rec in per_addr:
+        a = agg[line_at.get(rec[7] - base)]
         for j in range(6):
-            a[j] += per_addr[k][j]
+            a[j] += rec[j]
         a[6] += 1
+    line_of = line_at
     tot = [sum(v[j] for v in agg.values()) for j in range(7)]
     print("sass instrs %d (disasm %d), executed %d, samples %d (no_inst %d, long_sb %d, short_sb %d, wait %d)" % (
         len(per_addr), len(line_of), tot[0], tot[1], tot[2], tot[3], tot[4], tot[5]))
