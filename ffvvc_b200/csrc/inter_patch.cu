@@ -28,14 +28,19 @@ __device__ __noinline__ uint4 load8_clamped(const pel *row, int x, int W)
     return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
 }
 
-// One list of one patch, 4 columns x 8 rows: the 14-bit intermediate prediction put() produces, times the
-// list's weight, added to acc[4 * row + col].  (x, y) = integer position of the patch's first sample in the
-// reference plane; rows >= nrows are not computed.  gw != NULL: per-sample GPM weights (first sample's
-// address, steps gsx / gsy).
-template <int TAPS>
+struct Blend { int w0, w1, off, sh, ox; };
+
+// One list of one patch, 4 columns x 8 rows: the 14-bit intermediate prediction put() produces.  (x, y) =
+// integer position of the patch's first sample in the reference plane; rows >= nrows are not computed.
+// KEEP: the rows are kept as int16 pairs in keep[] (first list of a bi record).  Otherwise each finished row is
+// blended -- with keep[] when BI -- and stored at d: clip(((a * w0 + b * w1 + off) >> sh) + ox); gw != NULL
+// gives per-sample GPM weights (w0 = g, w1 = 8 - g; first sample's address, steps gsx / gsy, columns clamped
+// to cmax).
+template <int TAPS, bool KEEP, bool BI>
 __device__ __forceinline__ void mc_patch(const pel *plane, int pitch, int W, int H, int x, int y, int nrows,
                                          uint32_t hf0, uint32_t hf1, uint32_t vf0, uint32_t vf1, int shh, int shv,
-                                         int acc[32], int wl, const uint8_t *gw, int gsx, int gsy, int cmax, bool second)
+                                         uint32_t keep[16], const Blend &k, const uint8_t *gw, int gsx, int gsy, int cmax,
+                                         pel *d, int dpitch, bool two_words)
 {
     constexpr int B = TAPS / 2 - 1, NW = TAPS == 8 ? 6 : 4, NR = 8 + TAPS - 1;
     const int e = (x - B) & 1, bx = x - B - e, sh = e << 4, y0 = y - B;
@@ -50,8 +55,8 @@ __device__ __forceinline__ void mc_patch(const pel *plane, int pitch, int W, int
             uint32_t wd[NW];
             if (inside) {
 #pragma unroll
-                for (int k = 0; k < NW; k++)
-                    wd[k] = __ldg(src + r * wpitch + k);
+                for (int i = 0; i < NW; i++)
+                    wd[i] = __ldg(src + r * wpitch + i);
             } else {                                   // emulated_edge_mc: coordinates clamped to the picture
                 const pel *row = plane + (long long)d_clip3(y0 + r, 0, H - 1) * pitch;
                 const uint4 q0 = load8_clamped(row, bx, W);
@@ -82,27 +87,46 @@ __device__ __forceinline__ void mc_patch(const pel *plane, int pitch, int W, int
             }
             if (r >= TAPS - 1) {
                 const int yo = r - (TAPS - 1);
+                int o[4];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    int o;
                     if (TAPS == 8)
-                        o = __dp2a_lo((int)P[yo][c], (int)vf0, __dp2a_hi((int)P[yo + 2][c], (int)vf0,
-                            __dp2a_lo((int)P[yo + 4][c], (int)vf1, __dp2a_hi((int)P[yo + 6][c], (int)vf1, 0)))) >> shv;
+                        o[c] = __dp2a_lo((int)P[yo][c], (int)vf0, __dp2a_hi((int)P[yo + 2][c], (int)vf0,
+                               __dp2a_lo((int)P[yo + 4][c], (int)vf1, __dp2a_hi((int)P[yo + 6][c], (int)vf1, 0)))) >> shv;
                     else
-                        o = __dp2a_lo((int)P[yo][c], (int)vf0, __dp2a_hi((int)P[yo + 2][c], (int)vf0, 0)) >> shv;
-                    int wgt = wl;
-                    if (gw) {                              // put_gpm: weight of this sample, 8 - weight for the second list
-                        const int g = gw[yo * gsy + min(c, cmax) * gsx];
-                        wgt = second ? 8 - g : g;
+                        o[c] = __dp2a_lo((int)P[yo][c], (int)vf0, __dp2a_hi((int)P[yo + 2][c], (int)vf0, 0)) >> shv;
+                }
+                if (KEEP) {
+                    keep[2 * yo] = pack16(o[0], o[1]);
+                    keep[2 * yo + 1] = pack16(o[2], o[3]);
+                } else {
+                    const int a[4] = { lo16(keep[2 * yo]), hi16(keep[2 * yo]), lo16(keep[2 * yo + 1]), hi16(keep[2 * yo + 1]) };
+                    int out[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int cur = (short)o[c];            // put() stores int16_t
+                        int v;
+                        if (BI) {
+                            int w0 = k.w0, w1 = k.w1;
+                            if (gw) {
+                                w0 = gw[yo * gsy + min(c, cmax) * gsx];
+                                w1 = 8 - w0;
+                            }
+                            v = a[c] * w0 + cur * w1;
+                        } else {
+                            v = cur * k.w0;
+                        }
+                        out[c] = d_clip_pel(((v + k.off) >> k.sh) + k.ox, 10);
                     }
-                    acc[4 * yo + c] += (short)o * wgt;     // put() stores int16_t
+                    uint32_t *q = reinterpret_cast<uint32_t *>(d + (long long)yo * dpitch);
+                    q[0] = pack16(out[0], out[1]);
+                    if (two_words)
+                        q[1] = pack16(out[2], out[3]);
                 }
             }
         }
     }
 }
-
-struct Blend { int w0, w1, off, sh, ox; };
 
 // Final rounding of every record kind as ONE formula, clip(((a * w0 + b * w1 + off) >> sh) + ox):
 //   put_uni            w0 = 1,  off = 8, sh = 4                                  (h2656_inter_template.c:44-58)
@@ -126,40 +150,57 @@ __device__ __forceinline__ Blend blend_of(const Rec &pb, const VVCCudaWP *wp, bo
     return k;
 }
 
-__device__ __forceinline__ uint2 finish4(const int *acc, const Blend &k)
-{
-    int o[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-        o[c] = d_clip_pel(((acc[c] + k.off) >> k.sh) + k.ox, 10);
-    return make_uint2(pack16(o[0], o[1]), pack16(o[2], o[3]));
-}
-
 // ---- work lists -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, const InterLists ls)
 {
-    const int ri = blockIdx.x * 256 + threadIdx.x;
-    if (ri >= p.n)
-        return;
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(p.pbs + ri);
-    const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2);
-    const int w = r1 & 0xff, h = (r1 >> 8) & 0xff, planes = (r1 >> 16) & 0xff, pred = r1 >> 24, flags = r2 >> 24;
-    if (flags & VVC_PB_COOPERATIVE) {
-        ls.coop[atomicAdd(ls.count + 4, 1u)] = ri;
-        return;
+    // one reservation per list per CTA: block-wide exclusive scan of the five per-record counts
+    __shared__ uint32_t warp_tot[8][5], cta_base[5];
+    const int ri = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int cls_l = -1, cls_c = -1, n_l = 0, n_c = 0, coop = 0;
+    if (ri < p.n) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p.pbs + ri);
+        const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+        const int w = r1 & 0xff, h = (r1 >> 8) & 0xff, planes = (r1 >> 16) & 0xff, pred = r1 >> 24, flags = r2 >> 24;
+        if (flags & VVC_PB_COOPERATIVE) {
+            coop = 1;
+        } else {
+            const int bi = (flags & VVC_CUDA_PB_GPM) || pred == 3;
+            if (planes & VVC_CUDA_PB_LUMA) { cls_l = bi; n_l = (w >> 2) * ((h + 7) >> 3); }
+            if ((planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) { cls_c = bi; n_c = w > 8 ? 4 : 2; }   // 2 planes x patch columns
+        }
     }
-    const int bi = (flags & VVC_CUDA_PB_GPM) || pred == 3;
-    if (planes & VVC_CUDA_PB_LUMA) {
-        const int n = (w >> 2) * ((h + 7) >> 3);
-        const int base = (int)atomicAdd(ls.count + bi, (unsigned)n);
-        for (int k = 0; k < n; k++)
-            ls.luma[bi ? ls.cap_luma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+    uint32_t mine[5] = { cls_l == 0 ? (uint32_t)n_l : 0u, cls_l == 1 ? (uint32_t)n_l : 0u,
+                         cls_c == 0 ? (uint32_t)n_c : 0u, cls_c == 1 ? (uint32_t)n_c : 0u, (uint32_t)coop };
+    uint32_t excl[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        uint32_t v = mine[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        excl[c] = v - mine[c];
+        if (lane == 31) warp_tot[wid][c] = v;
     }
-    if ((planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) {
-        const int n = w > 8 ? 4 : 2;                             // 2 planes x patch columns of the (w / 2)-wide block
-        const int base = (int)atomicAdd(ls.count + 2 + bi, (unsigned)n);
-        for (int k = 0; k < n; k++)
-            ls.chroma[bi ? ls.cap_chroma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        uint32_t tot = 0;
+        for (int k = 0; k < 8; k++) { const uint32_t t = warp_tot[k][threadIdx.x]; warp_tot[k][threadIdx.x] = tot; tot += t; }
+        cta_base[threadIdx.x] = tot ? atomicAdd(ls.count + threadIdx.x, tot) : 0u;
+    }
+    __syncthreads();
+    if (coop)
+        ls.coop[cta_base[4] + warp_tot[wid][4] + excl[4]] = ri;
+    if (cls_l >= 0) {
+        const int base = (int)(cta_base[cls_l] + warp_tot[wid][cls_l] + excl[cls_l]);
+        for (int k = 0; k < n_l; k++)
+            ls.luma[cls_l ? ls.cap_luma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+    }
+    if (cls_c >= 0) {
+        const int base = (int)(cta_base[2 + cls_c] + warp_tot[wid][2 + cls_c] + excl[2 + cls_c]);
+        for (int k = 0; k < n_c; k++)
+            ls.chroma[cls_c ? ls.cap_chroma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
     }
 }
 
@@ -177,25 +218,28 @@ __device__ __forceinline__ void luma_task(const InterK &p, const Rec &pb, int pi
     const uint8_t *wt = &vvct_gpm_weights[0][0] + pb.gw;
     const int ox = (pi & ((w >> 2) - 1)) << 2, oy = (pi >> (lw - 2)) << 3, nrows = min(8, h - oy);
     const Blend k = blend_of(pb, p.wp, BI, lx, 0);
-    int acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++)
-        acc[i] = 0;
-#pragma unroll 1
-    for (int it = 0; it < (BI ? 2 : 1); it++) {
-        const int l = BI ? it : lx;
-        const int mvx = MV0(l, 0), mvy = MV0(l, 1), mx = mvx & 15, my = mvy & 15, filt = gpm ? 0 : pb.filt;
-        const uint2 fh = lumaf[filt * 16 + mx], fv = lumaf[filt * 16 + my];
-        mc_patch<8>(p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, pb.x0 + ox + (mvx >> 4), pb.y0 + oy + (mvy >> 4), nrows,
-                    mx ? fh.x : 0x01000000u, mx ? fh.y : 0u, my ? fv.x : (mx ? 0x01000000u : 0x10000000u), my ? fv.y : 0u,
-                    mx ? 2 : 0, my ? (mx ? 6 : 2) : 0, acc, (BI && l) ? k.w1 : k.w0,
-                    gpm ? wt + oy * pb.gsy + ox * pb.gsx : nullptr, pb.gsx, pb.gsy, 3, BI && l == 1);
-    }
     pel *d = p.dst[0] + pb.pic * p.db[0] + (long long)(pb.y0 + oy) * p.dp[0] + pb.x0 + ox;
-#pragma unroll
-    for (int y = 0; y < 8; y++)
-        if (y < nrows)
-            *reinterpret_cast<uint2 *>(d + (long long)y * p.dp[0]) = finish4(&acc[4 * y], k);
+    const uint8_t *gw = gpm ? wt + oy * pb.gsy + ox * pb.gsx : nullptr;
+    uint32_t keep[16];
+#define LUMA_ARGS(l) p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, pb.x0 + ox + (MV0(l, 0) >> 4), pb.y0 + oy + (MV0(l, 1) >> 4), nrows, \
+        (MV0(l, 0) & 15) ? fh.x : 0x01000000u, (MV0(l, 0) & 15) ? fh.y : 0u, \
+        (MV0(l, 1) & 15) ? fv.x : ((MV0(l, 0) & 15) ? 0x01000000u : 0x10000000u), (MV0(l, 1) & 15) ? fv.y : 0u, \
+        (MV0(l, 0) & 15) ? 2 : 0, (MV0(l, 1) & 15) ? ((MV0(l, 0) & 15) ? 6 : 2) : 0
+    const int filt = gpm ? 0 : pb.filt;
+    if (BI) {
+        {
+            const uint2 fh = lumaf[filt * 16 + (pb.mv[0][0] & 15)], fv = lumaf[filt * 16 + (pb.mv[0][1] & 15)];
+            mc_patch<8, true, true>(LUMA_ARGS(0), keep, k, gw, pb.gsx, pb.gsy, 3, d, p.dp[0], true);
+        }
+        {
+            const uint2 fh = lumaf[filt * 16 + (pb.mv[1][0] & 15)], fv = lumaf[filt * 16 + (pb.mv[1][1] & 15)];
+            mc_patch<8, false, true>(LUMA_ARGS(1), keep, k, gw, pb.gsx, pb.gsy, 3, d, p.dp[0], true);
+        }
+    } else {
+        const uint2 fh = lumaf[filt * 16 + (MV0(lx, 0) & 15)], fv = lumaf[filt * 16 + (MV0(lx, 1) & 15)];
+        mc_patch<8, false, false>(LUMA_ARGS(lx), keep, k, nullptr, 0, 0, 3, d, p.dp[0], true);
+    }
+#undef LUMA_ARGS
 }
 
 // ---- chroma (4:2:0): task pi = (plane, patch column) ----------------------------------------------------------
@@ -213,32 +257,23 @@ __device__ __forceinline__ void chroma_task(const InterK &p, const Rec &pb, int 
     const long long rb = pc ? p.rb[2] : p.rb[1];
     const int rp = pc ? p.rp[2] : p.rp[1];
     const Blend k = blend_of(pb, p.wp, BI, lx, pc + 1);
-    int acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++)
-        acc[i] = 0;
-#pragma unroll 1
-    for (int it = 0; it < (BI ? 2 : 1); it++) {
-        const int l = BI ? it : lx;
-        const int mvx = MV0(l, 0), mvy = MV0(l, 1), mx = mvx & 31, my = mvy & 31;
-        // GPM weights of chroma: every second luma weight; columns past a 2-wide block reuse its last weight
-        mc_patch<4>(rplane + REF(l) * rb, rp, p.w >> 1, p.h >> 1, x0 + ox + (mvx >> 5), y0 + (mvy >> 5), bh,
-                    mx ? chromaf[mx] : 0x00000100u, 0u, my ? chromaf[my] : (mx ? 0x00000100u : 0x00001000u), 0u,
-                    mx ? 2 : 0, my ? (mx ? 6 : 2) : 0, acc, (BI && l) ? k.w1 : k.w0,
-                    gpm ? wt + ox * 2 * pb.gsx : nullptr, 2 * pb.gsx, 2 * pb.gsy, bw - 1 - ox > 3 ? 3 : bw - 1 - ox, BI && l == 1);
-    }
     const int dpitch = pc ? p.dp[2] : p.dp[1];
     pel *d = (pc ? p.dst[2] + pb.pic * p.db[2] : p.dst[1] + pb.pic * p.db[1]) + (long long)y0 * dpitch + x0 + ox;
-#pragma unroll
-    for (int y = 0; y < 8; y++) {
-        if (y < bh) {
-            const uint2 o = finish4(&acc[4 * y], k);
-            uint32_t *q = reinterpret_cast<uint32_t *>(d + (long long)y * dpitch);
-            q[0] = o.x;
-            if (bw > 2)
-                q[1] = o.y;
-        }
+    // GPM weights of chroma: every second luma weight; columns past a 2-wide block reuse its last weight
+    const uint8_t *gw = gpm ? wt + ox * 2 * pb.gsx : nullptr;
+    const int cmax = bw - 1 - ox > 3 ? 3 : bw - 1 - ox;
+    uint32_t keep[16];
+#define CHROMA_ARGS(l) rplane + REF(l) * rb, rp, p.w >> 1, p.h >> 1, x0 + ox + (MV0(l, 0) >> 5), y0 + (MV0(l, 1) >> 5), bh, \
+        (MV0(l, 0) & 31) ? chromaf[MV0(l, 0) & 31] : 0x00000100u, 0u, \
+        (MV0(l, 1) & 31) ? chromaf[MV0(l, 1) & 31] : ((MV0(l, 0) & 31) ? 0x00000100u : 0x00001000u), 0u, \
+        (MV0(l, 0) & 31) ? 2 : 0, (MV0(l, 1) & 31) ? ((MV0(l, 0) & 31) ? 6 : 2) : 0
+    if (BI) {
+        mc_patch<4, true, true>(CHROMA_ARGS(0), keep, k, gw, 2 * pb.gsx, 2 * pb.gsy, cmax, d, dpitch, bw > 2);
+        mc_patch<4, false, true>(CHROMA_ARGS(1), keep, k, gw, 2 * pb.gsx, 2 * pb.gsy, cmax, d, dpitch, bw > 2);
+    } else {
+        mc_patch<4, false, false>(CHROMA_ARGS(lx), keep, k, nullptr, 0, 0, cmax, d, dpitch, bw > 2);
     }
+#undef CHROMA_ARGS
 }
 #undef MV0
 #undef REF
@@ -246,7 +281,7 @@ __device__ __forceinline__ void chroma_task(const InterK &p, const Rec &pb, int 
 // Persistent kernels, one per task class (own register budget each): a grid-stride loop over the class's
 // list, so every warp of the launch runs the same specialised code.
 template <bool LUMA, bool BI>
-__global__ void __launch_bounds__(kThreads, LUMA ? 3 : 4) inter_patch_kernel(const InterK p, const InterLists ls)
+__global__ void __launch_bounds__(kThreads, LUMA ? 4 : 5) inter_patch_kernel(const InterK p, const InterLists ls)
 {
     const int n = (int)ls.count[(LUMA ? 0 : 2) + (BI ? 1 : 0)];
     const uint32_t *list = LUMA ? ls.luma : ls.chroma;
@@ -277,13 +312,13 @@ int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
     VVC_TRY(ctx, cudaMemsetAsync(ls->count, 0, 64, ctx->stream));
     inter_classify_kernel<<<ceil_div(p.n, 256), 256, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<true, true><<<148 * 3, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<true, true><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<true, false><<<148 * 3, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<true, false><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<false, true><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<false, true><<<148 * 5, kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<false, false><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<false, false><<<148 * 5, kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }
