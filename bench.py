@@ -318,8 +318,8 @@ def main():
             coeffs=up(coeffs), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
             alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
     # kernels per picture group: inter = 6 (classify, four thread-per-patch class kernels, warp-per-record kernel),
-    # every other stage 1
-    launches_per_step = len(groups) * (len(STAGES) + 5)
+    # residual = 2 (warp-per-TB kernel + generic kernel over the blocks it leaves), every other stage 1
+    launches_per_step = len(groups) * (len(STAGES) + 6)
 
     def step(events=None):
         for gi, g in enumerate(groups):

@@ -17,6 +17,7 @@ struct VVCCudaCtx {
     char          msg[256];
     uint64_t      launches;
     int           force_generic;        // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_GENERIC_KERNELS)
+    bool          itx_packed;           // itx_warp.cu's packed transform matrices are built on this device
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;
     void         *h_stage;  size_t h_stage_size;    // pinned
@@ -62,3 +63,7 @@ void   vvc_stage_frame_layout(const VVCCudaFrame *host, void *dbase, VVCCudaFram
 int    vvc_stage_frame_h2d(VVCCudaCtx *ctx, const VVCCudaFrame *dev, const VVCCudaFrame *host);
 int    vvc_stage_frame_d2h(VVCCudaCtx *ctx, const VVCCudaFrame *host, const VVCCudaFrame *dev);
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// itx_warp.cu (10-bit pictures, log2_transform_range 15)
+int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs, const VVCCudaTB *tbs, int n_tbs,
+                        uint32_t *rest, uint32_t *rest_count);

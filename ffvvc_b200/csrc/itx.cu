@@ -33,6 +33,7 @@ struct ItxK {
     int32_t   *coeffs;
     const VVCCudaTB *tbs;
     int        n_tbs, range, bd;
+    const uint32_t *list, *list_count;   // optional: process tbs[list[0 .. *list_count)] instead of tbs[0 .. n_tbs)
 };
 
 __device__ __forceinline__ const int8_t *tx_matrix(int type, int n)
@@ -265,25 +266,27 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int *sC, int *sM,
 __global__ void __launch_bounds__(kThreads) itx_kernel(const ItxK p)
 {
     __shared__ alignas(16) int s_buf[2 * LARGE_BUF];
-    const int first = blockIdx.x * TBS_PER_CTA;
-    const int count = min(TBS_PER_CTA, p.n_tbs - first);
+    const int total = p.list ? (int)*p.list_count : p.n_tbs;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // phase A: small blocks, one warp each
-    {
-        int *sC = s_buf + warp * 2 * SMALL_BUF, *sM = sC + SMALL_BUF;
-        for (int i = warp; i < count; i += kThreads / 32) {
-            const VVCCudaTB tb = p.tbs[first + i];
-            if ((1 << (tb.log2_w + tb.log2_h)) <= SMALL_AREA && tb.log2_w <= 4 && tb.log2_h <= 4)
-                process_tb<32>(p, tb, sC, sM, lane);
+    for (int first = blockIdx.x * TBS_PER_CTA; first < total; first += gridDim.x * TBS_PER_CTA) {
+        const int count = min(TBS_PER_CTA, total - first);
+        __syncthreads();
+        // phase A: small blocks, one warp each
+        {
+            int *sC = s_buf + warp * 2 * SMALL_BUF, *sM = sC + SMALL_BUF;
+            for (int i = warp; i < count; i += kThreads / 32) {
+                const VVCCudaTB tb = p.tbs[p.list ? p.list[first + i] : first + i];
+                if ((1 << (tb.log2_w + tb.log2_h)) <= SMALL_AREA && tb.log2_w <= 4 && tb.log2_h <= 4)
+                    process_tb<32>(p, tb, sC, sM, lane);
+            }
         }
-    }
-    __syncthreads();
-    // phase B: large blocks, whole CTA
-    for (int i = 0; i < count; i++) {
-        const VVCCudaTB tb = p.tbs[first + i];
-        if (!((1 << (tb.log2_w + tb.log2_h)) <= SMALL_AREA && tb.log2_w <= 4 && tb.log2_h <= 4))
-            process_tb<kThreads>(p, tb, s_buf, s_buf + LARGE_BUF, threadIdx.x);
+        __syncthreads();
+        // phase B: large blocks, whole CTA
+        for (int i = 0; i < count; i++) {
+            const VVCCudaTB tb = p.tbs[p.list ? p.list[first + i] : first + i];
+            if (!((1 << (tb.log2_w + tb.log2_h)) <= SMALL_AREA && tb.log2_w <= 4 && tb.log2_h <= 4))
+                process_tb<kThreads>(p, tb, s_buf, s_buf + LARGE_BUF, threadIdx.x);
+        }
     }
 }
 
@@ -311,6 +314,20 @@ extern "C" int vvc_cuda_itx_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, in
         p.bstride[c] = frame->batch_stride[c] / 2;
     }
     p.coeffs = coeffs; p.tbs = tbs; p.n_tbs = n_tbs; p.range = log2_transform_range; p.bd = frame->bit_depth;
+    p.list = p.list_count = NULL;
+    if (p.bd == 10 && p.range == 15 && !ctx->force_generic) {
+        // common kinds: warp-per-TB kernel (itx_warp.cu); it lists what it leaves (transform skip, BDPCM, 1-D blocks)
+        uint32_t *rest = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + (size_t)n_tbs * sizeof(uint32_t));
+        if (!rest)
+            return ctx->err;
+        if (vvc_itx_launch_warp(ctx, frame, coeffs, tbs, n_tbs, rest + 16, rest))
+            return ctx->err;
+        p.list = rest + 16; p.list_count = rest;
+        const int ctas = ceil_div(n_tbs, TBS_PER_CTA);
+        itx_kernel<<<ctas < 148 * 2 ? ctas : 148 * 2, kThreads, 0, ctx->stream>>>(p);
+        VVC_LAUNCHED(ctx);
+        return VVC_CUDA_OK;
+    }
     itx_kernel<<<ceil_div(n_tbs, TBS_PER_CTA), kThreads, 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;

@@ -1,0 +1,336 @@
+// Residual stage, warp-per-TB kernel for 10-bit pictures with 16-bit coefficients (log2_transform_range 15).
+//
+// Same contract as itx.cu (the generic kernel) for the common kinds of transform block: 2-D blocks 2..64
+// per side, DCT-II / DST-VII / DCT-VIII, optional LFNST, add_residual / add_residual_joint or the residual
+// written back.  Reference: itx_2d + scale_clip (libavcodec/vvc/vvcdsp.c:67-117), the 1-D kernels
+// (libavcodec/vvc/vvc_itx_1d.c:70-706) as exact matrix products, ilfnst_transform (vvc_intra.c:65-127),
+// add_residual(_joint) (vvcdsp_template.c:32-63).  Transform skip, BDPCM and 1-D blocks stay in itx.cu.
+//
+// B200 design: both passes are int16 x int8 products with exact int32 accumulation, i.e. IDP.2A on pairs
+// along the reduction dimension (coefficients are clipped to 16 bits by dequant, the mid-stage clip keeps
+// the second pass in 16 bits too).
+//  * Pass 1 (vertical) is input-stationary: a lane owns one coefficient column of the non-zero window, packed
+//    in registers straight from HBM (rows are read coalesced across lanes), and sweeps the outputs with the
+//    matrix fetched as 128-bit words of the packed table (4 words = 16 taps of one output).
+//  * Pass 2 (horizontal) is matrix-stationary: a lane owns one (two for 64) output columns with their taps in
+//    registers, every mid-stage row is one broadcast 128-bit shared load per 8 inputs, and the residual goes
+//    straight into the picture -- it never exists in HBM.
+// Only the non-zero window of the dense int32 coefficients is read (what the reference's butterflies read).
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace {
+
+constexpr int kWarps = 4, kThreads = kWarps * 32;
+constexpr int P2 = 40;                        // pitch (int16) of the mid-stage rows: 32 inputs + pad, 16-byte multiple
+
+struct ItxW {
+    pel       *plane[3];
+    int        pitch[3];
+    long long  bstride[3];
+    int32_t   *coeffs;
+    const VVCCudaTB *tbs;
+    int        n_tbs;
+    uint32_t  *rest, *rest_count;   // indices of the blocks left to itx_kernel (transform skip, BDPCM, 1-D)
+};
+
+// Packed matrices: for output i of (type, n) the 8 words g_wpt[(base + i) * 8 + q] hold taps M[4q .. 4q+3][i]
+// (zero past the matrix's rows).  base(type, log2 n): DCT2 sizes 2..64, then DST7 4..32, then DCT8 4..32.
+__device__ __align__(16) uint32_t g_wpt[246 * 8];
+
+__host__ __device__ __forceinline__ int wpt_base(int type, int l2)
+{
+    return type == 0 ? (1 << l2) - 2 : (type == 1 ? 126 : 186) + (1 << l2) - 4;
+}
+
+__device__ __forceinline__ const int8_t *tx_matrix(int type, int n)
+{
+    if (type == 0) {
+        switch (n) {
+        case 2:  return &vvct_dct2_2[0][0];   case 4:  return &vvct_dct2_4[0][0];
+        case 8:  return &vvct_dct2_8[0][0];   case 16: return &vvct_dct2_16[0][0];
+        case 32: return &vvct_dct2_32[0][0];  default: return &vvct_dct2_64[0][0];
+        }
+    }
+    if (type == 1) {
+        switch (n) {
+        case 4:  return &vvct_dst7_4[0][0];   case 8:  return &vvct_dst7_8[0][0];
+        case 16: return &vvct_dst7_16[0][0];  default: return &vvct_dst7_32[0][0];
+        }
+    }
+    switch (n) {
+    case 4:  return &vvct_dct8_4[0][0];   case 8:  return &vvct_dct8_8[0][0];
+    case 16: return &vvct_dct8_16[0][0];  default: return &vvct_dct8_32[0][0];
+    }
+}
+
+__global__ void itx_pack_kernel()
+{
+    for (int type = 0; type < 3; type++)
+        for (int l2 = type ? 2 : 1; l2 <= (type ? 5 : 6); l2++) {
+            const int n = 1 << l2, rows = n == 64 ? 32 : n;
+            const int8_t *m = tx_matrix(type, n);
+            for (int idx = threadIdx.x; idx < n * 8; idx += blockDim.x) {
+                const int i = idx >> 3, q = idx & 7;
+                uint32_t word = 0;
+                for (int k = 0; k < 4; k++)
+                    if (4 * q + k < rows)
+                        word |= (uint32_t)(uint8_t)m[(4 * q + k) * n + i] << (8 * k);
+                g_wpt[(wpt_base(type, l2) + i) * 8 + q] = word;
+            }
+        }
+}
+
+// inputs the reference's 1-D transform reads for a declared nz (zero-out guards G2..G16, vvc_itx_1d.c:64-67)
+__device__ __forceinline__ int inputs_read(int type, int n, int nz)
+{
+    if (type != 0)
+        return nz;
+    const int r = nz <= 2 ? 2 : nz <= 4 ? 4 : nz <= 8 ? 8 : nz <= 16 ? 16 : 32;
+    return min(r, min(n, 32));
+}
+
+__device__ __forceinline__ int round_rd(int rd) { return rd <= 4 ? 4 : rd <= 8 ? 8 : rd <= 16 ? 16 : 32; }
+
+struct __align__(16) WarpSmem {
+    short mid[64 * P2];          // pass-1 output: [row][input of pass 2]
+    short lf[8 * 8];             // LFNST output window [row][col]
+};
+
+__constant__ uint8_t c_diag4_x[16] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 1, 2, 3, 2, 3, 3 };
+__constant__ uint8_t c_diag4_y[16] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 3, 2, 1, 3, 2, 3 };
+
+// Pass 1: mid[i][x] = clip16((sum_j in[j][x] * M[j][i] + 64) >> 7).  lane = (column x, output group g).
+template <int RD>
+__device__ __forceinline__ void pass1(WarpSmem &s, const int32_t *coef, int w, const short *lf, int nzw, int rd, int h,
+                                      const uint32_t *wpt, int lane)
+{
+    int xb = 0;
+    while ((1 << xb) < nzw)
+        xb++;
+    const int x = lane & ((1 << xb) - 1), g = lane >> xb, ng = 32 >> xb;
+    if (x >= nzw)
+        return;
+    uint32_t in[RD / 2];
+#pragma unroll
+    for (int jp = 0; jp < RD / 2; jp++) {
+        int v0 = 0, v1 = 0;
+        if (lf) {
+            if (2 * jp < rd)     v0 = lf[(2 * jp) * 8 + x];
+            if (2 * jp + 1 < rd) v1 = lf[(2 * jp + 1) * 8 + x];
+        } else {
+            if (2 * jp < rd)     v0 = __ldg(coef + (2 * jp) * w + x);
+            if (2 * jp + 1 < rd) v1 = __ldg(coef + (2 * jp + 1) * w + x);
+        }
+        in[jp] = (uint32_t)(v0 & 0xffff) | ((uint32_t)v1 << 16);
+    }
+    for (int i = g; i < h; i += ng) {
+        const uint4 *mp = reinterpret_cast<const uint4 *>(wpt + i * 8);
+        int acc = 0;
+        if (RD == 4) {
+            const uint32_t m = __ldg(reinterpret_cast<const uint32_t *>(mp));
+            acc = __dp2a_lo((int)in[0], (int)m, __dp2a_hi((int)in[1], (int)m, 0));
+        } else if (RD == 8) {
+            const uint2 m = __ldg(reinterpret_cast<const uint2 *>(mp));
+            acc = __dp2a_lo((int)in[0], (int)m.x, __dp2a_hi((int)in[1], (int)m.x, __dp2a_lo((int)in[2], (int)m.y, __dp2a_hi((int)in[3], (int)m.y, 0))));
+        } else {
+#pragma unroll
+            for (int q4 = 0; q4 < RD / 16; q4++) {
+                const uint4 m = __ldg(mp + q4);
+                acc = __dp2a_lo((int)in[8 * q4 + 0], (int)m.x, __dp2a_hi((int)in[8 * q4 + 1], (int)m.x, acc));
+                acc = __dp2a_lo((int)in[8 * q4 + 2], (int)m.y, __dp2a_hi((int)in[8 * q4 + 3], (int)m.y, acc));
+                acc = __dp2a_lo((int)in[8 * q4 + 4], (int)m.z, __dp2a_hi((int)in[8 * q4 + 5], (int)m.z, acc));
+                acc = __dp2a_lo((int)in[8 * q4 + 6], (int)m.w, __dp2a_hi((int)in[8 * q4 + 7], (int)m.w, acc));
+            }
+        }
+        s.mid[i * P2 + x] = (short)d_clip_sbits((acc + 64) >> 7, 15);
+    }
+}
+
+struct Epi {
+    int32_t *store;              // != NULL: residual written back as int32 [h][w]
+    pel     *d0, *d1;            // picture samples of the TB's first row (d1: joint CbCr plane or NULL)
+    int      pitch0, pitch1, sign, shift, w;
+};
+
+__device__ __forceinline__ void emit(const Epi &e, int y, int i, int acc)
+{
+    const int r = (acc + 512) >> 10;                      // shift = 5 + log2_transform_range - bit_depth
+    if (e.store) {
+        e.store[y * e.w + i] = r;
+        return;
+    }
+    pel *d = e.d0 + (long long)y * e.pitch0 + i;
+    *d = (pel)d_clip_pel(*d + r, 10);
+    if (e.d1) {
+        pel *q = e.d1 + (long long)y * e.pitch1 + i;
+        *q = (pel)d_clip_pel(*q + ((r * e.sign) >> e.shift), 10);
+    }
+}
+
+// Pass 2: out[y][i] = (sum_x mid[y][x] * M[x][i] + 512) >> 10.  lane = (output column, row group).
+template <int RD>
+__device__ __forceinline__ void pass2(const WarpSmem &s, int l2w, int h, const uint32_t *wpt, const Epi &e, int lane)
+{
+    const int cb = min(l2w, 5), ci = lane & ((1 << cb) - 1), g = lane >> cb, ng = 32 >> cb;
+    const bool two = l2w == 6;
+    uint32_t m0[RD / 4], m1[RD / 4];
+#pragma unroll
+    for (int q = 0; q < RD / 4; q++) {
+        m0[q] = __ldg(wpt + ci * 8 + q);
+        m1[q] = two ? __ldg(wpt + (ci + 32) * 8 + q) : 0u;
+    }
+    for (int y = g; y < h; y += ng) {
+        uint32_t in[RD / 2];
+        if (RD == 4) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(&s.mid[y * P2]);
+            in[0] = v.x; in[1] = v.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < RD / 8; k++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(&s.mid[y * P2 + 8 * k]);
+                in[4 * k] = v.x; in[4 * k + 1] = v.y; in[4 * k + 2] = v.z; in[4 * k + 3] = v.w;
+            }
+        }
+        int a0 = 0, a1 = 0;
+#pragma unroll
+        for (int q = 0; q < RD / 4; q++) {
+            a0 = __dp2a_lo((int)in[2 * q], (int)m0[q], __dp2a_hi((int)in[2 * q + 1], (int)m0[q], a0));
+            if (two)
+                a1 = __dp2a_lo((int)in[2 * q], (int)m1[q], __dp2a_hi((int)in[2 * q + 1], (int)m1[q], a1));
+        }
+        emit(e, y, ci, a0);
+        if (two)
+            emit(e, y, ci + 32, a1);
+    }
+}
+
+__device__ __forceinline__ bool eligible(int l2w, int l2h, int flags)
+{
+    return l2w >= 1 && l2h >= 1 && !(flags & (VVC_CUDA_TB_TS | VVC_CUDA_TB_BDPCM | VVC_CUDA_TB_BDPCM_VERT));
+}
+
+__global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
+{
+    __shared__ WarpSmem sm[kWarps];
+    const int lane = threadIdx.x & 31;
+    WarpSmem &s = sm[threadIdx.x >> 5];
+    const int nwarps = gridDim.x * kWarps;
+    for (int ti = blockIdx.x * kWarps + (threadIdx.x >> 5); ti < p.n_tbs; ti += nwarps) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
+        const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
+        const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, c_idx = (r2 >> 16) & 0xff, flags = r3 >> 24;
+        if (!eligible(l2w, l2h, flags)) {                   // itx_kernel's share
+            if (lane == 0)
+                p.rest[atomicAdd(p.rest_count, 1u)] = ti;
+            continue;
+        }
+        const int x0 = r1 & 0xffff, y0 = r1 >> 16, w = 1 << l2w, h = 1 << l2h;
+        int trh = r2 >> 24, trv = r3 & 0xff, nzw = (r3 >> 8) & 0xff, nzh = (r3 >> 16) & 0xff;
+        const int lfnst = r4 & 0xff, jsign = (int8_t)((r4 >> 8) & 0xff), jshift = (r4 >> 16) & 0xff, jc = r4 >> 24, pic = r5 & 0xff;
+        int32_t *coef = p.coeffs + r0;
+        __syncwarp();                                       // previous block is done with shared memory
+
+        // ---- inverse LFNST: 8/16 inputs in 4x4 diagonal order -> 16/48 outputs, top-left 4x4 / 8x8 ----
+        const short *lf = nullptr;
+        if (lfnst) {
+            const int idx = lfnst & 3, set = (lfnst >> 2) & 3, side = (w >= 8 && h >= 8) ? 8 : 4;
+            const bool transpose = (lfnst >> 4) & 1;
+            const int n_in = ((lfnst >> 5) & 1) ? 8 : 16, n_out = side == 8 ? 48 : 16;
+            const int8_t *M = side == 8 ? &vvct_lfnst_8x8[set][idx - 1][0][0] : &vvct_lfnst_4x4[set][idx - 1][0][0];
+            s.lf[lane] = 0; s.lf[lane + 32] = 0;
+            const int u = lane < n_in ? __ldg(coef + c_diag4_y[lane & 15] * w + c_diag4_x[lane & 15]) : 0;
+            __syncwarp();
+            for (int base = 0; base < n_out; base += 32) {
+                const bool act = base + lane < n_out;
+                const int j = act ? base + lane : 0;
+                int acc = 0;
+                for (int i = 0; i < n_in; i++)
+                    acc += __shfl_sync(0xffffffffu, u, i) * (int)M[i * n_out + j];
+                const int v = d_clip_sbits((acc + 64) >> 7, 15);
+                const int rr = j < 4 * side ? j / side : 4 + ((j - 4 * side) >> 2);
+                const int qq = j < 4 * side ? j % side : (j - 4 * side) & 3;
+                if (act)
+                    s.lf[transpose ? qq * 8 + rr : rr * 8 + qq] = (short)v;
+            }
+            nzw = nzh = side;
+            lf = s.lf;
+            __syncwarp();
+        }
+        // DC-only cells of square DCT2 x DCT2 blocks read nothing but c[0] (vvcdsp.c:101-108)
+        const bool dc_only = trh == 0 && trv == 0 && nzw == 1 && nzh == 1 && w == h;
+        const int rdv = dc_only ? 1 : inputs_read(trv, h, nzh), rdh = inputs_read(trh, w, nzw);
+        const int rdv_e = round_rd(rdv), rdh_e = round_rd(rdh);
+
+        // ---- pass 1 ----
+        {
+            const uint32_t *wpt = g_wpt + wpt_base(trv, l2h) * 8;
+            switch (rdv_e) {
+            case 4:  pass1<4>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
+            case 8:  pass1<8>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
+            case 16: pass1<16>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
+            default: pass1<32>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
+            }
+        }
+        // columns nzw .. of the mid stage are zero (scale_clip's memset); pad to the rounded reduction length
+        if (rdh_e > nzw) {
+            const int pad = rdh_e - nzw;                    // < 32
+            for (int idx = lane; idx < h * 32; idx += 32) {
+                const int y = idx >> 5, k = idx & 31;
+                if (k < pad)
+                    s.mid[y * P2 + nzw + k] = 0;
+            }
+        }
+        __syncwarp();
+
+        // ---- pass 2 + epilogue ----
+        Epi e;
+        e.w = w;
+        e.store = (flags & VVC_CUDA_TB_STORE_RESIDUAL) ? coef : nullptr;
+#define SEL3(a, c) ((c) == 0 ? (a)[0] : (c) == 1 ? (a)[1] : (a)[2])
+        e.pitch0 = SEL3(p.pitch, c_idx);
+        e.d0 = SEL3(p.plane, c_idx) + pic * SEL3(p.bstride, c_idx) + (long long)y0 * e.pitch0 + x0;
+        e.d1 = nullptr; e.pitch1 = 0; e.sign = jsign; e.shift = jshift;
+        if (flags & VVC_CUDA_TB_JOINT) {
+            e.pitch1 = SEL3(p.pitch, jc);
+            e.d1 = SEL3(p.plane, jc) + pic * SEL3(p.bstride, jc) + (long long)y0 * e.pitch1 + x0;
+#undef SEL3
+        }
+        {
+            const uint32_t *wpt = g_wpt + wpt_base(trh, l2w) * 8;
+            switch (rdh_e) {
+            case 4:  pass2<4>(s, l2w, h, wpt, e, lane); break;
+            case 8:  pass2<8>(s, l2w, h, wpt, e, lane); break;
+            case 16: pass2<16>(s, l2w, h, wpt, e, lane); break;
+            default: pass2<32>(s, l2w, h, wpt, e, lane); break;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// Launch over the whole list.  Blocks this kernel does not handle (transform skip, BDPCM, 1-D) are appended
+// to rest[] (count in rest_count[0], zeroed here) for itx_kernel (itx.cu).
+int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs, const VVCCudaTB *tbs, int n_tbs,
+                        uint32_t *rest, uint32_t *rest_count)
+{
+    if (!ctx->itx_packed) {
+        itx_pack_kernel<<<1, 256, 0, ctx->stream>>>();
+        if (vvc_ctx_check(ctx, cudaGetLastError(), "itx_pack_kernel"))
+            return ctx->err;
+        ctx->itx_packed = true;
+    }
+    VVC_TRY(ctx, cudaMemsetAsync(rest_count, 0, sizeof(uint32_t), ctx->stream));
+    ItxW p;
+    for (int c = 0; c < 3; c++) {
+        p.plane[c] = (pel *)frame->data[c];
+        p.pitch[c] = (int)(frame->stride[c] / 2);
+        p.bstride[c] = frame->batch_stride[c] / 2;
+    }
+    p.coeffs = coeffs; p.tbs = tbs; p.n_tbs = n_tbs; p.rest = rest; p.rest_count = rest_count;
+    const int ctas = ceil_div(n_tbs, kWarps);
+    itx_warp_kernel<<<ctas < 148 * 10 ? ctas : 148 * 10, kThreads, 0, ctx->stream>>>(p);
+    VVC_LAUNCHED(ctx);
+    return VVC_CUDA_OK;
+}
