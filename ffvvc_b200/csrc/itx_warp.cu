@@ -153,61 +153,88 @@ struct Epi {
     int      pitch0, pitch1, sign, shift, w;
 };
 
-__device__ __forceinline__ void emit(const Epi &e, int y, int i, int acc)
-{
-    const int r = (acc + 512) >> 10;                      // shift = 5 + log2_transform_range - bit_depth
-    if (e.store) {
-        e.store[y * e.w + i] = r;
-        return;
-    }
-    pel *d = e.d0 + (long long)y * e.pitch0 + i;
-    *d = (pel)d_clip_pel(*d + r, 10);
-    if (e.d1) {
-        pel *q = e.d1 + (long long)y * e.pitch1 + i;
-        *q = (pel)d_clip_pel(*q + ((r * e.sign) >> e.shift), 10);
-    }
-}
-
-// Pass 2: out[y][i] = (sum_x mid[y][x] * M[x][i] + 512) >> 10.  lane = (output column, row group).
+// Pass 2: out[y][i] = (sum_x mid[y][x] * M[x][i] + 512) >> 10.  lane = (4 adjacent output columns, row group):
+// the taps of its 4 columns live in registers, a mid-stage row is one broadcast 128-bit shared load per 8
+// inputs, and the picture is updated with one 64-bit load + store per row (32-bit for 2-wide blocks); the
+// samples of the next row are requested before the current row's products so their latency is hidden.
 template <int RD>
 __device__ __forceinline__ void pass2(const WarpSmem &s, int l2w, int h, const uint32_t *wpt, const Epi &e, int lane)
 {
-    const int cb = min(l2w, 5), ci = lane & ((1 << cb) - 1), g = lane >> cb, ng = 32 >> cb;
-    const bool two = l2w == 6;
-    uint32_t m0[RD / 4], m1[RD / 4];
+    const int qb = max(l2w - 2, 0), cq = lane & ((1 << qb) - 1), g = lane >> qb, ng = 32 >> qb;
+    const int c0 = cq << 2;
+    const bool narrow = l2w == 1;                          // 2 columns
+    uint32_t m[4][RD / 4];
 #pragma unroll
-    for (int q = 0; q < RD / 4; q++) {
-        m0[q] = __ldg(wpt + ci * 8 + q);
-        m1[q] = two ? __ldg(wpt + (ci + 32) * 8 + q) : 0u;
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int q = 0; q < RD / 4; q++)
+            m[c][q] = (narrow && c >= 2) ? 0u : __ldg(wpt + (c0 + c) * 8 + q);
+    const int step0 = ng * e.pitch0, step1 = ng * e.pitch1;
+    pel *d0 = e.d0 + g * e.pitch0 + c0, *d1 = e.d1 ? e.d1 + g * e.pitch1 + c0 : nullptr;
+    auto load4 = [&](const pel *p) -> uint2 {
+        if (narrow)
+            return make_uint2(*reinterpret_cast<const uint32_t *>(p), 0u);
+        return *reinterpret_cast<const uint2 *>(p);
+    };
+    uint2 cur0 = make_uint2(0u, 0u), cur1 = make_uint2(0u, 0u);
+    if (!e.store && g < h) {
+        cur0 = load4(d0);
+        if (d1) cur1 = load4(d1);
     }
-    for (int y = g; y < h; y += ng) {
+    for (int y = g; y < h; y += ng, d0 += step0, d1 += step1) {
+        uint2 nxt0 = make_uint2(0u, 0u), nxt1 = make_uint2(0u, 0u);
+        if (!e.store && y + ng < h) {
+            nxt0 = load4(d0 + step0);
+            if (d1) nxt1 = load4(d1 + step1);
+        }
         uint32_t in[RD / 2];
         if (RD == 4) {
             const uint2 v = *reinterpret_cast<const uint2 *>(&s.mid[y * P2]);
             in[0] = v.x; in[1] = v.y;
         } else {
 #pragma unroll
-            for (int k = 0; k < RD / 8; k++) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(&s.mid[y * P2 + 8 * k]);
-                in[4 * k] = v.x; in[4 * k + 1] = v.y; in[4 * k + 2] = v.z; in[4 * k + 3] = v.w;
+            for (int c = 0; c < RD / 8; c++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(&s.mid[y * P2 + 8 * c]);
+                in[4 * c] = v.x; in[4 * c + 1] = v.y; in[4 * c + 2] = v.z; in[4 * c + 3] = v.w;
             }
         }
-        int a0 = 0, a1 = 0;
+        int r[4];
 #pragma unroll
-        for (int q = 0; q < RD / 4; q++) {
-            a0 = __dp2a_lo((int)in[2 * q], (int)m0[q], __dp2a_hi((int)in[2 * q + 1], (int)m0[q], a0));
-            if (two)
-                a1 = __dp2a_lo((int)in[2 * q], (int)m1[q], __dp2a_hi((int)in[2 * q + 1], (int)m1[q], a1));
+        for (int c = 0; c < 4; c++) {
+            int a = 0;
+#pragma unroll
+            for (int q = 0; q < RD / 4; q++)
+                a = __dp2a_lo((int)in[2 * q], (int)m[c][q], __dp2a_hi((int)in[2 * q + 1], (int)m[c][q], a));
+            r[c] = (a + 512) >> 10;                         // shift = 5 + log2_transform_range - bit_depth
         }
-        emit(e, y, ci, a0);
-        if (two)
-            emit(e, y, ci + 32, a1);
+        if (e.store) {
+            int32_t *o = e.store + y * e.w + c0;
+            o[0] = r[0]; o[1] = r[1];
+            if (!narrow) { o[2] = r[2]; o[3] = r[3]; }
+        } else {
+            const uint32_t lo = (uint32_t)d_clip_pel((int)(cur0.x & 0xffff) + r[0], 10) | ((uint32_t)d_clip_pel((int)(cur0.x >> 16) + r[1], 10) << 16);
+            const uint32_t hi = (uint32_t)d_clip_pel((int)(cur0.y & 0xffff) + r[2], 10) | ((uint32_t)d_clip_pel((int)(cur0.y >> 16) + r[3], 10) << 16);
+            if (narrow) *reinterpret_cast<uint32_t *>(d0) = lo;
+            else        *reinterpret_cast<uint2 *>(d0) = make_uint2(lo, hi);
+            if (d1) {
+                const uint32_t jl = (uint32_t)d_clip_pel((int)(cur1.x & 0xffff) + ((r[0] * e.sign) >> e.shift), 10)
+                                  | ((uint32_t)d_clip_pel((int)(cur1.x >> 16) + ((r[1] * e.sign) >> e.shift), 10) << 16);
+                const uint32_t jh = (uint32_t)d_clip_pel((int)(cur1.y & 0xffff) + ((r[2] * e.sign) >> e.shift), 10)
+                                  | ((uint32_t)d_clip_pel((int)(cur1.y >> 16) + ((r[3] * e.sign) >> e.shift), 10) << 16);
+                if (narrow) *reinterpret_cast<uint32_t *>(d1) = jl;
+                else        *reinterpret_cast<uint2 *>(d1) = make_uint2(jl, jh);
+            }
+        }
+        cur0 = nxt0; cur1 = nxt1;
     }
 }
 
-__device__ __forceinline__ bool eligible(int l2w, int l2h, int flags)
+// 64-bit picture accesses need blocks of 4+ columns to start on a multiple of 4 samples (a 4-wide chroma block
+// under an 8-wide luma CU at x = 4 does not: left to the generic kernel)
+__device__ __forceinline__ bool eligible(int l2w, int l2h, int flags, int x0)
 {
-    return l2w >= 1 && l2h >= 1 && !(flags & (VVC_CUDA_TB_TS | VVC_CUDA_TB_BDPCM | VVC_CUDA_TB_BDPCM_VERT));
+    return l2w >= 1 && l2h >= 1 && !(flags & (VVC_CUDA_TB_TS | VVC_CUDA_TB_BDPCM | VVC_CUDA_TB_BDPCM_VERT)) &&
+           (l2w == 1 ? !(x0 & 1) : !(x0 & 3));
 }
 
 __global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
         const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
         const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, c_idx = (r2 >> 16) & 0xff, flags = r3 >> 24;
-        if (!eligible(l2w, l2h, flags)) {                   // itx_kernel's share
+        if (!eligible(l2w, l2h, flags, r1 & 0xffff)) {                   // itx_kernel's share
             if (lane == 0)
                 p.rest[atomicAdd(p.rest_count, 1u)] = ti;
             continue;
