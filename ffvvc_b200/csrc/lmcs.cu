@@ -80,11 +80,13 @@ __global__ void __launch_bounds__(kThreads) lmcs_rects_kernel(pel *plane, int pi
     }
 }
 
-int check(VVCCudaCtx *ctx, const VVCCudaFrame *f, const void *lut)
+// whole_rows: the CTB kernel walks rows with 128-bit accesses and needs the width to be a multiple of 8;
+// the rectangle kernel checks alignment per rectangle
+int check(VVCCudaCtx *ctx, const VVCCudaFrame *f, const void *lut, bool whole_rows)
 {
     if (!f || !lut)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "lmcs: null argument");
-    if ((f->bit_depth != 10 && f->bit_depth != 12) || (f->width & 7) || !frame_vec_ok(f))
+    if ((f->bit_depth != 10 && f->bit_depth != 12) || (whole_rows && (f->width & 7)) || !frame_vec_ok(f))
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "lmcs: unsupported picture format");
     return 0;
 }
@@ -95,7 +97,7 @@ extern "C" int vvc_cuda_lmcs_frame(VVCCudaCtx *ctx, const VVCCudaFrame *f, const
 {
     if (ctx->err)
         return ctx->err;
-    if (check(ctx, f, lut))
+    if (check(ctx, f, lut, true))
         return ctx->err;
     const int n = 1 << f->bit_depth;
     lmcs_frame_kernel<<<dim3(ceil_div(f->height, 8), f->batch), kThreads, n * sizeof(unsigned), ctx->stream>>>(
@@ -110,7 +112,7 @@ extern "C" int vvc_cuda_lmcs_rects(VVCCudaCtx *ctx, const VVCCudaFrame *f, const
 {
     if (ctx->err)
         return ctx->err;
-    if (check(ctx, f, lut) || !rects)
+    if (check(ctx, f, lut, false) || !rects)
         return ctx->err ? ctx->err : vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "lmcs: null rects");
     if (n_rects <= 0)
         return VVC_CUDA_OK;

@@ -13,6 +13,7 @@ from .dsp_tables import VVCDSPContext
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvvcdsp_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vvcdsp_cuda.h")
+TABLE_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vvcdsp_table.h")
 
 FP = C.POINTER(abi.VVCCudaFrame)
 CTX = C.c_void_p
@@ -25,10 +26,13 @@ class VVCCudaError(RuntimeError):
 
 
 def declared_symbols():
-    """Every function name include/vvcdsp_cuda.h declares (used by the export test)."""
-    src = open(HEADER_PATH).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:vvc_cuda|ff_vvc)_[a-z0-9_]+)\s*\(", src)))
+    """Every function name include/vvcdsp_cuda.h and include/vvcdsp_table.h declare (used by the export test)."""
+    names = set()
+    for path in (HEADER_PATH, TABLE_HEADER_PATH):
+        src = open(path).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b((?:vvc_cuda|ff_vvc)_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def load():
@@ -75,6 +79,12 @@ def load():
     lib.vvc_cuda_ctx_set_option.argtypes = [CTX, C.c_int, C.c_int]
     lib.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
     lib.vvc_cuda_abi_sizeof.restype = C.c_size_t
+    lib.ff_vvc_dsp_init_cuda.argtypes = [C.POINTER(VVCDSPContext), C.c_int]
+    lib.ff_vvc_dsp_init_cuda.restype = None
+    lib.ff_vvc_dsp_cuda_last_error.restype = C.c_int
+    lib.ff_vvc_dsp_cuda_error_string.restype = C.c_char_p
+    lib.ff_vvc_dsp_cuda_reset_error.restype = None
+    lib.ff_vvc_dsp_cuda_sizeof_table.restype = C.c_size_t
     _lib = lib
     return lib
 
