@@ -269,3 +269,15 @@ class VVCCudaReconDesc(C.Structure):
         ("lmcs_inv_lut", C.c_void_p), ("lmcs_ctb_enable", C.c_void_p),
         ("inloop", VVCCudaInloopDesc),
     ]
+
+
+# ---- intra leaf predictors / CIIP (include/vvcdsp_cuda.h) ----------------------------------------------
+INTRA_PLANAR, INTRA_DC, INTRA_VERT, INTRA_HORZ, INTRA_ANGULAR_V, INTRA_ANGULAR_H, INTRA_MIP = range(7)
+INTRA_PDPC, INTRA_MIP_TRANSPOSED = 1, 2
+INTRA_PB_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("w", np.uint8), ("h", np.uint8), ("c_idx", np.uint8),
+                           ("pic", np.uint8), ("kind", np.uint8), ("mode", np.int8), ("ref_idx", np.uint8),
+                           ("filter_flag", np.uint8), ("flags", np.uint8), ("reserved", np.uint8, 3),
+                           ("top", np.uint32), ("left", np.uint32)])
+CIIP_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("w", np.uint8), ("h", np.uint8), ("c_idx", np.uint8),
+                       ("pic", np.uint8), ("intra_weight", np.uint8), ("reserved", np.uint8, 3)])
+assert INTRA_PB_DTYPE.itemsize == 24 and CIIP_DTYPE.itemsize == 12

@@ -156,6 +156,8 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 11: return sizeof(VVCCudaDmvrOut);
     case 12: return sizeof(VVCCudaRect);
     case 13: return sizeof(VVCCudaReconDesc);
+    case 14: return sizeof(VVCCudaIntraPB);
+    case 15: return sizeof(VVCCudaCiip);
     default: return 0;
     }
 }

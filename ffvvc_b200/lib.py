@@ -77,6 +77,10 @@ def load():
     lib.vvc_cuda_recon_frame.argtypes = [CTX, FP, FP, FP, RP]
     lib.vvc_cuda_recon_frame_host.argtypes = [CTX, FP, FP, RP]
     lib.vvc_cuda_ctx_set_option.argtypes = [CTX, C.c_int, C.c_int]
+    lib.vvc_cuda_intra_leaf_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p]
+    lib.vvc_cuda_intra_leaf_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.vvc_cuda_ciip_frame.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int]
+    lib.vvc_cuda_ciip_frame_host.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int]
     lib.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
     lib.vvc_cuda_abi_sizeof.restype = C.c_size_t
     lib.ff_vvc_dsp_init_cuda.argtypes = [C.POINTER(VVCDSPContext), C.c_int]
@@ -192,6 +196,20 @@ class Context:
     def recon_frame_host(self, out, refs, descs):
         """descs: ctypes array of VVCCudaReconDesc, one per picture of `out` (host pointers everywhere)."""
         self.check(self.lib.vvc_cuda_recon_frame_host(self.handle, C.byref(out), C.byref(refs), descs))
+
+    def intra_leaf_frame(self, frame, pbs_ptr, n_pbs, edges_ptr):
+        """Intra leaf predictors (planar / DC / V / H / angular / MIP) of a list of independent blocks."""
+        self.check(self.lib.vvc_cuda_intra_leaf_frame(self.handle, C.byref(frame), pbs_ptr, n_pbs, edges_ptr))
+
+    def intra_leaf_frame_host(self, frame, pbs_ptr, n_pbs, edges_ptr, n_edges):
+        self.check(self.lib.vvc_cuda_intra_leaf_frame_host(self.handle, C.byref(frame), pbs_ptr, n_pbs, edges_ptr, n_edges))
+
+    def ciip_frame(self, dst, inter, blocks_ptr, n_blocks):
+        """CIIP blend of the intra prediction in dst with the inter prediction picture."""
+        self.check(self.lib.vvc_cuda_ciip_frame(self.handle, C.byref(dst), C.byref(inter), blocks_ptr, n_blocks))
+
+    def ciip_frame_host(self, dst, inter, blocks_ptr, n_blocks):
+        self.check(self.lib.vvc_cuda_ciip_frame_host(self.handle, C.byref(dst), C.byref(inter), blocks_ptr, n_blocks))
 
     def lmcs_rects(self, frame, lut_ptr, rects_ptr, n):
         self.check(self.lib.vvc_cuda_lmcs_rects(self.handle, C.byref(frame), lut_ptr, rects_ptr, n))

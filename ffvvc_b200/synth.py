@@ -570,3 +570,111 @@ def pb_list(geom, n_refs=2, seed=2024, dst_pics=None, mix=None):
     uni = pbs["pred_flag"] != abi.PF_BI
     pbs["bcw_idx"][uni] = 0
     return pbs, wp, prof
+
+
+# ---------------------------------------------------------------------------------------------
+# Intra leaf predictor records + their reference lines, and CIIP blocks.
+# ---------------------------------------------------------------------------------------------
+INTRA_ANGLES = np.array([0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29, 32, 35, 39, 45, 51, 57, 64, 73, 86, 102,
+                         128, 171, 256, 341, 512])
+
+
+def intra_angle(mode):
+    """ff_vvc_intra_pred_angle_derive (libavcodec/vvc/vvc_intra.c:661-681)."""
+    idx = mode - 50 if mode > 34 else (18 - mode if mode > 0 else 16 - mode)
+    return int(np.sign(idx)) * int(INTRA_ANGLES[abs(idx)]) if idx else 0
+
+
+def intra_nscale(w, h, mode):
+    """ff_vvc_nscale_derive for angular modes (vvc_intra.c:538-555); the float of inv_angle_derive is exact here."""
+    angle = intra_angle(mode)
+    inv = (32768 + angle) // (2 * angle)
+    side = h if mode >= 50 else w
+    return min(2, int(np.log2(side)) - int(np.floor(np.log2(3 * inv - 2))) + 8), inv
+
+
+def intra_list(geom, seed=606):
+    """Tile every plane with blocks and give each a random leaf predictor (planar, DC, V, H, angular with
+    reference-line index / filter / PDPC variants incl. wide angles, MIP) plus exactly the reference samples it
+    may read, as random samples of the picture's bit depth.  Returns (pbs, edges)."""
+    rng = LCG(seed)
+    maxv = (1 << geom.bit_depth) - 1
+    recs, edge_parts, at = [], [], 16
+    edge_parts.append(np.zeros(16, dtype=np.uint16))
+    for k in range(geom.batch):
+        lw, lh = tb_partition(geom, rng, stop_p=0.4)
+        uh, uw = lw.shape
+        uy, ux = np.mgrid[0:uh, 0:uw]
+        origin = ((ux * 4) % (1 << lw) == 0) & ((uy * 4) % (1 << lh) == 0)
+        x0, y0, l2w, l2h = ux[origin] * 4, uy[origin] * 4, lw[origin], lh[origin]
+        inside = (x0 + (1 << l2w) <= geom.width) & (y0 + (1 << l2h) <= geom.height)
+        x0, y0, l2w, l2h = x0[inside], y0[inside], l2w[inside], l2h[inside]
+        for c in range(3 if geom.chroma_format_idc else 1):
+            sh = 1 if c else 0
+            n = len(x0)
+            kind = rng.below(n, 7)
+            r_mode, r_ref, r_flt, r_pd, r_tr = rng.below(n, 1 << 16), rng.below(n, 3), rng.below(n, 2), rng.below(n, 4), rng.below(n, 2)
+            for i in range(n):
+                w, h = (1 << int(l2w[i])) >> sh, (1 << int(l2h[i])) >> sh
+                if w < 4:
+                    continue        # 2-wide chroma intra blocks do not exist in VVC (pred_dc / pred_h store 4 samples at a time)
+                r = np.zeros(1, dtype=abi.INTRA_PB_DTYPE)
+                kd = int(kind[i])
+                if kd == abi.INTRA_MIP and (c or w < 4 or h < 4):
+                    kd = abi.INTRA_PLANAR
+                r["x0"], r["y0"], r["w"], r["h"], r["c_idx"], r["pic"] = x0[i] >> sh, y0[i] >> sh, w, h, c, k
+                before = after_top = after_left = 8
+                if kd == abi.INTRA_MIP:
+                    size_id = 0 if (w == 4 and h == 4) else (1 if (w == 4 or h == 4 or (w == 8 and h == 8)) else 2)
+                    r["mode"] = int(r_mode[i]) % (16, 8, 6)[size_id]
+                    r["flags"] = abi.INTRA_MIP_TRANSPOSED if r_tr[i] else 0
+                elif kd in (abi.INTRA_ANGULAR_V, abi.INTRA_ANGULAR_H):
+                    if kd == abi.INTRA_ANGULAR_V:
+                        mode = 34 + int(r_mode[i]) % 47                       # 34..80
+                        mode = 51 if mode == 50 else mode
+                    else:
+                        mode = -14 + int(r_mode[i]) % 48                      # -14..33
+                        mode = {0: 2, 1: 3, 18: 19}.get(mode, mode)
+                    ref_idx = 0 if c else int(r_ref[i])
+                    angle = intra_angle(mode)
+                    pdpc = 0
+                    if w >= 4 and h >= 4 and not ref_idx and not (18 < mode < 50) and r_pd[i] != 0:
+                        ns, inv = intra_nscale(w, h, mode)
+                        if ns >= 0:
+                            pdpc = 1
+                            side_reach = ((256 + min(max(w, h), 3 << ns) * inv) >> 9) + 2
+                            after_top, after_left = after_top + side_reach, after_left + side_reach
+                    r["mode"], r["ref_idx"], r["filter_flag"], r["flags"] = mode, ref_idx, int(r_flt[i]), pdpc
+                    reach = (((max(w, h) + 1 + ref_idx) * abs(angle)) >> 5) + ref_idx + 6
+                    before += reach + ref_idx + 2
+                    after_top, after_left = after_top + reach, after_left + reach
+                r["kind"] = kd
+                n_top, n_left = before + w + after_top + 1, before + h + after_left + 1
+                e = (rng.take(n_top + n_left) & np.uint32(maxv)).astype(np.uint16)
+                r["top"], r["left"] = at + before, at + n_top + before
+                at += n_top + n_left
+                edge_parts.append(e)
+                recs.append(r)
+    return np.concatenate(recs), np.concatenate(edge_parts)
+
+
+def ciip_list(geom, seed=707):
+    """CIIP blocks on a random partition: every block of every plane with intra weight 1..3."""
+    rng = LCG(seed)
+    recs = []
+    for k in range(geom.batch):
+        lw, lh = tb_partition(geom, rng, stop_p=0.4)
+        uh, uw = lw.shape
+        uy, ux = np.mgrid[0:uh, 0:uw]
+        origin = ((ux * 4) % (1 << lw) == 0) & ((uy * 4) % (1 << lh) == 0)
+        x0, y0, l2w, l2h = ux[origin] * 4, uy[origin] * 4, lw[origin], lh[origin]
+        inside = (x0 + (1 << l2w) <= geom.width) & (y0 + (1 << l2h) <= geom.height)
+        x0, y0, l2w, l2h = x0[inside], y0[inside], l2w[inside], l2h[inside]
+        wi = rng.below(len(x0), 3) + 1
+        for c in range(3 if geom.chroma_format_idc else 1):
+            sh = 1 if c else 0
+            r = np.zeros(len(x0), dtype=abi.CIIP_DTYPE)
+            r["x0"], r["y0"], r["w"], r["h"] = x0 >> sh, y0 >> sh, (1 << l2w) >> sh, (1 << l2h) >> sh
+            r["c_idx"], r["pic"], r["intra_weight"] = c, k, wi
+            recs.append(r)
+    return np.concatenate(recs)

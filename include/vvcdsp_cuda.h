@@ -359,6 +359,61 @@ int vvc_cuda_inter_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VV
                               const VVCCudaProf *prof, int n_prof, VVCCudaDmvrOut *dmvr_out);
 
 /* ------------------------------------------------------------------------------------------
+ * Intra leaf predictors and the CIIP blend.  Batched form of the table entries intra.pred_planar /
+ * pred_dc / pred_v / pred_h / pred_angular_v / pred_angular_h / pred_mip
+ * (libavcodec/vvc/vvc_intra_template.c:686-1000) and inter.put_ciip (vvc_inter_template.c:60-76).
+ * The reference lines of a block are prepared by the host exactly as prepare_intra_edge_params()
+ * (vvc_intra_template.c:467-592) leaves them in IntraEdgeParams: that step (availability, substitution,
+ * [1 2 1] smoothing, the projected negative-index part), the PDPC of planar/DC/H/V, CCLM and the LMCS
+ * chroma scaling need the decoder's CTU state and stay with it (entries that take VVCLocalContext*).
+ * Blocks of one call must not depend on each other (a wavefront of the RECON stage, or CIIP blocks).
+ * ---------------------------------------------------------------------------------------- */
+#define VVC_CUDA_INTRA_PLANAR     0
+#define VVC_CUDA_INTRA_DC         1
+#define VVC_CUDA_INTRA_VERT       2   /* pred_v */
+#define VVC_CUDA_INTRA_HORZ       3   /* pred_h */
+#define VVC_CUDA_INTRA_ANGULAR_V  4   /* pred_angular_v: mode >= 34 (INTRA_DIAG) */
+#define VVC_CUDA_INTRA_ANGULAR_H  5   /* pred_angular_h */
+#define VVC_CUDA_INTRA_MIP        6
+
+#define VVC_CUDA_INTRA_PDPC       1   /* flags: need_pdpc argument of pred_angular_* */
+#define VVC_CUDA_INTRA_MIP_TRANSPOSED 2
+
+typedef struct VVCCudaIntraPB {
+    uint16_t x0, y0;          /* top-left sample, in plane c_idx's own units                          */
+    uint8_t  w, h;            /* w 4..64, h 2..64, powers of two (MIP: both 4..64)                    */
+    uint8_t  c_idx, pic;
+    uint8_t  kind;            /* VVC_CUDA_INTRA_*                                                      */
+    int8_t   mode;            /* angular: predModeIntra after wide-angle mapping (-14..80); MIP: mode id */
+    uint8_t  ref_idx;         /* intra_luma_ref_idx (angular)                                          */
+    uint8_t  filter_flag;     /* IntraEdgeParams.filter_flag (angular, luma: 0 cubic, 1 gauss)         */
+    uint8_t  flags;           /* VVC_CUDA_INTRA_PDPC | VVC_CUDA_INTRA_MIP_TRANSPOSED                    */
+    uint8_t  reserved[3];
+    uint32_t top, left;       /* index of top[0] / left[0] in the edge sample buffer; the samples the
+                                 reference reads at negative indices (top[-1 - ref_idx] ...) lie before */
+} VVCCudaIntraPB;             /* 24 bytes */
+
+/* frame: picture (ring) predicted into.  edges: 16-bit reference samples.  All arrays device memory. */
+int vvc_cuda_intra_leaf_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraPB *pbs, int n_pbs,
+                              const uint16_t *edges);
+int vvc_cuda_intra_leaf_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraPB *pbs, int n_pbs,
+                                   const uint16_t *edges, size_t n_edges);
+
+typedef struct VVCCudaCiip {
+    uint16_t x0, y0;          /* in plane c_idx's own units */
+    uint8_t  w, h, c_idx, pic;
+    uint8_t  intra_weight;    /* 1..3 (ciip_derive_intra_weight, vvc_inter.c:523-543)                  */
+    uint8_t  reserved[3];
+} VVCCudaCiip;                /* 12 bytes */
+
+/* dst holds the intra prediction of each block and receives (dst * wi + inter * (4 - wi) + 2) >> 2;
+ * inter: a picture (ring) of the same geometry holding the inter prediction at the same positions. */
+int vvc_cuda_ciip_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *inter,
+                        const VVCCudaCiip *blocks, int n_blocks);
+int vvc_cuda_ciip_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *inter,
+                             const VVCCudaCiip *blocks, int n_blocks);
+
+/* ------------------------------------------------------------------------------------------
  * Whole-picture reconstruction: INTER -> RECON (residual) -> LMCS -> DEBLOCK_V -> DEBLOCK_H -> SAO ->
  * ALF, the reference's per-CTU stage list (libavcodec/vvc/vvc_thread.c:41-51) run stage by stage
  * over the picture (7 launches, + 1 when forward-LMCS rectangles are given).

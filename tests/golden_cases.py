@@ -33,6 +33,8 @@ def build_case(name, lfnst_set_of):
     case["maps"] = synth.deblock_maps(geom, seed=seed + 4, qp_base=27, qp_span=16)
     case["sao"] = synth.sao_params(geom, seed=seed + 5)
     case["alf"], case["sets"] = synth.alf_params(geom, seed=seed + 6)
+    case["intra_pbs"], case["intra_edges"] = synth.intra_list(geom, seed=seed + 7)
+    case["ciip"] = synth.ciip_list(geom, seed=seed + 8)
     return case
 
 
@@ -67,6 +69,12 @@ class HostBackend:
     def alf(self, geom, dst, src, ctbs, sets):
         self.fn("alf_frame")(abi.frame_from_numpy(geom, dst), abi.frame_from_numpy(geom, src), ctbs.ctypes.data, sets.ctypes.data, 0)
 
+    def intra(self, geom, pic, pbs, edges):
+        self.fn("intra_leaf_frame")(abi.frame_from_numpy(geom, pic), pbs.ctypes.data, len(pbs), edges.ctypes.data)
+
+    def ciip(self, geom, dst, inter, blocks):
+        self.fn("ciip_frame")(abi.frame_from_numpy(geom, dst), abi.frame_from_numpy(geom, inter), blocks.ctypes.data, len(blocks))
+
 
 class CudaHostBackend:
     """The product library through its *_host C-ABI entries (host pointers in, host pointers out)."""
@@ -94,6 +102,12 @@ class CudaHostBackend:
     def alf(self, geom, dst, src, ctbs, sets):
         self.ctx.alf_frame_host(abi.frame_from_numpy(geom, dst), abi.frame_from_numpy(geom, src), ctbs.ctypes.data, sets.ctypes.data)
 
+    def intra(self, geom, pic, pbs, edges):
+        self.ctx.intra_leaf_frame_host(abi.frame_from_numpy(geom, pic), pbs.ctypes.data, len(pbs), edges.ctypes.data, len(edges))
+
+    def ciip(self, geom, dst, inter, blocks):
+        self.ctx.ciip_frame_host(abi.frame_from_numpy(geom, dst), abi.frame_from_numpy(geom, inter), blocks.ctypes.data, len(blocks))
+
 
 def run_case(case, be):
     """Returns {stage: [arrays]} after each stage of the reconstruction."""
@@ -104,6 +118,12 @@ def run_case(case, be):
     be.inter(g, case["gref"], pic, case["refs"], case["pbs"], case["wp"], case["prof"], dm)
     is_dm = (case["pbs"]["flags"] & abi.PB_DMVR) != 0
     out["inter"] = vis(pic) + [np.ascontiguousarray(dm[is_dm])]
+    # intra leaf predictors over a tiling of their own, then the CIIP blend of that picture with the inter one
+    ipic = abi.alloc_planes(g, fill=3)
+    be.intra(g, ipic, case["intra_pbs"], case["intra_edges"])
+    out["intra"] = vis(ipic)
+    be.ciip(g, ipic, [p.copy() for p in pic], case["ciip"])
+    out["ciip"] = vis(ipic)
     coeffs = case["coeffs"].copy()
     be.itx(g, pic, coeffs, case["tbs"], 15)
     out["residual"] = vis(pic)

@@ -20,7 +20,8 @@ def test_descriptor_sizes_match_the_header():
     want = {0: C.sizeof(abi.VVCCudaFrame), 1: C.sizeof(abi.VVCCudaALFCtb), 2: C.sizeof(abi.VVCCudaALFSets),
             3: C.sizeof(abi.VVCCudaDbkEdge), 4: C.sizeof(abi.VVCCudaDeblockMaps), 5: C.sizeof(abi.VVCCudaSAOCtb), 6: C.sizeof(abi.VVCCudaInloopDesc), 7: C.sizeof(abi.VVCCudaTB),
             8: abi.PB_DTYPE.itemsize, 9: abi.WP_DTYPE.itemsize, 10: abi.PROF_DTYPE.itemsize, 11: abi.DMVR_OUT_DTYPE.itemsize,
-            12: C.sizeof(abi.VVCCudaRect), 13: C.sizeof(abi.VVCCudaReconDesc)}
+            12: C.sizeof(abi.VVCCudaRect), 13: C.sizeof(abi.VVCCudaReconDesc),
+            14: abi.INTRA_PB_DTYPE.itemsize, 15: abi.CIIP_DTYPE.itemsize}
     for which, size in want.items():
         assert handle.vvc_cuda_abi_sizeof(which) == size, which
 

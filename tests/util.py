@@ -54,6 +54,10 @@ def oracle():
         lib.vvco_lmcs_rects.restype = None
         lib.vvco_inter_frame.argtypes = [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vvco_inter_frame.restype = None
+        lib.vvco_intra_leaf_frame.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p]
+        lib.vvco_intra_leaf_frame.restype = None
+        lib.vvco_ciip_frame.argtypes = [FP, FP, C.c_void_p, C.c_int]
+        lib.vvco_ciip_frame.restype = None
         _oracle = lib
     return _oracle
 
@@ -86,6 +90,10 @@ def ref():
         lib.vvcref_lmcs_rects.restype = None
         lib.vvcref_inter_frame.argtypes = [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vvcref_inter_frame.restype = None
+        lib.vvcref_intra_leaf_frame.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p]
+        lib.vvcref_intra_leaf_frame.restype = None
+        lib.vvcref_ciip_frame.argtypes = [FP, FP, C.c_void_p, C.c_int]
+        lib.vvcref_ciip_frame.restype = None
         _ref = lib
     return _ref
 
