@@ -317,9 +317,9 @@ def main():
             cur=sub_frame(cur, k0), out=sub_frame(out, k0), pbs=up(pbs), n_pbs=len(pbs), tbs=up(tbs), n_tbs=len(tbs),
             coeffs=up(coeffs), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
             alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
-    # kernels per picture group: inter = 6 (classify, four thread-per-patch class kernels, warp-per-record kernel),
+    # kernels per picture group: inter = 7 (classify, four thread-per-patch class kernels, two warp-per-record kernels),
     # residual = 2 (warp-per-TB kernel + generic kernel over the blocks it leaves), every other stage 1
-    launches_per_step = len(groups) * (len(STAGES) + 6)
+    launches_per_step = len(groups) * (len(STAGES) + 7)
 
     def step(events=None):
         for gi, g in enumerate(groups):

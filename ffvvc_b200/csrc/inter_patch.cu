@@ -154,26 +154,26 @@ __device__ __forceinline__ Blend blend_of(const Rec &pb, const VVCCudaWP *wp, bo
 __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, const InterLists ls)
 {
     // one reservation per list per CTA: block-wide exclusive scan of the five per-record counts
-    __shared__ uint32_t warp_tot[8][5], cta_base[5];
+    __shared__ uint32_t warp_tot[8][6], cta_base[6];
     const int ri = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int cls_l = -1, cls_c = -1, n_l = 0, n_c = 0, coop = 0;
+    int cls_l = -1, cls_c = -1, n_l = 0, n_c = 0, coop = -1;
     if (ri < p.n) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p.pbs + ri);
         const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2);
         const int w = r1 & 0xff, h = (r1 >> 8) & 0xff, planes = (r1 >> 16) & 0xff, pred = r1 >> 24, flags = r2 >> 24;
         if (flags & VVC_PB_COOPERATIVE) {
-            coop = 1;
+            coop = (flags & (VVC_CUDA_PB_PROF0 | VVC_CUDA_PB_PROF1)) ? 1 : 0;      // 0: DMVR / BDOF, 1: PROF
         } else {
             const int bi = (flags & VVC_CUDA_PB_GPM) || pred == 3;
             if (planes & VVC_CUDA_PB_LUMA) { cls_l = bi; n_l = (w >> 2) * ((h + 7) >> 3); }
             if ((planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) { cls_c = bi; n_c = w > 8 ? 4 : 2; }   // 2 planes x patch columns
         }
     }
-    uint32_t mine[5] = { cls_l == 0 ? (uint32_t)n_l : 0u, cls_l == 1 ? (uint32_t)n_l : 0u,
-                         cls_c == 0 ? (uint32_t)n_c : 0u, cls_c == 1 ? (uint32_t)n_c : 0u, (uint32_t)coop };
-    uint32_t excl[5];
+    uint32_t mine[6] = { cls_l == 0 ? (uint32_t)n_l : 0u, cls_l == 1 ? (uint32_t)n_l : 0u,
+                         cls_c == 0 ? (uint32_t)n_c : 0u, cls_c == 1 ? (uint32_t)n_c : 0u, coop == 0 ? 1u : 0u, coop == 1 ? 1u : 0u };
+    uint32_t excl[6];
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
+    for (int c = 0; c < 6; c++) {
         uint32_t v = mine[c];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -184,14 +184,16 @@ __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, con
         if (lane == 31) warp_tot[wid][c] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 5) {
+    if (threadIdx.x < 6) {
         uint32_t tot = 0;
         for (int k = 0; k < 8; k++) { const uint32_t t = warp_tot[k][threadIdx.x]; warp_tot[k][threadIdx.x] = tot; tot += t; }
         cta_base[threadIdx.x] = tot ? atomicAdd(ls.count + threadIdx.x, tot) : 0u;
     }
     __syncthreads();
-    if (coop)
-        ls.coop[cta_base[4] + warp_tot[wid][4] + excl[4]] = ri;
+    if (coop >= 0) {
+        const int at = (int)(cta_base[4 + coop] + warp_tot[wid][4 + coop] + excl[4 + coop]);
+        ls.coop[coop ? p.n - 1 - at : at] = ri;
+    }
     if (cls_l >= 0) {
         const int base = (int)(cta_base[cls_l] + warp_tot[wid][cls_l] + excl[cls_l]);
         for (int k = 0; k < n_l; k++)

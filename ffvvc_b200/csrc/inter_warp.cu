@@ -236,7 +236,10 @@ __device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, 
     }
 }
 
-__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, const uint32_t *__restrict__ count)   //@region rec_load
+// KIND 0: records with DMVR / BDOF and no PROF (always bi-predicted, never GPM): the uni, GPM and PROF paths are
+// compiled out.  KIND 1: the rest of the cooperative records (PROF), listed from the back of coop[].
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, int cap, const uint32_t *__restrict__ count)   //@region rec_load
 {
     __shared__ WarpSmem sm[kWarps];
     const int lane = threadIdx.x & 31;
@@ -245,14 +248,14 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
     const uint2 *lumaf = reinterpret_cast<const uint2 *>(&vvct_luma_mc_filters[0][0][0]);
     const uint32_t *chromaf = reinterpret_cast<const uint32_t *>(&vvct_chroma_mc_filters[0][0][0]);
 
-    const int n_coop = (int)count[4];
+    const int n_coop = (int)count[4 + KIND];
     for (int ci = blockIdx.x * kWarps + (threadIdx.x >> 5); ci < n_coop; ci += nwarps) {
         __syncwarp();
-        const int ri = (int)__ldg(coop + ci);
+        const int ri = (int)__ldg(coop + (KIND ? cap - 1 - ci : ci));
         const Rec pb = load_rec(p.pbs + ri);
         const int w = pb.w, h = pb.h, lw = 31 - __clz(w);
-        const bool gpm = pb.flags & VVC_CUDA_PB_GPM;
-        const bool bi = gpm || pb.pred == 3;
+        const bool gpm = KIND == 0 ? false : (pb.flags & VVC_CUDA_PB_GPM) != 0;
+        const bool bi = KIND == 0 ? true : gpm || pb.pred == 3;
         const bool dmvr = (pb.flags & VVC_CUDA_PB_DMVR) != 0;
         const int lx = pb.pred - 1;                                  // the list of a uni record
         int mvr[2][2] = { { pb.mv[0][0], pb.mv[0][1] }, { pb.mv[1][0], pb.mv[1][1] } };   // vectors used for MC
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                     }
                 }
             } else {
-                const int prof_mask = gpm ? 0 : pb.flags & (VVC_CUDA_PB_PROF0 | VVC_CUDA_PB_PROF1);   //@region bi_ring_prof
+                const int prof_mask = (KIND == 0 || gpm) ? 0 : pb.flags & (VVC_CUDA_PB_PROF0 | VVC_CUDA_PB_PROF1);   //@region bi_ring_prof
                 if (do_bdof || prof_mask) {
                     fetch_ring(s, 0, w, h, mvr[0][0] & 15, mvr[0][1] & 15, lane);
                     fetch_ring(s, 1, w, h, mvr[1][0] & 15, mvr[1][1] & 15, lane);
@@ -695,7 +698,9 @@ int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &li
 {
     const int ctas = ceil_div(p.n, kWarps);
     const int grid = ctas < 148 * 7 ? ctas : 148 * 7;            // persistent: 7 CTAs fit an SM (shared memory)
-    inter_warp_kernel<<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, lists.count);
+    inter_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count);
+    VVC_LAUNCHED(ctx);
+    inter_warp_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }
