@@ -67,44 +67,45 @@ struct __align__(16) WarpSmem {
 __device__ __forceinline__ uint32_t inv_rows(int d) { return d == 23 ? 2850u : d == 15 ? 4370u : d == 11 ? 5958u : d == 7 ? 9363u : 13108u; }
 
 // ---- window staging ----------------------------------------------------------------------------------
-// Core of a window: samples [wx0, wx0 + cols) x [wy0, wy0 + rows) of a plane, picture-clamped, stored from
-// the even column bx = wx0 & ~1 at word (row + padr) * pw + padw.  Lane = (word of the row, row group): 16
-// words x 2 rows or 8 words x 4 rows per step, no index division.  One out-of-line copy serves every caller
-// (the kernel's code size matters: warps sit in different record kinds and share the instruction cache).
-__device__ __noinline__ void stage_core(uint32_t *win, int pw, int padw, int padr, const pel *plane, int pitch, int W, int H,   //@region stage_core
-                                        int wx0, int wy0, int cols, int rows, int lane)
+// All units of a phase (the two lists of luma, or the (plane, list) pairs of chroma) are staged by ONE call: the
+// warp is split into equal lane groups, one per unit, and every lane passes its own unit's plane and window
+// origin.  Window = samples [wx0, wx0 + cols) x [wy0, wy0 + rows), picture-clamped, stored from the even
+// column wx0 & ~1 at word (row + 2 pad) * pw + pad of the unit's window.  Inside a group a lane is (word of
+// the row, row sub-group): no index division.  pad: replicated apron of a DMVR window (2 samples each side,
+// 2 rows above and below), which equals clamping the coordinates to the unrefined block's window
+// (emulated_edge_dmvr, vvc_inter.c:60-89).  One out-of-line copy serves every caller (the kernel's code size
+// matters: warps sit in different phases and share the instruction cache).
+__device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const pel *plane, int pitch, int W, int H,   //@region stage_core
+                                         int wx0, int wy0, int cols, int rows, int sub, int group)
 {
     const int e = wx0 & 1, bx = wx0 - e, nw = (cols + e + 1) >> 1;
     const int lk = nw > 8 ? 4 : 3;
-    const int k = lane & ((1 << lk) - 1), rsub = lane >> lk, rstep = 32 >> lk;
-    if (k >= nw)
-        return;
-    const bool inside = bx >= 0 && bx + 2 * nw <= W && wy0 >= 0 && wy0 + rows <= H;
-    uint32_t *dst = win + (padr + rsub) * pw + padw + k;
-    const int dstep = rstep * pw;
-    if (inside) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (long long)(wy0 + rsub) * pitch + bx) + k;
-        const int sstep = rstep * (pitch >> 1);
+    const int k = sub & ((1 << lk) - 1), rsub = sub >> lk, rstep = group >> lk;
+    if (k < nw) {
+        const bool inside = bx >= 0 && bx + 2 * nw <= W && wy0 >= 0 && wy0 + rows <= H;
+        uint32_t *dst = win + (2 * pad + rsub) * pw + pad + k;
+        const int dstep = rstep * pw;
+        if (inside) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (long long)(wy0 + rsub) * pitch + bx) + k;
+            const int sstep = rstep * (pitch >> 1);
 #pragma unroll 4
-        for (int r = rsub; r < rows; r += rstep, src += sstep, dst += dstep)
-            *dst = __ldg(src);
-    } else {
-        const int xa = d_clip3(bx + 2 * k, 0, W - 1), xb = d_clip3(bx + 2 * k + 1, 0, W - 1);
+            for (int r = rsub; r < rows; r += rstep, src += sstep, dst += dstep)
+                *dst = __ldg(src);
+        } else {
+            const int xa = d_clip3(bx + 2 * k, 0, W - 1), xb = d_clip3(bx + 2 * k + 1, 0, W - 1);
 #pragma unroll 2
-        for (int r = rsub; r < rows; r += rstep, dst += dstep) {
-            const pel *row = plane + (long long)d_clip3(wy0 + r, 0, H - 1) * pitch;
-            *dst = (uint32_t)__ldg(row + xa) | ((uint32_t)__ldg(row + xb) << 16);
+            for (int r = rsub; r < rows; r += rstep, dst += dstep) {
+                const pel *row = plane + (long long)d_clip3(wy0 + r, 0, H - 1) * pitch;
+                *dst = (uint32_t)__ldg(row + xa) | ((uint32_t)__ldg(row + xb) << 16);
+            }
         }
     }
-}
-
-// Replicated apron of a DMVR window (core at rows 2.., sample column 2 + e..): 2 samples each side, 2 rows
-// above and below.  Equals clamping the coordinates to the unrefined block's window (emulated_edge_dmvr).
-__device__ __noinline__ void pad_window(uint32_t *win, int pw, int e, int cols0, int rows0, int lane)   //@region pad_window
-{
-    if (lane < rows0) {                                    // lane = core row
-        uint16_t *row = reinterpret_cast<uint16_t *>(win) + (lane + 2) * (2 * pw);
-        const int first = 2 + e, last = 2 + e + cols0 - 1;
+    if (!pad)
+        return;
+    __syncwarp();
+    for (int r = sub; r < rows; r += group) {              // lane = core row
+        uint16_t *row = reinterpret_cast<uint16_t *>(win) + (r + 2) * (2 * pw);
+        const int first = 2 + e, last = 2 + e + cols - 1;
         const uint16_t a = row[first], b = row[last];
         row[0] = a; row[1] = a;
         if (e)
@@ -112,10 +113,10 @@ __device__ __noinline__ void pad_window(uint32_t *win, int pw, int e, int cols0,
         row[last + 1] = b; row[last + 2] = b;
     }
     __syncwarp();
-    if (lane < pw) {
-        const uint32_t top = win[2 * pw + lane], bot = win[(rows0 + 1) * pw + lane];
-        win[lane] = top; win[pw + lane] = top;
-        win[(rows0 + 2) * pw + lane] = bot; win[(rows0 + 3) * pw + lane] = bot;
+    for (int c = sub; c < pw; c += group) {
+        const uint32_t top = win[2 * pw + c], bot = win[(rows + 1) * pw + c];
+        win[c] = top; win[pw + c] = top;
+        win[(rows + 2) * pw + c] = bot; win[(rows + 3) * pw + c] = bot;
     }
 }
 
@@ -267,14 +268,11 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
 
         // ---- DMVR: stage both unrefined windows, bilinear prediction, 25 SADs, refinement -------------
         if (dmvr_luma) {   //@region dmvr_stage
-#pragma unroll 1
-            for (int l = 0; l < 2; l++)
-                stage_core(s.a.win + l * WUL, PWL, 1, 2, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h,
-                           pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane);
-            __syncwarp();
-#pragma unroll 1
-            for (int l = 0; l < 2; l++)
-                pad_window(s.a.win + l * WUL, PWL, (pb.x0 + (MV0(l, 0) >> 4) - 3) & 1, w + 7, h + 7, lane);
+            {
+                const int l = lane >> 4;                    // lanes 0-15: list 0, lanes 16-31: list 1
+                stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h,
+                            pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane & 15, 16);
+            }
             __syncwarp();
             // bilinear (dmvr / dmvr_h / dmvr_v / dmvr_hv, vvc_inter_template.c:324-409) on sample pairs; lane = row
             const int nwo = (w + 4) >> 1;   //@region dmvr_bilinear
@@ -307,45 +305,50 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 }
             }
             __syncwarp();
-            // SAD on every other row (vvc_sad, vvcdsp.c:49-65): task = (dy, row), the 5 dx share the loaded rows
+            // SAD on every other row (vvc_sad, vvcdsp.c:49-65).  A task is (dy, row[, quarter of the row]); the 5 dx of a
+            // dy share the loaded rows.  With 8 rows, dy = 0..3 fill the 32 lanes with whole rows and dy = 4 is split
+            // into row quarters over all 32 lanes; with 4 rows the 20 (dy, row) tasks fit one pass.
             {
-                const int lhr = 31 - __clz(h >> 1), ntask = 5 << lhr, nwr = w >> 1;   //@region dmvr_sad
-                for (int base = 0; base < ntask; base += 32) {
-                    const int t = base + lane;
-                    const bool act = t < ntask;
-                    const int dyi = act ? t >> lhr : 0, y = (t & ((1 << lhr) - 1)) << 1;
+                const int lhr = 31 - __clz(h >> 1), hr = h >> 1, nwr = w >> 1;   //@region dmvr_sad
+                const int passes = hr == 8 ? 2 : 1;
+                for (int pass = 0; pass < passes; pass++) {
+                    int dyi, yy, k0, k1;
+                    bool act = true;
+                    if (hr == 8 && pass == 1) { dyi = 4; yy = lane >> 2; k0 = (lane & 3) * (nwr >> 2); k1 = k0 + (nwr >> 2); }
+                    else { dyi = lane >> lhr; yy = lane & (hr - 1); k0 = 0; k1 = nwr; act = dyi < (hr == 8 ? 4 : 5); }
+                    if (!act) { dyi = 0; k1 = 0; }
+                    const int y = yy << 1;
                     const uint32_t *ra = reinterpret_cast<const uint32_t *>(&s.dm[0][(dyi + y) * DP]);
                     const uint32_t *rb = reinterpret_cast<const uint32_t *>(&s.dm[1][(4 - dyi + y) * DP]);
-                    uint32_t A[10], B[10], A1[9], B1[9];
-#pragma unroll
-                    for (int k = 0; k < 10; k++) {
-                        A[k] = k < nwr + 2 ? ra[k] : 0;
-                        B[k] = k < nwr + 2 ? rb[k] : 0;
+                    uint32_t sd[5] = { 0, 0, 0, 0, 0 };         // per dx: two 16-bit partial sums (at most 8 x 1023 each)
+                    uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+                    if (k0 < k1) {
+                        a0 = ra[k0]; a1 = ra[k0 + 1]; b0 = rb[k0]; b1 = rb[k0 + 1];
                     }
 #pragma unroll
-                    for (int k = 0; k < 9; k++) {
-                        A1[k] = __funnelshift_r(A[k], A[k + 1], 16);
-                        B1[k] = __funnelshift_r(B[k], B[k + 1], 16);
-                    }
-                    int sd[5] = { 0, 0, 0, 0, 0 };
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        if (k < nwr) {
-#define SADW(a, b) __dp2a_lo((int)(__vmaxu2(a, b) - __vminu2(a, b)), 0x0101, 0)
-                            sd[0] += SADW(A[k], B[k + 2]);         // dx = -2: a at 0, b at 4
-                            sd[1] += SADW(A1[k], B1[k + 1]);       // dx = -1: a at 1, b at 3
-                            sd[2] += SADW(A[k + 1], B[k + 1]);     // dx =  0
-                            sd[3] += SADW(A1[k + 1], B1[k]);       // dx = +1: a at 3, b at 1
-                            sd[4] += SADW(A[k + 2], B[k]);         // dx = +2
+                    for (int kk = 0; kk < 8; kk++) {
+                        const int k = k0 + kk;
+                        if (k < k1) {
+                            a2 = ra[k + 2]; b2 = rb[k + 2];
+                            const uint32_t a01 = __funnelshift_r(a0, a1, 16), a12 = __funnelshift_r(a1, a2, 16);
+                            const uint32_t b01 = __funnelshift_r(b0, b1, 16), b12 = __funnelshift_r(b1, b2, 16);
+#define SADW(acc, u, v) acc = acc + __vmaxu2(u, v) - __vminu2(u, v)
+                            SADW(sd[0], a0, b2);               // dx = -2: a at sample 0, b at sample 4
+                            SADW(sd[1], a01, b12);             // dx = -1: a at 1, b at 3
+                            SADW(sd[2], a1, b1);               // dx =  0
+                            SADW(sd[3], a12, b01);             // dx = +1: a at 3, b at 1
+                            SADW(sd[4], a2, b0);               // dx = +2
 #undef SADW
+                            a0 = a1; a1 = a2; b0 = b1; b1 = b2;
                         }
                     }
+                    const int span = (hr == 8 && pass == 1) ? 32 : hr;
 #pragma unroll
                     for (int d = 0; d < 5; d++) {
-                        int v = act ? sd[d] : 0;
-                        for (int o = 1; o < (h >> 1); o <<= 1)
+                        int v = (int)((sd[d] & 0xffff) + (sd[d] >> 16));
+                        for (int o = 1; o < span; o <<= 1)
                             v += __shfl_xor_sync(0xffffffffu, v, o);
-                        if (act && !(t & ((1 << lhr) - 1)))
+                        if (act && !(lane & (span - 1)))
                             s.sad[dyi * 5 + d] = v;
                     }
                 }
@@ -421,14 +424,10 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 if (lane < n_units)
                     s.um[lane] = m;
                 if (!dmvr_luma) {
-#pragma unroll 1
-                    for (int i = 0; i < 2; i++) {
-                        if (i < n_units) {
-                            const int li = bi ? i : lx;
-                            stage_core(s.a.win + i * WUL, PWL, 0, 0, p.ref[0] + REF(li) * p.rb[0], p.rp[0], p.w, p.h,
-                                            pb.x0 + (MVR(li, 0) >> 4) - 3, pb.y0 + (MVR(li, 1) >> 4) - 3, w + 7, h + 7, lane);
-                        }
-                    }
+                    const int i = bi ? lane >> 4 : 0, li = bi ? i : lx;
+                    stage_units(s.a.win + i * WUL, PWL, 0, p.ref[0] + REF(li) * p.rb[0], p.rp[0], p.w, p.h,
+                                pb.x0 + (MVR(li, 0) >> 4) - 3, pb.y0 + (MVR(li, 1) >> 4) - 3, w + 7, h + 7,
+                                bi ? lane & 15 : lane, bi ? 16 : 32);
                 }
             }
             __syncwarp();
@@ -631,30 +630,15 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 if (lane < n_units)
                     s.um[lane] = m;
             }
-#pragma unroll 1
-            for (int u = 0; u < 4; u++) {
-                if (u < n_units) {
-                    const int list = bi ? (u & 1) : lx, pc = bi ? (u >> 1) : u;
-                    const pel *plane = (pc ? p.ref[2] + REF(list) * p.rb[2] : p.ref[1] + REF(list) * p.rb[1]);
-                    const int rpitch = pc ? p.rp[2] : p.rp[1];
-                    if (dmvr)
-                        stage_core(s.a.win + u * WUC, PWC, 1, 2, plane, rpitch, pw, ph,
-                                        x0 + (MV0(list, 0) >> 5) - 1, y0 + (MV0(list, 1) >> 5) - 1, bw + 3, bh + 3, lane);
-                    else
-                        stage_core(s.a.win + u * WUC, PWC, 0, 0, plane, rpitch, pw, ph,
-                                        x0 + (MVR(list, 0) >> 5) - 1, y0 + (MVR(list, 1) >> 5) - 1, bw + 3, bh + 3, lane);
-                }
+            {   // bi: 4 units of 8 lanes, uni: 2 units of 16 lanes
+                const int u = bi ? lane >> 3 : lane >> 4;
+                const int list = bi ? (u & 1) : lx, pc = bi ? (u >> 1) : u;
+                const pel *plane = (pc ? p.ref[2] + REF(list) * p.rb[2] : p.ref[1] + REF(list) * p.rb[1]);
+                stage_units(s.a.win + u * WUC, PWC, dmvr ? 1 : 0, plane, pc ? p.rp[2] : p.rp[1], pw, ph,
+                            x0 + ((dmvr ? MV0(list, 0) : MVR(list, 0)) >> 5) - 1, y0 + ((dmvr ? MV0(list, 1) : MVR(list, 1)) >> 5) - 1,
+                            bw + 3, bh + 3, bi ? lane & 7 : lane & 15, bi ? 8 : 16);
             }
             __syncwarp();
-            if (dmvr) {
-#pragma unroll 1
-                for (int u = 0; u < 4; u++)
-                    if (u < n_units) {
-                        const int list = bi ? (u & 1) : lx;
-                        pad_window(s.a.win + u * WUC, PWC, (x0 + (MV0(list, 0) >> 5) - 1) & 1, bw + 3, bh + 3, lane);
-                    }
-                __syncwarp();
-            }
             pass_h<4>(s, lane, n_units, bh + 3, 0);   //@region chroma_passes
             __syncwarp();
             pass_v<4>(s, lane, n_units, lbw, bh);
