@@ -37,7 +37,7 @@ struct AlfSmem {
     alignas(16) pel     luma[TH + 6][LP];
     alignas(16) pel     chroma[2][TH / 2 + 4][CP];
     alignas(16) ushort4 cell[TH / 2 + 2][TW / 2 + 2];
-    alignas(16) short   coef[(TH / 4) * (TW / 4)][24];   // 12 coefficients then 12 clip values
+    alignas(16) uint32_t coef[(TH / 4) * (TW / 4)][24];  // per tap: the coefficient as the IDP.2A word (f, 0, 0, f), then the clip value in both halves
 };
 
 struct ClampWin { int xlo, xhi, ylo, yhi; };
@@ -183,14 +183,17 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
             else if (hi > 2 * lo) cls += (2 * hv_wins + 1) * 5;
             const int tr = d0_le_d1 * 2 + v_le_h;
 
-            short *out = sm.coef[b];
+            // coefficients are 8-bit by syntax (AlfCoeff in -128..127): byte 0 feeds the first sample of a pair (IDP.2A.LO),
+            // byte 3 the second (IDP.2A.HI)
+            uint32_t *out = sm.coef[b];
             const int set = a.filt_set_idx_y;
             if (set < 16) {
                 const int16_t *f = vvct_alf_fix_filt_coeff[vvct_alf_class_to_filt_map[set][cls]];
 #pragma unroll
                 for (int j = 0; j < 12; j++) {
-                    out[j]      = f[c_perm[tr][j]];
-                    out[12 + j] = (short)(1 << bd);
+                    const uint32_t fb = (uint32_t)f[c_perm[tr][j]] & 0xff, cv = 1u << bd;
+                    out[j]      = fb | (fb << 24);
+                    out[12 + j] = cv | (cv << 16);
                 }
             } else {
                 const int16_t *f  = sets->luma_coeff[set - 16][vvct_alf_aps_class_to_filt_map[cls]];
@@ -198,8 +201,9 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
 #pragma unroll
                 for (int j = 0; j < 12; j++) {
                     const int s = c_perm[tr][j];
-                    out[j]      = f[s];
-                    out[12 + j] = (short)(1 << (bd - c_clip_shift[ci[s]]));
+                    const uint32_t fb = (uint32_t)f[s] & 0xff, cv = 1u << (bd - c_clip_shift[ci[s]]);
+                    out[j]      = fb | (fb << 24);
+                    out[12 + j] = cv | (cv << 16);
                 }
             }
         }
@@ -222,43 +226,68 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                 const int t = (y - y0) - vb;
                 const int d1 = vb_reach(1, t, 4) * LP, d2 = vb_reach(2, t, 4) * LP, d3 = vb_reach(3, t, 4) * LP;
                 const bool near_vb = (t == -1 || t == 0);
-                const short *cf = sm.coef[(r >> 2) * BX + c4];
-                int f[12], c[12];
-                {
-                    const uint4 *cv = reinterpret_cast<const uint4 *>(cf);
-                    const uint4 v0 = cv[0], v1 = cv[1], v2 = cv[2];
-                    const unsigned raw[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
-#pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        f[2 * j]     = (short)(raw[j] & 0xffff);
-                        f[2 * j + 1] = (short)(raw[j] >> 16);
-                        c[2 * j]     = (short)(raw[6 + j] & 0xffff);
-                        c[2 * j + 1] = (short)(raw[6 + j] >> 16);
-                    }
+                const uint32_t *cf = sm.coef[(r >> 2) * BX + c4];
+                // The strip as two sample pairs in 16x2 arithmetic: clip3(-c, c, n - cur) = max(min(n + (-cur), c), -c) is
+                // VIADDMNMX + VIMNMX per pair, the two clipped differences add as VIADD.16x2, and IDP.2A multiplies the
+                // pair by the tap (exact 32-bit accumulate per sample).  wd[i] = samples (-4 + 2i, -3 + 2i) of a row.
+                const uint2 c01 = *reinterpret_cast<const uint2 *>(p0);
+                const uint32_t ncur[2] = { __vneg2(c01.x), __vneg2(c01.y) };
+                int sum[4] = { 0, 0, 0, 0 };
+#define ALF_ROW(w, row, lo, hi)                                                        \
+                {                                                                      \
+                    const pel *rp_ = (row);                                            \
+                    const uint2 m_ = *reinterpret_cast<const uint2 *>(rp_);            \
+                    (w)[2] = m_.x; (w)[3] = m_.y;                                      \
+                    if (lo) { if ((lo) > 1) { const uint2 l_ = *reinterpret_cast<const uint2 *>(rp_ - 4); (w)[0] = l_.x; (w)[1] = l_.y; } \
+                              else (w)[1] = *reinterpret_cast<const uint32_t *>(rp_ - 2); }                                            \
+                    if (hi) { if ((hi) > 1) { const uint2 h_ = *reinterpret_cast<const uint2 *>(rp_ + 4); (w)[4] = h_.x; (w)[5] = h_.y; } \
+                              else (w)[4] = *reinterpret_cast<const uint32_t *>(rp_ + 4); }                                            \
                 }
-                unsigned short res[4];
+#define ALF_AT(w, o) ((((o) + 4) & 1) ? __funnelshift_r((w)[((o) + 4) >> 1], (w)[(((o) + 4) >> 1) + 1], 16) : (w)[((o) + 4) >> 1])
+#define ALF_TAP(k, wp, wm, off)                                                        \
+                {                                                                      \
+                    const uint32_t fw_ = cf[k], c2_ = cf[12 + (k)], nc2_ = (~c2_) + 0x00010001u;                                       \
+                    _Pragma("unroll")                                                  \
+                    for (int j_ = 0; j_ < 2; j_++) {                                   \
+                        const uint32_t a_ = __vmaxs2(__viaddmin_s16x2(ALF_AT(wp, 2 * j_ + (off)), ncur[j_], c2_), nc2_);               \
+                        const uint32_t b_ = __vmaxs2(__viaddmin_s16x2(ALF_AT(wm, 2 * j_ - (off)), ncur[j_], c2_), nc2_);               \
+                        const uint32_t s_ = __vadd2(a_, b_);                           \
+                        sum[2 * j_] = __dp2a_lo((int)s_, (int)fw_, sum[2 * j_]);      \
+                        sum[2 * j_ + 1] = __dp2a_hi((int)s_, (int)fw_, sum[2 * j_ + 1]);                                              \
+                    }                                                                  \
+                }
+                {
+                    uint32_t w0[6];
+                    ALF_ROW(w0, p0, 2, 2)
+                    ALF_TAP(9, w0, w0, 3) ALF_TAP(10, w0, w0, 2) ALF_TAP(11, w0, w0, 1)
+                }
+                {
+                    uint32_t wp[6], wm[6];
+                    ALF_ROW(wp, p0 + d1, 1, 1) ALF_ROW(wm, p0 - d1, 1, 1)
+                    ALF_TAP(4, wp, wm, 2) ALF_TAP(5, wp, wm, 1) ALF_TAP(6, wp, wm, 0) ALF_TAP(7, wp, wm, -1) ALF_TAP(8, wp, wm, -2)
+                }
+                {
+                    uint32_t wp[6], wm[6];
+                    ALF_ROW(wp, p0 + d2, 1, 1) ALF_ROW(wm, p0 - d2, 1, 1)
+                    ALF_TAP(1, wp, wm, 1) ALF_TAP(2, wp, wm, 0) ALF_TAP(3, wp, wm, -1)
+                }
+                {
+                    uint32_t wp[6], wm[6];
+                    ALF_ROW(wp, p0 + d3, 0, 0) ALF_ROW(wm, p0 - d3, 0, 0)
+                    ALF_TAP(0, wp, wm, 0)
+                }
+#undef ALF_TAP
+#undef ALF_AT
+#undef ALF_ROW
+                const int cur[4] = { (int)(c01.x & 0xffff), (int)(c01.x >> 16), (int)(c01.y & 0xffff), (int)(c01.y >> 16) };
+                unsigned res[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const pel *q = p0 + j;
-                    const int cur = q[0];
-                    int sum = 0;
-                    sum += f[0]  * pair_clip(cur, q[d3],      q[-d3],     c[0]);
-                    sum += f[1]  * pair_clip(cur, q[d2 + 1],  q[-d2 - 1], c[1]);
-                    sum += f[2]  * pair_clip(cur, q[d2],      q[-d2],     c[2]);
-                    sum += f[3]  * pair_clip(cur, q[d2 - 1],  q[-d2 + 1], c[3]);
-                    sum += f[4]  * pair_clip(cur, q[d1 + 2],  q[-d1 - 2], c[4]);
-                    sum += f[5]  * pair_clip(cur, q[d1 + 1],  q[-d1 - 1], c[5]);
-                    sum += f[6]  * pair_clip(cur, q[d1],      q[-d1],     c[6]);
-                    sum += f[7]  * pair_clip(cur, q[d1 - 1],  q[-d1 + 1], c[7]);
-                    sum += f[8]  * pair_clip(cur, q[d1 - 2],  q[-d1 + 2], c[8]);
-                    sum += f[9]  * pair_clip(cur, q[3],       q[-3],      c[9]);
-                    sum += f[10] * pair_clip(cur, q[2],       q[-2],      c[10]);
-                    sum += f[11] * pair_clip(cur, q[1],       q[-1],      c[11]);
-                    sum = near_vb ? (sum + 512) >> 10 : (sum + 64) >> 7;
-                    res[j] = (unsigned short)d_clip_pel(cur + sum, bd);
+                    const int v = near_vb ? (sum[j] + 512) >> 10 : (sum[j] + 64) >> 7;
+                    res[j] = (unsigned)d_clip_pel(cur[j] + v, bd);
                 }
-                o.x = res[0] | ((unsigned)res[1] << 16);
-                o.y = res[2] | ((unsigned)res[3] << 16);
+                o.x = res[0] | (res[1] << 16);
+                o.y = res[2] | (res[3] << 16);
             }
             *reinterpret_cast<uint2 *>(dplane + (long long)y * p.dp[0] + x) = o;
         }
