@@ -62,8 +62,11 @@ class Inputs:
         gd = abi.FrameGeom(width, height, batch=distinct)
         self.ref_planes = synth.struct_planes(gd, seed=seed)          # reference pictures (distinct contents)
         self.pbs, self.tbs, self.coeffs, self.maps, self.sao, self.alf = [], [], [], [], [], []
+        profs = []
         for i in range(distinct):
-            pbs, self.wp, self.prof = synth.pb_list(self.g1, n_refs=2, seed=seed + 10 * i + 1)
+            pbs, self.wp, prof = synth.pb_list(self.g1, n_refs=2, seed=seed + 10 * i + 1)
+            pbs["prof"] += sum(len(q) for q in profs)          # every content indexes its own part of one PROF table
+            profs.append(prof)
             self.pbs.append(pbs)
             tbs, co = synth.tb_list(self.g1, seed=seed + 10 * i + 2, lfnst_set_of=lfnst_set_of, extras=False, saturate=False)
             self.tbs.append(tbs)
@@ -72,6 +75,7 @@ class Inputs:
             self.sao.append(synth.sao_params(self.g1, seed=seed + 10 * i + 4))
             alf, self.sets = synth.alf_params(self.g1, seed=seed + 10 * i + 5)
             self.alf.append(alf)
+        self.prof = np.concatenate(profs)
         _, self.inv_lut = synth.lmcs_luts(10, seed=seed + 7)
 
     def records(self, k, n_ref_slots, pic):
@@ -124,6 +128,11 @@ class ClockSampler(threading.Thread):
 
     def result(self):
         self.stop_flag = True
+        if not self.samples and self.nv:           # a timed region shorter than one sampling period: sample right at its end
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
@@ -211,6 +220,7 @@ def main():
     ap.add_argument("--frames", type=int, default=8, help="pictures in the ring = pictures per step")
     ap.add_argument("--group", type=int, default=8, help="pictures per launch (independent streams batched into one launch per stage)")
     ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=12345, help="seed of the synthetic inputs (rank r uses seed + r)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -232,7 +242,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        inp = Inputs(args.width, args.height, seed=12345, distinct=2, lfnst_set_of=lfnst_set_of)
+        inp = Inputs(args.width, args.height, seed=args.seed, distinct=2, lfnst_set_of=lfnst_set_of)
         kind, mpix, ms = run_cpu(inp, args.steps, max(args.warmup, 1), threads)
         sample = "%d pictures per step (one %dx%d picture per host thread) of the same synthetic workload" % (threads, args.width, args.height)
         line = {
@@ -254,12 +264,22 @@ def main():
     dev = "cuda:%d" % local_rank
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # NCCL may print its version banner on stdout: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     frames, group = args.frames, max(1, min(args.group, args.frames))
     while frames % group:
         group -= 1
-    inp = Inputs(args.width, args.height, seed=12345 + rank, distinct=2, lfnst_set_of=lfnst_set_of)
+    inp = Inputs(args.width, args.height, seed=args.seed + rank, distinct=2, lfnst_set_of=lfnst_set_of)
     g1 = inp.g1
     gring = abi.FrameGeom(args.width, args.height, batch=frames)
     ggrp = abi.FrameGeom(args.width, args.height, batch=group)
@@ -469,7 +489,12 @@ def main():
         got = out.to_numpy()
         for c in range(3):
             wv = g1.plane_wh(c)[0]
-            assert np.array_equal(h_out[c].numpy().view(np.uint16)[:, :, :wv], got[c][:, :, :wv]), "e2e result differs from device-resident result"
+            he, de = h_out[c].numpy().view(np.uint16)[:, :, :wv], got[c][:, :, :wv]
+            if not np.array_equal(he, de):
+                bad = np.argwhere(he != de)
+                per_pic = [int((he[k_] != de[k_]).sum()) for k_ in range(he.shape[0])]
+                raise AssertionError("e2e result differs from device-resident result: plane %d, %d samples (per picture %s), first (pic %d, y %d, x %d) %d vs %d" % (
+                    c, len(bad), per_pic, bad[0][0], bad[0][1], bad[0][2], he[tuple(bad[0])], de[tuple(bad[0])]))
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------------
     cpu_baseline = None

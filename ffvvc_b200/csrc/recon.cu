@@ -45,20 +45,31 @@ struct Carve {
     template <typename T> T *take(size_t n) { T *p = (T *)at; at += align_up(n * sizeof(T), 256); return p; }
 };
 
+// Bytes one picture's descriptors take in a slot: must mirror the Carve::take() sequence of the upload below
+// exactly (every array takes at least one element, every take is rounded up to 256 bytes).
 size_t desc_bytes(const VVCCudaFrame *f, const VVCCudaReconDesc *d)
 {
     const int planes = f->chroma_format_idc ? 3 : 1;
-    const int n_ctb = ceil_div(f->width, 1 << f->ctb_log2) * ceil_div(f->height, 1 << f->ctb_log2);
+    const size_t n_ctb = (size_t)ceil_div(f->width, 1 << f->ctb_log2) * ceil_div(f->height, 1 << f->ctb_log2);
     size_t n = 0;
-    n += align_up((size_t)d->n_pbs * sizeof(VVCCudaPB), 256) + align_up((size_t)(d->n_wp > 0 ? d->n_wp : 1) * sizeof(VVCCudaWP), 256);
-    n += align_up((size_t)(d->n_prof > 0 ? d->n_prof : 1) * sizeof(VVCCudaProf), 256) + align_up((size_t)d->n_pbs * sizeof(VVCCudaDmvrOut), 256);
-    n += align_up((size_t)d->n_lmcs_rects * sizeof(VVCCudaRect), 256) + 2 * align_up(sizeof(uint16_t) << f->bit_depth, 256);
-    n += align_up(d->n_coeffs * sizeof(int32_t), 256) + align_up((size_t)d->n_tbs * sizeof(VVCCudaTB), 256) + align_up(n_ctb, 256);
+    auto take = [&n](size_t count, size_t elem) { n += align_up((count > 0 ? count : 1) * elem, 256); };
+    take(d->n_pbs > 0 ? d->n_pbs : 0, sizeof(VVCCudaPB));
+    take(d->n_wp > 0 ? d->n_wp : 0, sizeof(VVCCudaWP));
+    take(d->n_prof > 0 ? d->n_prof : 0, sizeof(VVCCudaProf));
+    take(d->n_pbs > 0 ? d->n_pbs : 0, sizeof(VVCCudaDmvrOut));
+    take(d->n_lmcs_rects > 0 ? d->n_lmcs_rects : 0, sizeof(VVCCudaRect));
+    take((size_t)1 << f->bit_depth, sizeof(uint16_t));
+    take((size_t)1 << f->bit_depth, sizeof(uint16_t));
+    take(d->n_coeffs, sizeof(int32_t));
+    take(d->n_tbs > 0 ? d->n_tbs : 0, sizeof(VVCCudaTB));
+    take(n_ctb, sizeof(uint8_t));
     for (int dir = 0; dir < 2; dir++)
         for (int c = 0; c < planes; c++)
-            n += align_up((size_t)d->inloop.deblock->size[dir][c] * sizeof(VVCCudaDbkEdge), 256);
-    n += align_up((size_t)n_ctb * sizeof(VVCCudaSAOCtb), 256) + align_up((size_t)n_ctb * sizeof(VVCCudaALFCtb), 256) + align_up(sizeof(VVCCudaALFSets), 256);
-    return n;
+            take(d->inloop.deblock->size[dir][c] > 0 ? d->inloop.deblock->size[dir][c] : 0, sizeof(VVCCudaDbkEdge));
+    take(n_ctb, sizeof(VVCCudaSAOCtb));
+    take(n_ctb, sizeof(VVCCudaALFCtb));
+    take(1, sizeof(VVCCudaALFSets));
+    return n + 256;
 }
 
 }  // namespace
@@ -148,6 +159,8 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
         UP(dd.inloop.alf, h->inloop.alf, VVCCudaALFCtb, n_ctb);
         UP(dd.inloop.alf_sets, h->inloop.alf_sets, VVCCudaALFSets, 1);
 #undef UP
+        if (cv.at > base + rsz + 4 * psz + (size_t)(sl + 1) * dsz)
+            return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "recon_host: descriptor slot overflow (desc_bytes out of step with the upload)");
         dd.inloop.deblock = &dm;
         dd.inloop.alf_sets_per_frame = 0;
         VVC_TRY(ctx, cudaEventRecord(ctx->ev[1 + sl], cin));
