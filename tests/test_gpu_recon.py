@@ -1,0 +1,127 @@
+"""GPU parity: the whole-picture reconstruction entries (INTER -> residual -> inverse LMCS -> deblock V/H -> SAO ->
+ALF) - vvc_cuda_recon_frame on a device-resident ring and the pipelined vvc_cuda_recon_frame_host with PINNED host
+buffers (so its copies really overlap its kernels) - against the oracle's stage-by-stage chain."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ffvvc_b200 import abi, synth
+from tests import util
+from tests.golden_cases import STRESS_MIX
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from ffvvc_b200 import lib
+    c = lib.Context(0)
+    with torch.cuda.stream(c.torch_stream()):
+        yield c
+    c.close()
+
+
+def build(w, h, batch, seed):
+    g1 = abi.FrameGeom(w, h)
+    gr = abi.FrameGeom(w, h, batch=batch)
+    case = dict(g1=g1, gr=gr, refs=synth.struct_planes(gr, seed=seed))
+    case["pbs"], case["wp"], case["prof"] = synth.pb_list(gr, n_refs=batch, seed=seed + 1, mix=STRESS_MIX)
+    case["tbs"], case["coeffs"] = synth.tb_list(gr, seed=seed + 2, lfnst_set_of=util.oracle().vvco_lfnst_tr_set, extras=False)
+    _, case["inv"] = synth.lmcs_luts(10, seed=seed + 3)
+    case["maps"] = synth.deblock_maps(gr, seed=seed + 4, qp_base=27, qp_span=16)
+    case["sao"] = synth.sao_params(gr, seed=seed + 5)
+    case["alf"], case["sets"] = synth.alf_params(gr, seed=seed + 6)
+    return case
+
+
+def oracle_chain(case):
+    o, gr = util.oracle(), case["gr"]
+    cur = abi.alloc_planes(gr, fill=0)
+    o.vvco_inter_frame(abi.frame_from_numpy(gr, cur), abi.frame_from_numpy(gr, case["refs"]), case["pbs"].ctypes.data, len(case["pbs"]),
+                       case["wp"].ctypes.data, case["prof"].ctypes.data, None)
+    co = case["coeffs"].copy()
+    o.vvco_itx_frame(abi.frame_from_numpy(gr, cur), co.ctypes.data, case["tbs"].ctypes.data, len(case["tbs"]), 15)
+    o.vvco_lmcs_frame(abi.frame_from_numpy(gr, cur), case["inv"].ctypes.data, None)
+    md = abi.deblock_maps_desc(gr, case["maps"])
+    a, b = abi.alloc_planes(gr), abi.alloc_planes(gr)
+    o.vvco_deblock_frame(abi.frame_from_numpy(gr, a), abi.frame_from_numpy(gr, cur), C.byref(md), 1)
+    o.vvco_deblock_frame(abi.frame_from_numpy(gr, b), abi.frame_from_numpy(gr, a), C.byref(md), 0)
+    o.vvco_sao_frame(abi.frame_from_numpy(gr, a), abi.frame_from_numpy(gr, b), case["sao"].ctypes.data)
+    o.vvco_alf_frame(abi.frame_from_numpy(gr, b), abi.frame_from_numpy(gr, a), case["alf"].ctypes.data, case["sets"].ctypes.data, 0)
+    return b
+
+
+@pytest.mark.parametrize("w,h,batch,seed", [(416, 240, 4, 31), (256, 192, 5, 32)])
+def test_recon_entries_bit_exact(ctx, w, h, batch, seed):
+    import torch
+    from ffvvc_b200 import device
+    case = build(w, h, batch, seed)
+    g1, gr = case["g1"], case["gr"]
+    want = oracle_chain(case)
+    keep = []
+
+    def up(a):
+        t, p = device.to_device(a)
+        keep.append(t)
+        return p
+
+    # ---- device-resident ring ----
+    refs, cur, out = device.DeviceFrames(gr, planes=case["refs"]), device.DeviceFrames(gr), device.DeviceFrames(gr)
+    md = abi.deblock_maps_desc(gr, case["maps"], ptr_of=up)
+    d = abi.VVCCudaReconDesc()
+    d.pbs, d.n_pbs, d.wp, d.n_wp, d.prof, d.n_prof = up(case["pbs"]), len(case["pbs"]), up(case["wp"]), len(case["wp"]), up(case["prof"]), len(case["prof"])
+    d.log2_transform_range = 15
+    d.coeffs, d.n_coeffs, d.tbs, d.n_tbs = up(case["coeffs"]), len(case["coeffs"]), up(case["tbs"]), len(case["tbs"])
+    d.lmcs_inv_lut = up(case["inv"])
+    d.inloop.deblock = C.pointer(md)
+    d.inloop.sao, d.inloop.alf, d.inloop.alf_sets = up(case["sao"]), up(case["alf"]), up(case["sets"])
+    for _ in range(2):                      # in place: a second pass over the same ring must give the same pictures
+        ctx.recon_frame(out.desc, cur.desc, refs.desc, d)
+    ctx.sync()
+    util.assert_planes_equal(gr, out.to_numpy(), want, "recon_frame vs oracle chain")
+
+    # ---- pipelined host entry, one descriptor set per picture, everything in pinned memory ----
+    pins = []
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+        pins.append(t)
+        return t.data_ptr()
+
+    h_refs = [torch.from_numpy(p.view(np.int16)).pin_memory() for p in case["refs"]]
+    h_out = [torch.zeros_like(t).pin_memory() for t in h_refs]
+    f_refs = abi.frame_desc(gr, [t.data_ptr() for t in h_refs], [t.stride(1) * 2 for t in h_refs], [t.stride(0) * 2 for t in h_refs])
+    f_out = abi.frame_desc(gr, [t.data_ptr() for t in h_out], [t.stride(1) * 2 for t in h_out], [t.stride(0) * 2 for t in h_out])
+    descs = (abi.VVCCudaReconDesc * batch)()
+    hold = []
+    n_ctb = g1.ctb_count
+    for k in range(batch):
+        pb = case["pbs"][case["pbs"]["pic"] == k].copy()
+        pb["pic"] = 0
+        tb = case["tbs"][case["tbs"]["pic"] == k].copy()
+        tb["pic"] = 0
+        lo = int(tb["coeff_offset"].min())
+        area = (1 << tb["log2_w"].astype(np.int64)) * (1 << tb["log2_h"].astype(np.int64))
+        hi = int((tb["coeff_offset"].astype(np.int64) + area).max())
+        tb["coeff_offset"] -= lo
+        hmd = abi.VVCCudaDeblockMaps()
+        for dr in range(2):
+            for c in range(3):
+                rows, pitch = abi.deblock_map_shape(g1, dr, c)
+                hmd.edge[dr][c] = pin(case["maps"][dr][c][k])
+                hmd.pitch[dr][c], hmd.rows[dr][c], hmd.size[dr][c] = pitch, rows, rows * pitch
+        hold.append(hmd)
+        e = descs[k]
+        e.pbs, e.n_pbs, e.wp, e.n_wp, e.prof, e.n_prof = pin(pb), len(pb), pin(case["wp"]), len(case["wp"]), pin(case["prof"]), len(case["prof"])
+        e.log2_transform_range = 15
+        e.coeffs, e.n_coeffs, e.tbs, e.n_tbs = pin(case["coeffs"][lo:hi]), hi - lo, pin(tb), len(tb)
+        e.lmcs_inv_lut = pin(case["inv"])
+        e.inloop.deblock = C.pointer(hmd)
+        e.inloop.sao = pin(case["sao"][k * n_ctb:(k + 1) * n_ctb])
+        e.inloop.alf = pin(case["alf"][k * n_ctb:(k + 1) * n_ctb])
+        e.inloop.alf_sets = pin(case["sets"])
+    ctx.recon_frame_host(f_out, f_refs, descs)
+    got = [t.numpy().view(np.uint16) for t in h_out]
+    util.assert_planes_equal(gr, got, want, "recon_frame_host (pinned, pipelined) vs oracle chain")
