@@ -17,6 +17,20 @@
 namespace {
 
 constexpr int kThreads = 128;
+// resident CTAs per SM the class kernels are compiled for (register budget = 65536 / (128 * n)); measured sweep in profiles/README.md
+#ifndef PATCH_MB_LU
+#define PATCH_MB_LU 8
+#endif
+#ifndef PATCH_MB_LB
+#define PATCH_MB_LB 6
+#endif
+#ifndef PATCH_MB_CU
+#define PATCH_MB_CU 6
+#endif
+#ifndef PATCH_MB_CB
+#define PATCH_MB_CB 6
+#endif
+constexpr int patch_ctas(bool luma, bool bi) { return luma ? (bi ? PATCH_MB_LB : PATCH_MB_LU) : (bi ? PATCH_MB_CB : PATCH_MB_CU); }
 
 // 8 samples x .. x + 7 of a row with the column clamped to the picture (the rare path: one out-of-line copy)
 __device__ __noinline__ uint4 load8_clamped(const pel *row, int x, int W)
@@ -283,7 +297,7 @@ __device__ __forceinline__ void chroma_task(const InterK &p, const Rec &pb, int 
 // Persistent kernels, one per task class (own register budget each): a grid-stride loop over the class's
 // list, so every warp of the launch runs the same specialised code.
 template <bool LUMA, bool BI>
-__global__ void __launch_bounds__(kThreads, LUMA ? 4 : 5) inter_patch_kernel(const InterK p, const InterLists ls)
+__global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_kernel(const InterK p, const InterLists ls)
 {
     const int n = (int)ls.count[(LUMA ? 0 : 2) + (BI ? 1 : 0)];
     const uint32_t *list = LUMA ? ls.luma : ls.chroma;
@@ -314,13 +328,13 @@ int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
     VVC_TRY(ctx, cudaMemsetAsync(ls->count, 0, 64, ctx->stream));
     inter_classify_kernel<<<ceil_div(p.n, 256), 256, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<true, true><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<true, true><<<148 * patch_ctas(true, true), kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<true, false><<<148 * 4, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<true, false><<<148 * patch_ctas(true, false), kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<false, true><<<148 * 5, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<false, true><<<148 * patch_ctas(false, true), kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<false, false><<<148 * 5, kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<false, false><<<148 * patch_ctas(false, false), kThreads, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }
