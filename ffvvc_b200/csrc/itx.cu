@@ -324,7 +324,7 @@ extern "C" int vvc_cuda_itx_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, in
             return ctx->err;
         p.list = rest + 16; p.list_count = rest;
         const int ctas = ceil_div(n_tbs, TBS_PER_CTA);
-        itx_kernel<<<ctas < 148 * 2 ? ctas : 148 * 2, kThreads, 0, ctx->stream>>>(p);
+        itx_kernel<<<ctas < 148 * 6 ? ctas : 148 * 6, kThreads, 0, ctx->stream>>>(p);
         VVC_LAUNCHED(ctx);
         return VVC_CUDA_OK;
     }
