@@ -107,12 +107,20 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
     if (!base)
         return ctx->err;
     cudaStream_t cin = ctx->copy_in, cout = ctx->copy_out, run = ctx->stream;
+    // The DPB may already live in HBM (earlier output pictures of this context): device pointers are used in place,
+    // host pictures are staged once per call.
+    cudaPointerAttributes attr;
+    const bool refs_on_device = cudaPointerGetAttributes(&attr, refs->data[0]) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();                                    // unregistered host memory reports an error on old drivers: not ours
     VVCCudaFrame drefs;
-    vvc_stage_frame_layout(refs, base, &drefs);
+    if (refs_on_device)
+        drefs = *refs;
+    else
+        vvc_stage_frame_layout(refs, base, &drefs);
     VVC_TRY(ctx, cudaEventRecord(ctx->ev[0], run));           // earlier work on the context stream owns the staging area
     VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev[0], 0));
     VVC_TRY(ctx, cudaStreamWaitEvent(cout, ctx->ev[0], 0));
-    {
+    if (!refs_on_device) {
         cudaStream_t saved = ctx->stream;
         ctx->stream = cin;
         const int rc = vvc_stage_frame_h2d(ctx, &drefs, refs);

@@ -449,8 +449,9 @@ int vvc_cuda_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCuda
                          const VVCCudaFrame *refs, const VVCCudaReconDesc *desc);
 /* Host memory everywhere.  descs: one entry per picture of the `out` ring, its records use pic == 0.
  * Picture k's descriptors and coefficients are copied in on a copy stream while picture k-1 is being
- * reconstructed and picture k-2 is copied out; refs are copied in once.  Returns when all output
- * pictures (and dmvr_out arrays) are in host memory. */
+ * reconstructed and picture k-2 is copied out.  refs: the DPB ring, either host memory (copied in once per
+ * call) or device memory (a GPU-resident DPB, e.g. earlier outputs kept in HBM: used in place).  Returns when
+ * all output pictures (and dmvr_out arrays) are in host memory. */
 int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
                               const VVCCudaReconDesc *descs);
 

@@ -125,3 +125,9 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed):
     ctx.recon_frame_host(f_out, f_refs, descs)
     got = [t.numpy().view(np.uint16) for t in h_out]
     util.assert_planes_equal(gr, got, want, "recon_frame_host (pinned, pipelined) vs oracle chain")
+    # the same entry with the DPB resident in HBM (device pointers for refs)
+    for t in h_out:
+        t.zero_()
+    ctx.recon_frame_host(f_out, refs.desc, descs)
+    got = [t.numpy().view(np.uint16) for t in h_out]
+    util.assert_planes_equal(gr, got, want, "recon_frame_host with a device-resident DPB vs oracle chain")
