@@ -30,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from ffvvc_b200 import abi, synth  # noqa: E402
+from ffvvc_b200 import abi, streams, synth  # noqa: E402
 
 METRIC = "vvc_4k10_recon_loopfilter_mpix_per_s"
 UNIT = "Mpix/s"
@@ -279,7 +279,7 @@ def main():
     frames, group = args.frames, max(1, min(args.group, args.frames))
     while frames % group:
         group -= 1
-    inp = Inputs(args.width, args.height, seed=args.seed + rank, distinct=2, lfnst_set_of=lfnst_set_of)
+    inp = Inputs(args.width, args.height, seed=streams.seed_of_rank(args.seed, rank), distinct=2, lfnst_set_of=lfnst_set_of)
     g1 = inp.g1
     gring = abi.FrameGeom(args.width, args.height, batch=frames)
     ggrp = abi.FrameGeom(args.width, args.height, batch=group)
@@ -397,14 +397,13 @@ def main():
                 stage_ms[i] += g[i].elapsed_time(g[i + 1])
     stage_ms /= args.steps * len(groups)          # average duration of one launch of each stage
 
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-
+    # every rank runs its own streams (no data-path collective): units add up, the slowest rank's device time counts
     luma_px_per_step = args.width * args.height * frames
-    value = luma_px_per_step * args.steps * world / (elapsed_ms * 1e-3) / 1e6
+    dist_mod = None
+    if world > 1:
+        import torch.distributed as dist_mod
+    total_px, elapsed_ms = streams.aggregate(luma_px_per_step * args.steps, elapsed_ms, dist_mod, dev if world > 1 else None)
+    value = streams.throughput_mpix(total_px, elapsed_ms)
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = load_peaks()
