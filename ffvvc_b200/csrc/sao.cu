@@ -64,9 +64,16 @@ __device__ __forceinline__ Row10 load_row(const pel *plane, int pitch, int pw, i
     return r;
 }
 
-__device__ __forceinline__ int sgn(int a, int b) { return (a > b) - (a < b); }
+// byte (sel & 7) of {lo, hi} sign-extended to 32 bits: PTX prmt replicates the selected byte's sign where bit 3 of a
+// selector nibble is set (__byte_perm masks that bit)
+__device__ __forceinline__ int prmt_s8(unsigned lo, unsigned hi, unsigned sel)
+{
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+}
 
-__global__ void __launch_bounds__(32 * WARPS) sao_kernel(const SaoK p)
+__global__ void __launch_bounds__(32 * WARPS, 3) sao_kernel(const SaoK p)
 {
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int c = blockIdx.z % p.planes, k = blockIdx.z / p.planes;
@@ -87,6 +94,23 @@ __global__ void __launch_bounds__(32 * WARPS) sao_kernel(const SaoK p)
     const int cx = xs / ctb_w;
     const int bx0 = cx * ctb_w, bw = min(ctb_w, pw - bx0);
 
+    // The RPT rows of a thread start at a multiple of RPT, so they lie in one CTB: its parameters are read once.  The five
+    // edge offsets / four band offsets (6-bit magnitudes) become an 8-byte table indexed with PRMT (byte `idx`,
+    // sign-extended), instead of a chain of compares per sample.
+    const int cy = y0 / ctb_h;
+    const int by0 = cy * ctb_h, bh = min(ctb_h, ph - by0);
+    const VVCCudaSAOCtb *sp = p.ctbs + ((long long)k * p.ctb_rows + cy) * p.ctb_cols + cx;
+    const int type = sp->type_idx[c];
+    int off[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) off[i] = sp->offset_val[c][i];
+    const int bp = sp->band_position[c], eo = sp->eo_class[c];
+    // edge: category 0..4 -> offset index {1,2,0,3,4} (edge_idx, :53); band: band 0..3 -> offsets 1..4, band >= 4 -> 0
+    const unsigned tab_lo = type == 1 ? ((off[1] & 0xff) | ((off[2] & 0xff) << 8) | ((off[3] & 0xff) << 16) | ((unsigned)(off[4] & 0xff) << 24))
+                                      : ((off[1] & 0xff) | ((off[2] & 0xff) << 8) | ((off[0] & 0xff) << 16) | ((unsigned)(off[3] & 0xff) << 24));
+    const unsigned tab_hi = type == 1 ? 0u : (unsigned)(off[4] & 0xff);
+#define SAO_LOOKUP(idx) prmt_s8(tab_lo, tab_hi, (unsigned)(idx) * 0x1111u + 0x8880u)
+
     Row10 above, cur, below;
     cur   = load_row(src, pitch, pw, ph, xs, y0 - 1, lane);
     below = load_row(src, pitch, pw, ph, xs, y0, lane);
@@ -99,30 +123,16 @@ __global__ void __launch_bounds__(32 * WARPS) sao_kernel(const SaoK p)
         if (!live)
             continue;
 
-        const int cy = y / ctb_h;
-        const int by0 = cy * ctb_h, bh = min(ctb_h, ph - by0);
-        const VVCCudaSAOCtb *sp = p.ctbs + ((long long)k * p.ctb_rows + cy) * p.ctb_cols + cx;
-        const int type = sp->type_idx[c];
         int out[8];
         if (type == 1) {
-            const int bp = sp->band_position[c], sh = bd - 5;
-            int off[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) off[i] = sp->offset_val[c][i + 1];
+            const int sh = bd - 5;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int v = cur.v[1 + i];
                 const int band = ((v >> sh) - bp) & 31;
-                const int o = band == 0 ? off[0] : band == 1 ? off[1] : band == 2 ? off[2] : band == 3 ? off[3] : 0;
-                out[i] = d_clip_pel(v + o, bd);
+                out[i] = d_clip_pel(v + SAO_LOOKUP(min(band, 4)), bd);
             }
         } else if (type == 2) {
-            const int eo = sp->eo_class[c];
-            int off[5];
-#pragma unroll
-            for (int i = 0; i < 5; i++) off[i] = sp->offset_val[c][i];
-            // category -> offset index, edge_idx = {1,2,0,3,4} (:53)
-            const int sel[5] = { off[1], off[2], off[0], off[3], off[4] };
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int v = cur.v[1 + i];
@@ -131,9 +141,8 @@ __global__ void __launch_bounds__(32 * WARPS) sao_kernel(const SaoK p)
                 else if (eo == 1) { a = above.v[i + 1]; b = below.v[i + 1]; }
                 else if (eo == 2) { a = above.v[i];     b = below.v[i + 2]; }
                 else              { a = above.v[i + 2]; b = below.v[i]; }
-                const int cat = 2 + sgn(v, a) + sgn(v, b);
-                const int o = cat == 0 ? sel[0] : cat == 1 ? sel[1] : cat == 2 ? sel[2] : cat == 3 ? sel[3] : sel[4];
-                out[i] = d_clip_pel(v + o, bd);
+                const int cat = 2 + min(max(v - a, -1), 1) + min(max(v - b, -1), 1);
+                out[i] = d_clip_pel(v + SAO_LOOKUP(cat), bd);
             }
             // ---- CTB border rules (:81-215), only for groups that touch the CTB border ----
             const int ry = y - by0;
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(32 * WARPS) sao_kernel(const SaoK p)
                 drow[i] = (pel)out[i];
         }
     }
+#undef SAO_LOOKUP
 }
 
 }  // namespace
