@@ -62,6 +62,7 @@ class Inputs:
         gd = abi.FrameGeom(width, height, batch=distinct)
         self.ref_planes = synth.struct_planes(gd, seed=seed)          # reference pictures (distinct contents)
         self.pbs, self.tbs, self.coeffs, self.maps, self.sao, self.alf = [], [], [], [], [], []
+        self.quant, self.win_tbs, self.win, self.scaling = [], [], [], None
         profs = []
         for i in range(distinct):
             pbs, self.wp, prof = synth.pb_list(self.g1, n_refs=2, seed=seed + 10 * i + 1)
@@ -69,8 +70,19 @@ class Inputs:
             profs.append(prof)
             self.pbs.append(pbs)
             tbs, co = synth.tb_list(self.g1, seed=seed + 10 * i + 2, lfnst_set_of=lfnst_set_of, extras=False, saturate=False)
+            # the residual stage starts from quantised levels (TransCoeffLevel) like ff_vvc_reconstruct does: dequant()
+            # is part of the stage in every arm.  Dense int32 (the reference's tb->coeffs layout) for the reference arm
+            # and the device-resident number, the 16-bit window layout for the upload of the end-to-end number.
+            tbs = synth.tb_for_window(tbs)
+            co = (co >> 4).astype(np.int32)
+            q, sl = synth.tb_quant(tbs, seed=seed + 10 * i + 6, scaling=True, qp_lo=22, qp_hi=42)
+            wt, win = abi.pack_window16(tbs, co)
             self.tbs.append(tbs)
             self.coeffs.append(co)
+            self.quant.append(q)
+            self.scaling = sl if i == 0 else self.scaling
+            self.win_tbs.append(wt)
+            self.win.append(win)
             self.maps.append(synth.deblock_maps(self.g1, seed=seed + 10 * i + 3, qp_base=27, qp_span=16))
             self.sao.append(synth.sao_params(self.g1, seed=seed + 10 * i + 4))
             alf, self.sets = synth.alf_params(self.g1, seed=seed + 10 * i + 5)
@@ -150,7 +162,7 @@ def cpu_lib():
         lib, kind, pre = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so")), "port", "vvco_"
     fns = {}
     sig = {"inter_frame": [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
-           "itx_frame": [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int],
+           "itx_frame_q": [FP, C.POINTER(abi.VVCCudaCoeffs), C.c_void_p, C.c_int, C.c_int],
            "lmcs_frame": [FP, C.c_void_p, C.c_void_p],
            "deblock_frame": [FP, FP, MP, C.c_int], "sao_frame": [FP, FP, C.c_void_p],
            "alf_frame": [FP, FP, C.c_void_p, C.c_void_p, C.c_int]}
@@ -168,7 +180,8 @@ def cpu_reconstruct(fns, inp, i, refs, scratch):
     pbs = inp.pbs[i]
     fns["inter_frame"](abi.frame_from_numpy(g, cur), abi.frame_from_numpy(gr, refs), pbs.ctypes.data, len(pbs),
                        inp.wp.ctypes.data, inp.prof.ctypes.data, None)
-    fns["itx_frame"](abi.frame_from_numpy(g, cur), inp.coeffs[i].ctypes.data, inp.tbs[i].ctypes.data, len(inp.tbs[i]), 15)
+    co = abi.coeffs_desc(inp.coeffs[i].ctypes.data, inp.coeffs[i].size, abi.COEFF_DENSE32, inp.quant[i].ctypes.data, inp.scaling.ctypes.data)
+    fns["itx_frame_q"](abi.frame_from_numpy(g, cur), C.byref(co), inp.tbs[i].ctypes.data, len(inp.tbs[i]), 15)
     fns["lmcs_frame"](abi.frame_from_numpy(g, cur), inp.inv_lut.ctypes.data, None)
     md = abi.deblock_maps_desc(g, inp.maps[i])
     fns["deblock_frame"](abi.frame_from_numpy(g, a), abi.frame_from_numpy(g, cur), C.byref(md), 1)
@@ -229,7 +242,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     threads = args.cpu_threads or (os.cpu_count() or 1)
-    workload = ("recon_4k: INTER (MC/bi/DMVR/BDOF/PROF/GPM) -> residual (LFNST+itx+add) -> inverse LMCS -> deblock V+H -> SAO -> "
+    workload = ("recon_4k: INTER (MC/bi/DMVR/BDOF/PROF/GPM) -> residual (dequant+LFNST+itx+add) -> inverse LMCS -> deblock V+H -> SAO -> "
                 "ALF/CC-ALF on %dx%d 10-bit 4:2:0, 100%% inter area, coded fraction 1.0") % (args.width, args.height)
 
     oracle_so = os.path.join(ROOT, "oracle", "liboracle.so")
@@ -302,7 +315,7 @@ def main():
         keep.append(t)
         return p
 
-    p_wp, p_prof, p_sets, p_lut = up(inp.wp), up(inp.prof), up(inp.sets), up(inp.inv_lut)
+    p_wp, p_prof, p_sets, p_lut, p_sl = up(inp.wp), up(inp.prof), up(inp.sets), up(inp.inv_lut), up(inp.scaling)
     n_ctb = g1.ctb_count
 
     def sub_frame(df, k0):
@@ -326,6 +339,7 @@ def main():
             tb_parts.append(t)
             co_parts.append(inp.coeffs[k % inp.distinct])
         tbs, coeffs = np.concatenate(tb_parts), np.concatenate(co_parts)
+        quant = np.concatenate([inp.quant[k % inp.distinct] for k in ks])
         md = abi.VVCCudaDeblockMaps()
         for d in range(2):
             for c in range(3):
@@ -335,7 +349,7 @@ def main():
                 md.pitch[d][c], md.rows[d][c], md.size[d][c] = pitch, rows, rows * pitch
         groups.append(dict(
             cur=sub_frame(cur, k0), out=sub_frame(out, k0), pbs=up(pbs), n_pbs=len(pbs), tbs=up(tbs), n_tbs=len(tbs),
-            coeffs=up(coeffs), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
+            coeffs=abi.coeffs_desc(up(coeffs), len(coeffs), abi.COEFF_DENSE32, up(quant), p_sl), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
             alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
     # kernels per picture group: inter = 7 (classify, four thread-per-patch class kernels, two warp-per-record kernels),
     # residual = 2 (warp-per-TB kernel + generic kernel over the blocks it leaves), every other stage 1
@@ -347,7 +361,7 @@ def main():
             if ev: ev[0].record()
             ctx.inter_frame(g["cur"], refs.desc, g["pbs"], g["n_pbs"], p_wp, p_prof, None)
             if ev: ev[1].record()
-            ctx.itx_frame(g["cur"], g["coeffs"], g["tbs"], g["n_tbs"], 15)
+            ctx.itx_frame_q(g["cur"], g["coeffs"], g["tbs"], g["n_tbs"], 15)
             if ev: ev[2].record()
             ctx.lmcs_frame(g["cur"], p_lut, None)
             if ev: ev[3].record()
@@ -444,6 +458,7 @@ def main():
         f_refs = abi.frame_desc(gring, [t.data_ptr() for t in h_refs], [t.stride(1) * 2 for t in h_refs], [t.stride(0) * 2 for t in h_refs])
         f_out = abi.frame_desc(gring, [t.data_ptr() for t in h_out], [t.stride(1) * 2 for t in h_out], [t.stride(0) * 2 for t in h_out])
         (hp_wp, b_wp), (hp_prof, b_prof), (hp_sets, b_sets), (hp_lut, b_lut) = pin(inp.wp), pin(inp.prof), pin(inp.sets), pin(inp.inv_lut)
+        hp_sl, b_sl = pin(inp.scaling)
         per_content = []
         for i in range(inp.distinct):
             hmd = abi.VVCCudaDeblockMaps()
@@ -455,9 +470,13 @@ def main():
                     nb += n
                     hmd.pitch[d][c], hmd.rows[d][c], hmd.size[d][c] = pitch, rows, rows * pitch
             (p_co, b_co), (p_tb, b_tb), (p_sa, b_sa), (p_al, b_al) = pin(inp.coeffs[i]), pin(inp.tbs[i]), pin(inp.sao[i]), pin(inp.alf[i])
+            (p_win, b_win), (p_wtb, b_wtb), (p_q, b_q) = pin(inp.win[i]), pin(inp.win_tbs[i]), pin(inp.quant[i])
             per_content.append(dict(md=hmd, co=p_co, n_co=len(inp.coeffs[i]), tb=p_tb, n_tb=len(inp.tbs[i]), sao=p_sa, alf=p_al,
-                                    bytes=nb + b_co + b_tb + b_sa + b_al))
-        descs = (abi.VVCCudaReconDesc * frames)()
+                                    win=p_win, n_win=len(inp.win[i]), wtb=p_wtb, quant=p_q,
+                                    bytes=nb + b_sa + b_al + b_q + b_sl, bytes_dense=b_co + b_tb, bytes_win=b_win + b_wtb))
+        descs = (abi.VVCCudaReconDesc * frames)()            # 16-bit window layout (the upload format of the product)
+        descs_dense = (abi.VVCCudaReconDesc * frames)()      # the reference's dense int32 layout, for comparison
+        h2d_dense_extra = 0
         h2d = sum(t.numel() * 2 for t in h_refs)
         d2h = sum(t.numel() * 2 for t in h_out)
         for k in range(frames):
@@ -466,11 +485,16 @@ def main():
             d = descs[k]
             d.pbs, d.n_pbs, d.wp, d.n_wp, d.prof, d.n_prof = p_pb, len(inp.pbs[k % inp.distinct]), hp_wp, len(inp.wp), hp_prof, len(inp.prof)
             d.log2_transform_range = 15
-            d.coeffs, d.n_coeffs, d.tbs, d.n_tbs = pc["co"], pc["n_co"], pc["tb"], pc["n_tb"]
+            d.coeffs, d.n_coeffs, d.tbs, d.n_tbs = pc["win"], pc["n_win"], pc["wtb"], pc["n_tb"]
+            d.coeff_format, d.quant, d.scaling = abi.COEFF_WINDOW16, pc["quant"], hp_sl
             d.lmcs_inv_lut = hp_lut
             d.inloop.deblock = C.pointer(pc["md"])
             d.inloop.sao, d.inloop.alf, d.inloop.alf_sets = pc["sao"], pc["alf"], hp_sets
-            h2d += b_pb + b_wp + b_prof + b_lut + b_sets + pc["bytes"]
+            h2d += b_pb + b_wp + b_prof + b_lut + b_sets + pc["bytes"] + pc["bytes_win"]
+            h2d_dense_extra += pc["bytes_dense"] - pc["bytes_win"]
+            C.memmove(C.byref(descs_dense[k]), C.byref(d), C.sizeof(d))
+            dd = descs_dense[k]
+            dd.coeffs, dd.n_coeffs, dd.tbs, dd.coeff_format = pc["co"], pc["n_co"], pc["tb"], abi.COEFF_DENSE32
         e_steps = max(2, min(args.steps, 4))
         ctx.recon_frame_host(f_out, f_refs, descs)
         barrier()
@@ -490,7 +514,7 @@ def main():
             e_ms = float(t.item())
         e2e = {"value": luma_px_per_step * e_steps * world / (e_ms * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-               "api": "vvc_cuda_recon_frame_host (pinned host reference pictures, records, coefficients; output pictures copied back)"}
+               "api": "vvc_cuda_recon_frame_host (pinned host reference pictures, records, quantised levels in the 16-bit window layout; output pictures copied back)"}
         # the same call with the DPB already in HBM (reference pictures are earlier outputs in a decoder): only the
         # per-picture records / coefficients / filter parameters go up, the output pictures come back
         t0 = time.perf_counter()
@@ -505,6 +529,21 @@ def main():
             r_ms = float(t.item())
         e2e["dpb_resident"] = {"value": luma_px_per_step * e_steps * world / (r_ms * 1e-3) / 1e6, "unit": UNIT,
                                "h2d_bytes_per_step": int(h2d - sum(t.numel() * 2 for t in h_refs)), "d2h_bytes_per_step": int(d2h)}
+        # and with the reference's dense int32 coefficient layout going up (what round-1's first number measured)
+        ctx.recon_frame_host(f_out, f_refs, descs_dense)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            ctx.recon_frame_host(f_out, f_refs, descs_dense)
+        barrier()
+        d_ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([d_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            d_ms = float(t.item())
+        e2e["dense_int32_layout"] = {"value": luma_px_per_step * e_steps * world / (d_ms * 1e-3) / 1e6, "unit": UNIT,
+                                     "h2d_bytes_per_step": int(h2d + h2d_dense_extra), "d2h_bytes_per_step": int(d2h)}
+        ctx.recon_frame_host(f_out, f_refs, descs)
         # sanity: the host path produced the same pictures as the device-resident path
         got = out.to_numpy()
         for c in range(3):

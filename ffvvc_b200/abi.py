@@ -231,6 +231,47 @@ TB_DTYPE = np.dtype([
 assert TB_DTYPE.itemsize == C.sizeof(VVCCudaTB) == 24, (TB_DTYPE.itemsize, C.sizeof(VVCCudaTB))
 
 
+# compact coefficient layouts + fused dequantisation
+COEFF_DENSE32, COEFF_WINDOW16 = 0, 1
+TB_QUANT_DTYPE = np.dtype([("qp", np.uint8), ("dep_quant", np.uint8), ("sl_id", np.uint8), ("reserved", np.uint8)])
+SCALING_LIST_DTYPE = np.dtype([("matrix_rec", np.uint8, (28, 64)), ("dc_rec", np.uint8, (14,)), ("reserved", np.uint8, (2,))])
+assert TB_QUANT_DTYPE.itemsize == 4 and SCALING_LIST_DTYPE.itemsize == 28 * 64 + 16
+
+
+class VVCCudaCoeffs(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n", C.c_size_t), ("format", C.c_int32), ("reserved", C.c_int32),
+                ("quant", C.c_void_p), ("scaling", C.c_void_p)]
+
+
+def coeffs_desc(data_ptr, n, fmt=COEFF_DENSE32, quant_ptr=None, scaling_ptr=None):
+    d = VVCCudaCoeffs()
+    d.data, d.n, d.format, d.quant, d.scaling = data_ptr, n, fmt, quant_ptr, scaling_ptr
+    return d
+
+
+def pack_window16(tbs, coeffs):
+    """DENSE32 -> WINDOW16: (tbs with coeff_offset rewritten, int16 array).  Values outside each TB's
+    nzh x nzw window must be zero (they do not exist in the compact layout)."""
+    w = 1 << tbs["log2_w"].astype(np.int64)
+    nzw = np.minimum(tbs["nzw"].astype(np.int64), w)
+    nzh = np.minimum(tbs["nzh"].astype(np.int64), 1 << tbs["log2_h"].astype(np.int64))
+    sizes = nzw * nzh
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    out = np.zeros(int(offs[-1]) + 8, dtype=np.int16)
+    t2 = tbs.copy()
+    t2["coeff_offset"] = offs[:-1]
+    # group by (w, nzw, nzh) so each group is one fancy-indexed gather
+    key = (w << 16) | (nzw << 8) | nzh
+    for k in np.unique(key):
+        idx = np.nonzero(key == k)[0]
+        ww, a, b = int(k >> 16), int((k >> 8) & 255), int(k & 255)
+        yy, xx = np.meshgrid(np.arange(b), np.arange(a), indexing="ij")
+        src = tbs["coeff_offset"][idx].astype(np.int64)[:, None] + (yy * ww + xx).reshape(1, -1)
+        dst = offs[idx][:, None] + (yy * a + xx).reshape(1, -1)
+        out[dst] = coeffs[src].astype(np.int16)
+    return t2, out
+
+
 class VVCCudaRect(C.Structure):
     _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("w", C.c_uint16), ("h", C.c_uint16),
                 ("pic", C.c_uint16), ("reserved", C.c_uint16)]
@@ -266,6 +307,7 @@ class VVCCudaReconDesc(C.Structure):
         ("lmcs_fwd_lut", C.c_void_p), ("lmcs_rects", C.c_void_p),
         ("n_lmcs_rects", C.c_int32), ("n_tbs", C.c_int32),
         ("coeffs", C.c_void_p), ("n_coeffs", C.c_size_t), ("tbs", C.c_void_p),
+        ("coeff_format", C.c_int32), ("reserved", C.c_int32), ("quant", C.c_void_p), ("scaling", C.c_void_p),
         ("lmcs_inv_lut", C.c_void_p), ("lmcs_ctb_enable", C.c_void_p),
         ("inloop", VVCCudaInloopDesc),
     ]

@@ -158,6 +158,9 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 13: return sizeof(VVCCudaReconDesc);
     case 14: return sizeof(VVCCudaIntraPB);
     case 15: return sizeof(VVCCudaCiip);
+    case 16: return sizeof(VVCCudaTBQuant);
+    case 17: return sizeof(VVCCudaScalingList);
+    case 18: return sizeof(VVCCudaCoeffs);
     default: return 0;
     }
 }

@@ -16,6 +16,7 @@
 // load per 4 MACs), and the epilogue adds the residual straight into the picture - the residual
 // never goes back to HBM (8 B/sample -> <= 4*nz/area + 4 B/sample).
 #include "common.cuh"
+#include "coeff_src.cuh"
 #include "tables.cuh"
 
 namespace {
@@ -30,7 +31,8 @@ struct ItxK {
     pel       *plane[3];
     int        pitch[3];
     long long  bstride[3];
-    int32_t   *coeffs;
+    CoefSrc    src;
+    int32_t   *store;                    // DENSE32 buffer for VVC_CUDA_TB_STORE_RESIDUAL blocks (NULL otherwise)
     const VVCCudaTB *tbs;
     int        n_tbs, range, bd;
     const uint32_t *list, *list_count;   // optional: process tbs[list[0 .. *list_count)] instead of tbs[0 .. n_tbs)
@@ -123,8 +125,8 @@ __device__ __forceinline__ void run_pass(const int *src, int *dst, int pitch, in
 __constant__ uint8_t c_diag4_x[16] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 1, 2, 3, 2, 3, 3 };
 __constant__ uint8_t c_diag4_y[16] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 3, 2, 1, 3, 2, 3 };
 
-template <int NT>
-__device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int *sC, int *sM, int t)
+template <int NT, int MODE>
+__device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int ti, int *sC, int *sM, int t)
 {
     const int w = 1 << tb.log2_w, h = 1 << tb.log2_h, pitch = w + 1;
     const int flags = tb.flags;
@@ -132,7 +134,7 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int *sC, int *sM,
     const bool pcm = flags & (VVC_CUDA_TB_BDPCM | VVC_CUDA_TB_BDPCM_VERT);
     int nzw = tb.nzw, nzh = tb.nzh;
     const int lf_side = (w >= 8 && h >= 8) ? 8 : 4;
-    int32_t *coef = p.coeffs + tb.coeff_offset;
+    const TbCoef tc = tb_coef<MODE>(p.src, ti, tb.coeff_offset, tb.log2_w, tb.log2_h, nzw, nzh, ts);
 
     // ---- load the window of coefficients that will be read ----
     int LR, LC;
@@ -143,7 +145,8 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int *sC, int *sM,
     else                      { LR = inputs_read(tb.trv, h, nzh); LC = 1; }
     for (int i = t; i < LR * LC; i += NT) {
         const int y = i / LC, x = i - y * LC;
-        sC[y * pitch + x] = coef[y * w + x];
+        // BDPCM accumulates quantised levels; they are dequantised afterwards (vvc_intra.c:453-455)
+        sC[y * pitch + x] = pcm ? coef_raw<MODE>(tc, y, x) : coef_load<MODE>(tc, y, x);
     }
     group_sync<NT>();
 
@@ -159,6 +162,13 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int *sC, int *sM,
                     sC[y * pitch + x] = d_clip_sbits(sC[y * pitch + x] + sC[y * pitch + x - 1], p.range);
         }
         group_sync<NT>();
+        if (MODE & 2) {
+            for (int i = t; i < w * h; i += NT) {
+                const int y = i / w, x = i - y * w;
+                sC[y * pitch + x] = coef_dequant<MODE>(tc, sC[y * pitch + x], y, x);
+            }
+            group_sync<NT>();
+        }
     }
 
     if (!ts) {
@@ -228,9 +238,10 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int *sC, int *sM,
 
     // ---- epilogue ----
     if (flags & VVC_CUDA_TB_STORE_RESIDUAL) {
+        int32_t *out = p.store + tb.coeff_offset;
         for (int i = t; i < w * h; i += NT) {
             const int y = i / w, x = i - y * w;
-            coef[i] = sC[y * pitch + x];
+            out[i] = sC[y * pitch + x];
         }
     } else {
         const int planes = (flags & VVC_CUDA_TB_JOINT) ? 2 : 1;
@@ -263,6 +274,7 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int *sC, int *sM,
     group_sync<NT>();
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads) itx_kernel(const ItxK p)
 {
     __shared__ alignas(16) int s_buf[2 * LARGE_BUF];
@@ -275,62 +287,145 @@ __global__ void __launch_bounds__(kThreads) itx_kernel(const ItxK p)
         {
             int *sC = s_buf + warp * 2 * SMALL_BUF, *sM = sC + SMALL_BUF;
             for (int i = warp; i < count; i += kThreads / 32) {
-                const VVCCudaTB tb = p.tbs[p.list ? p.list[first + i] : first + i];
+                const int ti = p.list ? p.list[first + i] : first + i;
+                const VVCCudaTB tb = p.tbs[ti];
                 if ((1 << (tb.log2_w + tb.log2_h)) <= SMALL_AREA && tb.log2_w <= 4 && tb.log2_h <= 4)
-                    process_tb<32>(p, tb, sC, sM, lane);
+                    process_tb<32, MODE>(p, tb, ti, sC, sM, lane);
             }
         }
         __syncthreads();
         // phase B: large blocks, whole CTA
         for (int i = 0; i < count; i++) {
-            const VVCCudaTB tb = p.tbs[p.list ? p.list[first + i] : first + i];
+            const int ti = p.list ? p.list[first + i] : first + i;
+            const VVCCudaTB tb = p.tbs[ti];
             if (!((1 << (tb.log2_w + tb.log2_h)) <= SMALL_AREA && tb.log2_w <= 4 && tb.log2_h <= 4))
-                process_tb<kThreads>(p, tb, s_buf, s_buf + LARGE_BUF, threadIdx.x);
+                process_tb<kThreads, MODE>(p, tb, ti, s_buf, s_buf + LARGE_BUF, threadIdx.x);
         }
     }
 }
 
 }  // namespace
 
-extern "C" int vvc_cuda_itx_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs,
-                                  const VVCCudaTB *tbs, int n_tbs, int log2_transform_range)
+static void launch_generic(const ItxK &p, int mode, int grid, cudaStream_t st)
+{
+    switch (mode) {
+    case 0:  itx_kernel<0><<<grid, kThreads, 0, st>>>(p); break;
+    case 1:  itx_kernel<1><<<grid, kThreads, 0, st>>>(p); break;
+    case 2:  itx_kernel<2><<<grid, kThreads, 0, st>>>(p); break;
+    default: itx_kernel<3><<<grid, kThreads, 0, st>>>(p); break;
+    }
+}
+
+extern "C" int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *co,
+                                    const VVCCudaTB *tbs, int n_tbs, int log2_transform_range)
 {
     if (ctx->err)
         return ctx->err;
-    if (!frame || !coeffs || !tbs || n_tbs < 0)
+    if (!frame || !co || !co->data || !tbs || n_tbs < 0)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: null argument");
     if (frame->bit_depth != 10 && frame->bit_depth != 12)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: bit depth %d not accelerated", frame->bit_depth);
     if (log2_transform_range < 15 || log2_transform_range > 20)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: log2_transform_range %d out of range", log2_transform_range);
+    if (co->format != VVC_CUDA_COEFF_DENSE32 && co->format != VVC_CUDA_COEFF_WINDOW16)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: unknown coefficient layout %d", co->format);
+    if (co->format == VVC_CUDA_COEFF_WINDOW16 && log2_transform_range != 15)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: the 16-bit window layout needs log2_transform_range 15");
     if (!frame_vec_ok(frame))
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: planes and strides must be 16-byte aligned");
     if (!n_tbs)
         return VVC_CUDA_OK;
+    const int mode = coef_mode(co);
     ItxK p;
     for (int c = 0; c < 3; c++) {
         p.plane[c] = (pel *)frame->data[c];
         p.pitch[c] = (int)(frame->stride[c] / 2);
         p.bstride[c] = frame->batch_stride[c] / 2;
     }
-    p.coeffs = coeffs; p.tbs = tbs; p.n_tbs = n_tbs; p.range = log2_transform_range; p.bd = frame->bit_depth;
+    p.src.dense = (mode & 1) ? nullptr : (const int32_t *)co->data;
+    p.src.window = (mode & 1) ? (const int16_t *)co->data : nullptr;
+    p.src.quant = co->quant; p.src.scaling = co->scaling;
+    p.src.range = log2_transform_range; p.src.bd = frame->bit_depth;
+    p.store = (mode & 1) ? nullptr : (int32_t *)co->data;
+    p.tbs = tbs; p.n_tbs = n_tbs; p.range = log2_transform_range; p.bd = frame->bit_depth;
     p.list = p.list_count = NULL;
     if (p.bd == 10 && p.range == 15 && !ctx->force_generic) {
         // common kinds: warp-per-TB kernel (itx_warp.cu); it lists what it leaves (transform skip, BDPCM, 1-D blocks)
         uint32_t *rest = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + (size_t)n_tbs * sizeof(uint32_t));
         if (!rest)
             return ctx->err;
-        if (vvc_itx_launch_warp(ctx, frame, coeffs, tbs, n_tbs, rest + 16, rest))
+        if (vvc_itx_launch_warp(ctx, frame, co, tbs, n_tbs, rest + 16, rest))
             return ctx->err;
         p.list = rest + 16; p.list_count = rest;
         const int ctas = ceil_div(n_tbs, TBS_PER_CTA);
-        itx_kernel<<<ctas < 148 * 6 ? ctas : 148 * 6, kThreads, 0, ctx->stream>>>(p);
+        launch_generic(p, mode, ctas < 148 * 6 ? ctas : 148 * 6, ctx->stream);
         VVC_LAUNCHED(ctx);
         return VVC_CUDA_OK;
     }
-    itx_kernel<<<ceil_div(n_tbs, TBS_PER_CTA), kThreads, 0, ctx->stream>>>(p);
+    launch_generic(p, mode, ceil_div(n_tbs, TBS_PER_CTA), ctx->stream);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
+}
+
+extern "C" int vvc_cuda_itx_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs,
+                                  const VVCCudaTB *tbs, int n_tbs, int log2_transform_range)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!coeffs)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: null argument");
+    VVCCudaCoeffs co;
+    memset(&co, 0, sizeof(co));
+    co.data = coeffs; co.format = VVC_CUDA_COEFF_DENSE32;
+    return vvc_cuda_itx_frame_q(ctx, frame, &co, tbs, n_tbs, log2_transform_range);
+}
+
+extern "C" int vvc_cuda_itx_frame_q_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *co,
+                                         const VVCCudaTB *tbs, int n_tbs, int log2_transform_range)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!frame || !co || !co->data || !tbs || n_tbs < 0)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx_host: null argument");
+    const bool win = co->format == VVC_CUDA_COEFF_WINDOW16;
+    if (win)
+        for (int i = 0; i < n_tbs; i++)
+            if (tbs[i].flags & VVC_CUDA_TB_STORE_RESIDUAL)
+                return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx_host: VVC_CUDA_TB_STORE_RESIDUAL needs the dense int32 layout");
+    const size_t esz = win ? sizeof(int16_t) : sizeof(int32_t);
+    const size_t fsz = align_up(vvc_stage_frame_size(frame), 256);
+    const size_t csz = align_up(co->n * esz, 256);
+    const size_t tsz = align_up((size_t)n_tbs * sizeof(VVCCudaTB), 256);
+    const size_t qsz = align_up((size_t)n_tbs * sizeof(VVCCudaTBQuant), 256);
+    const size_t ssz = align_up(sizeof(VVCCudaScalingList), 256);
+    uint8_t *base = (uint8_t *)vvc_ctx_dev_stage(ctx, fsz + csz + tsz + qsz + ssz);
+    if (!base)
+        return ctx->err;
+    VVCCudaFrame df;
+    vvc_stage_frame_layout(frame, base, &df);
+    VVCCudaCoeffs dco = *co;
+    dco.data = base + fsz;
+    VVCCudaTB *dtb = (VVCCudaTB *)(base + fsz + csz);
+    if (vvc_stage_frame_h2d(ctx, &df, frame))
+        return ctx->err;
+    VVC_TRY(ctx, cudaMemcpyAsync(dco.data, co->data, co->n * esz, cudaMemcpyHostToDevice, ctx->stream));
+    VVC_TRY(ctx, cudaMemcpyAsync(dtb, tbs, (size_t)n_tbs * sizeof(VVCCudaTB), cudaMemcpyHostToDevice, ctx->stream));
+    if (co->quant) {
+        dco.quant = (const VVCCudaTBQuant *)(base + fsz + csz + tsz);
+        VVC_TRY(ctx, cudaMemcpyAsync((void *)dco.quant, co->quant, (size_t)n_tbs * sizeof(VVCCudaTBQuant), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (co->scaling) {
+        dco.scaling = (const VVCCudaScalingList *)(base + fsz + csz + tsz + qsz);
+        VVC_TRY(ctx, cudaMemcpyAsync((void *)dco.scaling, co->scaling, sizeof(VVCCudaScalingList), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (vvc_cuda_itx_frame_q(ctx, &df, &dco, dtb, n_tbs, log2_transform_range))
+        return ctx->err;
+    if (vvc_stage_frame_d2h(ctx, frame, &df))
+        return ctx->err;
+    // blocks flagged STORE_RESIDUAL return their residual in place, like the reference's itx entries
+    if (!win)
+        VVC_TRY(ctx, cudaMemcpyAsync(co->data, dco.data, co->n * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    return vvc_cuda_sync(ctx);
 }
 
 extern "C" int vvc_cuda_itx_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs, size_t n_coeffs,
@@ -338,27 +433,10 @@ extern "C" int vvc_cuda_itx_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *fram
 {
     if (ctx->err)
         return ctx->err;
-    if (!frame || !coeffs || !tbs)
+    if (!coeffs)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx_host: null argument");
-    const size_t fsz = align_up(vvc_stage_frame_size(frame), 256);
-    const size_t csz = align_up(n_coeffs * sizeof(int32_t), 256);
-    const size_t tsz = align_up((size_t)n_tbs * sizeof(VVCCudaTB), 256);
-    uint8_t *base = (uint8_t *)vvc_ctx_dev_stage(ctx, fsz + csz + tsz);
-    if (!base)
-        return ctx->err;
-    VVCCudaFrame df;
-    vvc_stage_frame_layout(frame, base, &df);
-    int32_t *dco = (int32_t *)(base + fsz);
-    VVCCudaTB *dtb = (VVCCudaTB *)(base + fsz + csz);
-    if (vvc_stage_frame_h2d(ctx, &df, frame))
-        return ctx->err;
-    VVC_TRY(ctx, cudaMemcpyAsync(dco, coeffs, n_coeffs * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    VVC_TRY(ctx, cudaMemcpyAsync(dtb, tbs, (size_t)n_tbs * sizeof(VVCCudaTB), cudaMemcpyHostToDevice, ctx->stream));
-    if (vvc_cuda_itx_frame(ctx, &df, dco, dtb, n_tbs, log2_transform_range))
-        return ctx->err;
-    if (vvc_stage_frame_d2h(ctx, frame, &df))
-        return ctx->err;
-    // blocks flagged STORE_RESIDUAL return their residual in place, like the reference's itx entries
-    VVC_TRY(ctx, cudaMemcpyAsync(coeffs, dco, n_coeffs * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    return vvc_cuda_sync(ctx);
+    VVCCudaCoeffs co;
+    memset(&co, 0, sizeof(co));
+    co.data = coeffs; co.n = n_coeffs; co.format = VVC_CUDA_COEFF_DENSE32;
+    return vvc_cuda_itx_frame_q_host(ctx, frame, &co, tbs, n_tbs, log2_transform_range);
 }

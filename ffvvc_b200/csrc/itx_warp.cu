@@ -17,6 +17,7 @@
 //    straight into the picture -- it never exists in HBM.
 // Only the non-zero window of the dense int32 coefficients is read (what the reference's butterflies read).
 #include "common.cuh"
+#include "coeff_src.cuh"
 #include "tables.cuh"
 
 namespace {
@@ -28,7 +29,8 @@ struct ItxW {
     pel       *plane[3];
     int        pitch[3];
     long long  bstride[3];
-    int32_t   *coeffs;
+    CoefSrc    src;
+    int32_t   *store;               // DENSE32 buffer for VVC_CUDA_TB_STORE_RESIDUAL blocks (NULL otherwise)
     const VVCCudaTB *tbs;
     int        n_tbs;
     uint32_t  *rest, *rest_count;   // indices of the blocks left to itx_kernel (transform skip, BDPCM, 1-D)
@@ -92,17 +94,19 @@ __device__ __forceinline__ int inputs_read(int type, int n, int nz)
 
 __device__ __forceinline__ int round_rd(int rd) { return rd <= 4 ? 4 : rd <= 8 ? 8 : rd <= 16 ? 16 : 32; }
 
+template <int MODE>
 struct __align__(16) WarpSmem {
     short mid[64 * P2];          // pass-1 output: [row][input of pass 2]
     short lf[8 * 8];             // LFNST output window [row][col]
+    short win[(MODE & 2) ? 32 * 32 : 8];   // dequantised input window [row][col] (pitch 32) when dequant() runs here
 };
 
 __constant__ uint8_t c_diag4_x[16] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 1, 2, 3, 2, 3, 3 };
 __constant__ uint8_t c_diag4_y[16] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 3, 2, 1, 3, 2, 3 };
 
 // Pass 1: mid[i][x] = clip16((sum_j in[j][x] * M[j][i] + 64) >> 7).  lane = (column x, output group g).
-template <int RD>
-__device__ __forceinline__ void pass1(WarpSmem &s, const int32_t *coef, int w, const short *lf, int nzw, int rd, int h,
+template <int RD, int MODE>
+__device__ __forceinline__ void pass1(WarpSmem<MODE> &s, const TbCoef &tc, const short *lf, int lfp, int nzw, int rd, int h,
                                       const uint32_t *wpt, int lane)
 {
     int xb = 0;
@@ -116,11 +120,11 @@ __device__ __forceinline__ void pass1(WarpSmem &s, const int32_t *coef, int w, c
     for (int jp = 0; jp < RD / 2; jp++) {
         int v0 = 0, v1 = 0;
         if (lf) {
-            if (2 * jp < rd)     v0 = lf[(2 * jp) * 8 + x];
-            if (2 * jp + 1 < rd) v1 = lf[(2 * jp + 1) * 8 + x];
+            if (2 * jp < rd)     v0 = lf[(2 * jp) * lfp + x];
+            if (2 * jp + 1 < rd) v1 = lf[(2 * jp + 1) * lfp + x];
         } else {
-            if (2 * jp < rd)     v0 = __ldg(coef + (2 * jp) * w + x);
-            if (2 * jp + 1 < rd) v1 = __ldg(coef + (2 * jp + 1) * w + x);
+            if (2 * jp < rd)     v0 = coef_load<MODE>(tc, 2 * jp, x);
+            if (2 * jp + 1 < rd) v1 = coef_load<MODE>(tc, 2 * jp + 1, x);
         }
         in[jp] = (uint32_t)(v0 & 0xffff) | ((uint32_t)v1 << 16);
     }
@@ -157,8 +161,8 @@ struct Epi {
 // the taps of its 4 columns live in registers, a mid-stage row is one broadcast 128-bit shared load per 8
 // inputs, and the picture is updated with one 64-bit load + store per row (32-bit for 2-wide blocks); the
 // samples of the next row are requested before the current row's products so their latency is hidden.
-template <int RD>
-__device__ __forceinline__ void pass2(const WarpSmem &s, int l2w, int h, const uint32_t *wpt, const Epi &e, int lane)
+template <int RD, int MODE>
+__device__ __forceinline__ void pass2(const WarpSmem<MODE> &s, int l2w, int h, const uint32_t *wpt, const Epi &e, int lane)
 {
     const int qb = max(l2w - 2, 0), cq = lane & ((1 << qb) - 1), g = lane >> qb, ng = 32 >> qb;
     const int c0 = cq << 2;
@@ -237,11 +241,15 @@ __device__ __forceinline__ bool eligible(int l2w, int l2h, int flags, int x0)
            (l2w == 1 ? !(x0 & 1) : !(x0 & 3));
 }
 
-__global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
+#ifndef ITX_WARP_MB
+#define ITX_WARP_MB 1            // resident CTAs per SM the kernel is compiled for (tools/sweep_itx.sh)
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const ItxW p)
 {
-    __shared__ WarpSmem sm[kWarps];
+    __shared__ WarpSmem<MODE> sm[kWarps];
     const int lane = threadIdx.x & 31;
-    WarpSmem &s = sm[threadIdx.x >> 5];
+    WarpSmem<MODE> &s = sm[threadIdx.x >> 5];
     const int nwarps = gridDim.x * kWarps;
     for (int ti = blockIdx.x * kWarps + (threadIdx.x >> 5); ti < p.n_tbs; ti += nwarps) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
@@ -255,18 +263,19 @@ __global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
         const int x0 = r1 & 0xffff, y0 = r1 >> 16, w = 1 << l2w, h = 1 << l2h;
         int trh = r2 >> 24, trv = r3 & 0xff, nzw = (r3 >> 8) & 0xff, nzh = (r3 >> 16) & 0xff;
         const int lfnst = r4 & 0xff, jsign = (int8_t)((r4 >> 8) & 0xff), jshift = (r4 >> 16) & 0xff, jc = r4 >> 24, pic = r5 & 0xff;
-        int32_t *coef = p.coeffs + r0;
+        const TbCoef tc = tb_coef<MODE>(p.src, ti, r0, l2w, l2h, nzw, nzh, false);
         __syncwarp();                                       // previous block is done with shared memory
 
         // ---- inverse LFNST: 8/16 inputs in 4x4 diagonal order -> 16/48 outputs, top-left 4x4 / 8x8 ----
         const short *lf = nullptr;
+        int lfp = 8;
         if (lfnst) {
             const int idx = lfnst & 3, set = (lfnst >> 2) & 3, side = (w >= 8 && h >= 8) ? 8 : 4;
             const bool transpose = (lfnst >> 4) & 1;
             const int n_in = ((lfnst >> 5) & 1) ? 8 : 16, n_out = side == 8 ? 48 : 16;
             const int8_t *M = side == 8 ? &vvct_lfnst_8x8[set][idx - 1][0][0] : &vvct_lfnst_4x4[set][idx - 1][0][0];
             s.lf[lane] = 0; s.lf[lane + 32] = 0;
-            const int u = lane < n_in ? __ldg(coef + c_diag4_y[lane & 15] * w + c_diag4_x[lane & 15]) : 0;
+            const int u = lane < n_in ? coef_load<MODE>(tc, c_diag4_y[lane & 15], c_diag4_x[lane & 15]) : 0;
             __syncwarp();
             for (int base = 0; base < n_out; base += 32) {
                 const bool act = base + lane < n_out;
@@ -289,14 +298,30 @@ __global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
         const int rdv = dc_only ? 1 : inputs_read(trv, h, nzh), rdh = inputs_read(trh, w, nzw);
         const int rdv_e = round_rd(rdv), rdh_e = round_rd(rdh);
 
+        // ---- dequant(): the rows pass 1 reads, all lanes over the window (one compact loop instead of a copy of
+        // scale_coeff per unrolled register of pass 1) ----
+        if ((MODE & 2) && !lf) {
+            int xb = 0;
+            while ((1 << xb) < nzw)
+                xb++;
+#pragma unroll 1
+            for (int idx = lane; idx < (rdv << xb); idx += 32) {
+                const int y = idx >> xb, x = idx & ((1 << xb) - 1);
+                if (x < nzw)
+                    s.win[y * 32 + x] = (short)coef_load<MODE>(tc, y, x);
+            }
+            lf = s.win;
+            lfp = 32;
+            __syncwarp();
+        }
         // ---- pass 1 ----
         {
             const uint32_t *wpt = g_wpt + wpt_base(trv, l2h) * 8;
             switch (rdv_e) {
-            case 4:  pass1<4>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
-            case 8:  pass1<8>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
-            case 16: pass1<16>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
-            default: pass1<32>(s, coef, w, lf, nzw, rdv, h, wpt, lane); break;
+            case 4:  pass1<4, MODE>(s, tc, lf, lfp, nzw, rdv, h, wpt, lane); break;
+            case 8:  pass1<8, MODE>(s, tc, lf, lfp, nzw, rdv, h, wpt, lane); break;
+            case 16: pass1<16, MODE>(s, tc, lf, lfp, nzw, rdv, h, wpt, lane); break;
+            default: pass1<32, MODE>(s, tc, lf, lfp, nzw, rdv, h, wpt, lane); break;
             }
         }
         // columns nzw .. of the mid stage are zero (scale_clip's memset); pad to the rounded reduction length
@@ -313,7 +338,7 @@ __global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
         // ---- pass 2 + epilogue ----
         Epi e;
         e.w = w;
-        e.store = (flags & VVC_CUDA_TB_STORE_RESIDUAL) ? coef : nullptr;
+        e.store = (flags & VVC_CUDA_TB_STORE_RESIDUAL) ? p.store + r0 : nullptr;
 #define SEL3(a, c) ((c) == 0 ? (a)[0] : (c) == 1 ? (a)[1] : (a)[2])
         e.pitch0 = SEL3(p.pitch, c_idx);
         e.d0 = SEL3(p.plane, c_idx) + pic * SEL3(p.bstride, c_idx) + (long long)y0 * e.pitch0 + x0;
@@ -326,10 +351,10 @@ __global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
         {
             const uint32_t *wpt = g_wpt + wpt_base(trh, l2w) * 8;
             switch (rdh_e) {
-            case 4:  pass2<4>(s, l2w, h, wpt, e, lane); break;
-            case 8:  pass2<8>(s, l2w, h, wpt, e, lane); break;
-            case 16: pass2<16>(s, l2w, h, wpt, e, lane); break;
-            default: pass2<32>(s, l2w, h, wpt, e, lane); break;
+            case 4:  pass2<4, MODE>(s, l2w, h, wpt, e, lane); break;
+            case 8:  pass2<8, MODE>(s, l2w, h, wpt, e, lane); break;
+            case 16: pass2<16, MODE>(s, l2w, h, wpt, e, lane); break;
+            default: pass2<32, MODE>(s, l2w, h, wpt, e, lane); break;
             }
         }
     }
@@ -339,7 +364,7 @@ __global__ void __launch_bounds__(kThreads) itx_warp_kernel(const ItxW p)
 
 // Launch over the whole list.  Blocks this kernel does not handle (transform skip, BDPCM, 1-D) are appended
 // to rest[] (count in rest_count[0], zeroed here) for itx_kernel (itx.cu).
-int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs, const VVCCudaTB *tbs, int n_tbs,
+int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *co, const VVCCudaTB *tbs, int n_tbs,
                         uint32_t *rest, uint32_t *rest_count)
 {
     if (!ctx->itx_packed) {
@@ -355,9 +380,19 @@ int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coe
         p.pitch[c] = (int)(frame->stride[c] / 2);
         p.bstride[c] = frame->batch_stride[c] / 2;
     }
-    p.coeffs = coeffs; p.tbs = tbs; p.n_tbs = n_tbs; p.rest = rest; p.rest_count = rest_count;
-    const int ctas = ceil_div(n_tbs, kWarps);
-    itx_warp_kernel<<<ctas < 148 * 10 ? ctas : 148 * 10, kThreads, 0, ctx->stream>>>(p);
+    const int mode = coef_mode(co);
+    p.src.dense = (mode & 1) ? nullptr : (const int32_t *)co->data;
+    p.src.window = (mode & 1) ? (const int16_t *)co->data : nullptr;
+    p.src.quant = co->quant; p.src.scaling = co->scaling; p.src.range = 15; p.src.bd = 10;
+    p.store = (mode & 1) ? nullptr : (int32_t *)co->data;
+    p.tbs = tbs; p.n_tbs = n_tbs; p.rest = rest; p.rest_count = rest_count;
+    const int ctas = ceil_div(n_tbs, kWarps), grid = ctas < 148 * 10 ? ctas : 148 * 10;
+    switch (mode) {
+    case 0:  itx_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p); break;
+    case 1:  itx_warp_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(p); break;
+    case 2:  itx_warp_kernel<2><<<grid, kThreads, 0, ctx->stream>>>(p); break;
+    default: itx_warp_kernel<3><<<grid, kThreads, 0, ctx->stream>>>(p); break;
+    }
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

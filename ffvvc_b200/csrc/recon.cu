@@ -16,8 +16,14 @@ extern "C" int vvc_cuda_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *out, co
     if (d->n_lmcs_rects > 0 && d->lmcs_fwd_lut &&
         vvc_cuda_lmcs_rects(ctx, cur, d->lmcs_fwd_lut, d->lmcs_rects, d->n_lmcs_rects))
         return ctx->err;
-    if (d->n_tbs > 0 && vvc_cuda_itx_frame(ctx, cur, d->coeffs, d->tbs, d->n_tbs, d->log2_transform_range))
-        return ctx->err;
+    if (d->n_tbs > 0) {
+        VVCCudaCoeffs co;
+        memset(&co, 0, sizeof(co));
+        co.data = d->coeffs; co.n = d->n_coeffs; co.format = d->coeff_format;
+        co.quant = d->quant; co.scaling = d->scaling;
+        if (vvc_cuda_itx_frame_q(ctx, cur, &co, d->tbs, d->n_tbs, d->log2_transform_range))
+            return ctx->err;
+    }
     if (d->lmcs_inv_lut && vvc_cuda_lmcs_frame(ctx, cur, d->lmcs_inv_lut, d->lmcs_ctb_enable))
         return ctx->err;
     return vvc_cuda_inloop_frame(ctx, out, cur, &d->inloop);
@@ -60,8 +66,10 @@ size_t desc_bytes(const VVCCudaFrame *f, const VVCCudaReconDesc *d)
     take(d->n_lmcs_rects > 0 ? d->n_lmcs_rects : 0, sizeof(VVCCudaRect));
     take((size_t)1 << f->bit_depth, sizeof(uint16_t));
     take((size_t)1 << f->bit_depth, sizeof(uint16_t));
-    take(d->n_coeffs, sizeof(int32_t));
+    take(d->n_coeffs, d->coeff_format == VVC_CUDA_COEFF_WINDOW16 ? sizeof(int16_t) : sizeof(int32_t));
     take(d->n_tbs > 0 ? d->n_tbs : 0, sizeof(VVCCudaTB));
+    take(d->n_tbs > 0 ? d->n_tbs : 0, sizeof(VVCCudaTBQuant));
+    take(1, sizeof(VVCCudaScalingList));
     take(n_ctb, sizeof(uint8_t));
     for (int dir = 0; dir < 2; dir++)
         for (int c = 0; c < planes; c++)
@@ -157,8 +165,16 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
         UP(dd.lmcs_rects, h->lmcs_rects, VVCCudaRect, h->n_lmcs_rects);
         UP(dd.lmcs_fwd_lut, h->lmcs_fwd_lut, uint16_t, 1 << out->bit_depth);
         UP(dd.lmcs_inv_lut, h->lmcs_inv_lut, uint16_t, 1 << out->bit_depth);
-        UP(dd.coeffs, h->coeffs, int32_t, (long long)h->n_coeffs);
+        if (h->coeff_format == VVC_CUDA_COEFF_WINDOW16) {
+            int16_t *dco = NULL;
+            UP(dco, (const int16_t *)h->coeffs, int16_t, (long long)h->n_coeffs);
+            dd.coeffs = (int32_t *)dco;
+        } else {
+            UP(dd.coeffs, h->coeffs, int32_t, (long long)h->n_coeffs);
+        }
         UP(dd.tbs, h->tbs, VVCCudaTB, h->n_tbs);
+        UP(dd.quant, h->quant, VVCCudaTBQuant, h->n_tbs);
+        UP(dd.scaling, h->scaling, VVCCudaScalingList, 1);
         UP(dd.lmcs_ctb_enable, h->lmcs_ctb_enable, uint8_t, n_ctb);
         for (int dir = 0; dir < 2; dir++)
             for (int c = 0; c < planes; c++)

@@ -68,6 +68,9 @@ def load():
     lib.vvc_cuda_inloop_frame_host.argtypes = [CTX, FP, FP, IP]
     lib.vvc_cuda_itx_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.vvc_cuda_itx_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]
+    CP = C.POINTER(abi.VVCCudaCoeffs)
+    lib.vvc_cuda_itx_frame_q.argtypes = [CTX, FP, CP, C.c_void_p, C.c_int, C.c_int]
+    lib.vvc_cuda_itx_frame_q_host.argtypes = [CTX, FP, CP, C.c_void_p, C.c_int, C.c_int]
     lib.vvc_cuda_lmcs_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_lmcs_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_lmcs_rects.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, C.c_int]
@@ -174,6 +177,13 @@ class Context:
 
     def itx_frame_host(self, frame, coeffs_ptr, n_coeffs, tbs_ptr, n_tbs, log2_transform_range=15):
         self.check(self.lib.vvc_cuda_itx_frame_host(self.handle, C.byref(frame), coeffs_ptr, n_coeffs, tbs_ptr, n_tbs, log2_transform_range))
+
+    def itx_frame_q(self, frame, coeffs_desc, tbs_ptr, n_tbs, log2_transform_range=15):
+        """Same stage on a VVCCudaCoeffs (dense int32 or 16-bit window layout, optional dequant on the device)."""
+        self.check(self.lib.vvc_cuda_itx_frame_q(self.handle, C.byref(frame), C.byref(coeffs_desc), tbs_ptr, n_tbs, log2_transform_range))
+
+    def itx_frame_q_host(self, frame, coeffs_desc, tbs_ptr, n_tbs, log2_transform_range=15):
+        self.check(self.lib.vvc_cuda_itx_frame_q_host(self.handle, C.byref(frame), C.byref(coeffs_desc), tbs_ptr, n_tbs, log2_transform_range))
 
     def lmcs_frame(self, frame, lut_ptr, ctb_enable_ptr=None):
         self.check(self.lib.vvc_cuda_lmcs_frame(self.handle, C.byref(frame), lut_ptr, ctb_enable_ptr))

@@ -370,6 +370,47 @@ def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True):
     return tbs, coeffs
 
 
+# Table 38 of H.266 (scaling matrix id by predMode, cIdx, max(nTbW, nTbH)); rows as in derive_scale_m,
+# libavcodec/vvc/vvc_intra.c:344-355
+SL_IDS = np.array([[[0, 2, 8, 14, 20, 26], [0, 3, 9, 15, 21, 21], [0, 4, 10, 16, 22, 22]],
+                   [[0, 5, 11, 17, 23, 27], [0, 6, 12, 18, 24, 24], [1, 7, 13, 19, 25, 25]]])
+
+
+def tb_for_window(tbs):
+    """Make nzw/nzh of a TB list describe the window the residual coder wrote (what the WINDOW16 layout stores):
+    transform-skip blocks cover the block, LFNST blocks at least their 4x4 corner."""
+    t = tbs.copy()
+    w, h = 1 << t["log2_w"].astype(np.int64), 1 << t["log2_h"].astype(np.int64)
+    ts = (t["flags"] & abi.TB_TS) != 0
+    lf = t["lfnst"] != 0
+    t["nzw"] = np.where(ts, w, np.where(lf, np.minimum(w, 4), np.minimum(t["nzw"], w)))
+    t["nzh"] = np.where(ts, h, np.where(lf, np.minimum(h, 4), np.minimum(t["nzh"], h)))
+    return t
+
+
+def tb_quant(tbs, seed=77, scaling=True, qp_lo=4, qp_hi=74):
+    """Per-TB quantisation records (TB_QUANT_DTYPE) and one scaling list (SCALING_LIST_DTYPE, or None):
+    qp uniform in [qp_lo, qp_hi], dependent quantisation on half of the pictures' TBs, explicit scaling
+    matrices (Table 38 id by a per-TB intra/inter draw) on 60 % of the non-skipped blocks."""
+    rng = LCG(seed)
+    n = len(tbs)
+    q = np.zeros(n, dtype=abi.TB_QUANT_DTYPE)
+    q["qp"] = qp_lo + rng.below(n, qp_hi - qp_lo + 1)
+    q["dep_quant"] = rng.below(n, 2)
+    sl = None
+    if scaling:
+        sl = np.zeros(1, dtype=abi.SCALING_LIST_DTYPE)
+        sl["matrix_rec"][0] = (1 + rng.below(28 * 64, 255)).reshape(28, 64)
+        sl["dc_rec"][0] = 1 + rng.below(14, 255)
+        inter = rng.below(n, 2)
+        size_idx = np.maximum(tbs["log2_w"], tbs["log2_h"]).astype(np.int64) - 1
+        ids = SL_IDS[inter, tbs["c_idx"].astype(np.int64), np.maximum(size_idx, 0)]
+        ts = (tbs["flags"] & abi.TB_TS) != 0
+        use = (rng.below(n, 100) < 60) & ~ts & (size_idx >= 0)
+        q["sl_id"] = np.where(use, ids + 1, 0)
+    return q, sl
+
+
 def lmcs_luts(bit_depth=10, seed=5):
     """A forward/inverse LMCS look-up pair shaped like the ones vvc_ps.c:592-672 derives: 16 bins,
     piecewise linear, monotone; the inverse LUT is the numeric inverse of the forward one."""

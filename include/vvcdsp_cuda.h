@@ -62,7 +62,7 @@ const char *vvc_cuda_version(void);
 #define VVC_CUDA_OPT_GENERIC_KERNELS 1
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -222,8 +222,9 @@ int vvc_cuda_inloop_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const V
  * ilfnst_transform :65-127 / ff_vvc_inv_lfnst_1d vvc_itx_1d.c:708-721, the table entries
  * itx.itx[trh][trv][log2w][log2h] (vvcdsp.c:94-195, vvc_itx_1d.c:70-706), itx.transform_bdpcm,
  * itx.add_residual, itx.add_residual_joint (vvcdsp_template.c:32-95)).
- * Dequantisation stays on the host, so coefficients arrive as the
- * reference stores them after dequant(): one dense row-major int32[h][w] per TB.
+ * vvc_cuda_itx_frame takes coefficients as the reference stores them after dequant(): one dense
+ * row-major int32[h][w] per TB.  vvc_cuda_itx_frame_q (below) takes the compact window layout and
+ * can run dequant() on the device in front of the transform.
  * ---------------------------------------------------------------------------------------- */
 #define VVC_CUDA_TB_TS              1   /* transform skip: no LFNST / transform (tb->ts)                 */
 #define VVC_CUDA_TB_BDPCM           2   /* run itx.transform_bdpcm first (horizontal accumulate)         */
@@ -257,6 +258,56 @@ int vvc_cuda_itx_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coef
                        const VVCCudaTB *tbs, int n_tbs, int log2_transform_range);
 int vvc_cuda_itx_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs, size_t n_coeffs,
                             const VVCCudaTB *tbs, int n_tbs, int log2_transform_range);
+
+/* ------------------------------------------------------------------------------------------
+ * Compact coefficient input and fused dequantisation (replaces dequant() with derive_qp's shift,
+ * derive_scale, derive_scale_m and scale_coeff, libavcodec/vvc/vvc_intra.c:277-417, in front of the
+ * residual stage; the reference's order transform_bdpcm -> dequant -> LFNST -> itx -> add_residual,
+ * vvc_intra.c:453-470, is kept).
+ *
+ * Coefficient layouts (VVCCudaTB.coeff_offset counts elements of the layout's own type):
+ *   VVC_CUDA_COEFF_DENSE32   int32[h][w] per TB, as tb->coeffs
+ *   VVC_CUDA_COEFF_WINDOW16  int16[nzh][nzw] per TB: only the window the residual coder wrote,
+ *                            rows 0..max_scan_y, columns 0..max_scan_x, row pitch nzw.  Quantised levels
+ *                            and dequantised coefficients are both 16-bit at log2_transform_range 15
+ *                            (CoeffMinY..CoeffMaxY), so the layout is lossless there; it is rejected for
+ *                            larger ranges.  4-8x fewer bytes over PCIe than DENSE32.
+ * ---------------------------------------------------------------------------------------- */
+#define VVC_CUDA_COEFF_DENSE32   0
+#define VVC_CUDA_COEFF_WINDOW16  1
+
+/* per-TB quantisation parameters, entry i belongs to tbs[i] */
+typedef struct VVCCudaTBQuant {
+    uint8_t qp;          /* tb->qp as derive_qp leaves it (offsets applied, clipped), vvc_intra.c:277-308   */
+    uint8_t dep_quant;   /* sh_dep_quant_used_flag of the slice                                            */
+    uint8_t sl_id;       /* 0: flat scaling (ff_vvc_default_scale_m, m = 16); else 1 + the scaling matrix id
+                            of Table 38 (ids[][][] in derive_scale_m, vvc_intra.c:341-355)                */
+    uint8_t reserved;
+} VVCCudaTBQuant;        /* 4 bytes */
+
+/* mirrors VVCScalingList (libavcodec/vvc/vvc_ps.h:187-190) */
+typedef struct VVCCudaScalingList {
+    uint8_t matrix_rec[28][64];   /* ScalingMatrixRec[id][8 * y + x]      */
+    uint8_t dc_rec[14];           /* ScalingMatrixDcRec[id - 14]          */
+    uint8_t reserved[2];
+} VVCCudaScalingList;
+
+typedef struct VVCCudaCoeffs {
+    void                     *data;      /* int32_t* or int16_t*, by `format`                              */
+    size_t                    n;         /* elements in data (read by the _host entries only)              */
+    int32_t                   format;    /* VVC_CUDA_COEFF_*                                               */
+    int32_t                   reserved;
+    const VVCCudaTBQuant     *quant;     /* NULL: data holds dequantised coefficients; else quantised levels
+                                            (TransCoeffLevel) and the device runs dequant()                */
+    const VVCCudaScalingList *scaling;   /* the picture's scaling list (fc->ps.sl); may be NULL when every
+                                            sl_id is 0                                                     */
+} VVCCudaCoeffs;
+
+/* Same stage as vvc_cuda_itx_frame.  VVC_CUDA_TB_STORE_RESIDUAL needs DENSE32. */
+int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *coeffs,
+                         const VVCCudaTB *tbs, int n_tbs, int log2_transform_range);
+int vvc_cuda_itx_frame_q_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *coeffs,
+                              const VVCCudaTB *tbs, int n_tbs, int log2_transform_range);
 
 /* ------------------------------------------------------------------------------------------
  * LMCS stage (replaces lmcs.filter, libavcodec/vvc/vvc_filter_template.c:25-36, as driven by
@@ -432,9 +483,13 @@ typedef struct VVCCudaReconDesc {
     int32_t            n_lmcs_rects;
     /* RECON: residual of every TB */
     int32_t            n_tbs;
-    int32_t           *coeffs;
-    size_t             n_coeffs;          /* only read by the _host entry (bytes to copy = 4 * n_coeffs) */
+    int32_t           *coeffs;            /* int16_t* when coeff_format == VVC_CUDA_COEFF_WINDOW16 */
+    size_t             n_coeffs;          /* elements; only read by the _host entry */
     const VVCCudaTB   *tbs;
+    int32_t            coeff_format;      /* VVC_CUDA_COEFF_* */
+    int32_t            reserved;
+    const VVCCudaTBQuant     *quant;      /* optional: n_tbs entries, dequant() on the device */
+    const VVCCudaScalingList *scaling;    /* optional */
     /* LMCS inverse mapping per CTU; NULL lut = stage skipped (sh_lmcs_used_flag == 0) */
     const uint16_t    *lmcs_inv_lut;
     const uint8_t     *lmcs_ctb_enable;

@@ -151,21 +151,69 @@ int vvco_lfnst_tr_set(int pred_mode_intra)
     return pred_mode_intra < 0 ? 1 : vvct_lfnst_tr_set_index[pred_mode_intra];
 }
 
-void vvco_itx_frame(const VVCCudaFrame *f, int32_t *coeffs, const VVCCudaTB *tbs, int n_tbs, int range)
+/*
+ * dequant() of one TB, in place on the dense block (libavcodec/vvc/vvc_intra.c:397-417):
+ *   shift / rounding offset of derive_qp (:294-308), level scale of derive_scale (:311-338), the
+ *   matrix entry of derive_scale_m (:341-384; flat 16 = ff_vvc_default_scale_m), scale_coeff (:387-395).
+ * q->qp is tb->qp after derive_qp's offsets and clip.  Zero levels are skipped like the reference does, so
+ * running over the whole block equals running over [min_scan, max_scan].
+ */
+static void dequant_tb(int *c, int log2_w, int log2_h, int ts, const VVCCudaTBQuant *q, const VVCCudaScalingList *sl,
+                       int range, int bd)
+{
+    static const int level_scale[2][6] = { { 40, 45, 51, 57, 64, 72 }, { 57, 64, 72, 80, 90, 102 } };
+    const int w = 1 << log2_w, h = 1 << log2_h, log_sum = log2_w + log2_h;
+    const int rect = ts ? 0 : (log_sum & 1);
+    const int shift = ts ? 10 : bd + rect + log_sum / 2 + 10 - range + q->dep_quant;
+    const int add = (1 << shift) >> 1;
+    const int qp = q->qp + (q->dep_quant && !ts);
+    const int scale = level_scale[rect][qp % 6] << (qp / 6);
+    const int id = q->sl_id - 1;
+    const int lms = id < 2 ? 1 : id < 8 ? 2 : 3;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int m = 16;
+            if (!c[y * w + x])
+                continue;
+            if (q->sl_id && sl) {
+                m = sl->matrix_rec[id][(((y << lms) >> log2_h) << lms) + ((x << lms) >> log2_w)];
+                if (id >= 14 && !x && !y)
+                    m = sl->dc_rec[id - 14];
+            }
+            c[y * w + x] = o_clip_sbits((c[y * w + x] * scale * m + add) >> shift, range);   /* wraps: -fwrapv */
+        }
+}
+
+/* Residual stage on either coefficient layout, with optional dequantisation; order of itransform()
+ * (vvc_intra.c:453-470): transform_bdpcm -> dequant -> LFNST -> inverse transform -> add_residual(_joint). */
+void vvco_itx_frame_q(const VVCCudaFrame *f, const VVCCudaCoeffs *co, const VVCCudaTB *tbs, int n_tbs, int range)
 {
     const int bd = f->bit_depth;
     int tmp[64 * 64];
     for (int i = 0; i < n_tbs; i++) {
         const VVCCudaTB *tb = &tbs[i];
         const int w = 1 << tb->log2_w, h = 1 << tb->log2_h;
+        const int ts = !!(tb->flags & VVC_CUDA_TB_TS);
         int nzw = tb->nzw, nzh = tb->nzh;
-        int *src = coeffs + tb->coeff_offset;
-        int *c = (tb->flags & VVC_CUDA_TB_STORE_RESIDUAL) ? src : tmp;
-        if (c != src)
-            memcpy(c, src, sizeof(int) * w * h);
+        int *c = tmp;
+        if (co->format == VVC_CUDA_COEFF_WINDOW16) {
+            const int16_t *src = (const int16_t *)co->data + tb->coeff_offset;
+            memset(c, 0, sizeof(int) * w * h);
+            for (int y = 0; y < nzh && y < h; y++)
+                for (int x = 0; x < nzw && x < w; x++)
+                    c[y * w + x] = src[y * nzw + x];
+        } else {
+            int *src = (int32_t *)co->data + tb->coeff_offset;
+            if (tb->flags & VVC_CUDA_TB_STORE_RESIDUAL)
+                c = src;
+            else
+                memcpy(c, src, sizeof(int) * w * h);
+        }
         if (tb->flags & (VVC_CUDA_TB_BDPCM | VVC_CUDA_TB_BDPCM_VERT))
             bdpcm(c, w, h, !!(tb->flags & VVC_CUDA_TB_BDPCM_VERT), range);
-        if (!(tb->flags & VVC_CUDA_TB_TS)) {
+        if (co->quant)
+            dequant_tb(c, tb->log2_w, tb->log2_h, ts, &co->quant[i], co->scaling, range, bd);
+        if (!ts) {
             if (tb->lfnst)
                 inverse_lfnst(c, w, h, tb->lfnst, range, &nzw, &nzh);
             inverse_transform(c, w, h, tb->trh, tb->trv, nzw, nzh, range, bd);
@@ -189,4 +237,21 @@ void vvco_itx_frame(const VVCCudaFrame *f, int32_t *coeffs, const VVCCudaTB *tbs
                 }
         }
     }
+}
+
+void vvco_itx_frame(const VVCCudaFrame *f, int32_t *coeffs, const VVCCudaTB *tbs, int n_tbs, int range)
+{
+    VVCCudaCoeffs co;
+    memset(&co, 0, sizeof(co));
+    co.data = coeffs;
+    co.format = VVC_CUDA_COEFF_DENSE32;
+    vvco_itx_frame_q(f, &co, tbs, n_tbs, range);
+}
+
+/* dequant() alone on a dense block (pinned against the reference's static dequant() through
+ * oracle/refbuild/ref_glue_dequant.c) */
+void vvco_dequant_tb(int32_t *c, int log2_w, int log2_h, int ts, const VVCCudaTBQuant *q, const VVCCudaScalingList *sl,
+                     int range, int bd)
+{
+    dequant_tb(c, log2_w, log2_h, ts, q, sl, range, bd);
 }

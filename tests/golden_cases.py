@@ -29,6 +29,9 @@ def build_case(name, lfnst_set_of):
     case = dict(geom=geom, gref=gref, refs=gen(gref, seed=seed))
     case["pbs"], case["wp"], case["prof"] = synth.pb_list(geom, n_refs=3, seed=seed + 1, mix=STRESS_MIX)
     case["tbs"], case["coeffs"] = synth.tb_list(geom, seed=seed + 2, lfnst_set_of=lfnst_set_of, extras=False)
+    # the same tiling as quantised levels in the 16-bit window layout, dequantised by the stage itself
+    case["qtbs"], case["qwin"] = abi.pack_window16(synth.tb_for_window(case["tbs"]), case["coeffs"])
+    case["quant"], case["sl"] = synth.tb_quant(case["qtbs"], seed=seed + 9, scaling=True)
     case["fwd"], case["inv"] = synth.lmcs_luts(bd, seed=seed + 3)
     case["maps"] = synth.deblock_maps(geom, seed=seed + 4, qp_base=27, qp_span=16)
     case["sao"] = synth.sao_params(geom, seed=seed + 5)
@@ -53,6 +56,13 @@ class HostBackend:
 
     def itx(self, geom, pic, coeffs, tbs, rng):
         self.fn("itx_frame")(abi.frame_from_numpy(geom, pic), coeffs.ctypes.data, tbs.ctypes.data, len(tbs), rng)
+
+    def itx_q(self, geom, pic, win, tbs, quant, sl, rng):
+        co = abi.coeffs_desc(win.ctypes.data, win.size, abi.COEFF_WINDOW16, quant.ctypes.data, sl.ctypes.data)
+        fn = self.fn("itx_frame_q")
+        fn.argtypes = [C.POINTER(abi.VVCCudaFrame), C.POINTER(abi.VVCCudaCoeffs), C.c_void_p, C.c_int, C.c_int]
+        fn.restype = None
+        fn(abi.frame_from_numpy(geom, pic), C.byref(co), tbs.ctypes.data, len(tbs), rng)
 
     def lmcs(self, geom, pic, lut):
         self.fn("lmcs_frame")(abi.frame_from_numpy(geom, pic), lut.ctypes.data, None)
@@ -89,6 +99,10 @@ class CudaHostBackend:
     def itx(self, geom, pic, coeffs, tbs, rng):
         self.ctx.itx_frame_host(abi.frame_from_numpy(geom, pic), coeffs.ctypes.data, len(coeffs), tbs.ctypes.data, len(tbs), rng)
 
+    def itx_q(self, geom, pic, win, tbs, quant, sl, rng):
+        co = abi.coeffs_desc(win.ctypes.data, win.size, abi.COEFF_WINDOW16, quant.ctypes.data, sl.ctypes.data)
+        self.ctx.itx_frame_q_host(abi.frame_from_numpy(geom, pic), co, tbs.ctypes.data, len(tbs), rng)
+
     def lmcs(self, geom, pic, lut):
         self.ctx.lmcs_frame_host(abi.frame_from_numpy(geom, pic), lut.ctypes.data, None)
 
@@ -124,6 +138,9 @@ def run_case(case, be):
     out["intra"] = vis(ipic)
     be.ciip(g, ipic, [p.copy() for p in pic], case["ciip"])
     out["ciip"] = vis(ipic)
+    qpic = [p.copy() for p in pic]
+    be.itx_q(g, qpic, case["qwin"], case["qtbs"], case["quant"], case["sl"], 15)
+    out["residual_q"] = vis(qpic)
     coeffs = case["coeffs"].copy()
     be.itx(g, pic, coeffs, case["tbs"], 15)
     out["residual"] = vis(pic)

@@ -39,4 +39,4 @@ def test_cuda_reproduces_reference_vectors(name):
 def test_golden_file_covers_every_case_and_stage():
     assert set(GOLDEN) == set(gc.CASES)
     for c in GOLDEN.values():
-        assert set(c) == {"inter", "intra", "ciip", "residual", "lmcs", "deblock", "sao", "alf"}
+        assert set(c) == {"inter", "intra", "ciip", "residual", "residual_q", "lmcs", "deblock", "sao", "alf"}

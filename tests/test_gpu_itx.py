@@ -98,3 +98,84 @@ def test_host_entry_and_4k_linearity(ctx):
     pred4 = synth.uniform_planes(g4, seed=12)
     gp, _ = cuda_itx(ctx, g4, tbs4, np.zeros_like(co4), pred4)
     util.assert_planes_equal(g4, gp, pred4, "zero residual must be the identity")
+
+
+# ---- compact coefficient layout + dequantisation on the device (vvc_cuda_itx_frame_q) ----
+def _q_case(geom, seed, scaling=True):
+    tbs, levels = synth.tb_list(geom, seed=seed, lfnst_set_of=util.oracle().vvco_lfnst_tr_set, extras=False)
+    tbs = synth.tb_for_window(tbs)
+    quant, sl = synth.tb_quant(tbs, seed=seed + 50, scaling=scaling)
+    wt, win = abi.pack_window16(tbs, levels)
+    return tbs, levels, wt, win, quant, sl
+
+
+def _oracle_q(geom, pred, data, fmt, tbs, quant, sl):
+    import ctypes as C
+    planes = [p.copy() for p in pred]
+    d = data.copy()
+    co = abi.coeffs_desc(d.ctypes.data, d.size, fmt, quant.ctypes.data if quant is not None else None,
+                         sl.ctypes.data if sl is not None else None)
+    util.oracle().vvco_itx_frame_q(abi.frame_from_numpy(geom, planes), C.byref(co), tbs.ctypes.data, len(tbs), 15)
+    return planes
+
+
+def _cuda_q(ctx, geom, pred, data, fmt, tbs, quant, sl):
+    from ffvvc_b200 import device
+    fr = device.DeviceFrames(geom, planes=pred)
+    keep = [device.to_device(data), device.to_device(tbs)]
+    qp = sp = None
+    if quant is not None:
+        keep.append(device.to_device(quant))
+        qp = keep[-1][1]
+    if sl is not None:
+        keep.append(device.to_device(sl))
+        sp = keep[-1][1]
+    co = abi.coeffs_desc(keep[0][1], data.size, fmt, qp, sp)
+    ctx.itx_frame_q(fr.desc, co, keep[1][1], len(tbs), 15)
+    ctx.sync()
+    return fr.to_numpy()
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("layout", ["dense", "window"])
+@pytest.mark.parametrize("with_quant,scaling", [(False, False), (True, False), (True, True)])
+def test_compact_layout_and_device_dequant_bit_exact(ctx, layout, with_quant, scaling, generic):
+    geom = abi.FrameGeom(832, 480, batch=2)
+    tbs, levels, wt, win, quant, sl = _q_case(geom, seed=21 + generic, scaling=scaling)
+    pred = synth.uniform_planes(geom, seed=33)
+    data, fmt, t = (levels, abi.COEFF_DENSE32, tbs) if layout == "dense" else (win, abi.COEFF_WINDOW16, wt)
+    q = quant if with_quant else None
+    s = sl if (with_quant and scaling) else None
+    ctx.set_option(1, generic)
+    try:
+        got = _cuda_q(ctx, geom, pred, data, fmt, t, q, s)
+    finally:
+        ctx.set_option(1, 0)
+    util.assert_planes_equal(geom, got, _oracle_q(geom, pred, data, fmt, t, q, s), "cuda vs oracle (%s)" % layout)
+
+
+def test_quantised_host_entry_and_4k_layout_equivalence(ctx):
+    import ctypes as C
+    geom = abi.FrameGeom(416, 240)
+    tbs, levels, wt, win, quant, sl = _q_case(geom, seed=41)
+    pred = synth.uniform_planes(geom, seed=42)
+    planes = [p.copy() for p in pred]
+    co = abi.coeffs_desc(win.ctypes.data, win.size, abi.COEFF_WINDOW16, quant.ctypes.data, sl.ctypes.data)
+    ctx.itx_frame_q_host(abi.frame_from_numpy(geom, planes), co, wt.ctypes.data, len(wt), 15)
+    util.assert_planes_equal(geom, planes, _oracle_q(geom, pred, win, abi.COEFF_WINDOW16, wt, quant, sl), "host entry vs oracle")
+    # a STORE_RESIDUAL block has nowhere to go in the window layout: refused (errors are sticky, so on a throwaway context)
+    bad = wt.copy()
+    bad["flags"][0] |= abi.TB_STORE_RESIDUAL
+    from ffvvc_b200 import lib
+    c2 = lib.Context(0)
+    with pytest.raises(Exception):
+        c2.itx_frame_q_host(abi.frame_from_numpy(geom, [p.copy() for p in pred]), co, bad.ctypes.data, len(bad), 15)
+    c2.close()
+    # 4K property: both layouts of the same levels reconstruct the same picture (size-independent check)
+    g4 = abi.FrameGeom(3840, 2160)
+    tbs4, lv4, wt4, win4, q4, sl4 = _q_case(g4, seed=43)
+    pred4 = synth.uniform_planes(g4, seed=44)
+    a = _cuda_q(ctx, g4, pred4, lv4, abi.COEFF_DENSE32, tbs4, q4, sl4)
+    b = _cuda_q(ctx, g4, pred4, win4, abi.COEFF_WINDOW16, wt4, q4, sl4)
+    util.assert_planes_equal(g4, a, b, "4K: window layout vs dense layout")
+    assert win4.nbytes * 3 < lv4.nbytes

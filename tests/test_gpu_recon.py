@@ -23,12 +23,17 @@ def ctx():
     c.close()
 
 
-def build(w, h, batch, seed):
+def build(w, h, batch, seed, coeff_mode="dense"):
     g1 = abi.FrameGeom(w, h)
     gr = abi.FrameGeom(w, h, batch=batch)
     case = dict(g1=g1, gr=gr, refs=synth.struct_planes(gr, seed=seed))
     case["pbs"], case["wp"], case["prof"] = synth.pb_list(gr, n_refs=batch, seed=seed + 1, mix=STRESS_MIX)
     case["tbs"], case["coeffs"] = synth.tb_list(gr, seed=seed + 2, lfnst_set_of=util.oracle().vvco_lfnst_tr_set, extras=False)
+    case["fmt"], case["quant"], case["sl"] = abi.COEFF_DENSE32, None, None
+    if coeff_mode == "window_q":        # quantised levels in the 16-bit window layout, dequantised on the device
+        case["tbs"], case["coeffs"] = abi.pack_window16(synth.tb_for_window(case["tbs"]), case["coeffs"])
+        case["quant"], case["sl"] = synth.tb_quant(case["tbs"], seed=seed + 7, scaling=True)
+        case["fmt"] = abi.COEFF_WINDOW16
     _, case["inv"] = synth.lmcs_luts(10, seed=seed + 3)
     case["maps"] = synth.deblock_maps(gr, seed=seed + 4, qp_base=27, qp_span=16)
     case["sao"] = synth.sao_params(gr, seed=seed + 5)
@@ -42,7 +47,9 @@ def oracle_chain(case):
     o.vvco_inter_frame(abi.frame_from_numpy(gr, cur), abi.frame_from_numpy(gr, case["refs"]), case["pbs"].ctypes.data, len(case["pbs"]),
                        case["wp"].ctypes.data, case["prof"].ctypes.data, None)
     co = case["coeffs"].copy()
-    o.vvco_itx_frame(abi.frame_from_numpy(gr, cur), co.ctypes.data, case["tbs"].ctypes.data, len(case["tbs"]), 15)
+    cd = abi.coeffs_desc(co.ctypes.data, co.size, case["fmt"], case["quant"].ctypes.data if case["quant"] is not None else None,
+                         case["sl"].ctypes.data if case["sl"] is not None else None)
+    o.vvco_itx_frame_q(abi.frame_from_numpy(gr, cur), C.byref(cd), case["tbs"].ctypes.data, len(case["tbs"]), 15)
     o.vvco_lmcs_frame(abi.frame_from_numpy(gr, cur), case["inv"].ctypes.data, None)
     md = abi.deblock_maps_desc(gr, case["maps"])
     a, b = abi.alloc_planes(gr), abi.alloc_planes(gr)
@@ -53,11 +60,12 @@ def oracle_chain(case):
     return b
 
 
-@pytest.mark.parametrize("w,h,batch,seed", [(416, 240, 4, 31), (256, 192, 5, 32)])
-def test_recon_entries_bit_exact(ctx, w, h, batch, seed):
+@pytest.mark.parametrize("w,h,batch,seed,coeff_mode", [(416, 240, 4, 31, "dense"), (256, 192, 5, 32, "dense"),
+                                                       (416, 240, 3, 33, "window_q")])
+def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode):
     import torch
     from ffvvc_b200 import device
-    case = build(w, h, batch, seed)
+    case = build(w, h, batch, seed, coeff_mode)
     g1, gr = case["g1"], case["gr"]
     want = oracle_chain(case)
     keep = []
@@ -74,6 +82,9 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed):
     d.pbs, d.n_pbs, d.wp, d.n_wp, d.prof, d.n_prof = up(case["pbs"]), len(case["pbs"]), up(case["wp"]), len(case["wp"]), up(case["prof"]), len(case["prof"])
     d.log2_transform_range = 15
     d.coeffs, d.n_coeffs, d.tbs, d.n_tbs = up(case["coeffs"]), len(case["coeffs"]), up(case["tbs"]), len(case["tbs"])
+    d.coeff_format = case["fmt"]
+    if case["quant"] is not None:
+        d.quant, d.scaling = up(case["quant"]), up(case["sl"])
     d.lmcs_inv_lut = up(case["inv"])
     d.inloop.deblock = C.pointer(md)
     d.inloop.sao, d.inloop.alf, d.inloop.alf_sets = up(case["sao"]), up(case["alf"]), up(case["sets"])
@@ -100,10 +111,14 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed):
     for k in range(batch):
         pb = case["pbs"][case["pbs"]["pic"] == k].copy()
         pb["pic"] = 0
-        tb = case["tbs"][case["tbs"]["pic"] == k].copy()
+        of_k = case["tbs"]["pic"] == k
+        tb = case["tbs"][of_k].copy()
         tb["pic"] = 0
         lo = int(tb["coeff_offset"].min())
-        area = (1 << tb["log2_w"].astype(np.int64)) * (1 << tb["log2_h"].astype(np.int64))
+        if case["fmt"] == abi.COEFF_WINDOW16:
+            area = tb["nzw"].astype(np.int64) * tb["nzh"].astype(np.int64)
+        else:
+            area = (1 << tb["log2_w"].astype(np.int64)) * (1 << tb["log2_h"].astype(np.int64))
         hi = int((tb["coeff_offset"].astype(np.int64) + area).max())
         tb["coeff_offset"] -= lo
         hmd = abi.VVCCudaDeblockMaps()
@@ -117,6 +132,9 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed):
         e.pbs, e.n_pbs, e.wp, e.n_wp, e.prof, e.n_prof = pin(pb), len(pb), pin(case["wp"]), len(case["wp"]), pin(case["prof"]), len(case["prof"])
         e.log2_transform_range = 15
         e.coeffs, e.n_coeffs, e.tbs, e.n_tbs = pin(case["coeffs"][lo:hi]), hi - lo, pin(tb), len(tb)
+        e.coeff_format = case["fmt"]
+        if case["quant"] is not None:
+            e.quant, e.scaling = pin(case["quant"][of_k]), pin(case["sl"])
         e.lmcs_inv_lut = pin(case["inv"])
         e.inloop.deblock = C.pointer(hmd)
         e.inloop.sao = pin(case["sao"][k * n_ctb:(k + 1) * n_ctb])

@@ -47,6 +47,10 @@ def oracle():
         lib.vvco_sao_frame.restype = None
         lib.vvco_itx_frame.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.vvco_itx_frame.restype = None
+        lib.vvco_itx_frame_q.argtypes = [FP, C.POINTER(abi.VVCCudaCoeffs), C.c_void_p, C.c_int, C.c_int]
+        lib.vvco_itx_frame_q.restype = None
+        lib.vvco_dequant_tb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.vvco_dequant_tb.restype = None
         lib.vvco_lfnst_tr_set.argtypes = [C.c_int]
         lib.vvco_lmcs_frame.argtypes = [FP, C.c_void_p, C.c_void_p]
         lib.vvco_lmcs_frame.restype = None
@@ -84,6 +88,8 @@ def ref():
         lib.vvcref_sao_frame.restype = None
         lib.vvcref_itx_frame.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.vvcref_itx_frame.restype = None
+        lib.vvcref_dequant_tb.argtypes = [C.c_void_p] + [C.c_int] * 20 + [C.c_void_p]
+        lib.vvcref_dequant_tb.restype = C.c_int
         lib.vvcref_lmcs_frame.argtypes = [FP, C.c_void_p, C.c_void_p]
         lib.vvcref_lmcs_frame.restype = None
         lib.vvcref_lmcs_rects.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int]
