@@ -487,6 +487,7 @@ def main():
             d.log2_transform_range = 15
             d.coeffs, d.n_coeffs, d.tbs, d.n_tbs = pc["win"], pc["n_win"], pc["wtb"], pc["n_tb"]
             d.coeff_format, d.quant, d.scaling = abi.COEFF_WINDOW16, pc["quant"], hp_sl
+            d.ref_slots = (1 << ((2 * k) % frames)) | (1 << ((2 * k + 1) % frames))     # what Inputs.records() references
             d.lmcs_inv_lut = hp_lut
             d.inloop.deblock = C.pointer(pc["md"])
             d.inloop.sao, d.inloop.alf, d.inloop.alf_sets = pc["sao"], pc["alf"], hp_sets

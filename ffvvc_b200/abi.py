@@ -307,7 +307,7 @@ class VVCCudaReconDesc(C.Structure):
         ("lmcs_fwd_lut", C.c_void_p), ("lmcs_rects", C.c_void_p),
         ("n_lmcs_rects", C.c_int32), ("n_tbs", C.c_int32),
         ("coeffs", C.c_void_p), ("n_coeffs", C.c_size_t), ("tbs", C.c_void_p),
-        ("coeff_format", C.c_int32), ("reserved", C.c_int32), ("quant", C.c_void_p), ("scaling", C.c_void_p),
+        ("coeff_format", C.c_int32), ("ref_slots", C.c_uint32), ("quant", C.c_void_p), ("scaling", C.c_void_p),
         ("lmcs_inv_lut", C.c_void_p), ("lmcs_ctb_enable", C.c_void_p),
         ("inloop", VVCCudaInloopDesc),
     ]

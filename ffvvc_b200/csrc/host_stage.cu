@@ -34,10 +34,18 @@ void vvc_stage_frame_layout(const VVCCudaFrame *host, void *dbase, VVCCudaFrame 
 static int copy_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src, cudaMemcpyKind kind)
 {
     for (int c = 0; c < plane_count(src); c++)
-        for (int k = 0; k < src->batch; k++)
+        for (int k = 0; k < src->batch; k++) {
+            const size_t row = (size_t)plane_w(src, c) * sizeof(pel);
+            if ((size_t)dst->stride[c] == row && (size_t)src->stride[c] == row) {      // both sides dense: one linear copy
+                VVC_TRY(ctx, cudaMemcpyAsync((uint8_t *)dst->data[c] + k * dst->batch_stride[c],
+                                             (const uint8_t *)src->data[c] + k * src->batch_stride[c],
+                                             row * plane_h(src, c), kind, ctx->stream));
+                continue;
+            }
             VVC_TRY(ctx, cudaMemcpy2DAsync((uint8_t *)dst->data[c] + k * dst->batch_stride[c], dst->stride[c],
                                            (const uint8_t *)src->data[c] + k * src->batch_stride[c], src->stride[c],
-                                           (size_t)plane_w(src, c) * sizeof(pel), plane_h(src, c), kind, ctx->stream));
+                                           row, plane_h(src, c), kind, ctx->stream));
+        }
     return 0;
 }
 

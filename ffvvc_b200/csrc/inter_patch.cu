@@ -17,6 +17,11 @@
 namespace {
 
 constexpr int kThreads = 128;
+// window rows requested ahead of the row being filtered (the loads and the funnel shifts are volatile asm, so the
+// compiler keeps their program order: without this every row costs one full memory round trip)
+#ifndef PATCH_DEPTH
+#define PATCH_DEPTH 2
+#endif
 // resident CTAs per SM the class kernels are compiled for (register budget = 65536 / (128 * n)); measured sweep in profiles/README.md
 #ifndef PATCH_MB_LU
 #define PATCH_MB_LU 8
@@ -63,23 +68,36 @@ __device__ __forceinline__ void mc_patch(const pel *plane, int pitch, int W, int
     const int wpitch = pitch >> 1;
     uint32_t P[NR - 1][4];
     int prev[4] = { 0, 0, 0, 0 };
+    constexpr int D = PATCH_DEPTH;
+    uint32_t ahead[D][NW];
+    auto fetch = [&](int r, uint32_t (&wd)[NW]) {
+        if (inside) {
+#pragma unroll
+            for (int i = 0; i < NW; i++)
+                wd[i] = __ldg(src + r * wpitch + i);
+        } else {                                       // emulated_edge_mc: coordinates clamped to the picture
+            const pel *row = plane + (long long)d_clip3(y0 + r, 0, H - 1) * pitch;
+            const uint4 q0 = load8_clamped(row, bx, W);
+            wd[0] = q0.x; wd[1] = q0.y; wd[2] = q0.z; wd[3] = q0.w;
+            if (NW > 4) {
+                const uint4 q1 = load8_clamped(row, bx + 8, W);
+                wd[NW - 2] = q1.x; wd[NW - 1] = q1.y;
+            }
+        }
+    };
+#pragma unroll
+    for (int r = 0; r < D; r++)
+        if (r < nrows + TAPS - 1)
+            fetch(r, ahead[r]);
 #pragma unroll
     for (int r = 0; r < NR; r++) {
         if (r < nrows + TAPS - 1) {
             uint32_t wd[NW];
-            if (inside) {
 #pragma unroll
-                for (int i = 0; i < NW; i++)
-                    wd[i] = __ldg(src + r * wpitch + i);
-            } else {                                   // emulated_edge_mc: coordinates clamped to the picture
-                const pel *row = plane + (long long)d_clip3(y0 + r, 0, H - 1) * pitch;
-                const uint4 q0 = load8_clamped(row, bx, W);
-                wd[0] = q0.x; wd[1] = q0.y; wd[2] = q0.z; wd[3] = q0.w;
-                if (NW > 4) {
-                    const uint4 q1 = load8_clamped(row, bx + 8, W);
-                    wd[NW - 2] = q1.x; wd[NW - 1] = q1.y;
-                }
-            }
+            for (int i = 0; i < NW; i++)
+                wd[i] = ahead[r % D][i];
+            if (r + D < NR && r + D < nrows + TAPS - 1)
+                fetch(r + D, ahead[r % D]);
             uint32_t A[2 * NW - 2];
 #pragma unroll
             for (int i = 0; i < NW - 1; i++) {

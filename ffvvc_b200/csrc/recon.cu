@@ -128,14 +128,25 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
     VVC_TRY(ctx, cudaEventRecord(ctx->ev[0], run));           // earlier work on the context stream owns the staging area
     VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev[0], 0));
     VVC_TRY(ctx, cudaStreamWaitEvent(cout, ctx->ev[0], 0));
-    if (!refs_on_device) {
-        cudaStream_t saved = ctx->stream;
-        ctx->stream = cin;
-        const int rc = vvc_stage_frame_h2d(ctx, &drefs, refs);
-        ctx->stream = saved;
-        if (rc)
-            return ctx->err;
-    }
+    // Host reference pictures: slot s goes up (on the copy-in stream) right before the descriptors of the first
+    // picture whose ref_slots names it, so the upload of later references overlaps the kernels of earlier pictures;
+    // a picture with ref_slots == 0 (unknown) waits for the whole ring.
+    uint64_t refs_up = refs_on_device ? ~0ull : 0ull;
+    auto upload_refs = [&](uint64_t want) -> int {
+        for (int s = 0; s < refs->batch && s < 64; s++) {
+            if (!((want >> s) & 1) || ((refs_up >> s) & 1))
+                continue;
+            const VVCCudaFrame hs = one_picture(refs, s), ds = one_picture(&drefs, s);
+            cudaStream_t saved = ctx->stream;
+            ctx->stream = cin;
+            const int rc = vvc_stage_frame_h2d(ctx, &ds, &hs);
+            ctx->stream = saved;
+            if (rc)
+                return rc;
+            refs_up |= 1ull << s;
+        }
+        return 0;
+    };
     // events: ev[1+s] descriptors of slot s uploaded, ev[3+s] kernels of slot s done, ev[5+s] output of slot s downloaded
     for (int k = 0; k < out->batch; k++) {
         const int sl = k & 1;
@@ -150,6 +161,8 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
             VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev[3 + sl], 0));     // slot's previous kernels finished reading descriptors
             VVC_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev[5 + sl], 0));     // slot's previous output has left
         }
+        if (upload_refs(h->ref_slots && refs->batch <= 32 ? (uint64_t)h->ref_slots : ~0ull))
+            return ctx->err;
 #define UP(dst_ptr, src_ptr, type, count)                                                                             \
         do {                                                                                                          \
             type *dev_ = cv.take<type>((count) > 0 ? (count) : 1);                                                    \

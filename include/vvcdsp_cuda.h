@@ -487,7 +487,10 @@ typedef struct VVCCudaReconDesc {
     size_t             n_coeffs;          /* elements; only read by the _host entry */
     const VVCCudaTB   *tbs;
     int32_t            coeff_format;      /* VVC_CUDA_COEFF_* */
-    int32_t            reserved;
+    uint32_t           ref_slots;         /* _host entry: bit s set = this picture reads DPB ring slot s (the slice's
+                                             reference picture lists); host reference pictures are then copied in right
+                                             before the first picture that needs them, overlapping earlier kernels.
+                                             0 = unknown: the whole ring goes up before the first picture */
     const VVCCudaTBQuant     *quant;      /* optional: n_tbs entries, dequant() on the device */
     const VVCCudaScalingList *scaling;    /* optional */
     /* LMCS inverse mapping per CTU; NULL lut = stage skipped (sh_lmcs_used_flag == 0) */

@@ -133,6 +133,10 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode):
         e.log2_transform_range = 15
         e.coeffs, e.n_coeffs, e.tbs, e.n_tbs = pin(case["coeffs"][lo:hi]), hi - lo, pin(tb), len(tb)
         e.coeff_format = case["fmt"]
+        if coeff_mode == "window_q":      # name the DPB slots the picture reads: references go up lazily, picture by picture
+            gpm = (pb["flags"] & abi.PB_GPM) != 0
+            used = np.concatenate([pb["ref"][((pb["pred_flag"] & 1) != 0) | gpm, 0], pb["ref"][((pb["pred_flag"] & 2) != 0) | gpm, 1]])
+            e.ref_slots = int(np.bitwise_or.reduce(1 << np.unique(used).astype(np.int64))) if k else 0
         if case["quant"] is not None:
             e.quant, e.scaling = pin(case["quant"][of_k]), pin(case["sl"])
         e.lmcs_inv_lut = pin(case["inv"])
