@@ -66,4 +66,4 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 // itx_warp.cu (10-bit pictures, log2_transform_range 15)
 int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *coeffs, const VVCCudaTB *tbs, int n_tbs,
-                        uint32_t *rest, uint32_t *rest_count);
+                        uint32_t *scratch, const uint32_t **rest, const uint32_t **rest_count);

@@ -351,12 +351,11 @@ extern "C" int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, 
     p.list = p.list_count = NULL;
     if (p.bd == 10 && p.range == 15 && !ctx->force_generic) {
         // common kinds: warp-per-TB kernel (itx_warp.cu); it lists what it leaves (transform skip, BDPCM, 1-D blocks)
-        uint32_t *rest = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + (size_t)n_tbs * sizeof(uint32_t));
-        if (!rest)
+        uint32_t *scratch = (uint32_t *)vvc_ctx_scratch(ctx, 2, (16 + 5 * (size_t)n_tbs) * sizeof(uint32_t));
+        if (!scratch)
             return ctx->err;
-        if (vvc_itx_launch_warp(ctx, frame, co, tbs, n_tbs, rest + 16, rest))
+        if (vvc_itx_launch_warp(ctx, frame, co, tbs, n_tbs, scratch, &p.list, &p.list_count))
             return ctx->err;
-        p.list = rest + 16; p.list_count = rest;
         const int ctas = ceil_div(n_tbs, TBS_PER_CTA);
         launch_generic(p, mode, ctas < 148 * 6 ? ctas : 148 * 6, ctx->stream);
         VVC_LAUNCHED(ctx);

@@ -22,6 +22,15 @@
 
 namespace {
 
+// CUDA's __dp2a_* and __ldg are `asm volatile`: the compiler keeps them in program order, so a loop of them runs as one
+// dependent chain behind its loads.  These are the same instructions as plain asm (pure functions of their operands;
+// the tables and coefficients they read are constant for the launch), which lets independent chains interleave.
+__device__ __forceinline__ int dp2a_lo(int a, int b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi(int a, int b, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint4 ldg_nc(const uint4 *p) { uint4 v; asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v; }
+__device__ __forceinline__ uint2 ldg_nc(const uint2 *p) { uint2 v; asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_nc(const uint32_t *p) { uint32_t v; asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
 constexpr int kWarps = 4, kThreads = kWarps * 32;
 constexpr int P2 = 40;                        // pitch (int16) of the mid-stage rows: 32 inputs + pad, 16-byte multiple
 
@@ -33,7 +42,9 @@ struct ItxW {
     int32_t   *store;               // DENSE32 buffer for VVC_CUDA_TB_STORE_RESIDUAL blocks (NULL otherwise)
     const VVCCudaTB *tbs;
     int        n_tbs;
-    uint32_t  *rest, *rest_count;   // indices of the blocks left to itx_kernel (transform skip, BDPCM, 1-D)
+    uint32_t  *counts;              // [0..4] blocks per class, [5] work counter (zeroed per launch)
+    uint32_t  *lists;               // class c: lists[c * n_tbs ..): 0/1/2 = 4096/2048/1024+ samples, 3 = smaller, 4 = left to
+                                    // itx_kernel (transform skip, BDPCM, 1-D)
 };
 
 // Packed matrices: for output i of (type, n) the 8 words g_wpt[(base + i) * 8 + q] hold taps M[4q .. 4q+3][i]
@@ -128,26 +139,48 @@ __device__ __forceinline__ void pass1(WarpSmem<MODE> &s, const TbCoef &tc, const
         }
         in[jp] = (uint32_t)(v0 & 0xffff) | ((uint32_t)v1 << 16);
     }
-    for (int i = g; i < h; i += ng) {
-        const uint4 *mp = reinterpret_cast<const uint4 *>(wpt + i * 8);
+    // two outputs per iteration: their matrix words are requested together and the two tap chains are independent
+    auto taps = [&](const uint4 (&m)[RD >= 16 ? RD / 16 : 1]) -> int {
         int acc = 0;
         if (RD == 4) {
-            const uint32_t m = __ldg(reinterpret_cast<const uint32_t *>(mp));
-            acc = __dp2a_lo((int)in[0], (int)m, __dp2a_hi((int)in[1], (int)m, 0));
+            acc = dp2a_lo((int)in[0], (int)m[0].x, dp2a_hi((int)in[1], (int)m[0].x, 0));
         } else if (RD == 8) {
-            const uint2 m = __ldg(reinterpret_cast<const uint2 *>(mp));
-            acc = __dp2a_lo((int)in[0], (int)m.x, __dp2a_hi((int)in[1], (int)m.x, __dp2a_lo((int)in[2], (int)m.y, __dp2a_hi((int)in[3], (int)m.y, 0))));
+            acc = dp2a_lo((int)in[0], (int)m[0].x, dp2a_hi((int)in[1], (int)m[0].x, 0)) +
+                  dp2a_lo((int)in[2], (int)m[0].y, dp2a_hi((int)in[3], (int)m[0].y, 0));
         } else {
+            int a0 = 0, a1 = 0;
 #pragma unroll
             for (int q4 = 0; q4 < RD / 16; q4++) {
-                const uint4 m = __ldg(mp + q4);
-                acc = __dp2a_lo((int)in[8 * q4 + 0], (int)m.x, __dp2a_hi((int)in[8 * q4 + 1], (int)m.x, acc));
-                acc = __dp2a_lo((int)in[8 * q4 + 2], (int)m.y, __dp2a_hi((int)in[8 * q4 + 3], (int)m.y, acc));
-                acc = __dp2a_lo((int)in[8 * q4 + 4], (int)m.z, __dp2a_hi((int)in[8 * q4 + 5], (int)m.z, acc));
-                acc = __dp2a_lo((int)in[8 * q4 + 6], (int)m.w, __dp2a_hi((int)in[8 * q4 + 7], (int)m.w, acc));
+                a0 = dp2a_lo((int)in[8 * q4 + 0], (int)m[q4].x, dp2a_hi((int)in[8 * q4 + 1], (int)m[q4].x, a0));
+                a1 = dp2a_lo((int)in[8 * q4 + 2], (int)m[q4].y, dp2a_hi((int)in[8 * q4 + 3], (int)m[q4].y, a1));
+                a0 = dp2a_lo((int)in[8 * q4 + 4], (int)m[q4].z, dp2a_hi((int)in[8 * q4 + 5], (int)m[q4].z, a0));
+                a1 = dp2a_lo((int)in[8 * q4 + 6], (int)m[q4].w, dp2a_hi((int)in[8 * q4 + 7], (int)m[q4].w, a1));
             }
+            acc = a0 + a1;
         }
-        s.mid[i * P2 + x] = (short)d_clip_sbits((acc + 64) >> 7, 15);
+        return acc;
+    };
+    auto fetch = [&](int i, uint4 (&m)[RD >= 16 ? RD / 16 : 1]) {
+        const uint4 *mp = reinterpret_cast<const uint4 *>(wpt + i * 8);
+        if (RD == 4) {
+            m[0].x = ldg_nc(reinterpret_cast<const uint32_t *>(mp));
+        } else if (RD == 8) {
+            const uint2 v = ldg_nc(reinterpret_cast<const uint2 *>(mp));
+            m[0].x = v.x; m[0].y = v.y;
+        } else {
+#pragma unroll
+            for (int q4 = 0; q4 < RD / 16; q4++)
+                m[q4] = ldg_nc(mp + q4);
+        }
+    };
+    for (int i = g; i < h; i += 2 * ng) {
+        uint4 ma[RD >= 16 ? RD / 16 : 1], mb[RD >= 16 ? RD / 16 : 1];
+        const int i2 = i + ng < h ? i + ng : i;             // odd tail: the second chain repeats the first
+        fetch(i, ma);
+        fetch(i2, mb);
+        const int ra = taps(ma), rb = taps(mb);
+        s.mid[i * P2 + x] = (short)d_clip_sbits((ra + 64) >> 7, 15);
+        s.mid[i2 * P2 + x] = (short)d_clip_sbits((rb + 64) >> 7, 15);
     }
 }
 
@@ -172,7 +205,7 @@ __device__ __forceinline__ void pass2(const WarpSmem<MODE> &s, int l2w, int h, c
     for (int c = 0; c < 4; c++)
 #pragma unroll
         for (int q = 0; q < RD / 4; q++)
-            m[c][q] = (narrow && c >= 2) ? 0u : __ldg(wpt + (c0 + c) * 8 + q);
+            m[c][q] = (narrow && c >= 2) ? 0u : ldg_nc(wpt + (c0 + c) * 8 + q);
     const int step0 = ng * e.pitch0, step1 = ng * e.pitch1;
     pel *d0 = e.d0 + g * e.pitch0 + c0, *d1 = e.d1 ? e.d1 + g * e.pitch1 + c0 : nullptr;
     auto load4 = [&](const pel *p) -> uint2 {
@@ -208,7 +241,7 @@ __device__ __forceinline__ void pass2(const WarpSmem<MODE> &s, int l2w, int h, c
             int a = 0;
 #pragma unroll
             for (int q = 0; q < RD / 4; q++)
-                a = __dp2a_lo((int)in[2 * q], (int)m[c][q], __dp2a_hi((int)in[2 * q + 1], (int)m[c][q], a));
+                a = dp2a_lo((int)in[2 * q], (int)m[c][q], dp2a_hi((int)in[2 * q + 1], (int)m[c][q], a));
             r[c] = (a + 512) >> 10;                         // shift = 5 + log2_transform_range - bit_depth
         }
         if (e.store) {
@@ -241,6 +274,36 @@ __device__ __forceinline__ bool eligible(int l2w, int l2h, int flags, int x0)
            (l2w == 1 ? !(x0 & 1) : !(x0 & 3));
 }
 
+// Work lists.  A 64x64 block keeps a warp busy a hundred times longer than a 4x4 one, and with a fixed stride the
+// launch lasted as long as the warp that happened to draw the most large blocks.  The blocks are binned by size on
+// the device; the transform kernel then hands them out through a counter, largest first, small ones in chunks.
+constexpr int kSmallChunk = 16;
+
+__global__ void __launch_bounds__(256) itx_sort_kernel(const ItxW p)
+{
+    const int ti = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
+    int cls = -1;
+    if (ti < p.n_tbs) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
+        const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3);
+        const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, flags = r3 >> 24;
+        if (!eligible(l2w, l2h, flags, r1 & 0xffff)) cls = 4;
+        else cls = l2w + l2h >= 12 ? 0 : l2w + l2h == 11 ? 1 : l2w + l2h == 10 ? 2 : 3;
+    }
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (!m)
+            continue;
+        uint32_t base = 0;
+        if (lane == __ffs(m) - 1)
+            base = atomicAdd(p.counts + c, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (cls == c)
+            p.lists[(size_t)c * p.n_tbs + base + __popc(m & ((1u << lane) - 1))] = ti;
+    }
+}
+
 #ifndef ITX_WARP_MB
 #define ITX_WARP_MB 1            // resident CTAs per SM the kernel is compiled for (tools/sweep_itx.sh)
 #endif
@@ -250,20 +313,42 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
     __shared__ WarpSmem<MODE> sm[kWarps];
     const int lane = threadIdx.x & 31;
     WarpSmem<MODE> &s = sm[threadIdx.x >> 5];
-    const int nwarps = gridDim.x * kWarps;
-    for (int ti = blockIdx.x * kWarps + (threadIdx.x >> 5); ti < p.n_tbs; ti += nwarps) {
+    const uint32_t nA = p.counts[0], nB = p.counts[1], nC = p.counts[2], nS = p.counts[3];
+    const uint32_t nbig = nA + nB + nC, total = nbig + (nS + kSmallChunk - 1) / kSmallChunk;
+    for (;;) {
+        uint32_t v = 0;
+        if (lane == 0)
+            v = atomicAdd(p.counts + 5, 1u);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if (v >= total)
+            break;
+        const uint32_t *list;
+        int cnt = 1;
+        if (v < nA)             list = p.lists + v;
+        else if (v < nA + nB)   list = p.lists + (size_t)p.n_tbs + (v - nA);
+        else if (v < nbig)      list = p.lists + 2 * (size_t)p.n_tbs + (v - nA - nB);
+        else {
+            const uint32_t c = (v - nbig) * kSmallChunk;
+            list = p.lists + 3 * (size_t)p.n_tbs + c;
+            cnt = min(kSmallChunk, (int)(nS - c));
+        }
+    for (int k = 0; k < cnt; k++) {
+        const int ti = (int)__ldg(list + k);
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
         const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
         const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, c_idx = (r2 >> 16) & 0xff, flags = r3 >> 24;
-        if (!eligible(l2w, l2h, flags, r1 & 0xffff)) {                   // itx_kernel's share
-            if (lane == 0)
-                p.rest[atomicAdd(p.rest_count, 1u)] = ti;
-            continue;
-        }
         const int x0 = r1 & 0xffff, y0 = r1 >> 16, w = 1 << l2w, h = 1 << l2h;
         int trh = r2 >> 24, trv = r3 & 0xff, nzw = (r3 >> 8) & 0xff, nzh = (r3 >> 16) & 0xff;
         const int lfnst = r4 & 0xff, jsign = (int8_t)((r4 >> 8) & 0xff), jshift = (r4 >> 16) & 0xff, jc = r4 >> 24, pic = r5 & 0xff;
         const TbCoef tc = tb_coef<MODE>(p.src, ti, r0, l2w, l2h, nzw, nzh, false);
+        // the warp's next block of the chunk: its record is requested now, its coefficient window is prefetched into L2 once the
+        // record has arrived (after pass 1), so the next iteration does not start with a DRAM round trip
+        const int tn = k + 1 < cnt ? (int)__ldg(list + k + 1) : -1;
+        uint32_t nr0 = 0, nr2 = 0, nr3 = 0;
+        if (tn >= 0) {
+            const uint32_t *qn = reinterpret_cast<const uint32_t *>(p.tbs + tn);
+            nr0 = __ldg(qn); nr2 = __ldg(qn + 2); nr3 = __ldg(qn + 3);
+        }
         __syncwarp();                                       // previous block is done with shared memory
 
         // ---- inverse LFNST: 8/16 inputs in 4x4 diagonal order -> 16/48 outputs, top-left 4x4 / 8x8 ----
@@ -324,6 +409,21 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
             default: pass1<32, MODE>(s, tc, lf, lfp, nzw, rdv, h, wpt, lane); break;
             }
         }
+        if (tn >= 0) {
+            const int nl2w = nr2 & 0xff, nl2h = (nr2 >> 8) & 0xff, nnzw = (nr3 >> 8) & 0xff, nnzh = (nr3 >> 16) & 0xff;
+            if (MODE & 1) {
+                const char *b = reinterpret_cast<const char *>(p.src.window + nr0);
+                if (lane * 64 < nnzw * nnzh * 2)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(b + lane * 64));
+            } else {
+                const int rows = min(round_rd(max(nnzh, 2)), 1 << nl2h);
+                if (lane < rows && nnzw > 0) {
+                    const int32_t *row = p.src.dense + nr0 + (lane << nl2w);
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(row));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(row + nnzw - 1));
+                }
+            }
+        }
         // columns nzw .. of the mid stage are zero (scale_clip's memset); pad to the rounded reduction length
         if (rdh_e > nzw) {
             const int pad = rdh_e - nzw;                    // < 32
@@ -358,14 +458,15 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
             }
         }
     }
+    }
 }
 
 }  // namespace
 
-// Launch over the whole list.  Blocks this kernel does not handle (transform skip, BDPCM, 1-D) are appended
-// to rest[] (count in rest_count[0], zeroed here) for itx_kernel (itx.cu).
+// Launch over the whole list.  scratch: 16 + 5 * n_tbs words; blocks this kernel does not handle (transform skip,
+// BDPCM, 1-D) end up in list 4 (*rest, count in *rest_count) for itx_kernel (itx.cu).
 int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *co, const VVCCudaTB *tbs, int n_tbs,
-                        uint32_t *rest, uint32_t *rest_count)
+                        uint32_t *scratch, const uint32_t **rest, const uint32_t **rest_count)
 {
     if (!ctx->itx_packed) {
         itx_pack_kernel<<<1, 256, 0, ctx->stream>>>();
@@ -373,7 +474,7 @@ int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCud
             return ctx->err;
         ctx->itx_packed = true;
     }
-    VVC_TRY(ctx, cudaMemsetAsync(rest_count, 0, sizeof(uint32_t), ctx->stream));
+    VVC_TRY(ctx, cudaMemsetAsync(scratch, 0, 16 * sizeof(uint32_t), ctx->stream));
     ItxW p;
     for (int c = 0; c < 3; c++) {
         p.plane[c] = (pel *)frame->data[c];
@@ -385,7 +486,10 @@ int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCud
     p.src.window = (mode & 1) ? (const int16_t *)co->data : nullptr;
     p.src.quant = co->quant; p.src.scaling = co->scaling; p.src.range = 15; p.src.bd = 10;
     p.store = (mode & 1) ? nullptr : (int32_t *)co->data;
-    p.tbs = tbs; p.n_tbs = n_tbs; p.rest = rest; p.rest_count = rest_count;
+    p.tbs = tbs; p.n_tbs = n_tbs; p.counts = scratch; p.lists = scratch + 16;
+    *rest = p.lists + 4 * (size_t)n_tbs; *rest_count = p.counts + 4;
+    itx_sort_kernel<<<ceil_div(n_tbs, 256), 256, 0, ctx->stream>>>(p);
+    VVC_LAUNCHED(ctx);
     const int ctas = ceil_div(n_tbs, kWarps), grid = ctas < 148 * 10 ? ctas : 148 * 10;
     switch (mode) {
     case 0:  itx_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p); break;
