@@ -22,8 +22,10 @@ struct InterK {
 struct InterLists {
     uint32_t *luma;    int cap_luma;     // 8 tasks per record at most: patches of 4 columns x 8 rows
     uint32_t *chroma;  int cap_chroma;   // 4 tasks per record at most: (plane, patch column)
+    uint32_t *luma_b, *chroma_b;         // the same for records whose reference windows may leave the picture (clamped loads)
     uint32_t *coop;                      // records of the warp-per-record kernels: DMVR / BDOF from the front, PROF from the back
-    uint32_t *count;                     // [0] luma uni, [1] luma bi, [2] chroma uni, [3] chroma bi, [4] DMVR / BDOF, [5] PROF
+    uint32_t *count;                     // [0] luma uni, [1] luma bi, [2] chroma uni, [3] chroma bi, [4] DMVR / BDOF, [5] PROF,
+                                         // [8], [9] work counters of the two warp kernels, [10..13] = [0..3] of the border lists
 };
 
 // 10-bit path (bd == 10, 4:2:0 or 4:0:0, 16-byte aligned planes / pitches): classify + patch kernel

@@ -186,12 +186,12 @@ __device__ __forceinline__ Blend blend_of(const Rec &pb, const VVCCudaWP *wp, bo
 __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, const InterLists ls)
 {
     // one reservation per list per CTA: block-wide exclusive scan of the five per-record counts
-    __shared__ uint32_t warp_tot[8][6], cta_base[6];
+    __shared__ uint32_t warp_tot[8][10], cta_base[10];
     const int ri = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int cls_l = -1, cls_c = -1, n_l = 0, n_c = 0, coop = -1;
+    int cls_l = -1, cls_c = -1, n_l = 0, n_c = 0, coop = -1, border = 0;
     if (ri < p.n) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p.pbs + ri);
-        const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+        const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
         const int w = r1 & 0xff, h = (r1 >> 8) & 0xff, planes = (r1 >> 16) & 0xff, pred = r1 >> 24, flags = r2 >> 24;
         if (flags & VVC_PB_COOPERATIVE) {
             coop = (flags & (VVC_CUDA_PB_PROF0 | VVC_CUDA_PB_PROF1)) ? 1 : 0;      // 0: DMVR / BDOF, 1: PROF
@@ -199,13 +199,32 @@ __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, con
             const int bi = (flags & VVC_CUDA_PB_GPM) || pred == 3;
             if (planes & VVC_CUDA_PB_LUMA) { cls_l = bi; n_l = (w >> 2) * ((h + 7) >> 3); }
             if ((planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) { cls_c = bi; n_c = w > 8 ? 4 : 2; }   // 2 planes x patch columns
+            // Records whose windows may leave the picture (a conservative test; mc_patch decides per patch) go to lists
+            // of their own: their clamped loads cost ten times a plain patch, and one such lane stalls its whole warp.
+            const int x0 = r0 & 0xffff, y0 = r0 >> 16;
+            for (int l = 0; l < 2; l++) {
+                if (!bi && l != pred - 1)
+                    continue;
+                const int mx = (int)__ldg(q + 3 + 2 * l), my = (int)__ldg(q + 4 + 2 * l);
+                const int xx = x0 + (mx >> 4), yy = y0 + (my >> 4);
+                border |= xx - 4 < 0 || xx + w + 5 > p.w || yy - 3 < 0 || yy + h + 4 > p.h;
+                const int xc = (x0 >> 1) + (mx >> 5), yc = (y0 >> 1) + (my >> 5);
+                border |= xc - 2 < 0 || xc + (w >> 1) + 6 > (p.w >> 1) || yc - 1 < 0 || yc + (h >> 1) + 2 > (p.h >> 1);
+            }
         }
     }
-    uint32_t mine[6] = { cls_l == 0 ? (uint32_t)n_l : 0u, cls_l == 1 ? (uint32_t)n_l : 0u,
-                         cls_c == 0 ? (uint32_t)n_c : 0u, cls_c == 1 ? (uint32_t)n_c : 0u, coop == 0 ? 1u : 0u, coop == 1 ? 1u : 0u };
-    uint32_t excl[6];
+    const int bl = border ? 6 : 0, bc = border ? 8 : 2;       // slots of this record's luma / chroma class in mine[]
+    uint32_t mine[10] = { 0, 0, 0, 0, coop == 0 ? 1u : 0u, coop == 1 ? 1u : 0u, 0, 0, 0, 0 };
 #pragma unroll
-    for (int c = 0; c < 6; c++) {
+    for (int c = 0; c < 2; c++) {
+        mine[c]     = (!border && cls_l == c) ? (uint32_t)n_l : 0u;
+        mine[2 + c] = (!border && cls_c == c) ? (uint32_t)n_c : 0u;
+        mine[6 + c] = (border && cls_l == c) ? (uint32_t)n_l : 0u;
+        mine[8 + c] = (border && cls_c == c) ? (uint32_t)n_c : 0u;
+    }
+    uint32_t excl[10];
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
         uint32_t v = mine[c];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -216,25 +235,32 @@ __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, con
         if (lane == 31) warp_tot[wid][c] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < 10) {
         uint32_t tot = 0;
         for (int k = 0; k < 8; k++) { const uint32_t t = warp_tot[k][threadIdx.x]; warp_tot[k][threadIdx.x] = tot; tot += t; }
-        cta_base[threadIdx.x] = tot ? atomicAdd(ls.count + threadIdx.x, tot) : 0u;
+        // count[] slots: 0..5 as documented, border lists at 10..13
+        cta_base[threadIdx.x] = tot ? atomicAdd(ls.count + (threadIdx.x < 6 ? threadIdx.x : threadIdx.x + 4), tot) : 0u;
     }
     __syncthreads();
+    auto at = [&](int c) { uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < 10; k++) if (k == c) r = cta_base[k] + warp_tot[wid][k] + excl[k];
+        return (int)r; };
     if (coop >= 0) {
-        const int at = (int)(cta_base[4 + coop] + warp_tot[wid][4 + coop] + excl[4 + coop]);
-        ls.coop[coop ? p.n - 1 - at : at] = ri;
+        const int pos = at(4 + coop);
+        ls.coop[coop ? p.n - 1 - pos : pos] = ri;
     }
     if (cls_l >= 0) {
-        const int base = (int)(cta_base[cls_l] + warp_tot[wid][cls_l] + excl[cls_l]);
+        const int base = at(bl + cls_l);
+        uint32_t *list = border ? ls.luma_b : ls.luma;
         for (int k = 0; k < n_l; k++)
-            ls.luma[cls_l ? ls.cap_luma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+            list[cls_l ? ls.cap_luma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
     }
     if (cls_c >= 0) {
-        const int base = (int)(cta_base[2 + cls_c] + warp_tot[wid][2 + cls_c] + excl[2 + cls_c]);
+        const int base = at(bc + cls_c);
+        uint32_t *list = border ? ls.chroma_b : ls.chroma;
         for (int k = 0; k < n_c; k++)
-            ls.chroma[cls_c ? ls.cap_chroma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+            list[cls_c ? ls.cap_chroma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
     }
 }
 
@@ -317,11 +343,13 @@ __device__ __forceinline__ void chroma_task(const InterK &p, const Rec &pb, int 
 template <bool LUMA, bool BI>
 __global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_kernel(const InterK p, const InterLists ls)
 {
-    const int n = (int)ls.count[(LUMA ? 0 : 2) + (BI ? 1 : 0)];
-    const uint32_t *list = LUMA ? ls.luma : ls.chroma;
+    // the class's border tasks, then its plain tasks: border tasks are contiguous in the index range, so the warps that
+    // run the clamped path are full of such tasks instead of dragging plain patches through it, and they start first
+    const int n = (int)ls.count[(LUMA ? 0 : 2) + (BI ? 1 : 0)], nb = (int)ls.count[10 + (LUMA ? 0 : 2) + (BI ? 1 : 0)];
+    const uint32_t *list = LUMA ? ls.luma : ls.chroma, *blist = LUMA ? ls.luma_b : ls.chroma_b;
     const int cap = LUMA ? ls.cap_luma : ls.cap_chroma;
-    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
-        const uint32_t t = __ldg(list + (BI ? cap - 1 - i : i));
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n + nb; i += gridDim.x * kThreads) {
+        const uint32_t t = i < nb ? __ldg(blist + (BI ? cap - 1 - i : i)) : __ldg(list + (BI ? cap - 1 - (i - nb) : i - nb));
         const Rec pb = load_rec(p.pbs + (t >> 3));
         if (LUMA)
             luma_task<BI>(p, pb, t & 7);
@@ -334,15 +362,17 @@ __global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_ke
 
 int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
 {
-    // scratch: [count: 64 bytes][luma: 8 n][chroma: 4 n][coop: n] words
+    // scratch: [count: 64 bytes][luma: 8 n][chroma: 4 n][coop: n][luma border: 8 n][chroma border: 4 n] words
     const size_t n = (size_t)p.n;
-    uint32_t *base = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + 13 * n * sizeof(uint32_t));
+    uint32_t *base = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + 25 * n * sizeof(uint32_t));
     if (!base)
         return ctx->err;
     ls->count = base;
     ls->luma = base + 16;            ls->cap_luma = (int)(8 * n);
     ls->chroma = ls->luma + 8 * n;   ls->cap_chroma = (int)(4 * n);
     ls->coop = ls->chroma + 4 * n;
+    ls->luma_b = ls->coop + n;
+    ls->chroma_b = ls->luma_b + 8 * n;
     VVC_TRY(ctx, cudaMemsetAsync(ls->count, 0, 64, ctx->stream));
     inter_classify_kernel<<<ceil_div(p.n, 256), 256, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);

@@ -240,17 +240,26 @@ __device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, 
 // KIND 0: records with DMVR / BDOF and no PROF (always bi-predicted, never GPM): the uni, GPM and PROF paths are
 // compiled out.  KIND 1: the rest of the cooperative records (PROF), listed from the back of coop[].
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, int cap, const uint32_t *__restrict__ count)   //@region rec_load
+__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, int cap, uint32_t *count)   //@region rec_load
 {
     __shared__ WarpSmem sm[kWarps];
     const int lane = threadIdx.x & 31;
     WarpSmem &s = sm[threadIdx.x >> 5];
-    const int nwarps = gridDim.x * kWarps;
     const uint2 *lumaf = reinterpret_cast<const uint2 *>(&vvct_luma_mc_filters[0][0][0]);
     const uint32_t *chromaf = reinterpret_cast<const uint32_t *>(&vvct_chroma_mc_filters[0][0][0]);
 
+    // Records are drawn from a counter (count[8 + KIND], zeroed with the list counts), two at a time: DMVR's early
+    // termination and the per-record BDOF switch make their cost uneven, and with a fixed stride the launch lasted as
+    // long as its unluckiest warp.
     const int n_coop = (int)count[4 + KIND];
-    for (int ci = blockIdx.x * kWarps + (threadIdx.x >> 5); ci < n_coop; ci += nwarps) {
+    for (;;) {
+        int first = 0;
+        if (lane == 0)
+            first = (int)atomicAdd(count + 8 + KIND, 2u);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= n_coop)
+            break;
+    for (int ci = first; ci < min(first + 2, n_coop); ci++) {
         __syncwarp();
         const int ri = (int)__ldg(coop + (KIND ? cap - 1 - ci : ci));
         const Rec pb = load_rec(p.pbs + ri);
@@ -673,6 +682,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
 #undef MVR
 #undef MV0
 #undef REF
+    }
     }
 }
 
