@@ -23,6 +23,8 @@ struct VVCCudaCtx {
     void         *h_stage;  size_t h_stage_size;    // pinned
     void         *d_scratch[3]; size_t d_scratch_size[3];   // [0],[1] intermediate pictures of chained stages, [2] inter task lists
     cudaStream_t  copy_in, copy_out;                 // lazily created, *_host pipelines
+    cudaStream_t  side[3];                           // lazily created: independent kernels of one stage run beside the context stream
+    cudaEvent_t   fork_ev, join_ev[3];
     cudaEvent_t   ev[8];
 };
 
@@ -32,6 +34,12 @@ int  vvc_ctx_check(VVCCudaCtx *ctx, cudaError_t e, const char *what);
 void *vvc_ctx_dev_stage(VVCCudaCtx *ctx, size_t bytes);
 void *vvc_ctx_host_stage(VVCCudaCtx *ctx, size_t bytes);
 void *vvc_ctx_scratch(VVCCudaCtx *ctx, int slot, size_t bytes);
+// Fork / join inside a stage: after vvc_ctx_fork the side streams ctx->side[0 .. n) see everything issued on
+// ctx->stream so far; vvc_ctx_join makes ctx->stream wait for what was issued on them since.  The kernels of one stage
+// that touch disjoint samples (task classes of the inter stage, the two residual kernels) are issued this way so that
+// the tail of one fills with the next instead of draining the machine between launches.
+int   vvc_ctx_fork(VVCCudaCtx *ctx, int n);
+int   vvc_ctx_join(VVCCudaCtx *ctx, int n);
 
 #define VVC_TRY(ctx, call)  do { if (vvc_ctx_check((ctx), (call), #call)) return (ctx)->err; } while (0)
 #define VVC_LAUNCHED(ctx)   do { (ctx)->launches++; if (vvc_ctx_check((ctx), cudaGetLastError(), "kernel launch")) return (ctx)->err; } while (0)

@@ -72,6 +72,30 @@ void *vvc_ctx_scratch(VVCCudaCtx *ctx, int slot, size_t bytes)
     return ctx->d_scratch[slot];
 }
 
+int vvc_ctx_fork(VVCCudaCtx *ctx, int n)
+{
+    if (!ctx->fork_ev) {
+        VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < 3; i++) {
+            VVC_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+            VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming));
+        }
+    }
+    VVC_TRY(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+    for (int i = 0; i < n; i++)
+        VVC_TRY(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0));
+    return 0;
+}
+
+int vvc_ctx_join(VVCCudaCtx *ctx, int n)
+{
+    for (int i = 0; i < n; i++) {
+        VVC_TRY(ctx, cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
+        VVC_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
+    }
+    return 0;
+}
+
 extern "C" {
 
 const char *vvc_cuda_version(void) { return "vvcdsp-b200 0.1 (sm_100a)"; }
@@ -108,6 +132,10 @@ void vvc_cuda_ctx_destroy(VVCCudaCtx *ctx)
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 3; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+    if (ctx->fork_ev) {
+        cudaEventDestroy(ctx->fork_ev);
+        for (int i = 0; i < 3; i++) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->join_ev[i]); }
+    }
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

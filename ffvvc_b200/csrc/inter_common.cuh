@@ -30,7 +30,10 @@ struct InterLists {
 
 // 10-bit path (bd == 10, 4:2:0 or 4:0:0, 16-byte aligned planes / pitches): classify + patch kernel
 // (inter_patch.cu), then the warp-per-record kernel over the cooperative records (inter_warp.cu)
-int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, InterLists *lists);
+// classify runs on the context stream; the six task-class kernels write disjoint samples and are spread over the
+// context stream and its side streams (vvc_ctx_fork / vvc_ctx_join around the two calls below)
+int vvc_inter_launch_classify(VVCCudaCtx *ctx, const InterK &p, InterLists *lists);
+int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists, bool spread);
 int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists);
 
 // Records whose prediction needs a cooperative tile (DMVR search, BDOF windows, PROF gradients) go to the

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_ke
 
 }  // namespace
 
-int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
+int vvc_inter_launch_classify(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
 {
     // scratch: [count: 64 bytes][luma: 8 n][chroma: 4 n][coop: n][luma border: 8 n][chroma border: 4 n] words
     const size_t n = (size_t)p.n;
@@ -376,13 +376,21 @@ int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
     VVC_TRY(ctx, cudaMemsetAsync(ls->count, 0, 64, ctx->stream));
     inter_classify_kernel<<<ceil_div(p.n, 256), 256, 0, ctx->stream>>>(p, *ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<true, true><<<148 * patch_ctas(true, true), kThreads, 0, ctx->stream>>>(p, *ls);
+    return VVC_CUDA_OK;
+}
+
+// spread: luma bi on side stream 0, luma uni on 1, both chroma classes on 2 (the warp kernels take the context stream);
+// otherwise everything on the context stream
+int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, const InterLists &ls, bool spread)
+{
+    cudaStream_t s0 = spread ? ctx->side[0] : ctx->stream, s1 = spread ? ctx->side[1] : ctx->stream, s2 = spread ? ctx->side[2] : ctx->stream;
+    inter_patch_kernel<true, true><<<148 * patch_ctas(true, true), kThreads, 0, s0>>>(p, ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<true, false><<<148 * patch_ctas(true, false), kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<true, false><<<148 * patch_ctas(true, false), kThreads, 0, s1>>>(p, ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<false, true><<<148 * patch_ctas(false, true), kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<false, true><<<148 * patch_ctas(false, true), kThreads, 0, s2>>>(p, ls);
     VVC_LAUNCHED(ctx);
-    inter_patch_kernel<false, false><<<148 * patch_ctas(false, false), kThreads, 0, ctx->stream>>>(p, *ls);
+    inter_patch_kernel<false, false><<<148 * patch_ctas(false, false), kThreads, 0, s2>>>(p, ls);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

@@ -357,9 +357,9 @@ extern "C" int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, 
         if (vvc_itx_launch_warp(ctx, frame, co, tbs, n_tbs, scratch, &p.list, &p.list_count))
             return ctx->err;
         const int ctas = ceil_div(n_tbs, TBS_PER_CTA);
-        launch_generic(p, mode, ctas < 148 * 6 ? ctas : 148 * 6, ctx->stream);
+        launch_generic(p, mode, ctas < 148 * 6 ? ctas : 148 * 6, ctx->side[0]);      // beside the warp kernel: disjoint blocks
         VVC_LAUNCHED(ctx);
-        return VVC_CUDA_OK;
+        return vvc_ctx_join(ctx, 1) ? ctx->err : VVC_CUDA_OK;
     }
     launch_generic(p, mode, ceil_div(n_tbs, TBS_PER_CTA), ctx->stream);
     VVC_LAUNCHED(ctx);

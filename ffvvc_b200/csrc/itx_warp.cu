@@ -490,6 +490,8 @@ int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCud
     *rest = p.lists + 4 * (size_t)n_tbs; *rest_count = p.counts + 4;
     itx_sort_kernel<<<ceil_div(n_tbs, 256), 256, 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);
+    if (vvc_ctx_fork(ctx, 1))           // itx_kernel (side stream 0) only needs the lists; the caller joins
+        return ctx->err;
     const int ctas = ceil_div(n_tbs, kWarps), grid = ctas < 148 * 10 ? ctas : 148 * 10;
     switch (mode) {
     case 0:  itx_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p); break;
