@@ -24,13 +24,13 @@ constexpr int kThreads = 128;
 #endif
 // resident CTAs per SM the class kernels are compiled for (register budget = 65536 / (128 * n)); measured sweep in profiles/README.md
 #ifndef PATCH_MB_LU
-#define PATCH_MB_LU 8
+#define PATCH_MB_LU 4
 #endif
 #ifndef PATCH_MB_LB
-#define PATCH_MB_LB 6
+#define PATCH_MB_LB 4
 #endif
 #ifndef PATCH_MB_CU
-#define PATCH_MB_CU 6
+#define PATCH_MB_CU 7
 #endif
 #ifndef PATCH_MB_CB
 #define PATCH_MB_CB 6

@@ -690,8 +690,11 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
 
 int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists)
 {
+#ifndef INTER_WARP_CTAS
+#define INTER_WARP_CTAS 7                                        // persistent: 7 CTAs fit an SM (shared memory)
+#endif
     const int ctas = ceil_div(p.n, kWarps);
-    const int grid = ctas < 148 * 7 ? ctas : 148 * 7;            // persistent: 7 CTAs fit an SM (shared memory)
+    const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
     inter_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count);
     VVC_LAUNCHED(ctx);
     inter_warp_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count);

@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(256) itx_sort_kernel(const ItxW p)
 }
 
 #ifndef ITX_WARP_MB
-#define ITX_WARP_MB 1            // resident CTAs per SM the kernel is compiled for (tools/sweep_itx.sh)
+#define ITX_WARP_MB 7            // resident CTAs per SM the kernel is compiled for (tools/sweep_itx.sh: 1 / 6 / 7 / 8 ->
+                                 // 0.80 / 0.65 / 0.63 / 0.65 ms per 8 pictures once the work is balanced)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const ItxW p)
@@ -492,7 +493,7 @@ int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCud
     VVC_LAUNCHED(ctx);
     if (vvc_ctx_fork(ctx, 1))           // itx_kernel (side stream 0) only needs the lists; the caller joins
         return ctx->err;
-    const int ctas = ceil_div(n_tbs, kWarps), grid = ctas < 148 * 10 ? ctas : 148 * 10;
+    const int ctas = ceil_div(n_tbs, kWarps), grid = ctas < 148 * ITX_WARP_MB ? ctas : 148 * ITX_WARP_MB;
     switch (mode) {
     case 0:  itx_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p); break;
     case 1:  itx_warp_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(p); break;

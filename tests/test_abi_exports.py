@@ -21,7 +21,8 @@ def test_descriptor_sizes_match_the_header():
             3: C.sizeof(abi.VVCCudaDbkEdge), 4: C.sizeof(abi.VVCCudaDeblockMaps), 5: C.sizeof(abi.VVCCudaSAOCtb), 6: C.sizeof(abi.VVCCudaInloopDesc), 7: C.sizeof(abi.VVCCudaTB),
             8: abi.PB_DTYPE.itemsize, 9: abi.WP_DTYPE.itemsize, 10: abi.PROF_DTYPE.itemsize, 11: abi.DMVR_OUT_DTYPE.itemsize,
             12: C.sizeof(abi.VVCCudaRect), 13: C.sizeof(abi.VVCCudaReconDesc),
-            14: abi.INTRA_PB_DTYPE.itemsize, 15: abi.CIIP_DTYPE.itemsize}
+            14: abi.INTRA_PB_DTYPE.itemsize, 15: abi.CIIP_DTYPE.itemsize,
+            16: abi.TB_QUANT_DTYPE.itemsize, 17: abi.SCALING_LIST_DTYPE.itemsize, 18: C.sizeof(abi.VVCCudaCoeffs)}
     for which, size in want.items():
         assert handle.vvc_cuda_abi_sizeof(which) == size, which
 
@@ -33,3 +34,23 @@ def test_ctx_create_fails_loudly_without_device():
     import pytest
     with pytest.raises(lib.VVCCudaError):
         lib.Context(0)
+
+
+def test_window_layout_packing_round_trip():
+    """abi.pack_window16 (what a host would do while writing levels): every value inside a TB's window survives,
+    offsets are dense, nothing outside the windows is stored."""
+    import numpy as np
+    from ffvvc_b200 import synth
+    geom = abi.FrameGeom(256, 128)
+    tbs, coeffs = synth.tb_list(geom, seed=3, extras=False)
+    tbs = synth.tb_for_window(tbs)
+    wt, win = abi.pack_window16(tbs, coeffs)
+    sizes = wt["nzw"].astype(np.int64) * wt["nzh"].astype(np.int64)
+    assert np.array_equal(wt["coeff_offset"], np.concatenate([[0], np.cumsum(sizes)[:-1]]))
+    for i in (0, 1, len(tbs) // 2, len(tbs) - 1):
+        t, u = tbs[i], wt[i]
+        w = 1 << int(t["log2_w"])
+        block = coeffs[int(t["coeff_offset"]):int(t["coeff_offset"]) + w * (1 << int(t["log2_h"]))].reshape(-1, w)
+        got = win[int(u["coeff_offset"]):int(u["coeff_offset"]) + int(u["nzw"]) * int(u["nzh"])].reshape(int(u["nzh"]), int(u["nzw"]))
+        assert np.array_equal(got, block[:int(u["nzh"]), :int(u["nzw"])])
+        assert not block[int(u["nzh"]):, :].any() and not block[:, int(u["nzw"]):].any()

@@ -179,3 +179,21 @@ def test_quantised_host_entry_and_4k_layout_equivalence(ctx):
     b = _cuda_q(ctx, g4, pred4, win4, abi.COEFF_WINDOW16, wt4, q4, sl4)
     util.assert_planes_equal(g4, a, b, "4K: window layout vs dense layout")
     assert win4.nbytes * 3 < lv4.nbytes
+
+
+def test_quantised_entry_argument_errors():
+    """Unsupported combinations are refused with VVC_CUDA_ERR_ARG (sticky, so one context per case), an empty list is a no-op."""
+    from ffvvc_b200 import device, lib
+    geom = abi.FrameGeom(64, 64)
+    fr = device.DeviceFrames(geom, planes=synth.uniform_planes(geom, seed=1))
+    buf = device.to_device(np.zeros(64, dtype=np.int16))
+    tb = device.to_device(np.zeros(1, dtype=abi.TB_DTYPE))
+    c = lib.Context(0)
+    c.itx_frame_q(fr.desc, abi.coeffs_desc(buf[1], 64, abi.COEFF_WINDOW16), tb[1], 0, 15)      # n_tbs == 0
+    c.sync()
+    c.close()
+    for fmt, rng in ((abi.COEFF_WINDOW16, 16), (7, 15)):          # 16-bit window needs range 15; unknown layout
+        c = lib.Context(0)
+        with pytest.raises(lib.VVCCudaError):
+            c.itx_frame_q(fr.desc, abi.coeffs_desc(buf[1], 64, fmt), tb[1], 1, rng)
+        c.close()
