@@ -52,6 +52,10 @@ desc = abi.VVCCudaReconDesc()
 desc.pbs, desc.n_pbs, desc.wp, desc.n_wp, desc.prof, desc.n_prof = up(pbs), len(pbs), up(inp.wp), len(inp.wp), up(inp.prof), len(inp.prof)
 desc.log2_transform_range = 15
 desc.coeffs, desc.n_coeffs, desc.tbs, desc.n_tbs = up(coeffs), len(coeffs), up(tbs), len(tbs)
+# quantised levels in the reference's dense layout, dequantised by the stage (what bench.py's device-resident number runs)
+desc.coeff_format = abi.COEFF_DENSE32
+desc.quant = up(np.concatenate([inp.quant[k % inp.distinct] for k in range(frames)]))
+desc.scaling = up(inp.scaling)
 desc.lmcs_inv_lut = up(inp.inv_lut)
 desc.inloop.deblock = C.pointer(md)
 desc.inloop.sao = up(np.concatenate([inp.sao[k % inp.distinct] for k in range(frames)]))
