@@ -352,8 +352,9 @@ def main():
             coeffs=abi.coeffs_desc(up(coeffs), len(coeffs), abi.COEFF_DENSE32, up(quant), p_sl), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
             alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
     # kernels per picture group: inter = 7 (classify, four thread-per-patch class kernels, two warp-per-record kernels),
-    # residual = 3 (size binning, warp-per-TB kernel, generic kernel over the blocks it leaves), every other stage 1
-    launches_per_step = len(groups) * (len(STAGES) + 8)
+    # residual = 4 (size binning, thread-per-block kernel for 2x2..4x4, warp-per-TB kernel, generic kernel over the
+    # blocks those leave), every other stage 1
+    launches_per_step = len(groups) * (len(STAGES) + 9)
 
     def step(events=None):
         for gi, g in enumerate(groups):

@@ -351,7 +351,7 @@ extern "C" int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, 
     p.list = p.list_count = NULL;
     if (p.bd == 10 && p.range == 15 && !ctx->force_generic) {
         // common kinds: warp-per-TB kernel (itx_warp.cu); it lists what it leaves (transform skip, BDPCM, 1-D blocks)
-        uint32_t *scratch = (uint32_t *)vvc_ctx_scratch(ctx, 2, (16 + 5 * (size_t)n_tbs) * sizeof(uint32_t));
+        uint32_t *scratch = (uint32_t *)vvc_ctx_scratch(ctx, 2, (16 + 6 * (size_t)n_tbs) * sizeof(uint32_t));
         if (!scratch)
             return ctx->err;
         if (vvc_itx_launch_warp(ctx, frame, co, tbs, n_tbs, scratch, &p.list, &p.list_count))

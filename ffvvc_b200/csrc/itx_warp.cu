@@ -42,9 +42,9 @@ struct ItxW {
     int32_t   *store;               // DENSE32 buffer for VVC_CUDA_TB_STORE_RESIDUAL blocks (NULL otherwise)
     const VVCCudaTB *tbs;
     int        n_tbs;
-    uint32_t  *counts;              // [0..4] blocks per class, [5] work counter (zeroed per launch)
+    uint32_t  *counts;              // [0..5] blocks per class, [8] work counter (zeroed per launch)
     uint32_t  *lists;               // class c: lists[c * n_tbs ..): 0/1/2 = 4096/2048/1024+ samples, 3 = smaller, 4 = left to
-                                    // itx_kernel (transform skip, BDPCM, 1-D)
+                                    // itx_kernel (transform skip, BDPCM, 1-D), 5 = 2x2 .. 4x4 blocks of itx_tiny_kernel
 };
 
 // Packed matrices: for output i of (type, n) the 8 words g_wpt[(base + i) * 8 + q] hold taps M[4q .. 4q+3][i]
@@ -286,12 +286,13 @@ __global__ void __launch_bounds__(256) itx_sort_kernel(const ItxW p)
     if (ti < p.n_tbs) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
         const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3);
-        const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, flags = r3 >> 24;
+        const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, flags = r3 >> 24, lfnst = __ldg(q + 4) & 0xff;
         if (!eligible(l2w, l2h, flags, r1 & 0xffff)) cls = 4;
+        else if (l2w <= 2 && l2h <= 2 && !lfnst && !(flags & VVC_CUDA_TB_STORE_RESIDUAL)) cls = 5;
         else cls = l2w + l2h >= 12 ? 0 : l2w + l2h == 11 ? 1 : l2w + l2h == 10 ? 2 : 3;
     }
 #pragma unroll
-    for (int c = 0; c < 5; c++) {
+    for (int c = 0; c < 6; c++) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == c);
         if (!m)
             continue;
@@ -301,6 +302,98 @@ __global__ void __launch_bounds__(256) itx_sort_kernel(const ItxW p)
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
         if (cls == c)
             p.lists[(size_t)c * p.n_tbs + base + __popc(m & ((1u << lane) - 1))] = ti;
+    }
+}
+
+// Blocks of 2x2 .. 4x4 samples (44 % of the blocks of a picture, 1.5 % of its samples): one THREAD per block.  The warp
+// kernel spends ~400 warp-instructions of bookkeeping on each of them with 28 lanes idle; here a block is ~300
+// thread-instructions: up to 16 coefficients, two passes of 4-tap IDP.2A pairs from the packed matrices, the residual
+// added with one 32- or 64-bit access per row.  Same arithmetic as itx_warp_kernel (same inputs read, same clips).
+template <int MODE>
+__global__ void __launch_bounds__(128) itx_tiny_kernel(const ItxW p)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= (int)p.counts[5])
+        return;
+    const int ti = (int)__ldg(p.lists + 5 * (size_t)p.n_tbs + i);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
+    const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3), r4 = __ldg(q + 4), r5 = __ldg(q + 5);
+    const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, c_idx = (r2 >> 16) & 0xff, flags = r3 >> 24;
+    const int x0 = r1 & 0xffff, y0 = r1 >> 16, w = 1 << l2w, h = 1 << l2h;
+    const int trh = r2 >> 24, trv = r3 & 0xff, nzw = (r3 >> 8) & 0xff, nzh = (r3 >> 16) & 0xff;
+    const int jsign = (int8_t)((r4 >> 8) & 0xff), jshift = (r4 >> 16) & 0xff, jc = r4 >> 24, pic = r5 & 0xff;
+    const TbCoef tc = tb_coef<MODE>(p.src, ti, r0, l2w, l2h, nzw, nzh, false);
+    const bool dc_only = trh == 0 && trv == 0 && nzw == 1 && nzh == 1 && w == h;
+    const int rdv = dc_only ? 1 : inputs_read(trv, h, nzh);
+    // pass 1 per column x < nzw: inputs (rows 0..rdv-1) as two pairs, outputs i < h
+    uint32_t mid01[4] = { 0, 0, 0, 0 }, mid23[4] = { 0, 0, 0, 0 };       // row y: (col 0, col 1), (col 2, col 3)
+    uint32_t wv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        wv[k] = k < h ? ldg_nc(g_wpt + (wpt_base(trv, l2h) + k) * 8) : 0u;
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        if (x < nzw && x < w) {
+            int v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                v[j] = j < rdv ? coef_load<MODE>(tc, j, x) : 0;
+            const uint32_t p01 = (uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16), p23 = (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < h) {
+                    const int acc = dp2a_lo((int)p01, (int)wv[k], dp2a_hi((int)p23, (int)wv[k], 0));
+                    const uint32_t m = (uint32_t)d_clip_sbits((acc + 64) >> 7, 15) & 0xffff;
+                    if (x < 2) mid01[k] |= m << (16 * (x & 1));
+                    else       mid23[k] |= m << (16 * (x & 1));
+                }
+            }
+        }
+    }
+    // pass 2 per row + epilogue
+    uint32_t wh[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        wh[k] = k < w ? ldg_nc(g_wpt + (wpt_base(trh, l2w) + k) * 8) : 0u;
+#define SEL3(a, c) ((c) == 0 ? (a)[0] : (c) == 1 ? (a)[1] : (a)[2])
+    const int pitch0 = SEL3(p.pitch, c_idx);
+    pel *d0 = SEL3(p.plane, c_idx) + pic * SEL3(p.bstride, c_idx) + (long long)y0 * pitch0 + x0;
+    pel *d1 = nullptr;
+    int pitch1 = 0;
+    if (flags & VVC_CUDA_TB_JOINT) {
+        pitch1 = SEL3(p.pitch, jc);
+        d1 = SEL3(p.plane, jc) + pic * SEL3(p.bstride, jc) + (long long)y0 * pitch1 + x0;
+    }
+#undef SEL3
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        if (y < h) {
+            int r[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                r[k] = (dp2a_lo((int)mid01[y], (int)wh[k], dp2a_hi((int)mid23[y], (int)wh[k], 0)) + 512) >> 10;
+            auto add2 = [&](uint32_t cur, int a, int b) -> uint32_t {
+                return (uint32_t)d_clip_pel((int)(cur & 0xffff) + a, 10) | ((uint32_t)d_clip_pel((int)(cur >> 16) + b, 10) << 16);
+            };
+            if (w == 4) {
+                uint2 *t = reinterpret_cast<uint2 *>(d0 + y * pitch0);
+                const uint2 cur = *t;
+                *t = make_uint2(add2(cur.x, r[0], r[1]), add2(cur.y, r[2], r[3]));
+                if (d1) {
+                    uint2 *u = reinterpret_cast<uint2 *>(d1 + y * pitch1);
+                    const uint2 c1 = *u;
+                    *u = make_uint2(add2(c1.x, (r[0] * jsign) >> jshift, (r[1] * jsign) >> jshift),
+                                    add2(c1.y, (r[2] * jsign) >> jshift, (r[3] * jsign) >> jshift));
+                }
+            } else {
+                uint32_t *t = reinterpret_cast<uint32_t *>(d0 + y * pitch0);
+                *t = add2(*t, r[0], r[1]);
+                if (d1) {
+                    uint32_t *u = reinterpret_cast<uint32_t *>(d1 + y * pitch1);
+                    *u = add2(*u, (r[0] * jsign) >> jshift, (r[1] * jsign) >> jshift);
+                }
+            }
+        }
     }
 }
 
@@ -319,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
     for (;;) {
         uint32_t v = 0;
         if (lane == 0)
-            v = atomicAdd(p.counts + 5, 1u);
+            v = atomicAdd(p.counts + 8, 1u);
         v = __shfl_sync(0xffffffffu, v, 0);
         if (v >= total)
             break;
@@ -464,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
 
 }  // namespace
 
-// Launch over the whole list.  scratch: 16 + 5 * n_tbs words; blocks this kernel does not handle (transform skip,
+// Launch over the whole list.  scratch: 16 + 6 * n_tbs words; blocks this kernel does not handle (transform skip,
 // BDPCM, 1-D) end up in list 4 (*rest, count in *rest_count) for itx_kernel (itx.cu).
 int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *co, const VVCCudaTB *tbs, int n_tbs,
                         uint32_t *scratch, const uint32_t **rest, const uint32_t **rest_count)
@@ -491,8 +584,18 @@ int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCud
     *rest = p.lists + 4 * (size_t)n_tbs; *rest_count = p.counts + 4;
     itx_sort_kernel<<<ceil_div(n_tbs, 256), 256, 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);
-    if (vvc_ctx_fork(ctx, 1))           // itx_kernel (side stream 0) only needs the lists; the caller joins
+    if (vvc_ctx_fork(ctx, 1))           // side stream 0: the tiny blocks here, then the caller's itx_kernel; the caller joins
         return ctx->err;
+    {
+        const int tg = ceil_div(n_tbs, 128);
+        switch (mode) {
+        case 0:  itx_tiny_kernel<0><<<tg, 128, 0, ctx->side[0]>>>(p); break;
+        case 1:  itx_tiny_kernel<1><<<tg, 128, 0, ctx->side[0]>>>(p); break;
+        case 2:  itx_tiny_kernel<2><<<tg, 128, 0, ctx->side[0]>>>(p); break;
+        default: itx_tiny_kernel<3><<<tg, 128, 0, ctx->side[0]>>>(p); break;
+        }
+        VVC_LAUNCHED(ctx);
+    }
     const int ctas = ceil_div(n_tbs, kWarps), grid = ctas < 148 * ITX_WARP_MB ? ctas : 148 * ITX_WARP_MB;
     switch (mode) {
     case 0:  itx_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p); break;
