@@ -105,3 +105,29 @@ def test_inter_4k_properties(ctx):
             assert np.array_equal(gp[c][0, y0:y0 + bh, x0:x0 + bw], od[c][0, y0:y0 + bh, x0:x0 + bw]), (r, c)
     dm = (sub["flags"] & abi.PB_DMVR) != 0
     assert np.array_equal(go[pick][dm], oo[dm])
+
+
+def test_inter_long_launch_matches_short_launches(ctx):
+    """A record list above the library's 200 k-record threshold runs its class kernels on one stream, shorter lists on
+    parallel streams: the same 4K records as one long launch and as per-picture launches must give the same pictures
+    (and one of those pictures is checked against the oracle)."""
+    from ffvvc_b200 import device
+    batch = 3
+    g1 = abi.FrameGeom(3840, 2160)
+    gd = abi.FrameGeom(3840, 2160, batch=batch)
+    refs = synth.struct_planes(abi.FrameGeom(3840, 2160, batch=2), seed=5)
+    pbs1, wp, prof = synth.pb_list(g1, n_refs=2, seed=6)
+    parts = []
+    for k in range(batch):
+        p = pbs1.copy()
+        p["pic"] = k
+        parts.append(p)
+    pbs = np.concatenate(parts)
+    assert len(pbs) > 200000 > len(pbs1)
+    gr = abi.FrameGeom(3840, 2160, batch=2)
+    long_run, _ = cuda_inter(ctx, gd, gr, refs, pbs, wp, prof)
+    short_run, _ = cuda_inter(ctx, g1, gr, refs, pbs1, wp, prof)
+    for k in range(batch):
+        util.assert_planes_equal(g1, [p[k:k + 1] for p in long_run], short_run, "long launch picture %d vs short launch" % k)
+    od, _ = run_inter(util.oracle().vvco_inter_frame, g1, gr, refs, pbs1, wp, prof)
+    util.assert_planes_equal(g1, short_run, od, "4K picture vs oracle")

@@ -2,8 +2,8 @@
 # Sweep load-pipeline depth x compiled occupancy of the inter patch kernels (ncu gpu__time_duration per launch of
 # 2 x 4K pictures, us; columns luma-bi, luma-uni, chroma-bi, chroma-uni)
 cd /root/repo
-for d in ${DEPTHS:-1 2 3 4}; do
-for cfg in "8 6 6 6" "6 4 5 5" "4 3 4 4"; do
+for d in ${DEPTHS:-2 4 6}; do
+for cfg in "4 4 7 6" "3 3 5 5"; do
   set -- $cfg
   rm -f ffvvc_b200/csrc/build/inter_patch.o
   make -s -C ffvvc_b200/csrc EXTRA="-DPATCH_DEPTH=$d -DPATCH_MB_LU=$1 -DPATCH_MB_LB=$2 -DPATCH_MB_CU=$3 -DPATCH_MB_CB=$4" > /dev/null 2>&1
