@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line executed-instruction and stall-sample totals of one kernel in an .ncu-rep.
 Joins `ncu --page source --print-source sass` (per SASS address) with `nvdisasm --print-line-info`
-of the object the kernel was built from.  Usage: ncu_lines.py rep.ncu-rep build/x.o [top]"""
+of the object the kernel was built from.  Usage: ncu_lines.py rep.ncu-rep build/x.o [top [kernel-filter]]"""
 import collections
 import csv
 import glob
@@ -12,8 +12,9 @@ import sys
 import tempfile
 
 
-def main(rep, obj, top=40):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+def main(rep, obj, top=40, kernel=None):
+    # kernel: optional name filter (ncu --kernel-name syntax, e.g. regex:itx_warp) for reports holding several kernels
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + (["--kernel-name", kernel] if kernel else []),
                          capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -22,6 +23,8 @@ def main(rep, obj, top=40):
     ilong, ishort, iwait = h.index("stall_long_sb"), h.index("stall_short_sb"), h.index("stall_wait")
     per_addr = []
     for r in rows[hdr + 1:]:
+        if r and r[0] == "Kernel Name":         # a report with several launches of the kernel: the first one only
+            break
         if len(r) <= ino or not r[ia]:
             continue
         per_addr.append((int(r[ii] or 0), int(r[isamp] or 0), int(r[ino] or 0), int(r[ilong] or 0), int(r[ishort] or 0), int(r[iwait] or 0), r[1], int(r[ia], 16)))
