@@ -230,8 +230,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--frames", type=int, default=8, help="pictures in the ring = pictures per step")
-    ap.add_argument("--group", type=int, default=8, help="pictures per launch (independent streams batched into one launch per stage)")
+    ap.add_argument("--frames", type=int, default=16, help="pictures in the ring = pictures per step")
+    ap.add_argument("--group", type=int, default=16, help="pictures per launch (independent streams batched into one launch per stage)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--seed", type=int, default=12345, help="seed of the synthetic inputs (rank r uses seed + r)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
