@@ -391,6 +391,11 @@ extern "C" int vvc_cuda_itx_frame_q_host(VVCCudaCtx *ctx, const VVCCudaFrame *fr
         for (int i = 0; i < n_tbs; i++)
             if (tbs[i].flags & VVC_CUDA_TB_STORE_RESIDUAL)
                 return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx_host: VVC_CUDA_TB_STORE_RESIDUAL needs the dense int32 layout");
+    if (co->quant)                  // the lists are in host memory here: refuse ids the device would index out of range with
+        for (int i = 0; i < n_tbs; i++)
+            if (co->quant[i].sl_id > 28 || (co->quant[i].sl_id && !co->scaling))
+                return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx_host: TB %d names scaling matrix %d (%s)", i, co->quant[i].sl_id - 1,
+                                    co->scaling ? "ids are 0..27" : "no scaling list given");
     const size_t esz = win ? sizeof(int16_t) : sizeof(int32_t);
     const size_t fsz = align_up(vvc_stage_frame_size(frame), 256);
     const size_t csz = align_up(co->n * esz, 256);

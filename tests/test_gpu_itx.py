@@ -192,6 +192,17 @@ def test_quantised_entry_argument_errors():
     c.itx_frame_q(fr.desc, abi.coeffs_desc(buf[1], 64, abi.COEFF_WINDOW16), tb[1], 0, 15)      # n_tbs == 0
     c.sync()
     c.close()
+    # host entry: a scaling matrix id without a scaling list (or beyond Table 38) is refused before anything is launched
+    q = np.zeros(1, dtype=abi.TB_QUANT_DTYPE)
+    q["sl_id"] = 3
+    planes = synth.uniform_planes(geom, seed=2)
+    hb, ht = np.zeros(64, dtype=np.int16), np.zeros(1, dtype=abi.TB_DTYPE)
+    ht["log2_w"], ht["log2_h"], ht["nzw"], ht["nzh"] = 2, 2, 4, 4
+    c = lib.Context(0)
+    with pytest.raises(lib.VVCCudaError):
+        c.itx_frame_q_host(abi.frame_from_numpy(geom, planes), abi.coeffs_desc(hb.ctypes.data, 64, abi.COEFF_WINDOW16, q.ctypes.data, None),
+                           ht.ctypes.data, 1, 15)
+    c.close()
     for fmt, rng in ((abi.COEFF_WINDOW16, 16), (7, 15)):          # 16-bit window needs range 15; unknown layout
         c = lib.Context(0)
         with pytest.raises(lib.VVCCudaError):
