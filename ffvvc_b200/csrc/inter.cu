@@ -615,17 +615,27 @@ extern "C" int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, co
         // samples) go to parallel streams, the longest first, so that each one's tail is filled by the others (281 ->
         // 211 us for one 4K picture).  Long launches keep one stream: there the kernels only disturb each other's
         // caches (measured 1385 -> 1533 us for eight pictures).
+#ifndef INTER_LONG_SPREAD
+#define INTER_LONG_SPREAD 1         // long launches move the small kernels (chroma classes, PROF) to a side stream: inter 2.77 -> 2.65 ms per 16 pictures (tools/sweep_long_spread.sh)
+#endif
         const bool spread = p.n < 200000;
-        if (spread && vvc_ctx_fork(ctx, 3))
-            return ctx->err;
         if (spread) {
-            if (vvc_inter_launch_warp(ctx, p, lists) || vvc_inter_launch_patch(ctx, p, lists, true))
+            if (vvc_ctx_fork(ctx, 3))
+                return ctx->err;
+            if (vvc_inter_launch_warp(ctx, p, lists, 1) || vvc_inter_launch_patch(ctx, p, lists, 1))
                 return ctx->err;
             return vvc_ctx_join(ctx, 3) ? ctx->err : VVC_CUDA_OK;
         }
-        if (vvc_inter_launch_patch(ctx, p, lists, false))
+        if (INTER_LONG_SPREAD) {
+            if (vvc_ctx_fork(ctx, 3))
+                return ctx->err;
+            if (vvc_inter_launch_patch(ctx, p, lists, 2) || vvc_inter_launch_warp(ctx, p, lists, 2))
+                return ctx->err;
+            return vvc_ctx_join(ctx, 3) ? ctx->err : VVC_CUDA_OK;
+        }
+        if (vvc_inter_launch_patch(ctx, p, lists, 0))
             return ctx->err;
-        return vvc_inter_launch_warp(ctx, p, lists);
+        return vvc_inter_launch_warp(ctx, p, lists, 0);
     }
     const int grid = n_pbs < 148 * 12 ? n_pbs : 148 * 12;
     inter_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);

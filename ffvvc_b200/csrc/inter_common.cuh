@@ -33,8 +33,8 @@ struct InterLists {
 // classify runs on the context stream; the six task-class kernels write disjoint samples and are spread over the
 // context stream and its side streams (vvc_ctx_fork / vvc_ctx_join around the two calls below)
 int vvc_inter_launch_classify(VVCCudaCtx *ctx, const InterK &p, InterLists *lists);
-int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists, bool spread);
-int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists);
+int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists, int spread);
+int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists, int spread);
 
 // Records whose prediction needs a cooperative tile (DMVR search, BDOF windows, PROF gradients) go to the
 // warp-per-record kernel; everything else (plain uni / bi, BCW, explicit weights, GPM) to the

@@ -381,9 +381,10 @@ int vvc_inter_launch_classify(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
 
 // spread: luma bi on side stream 0, luma uni on 1, both chroma classes on 2 (the warp kernels take the context stream);
 // otherwise everything on the context stream
-int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, const InterLists &ls, bool spread)
+// spread == 2 (long launches): only the two chroma classes leave the context stream (side stream 2)
+int vvc_inter_launch_patch(VVCCudaCtx *ctx, const InterK &p, const InterLists &ls, int spread)
 {
-    cudaStream_t s0 = spread ? ctx->side[0] : ctx->stream, s1 = spread ? ctx->side[1] : ctx->stream, s2 = spread ? ctx->side[2] : ctx->stream;
+    cudaStream_t s0 = spread == 1 ? ctx->side[0] : ctx->stream, s1 = spread == 1 ? ctx->side[1] : ctx->stream, s2 = spread ? ctx->side[2] : ctx->stream;
     inter_patch_kernel<true, true><<<148 * patch_ctas(true, true), kThreads, 0, s0>>>(p, ls);
     VVC_LAUNCHED(ctx);
     inter_patch_kernel<true, false><<<148 * patch_ctas(true, false), kThreads, 0, s1>>>(p, ls);

@@ -688,7 +688,8 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
 
 }  // namespace
 
-int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists)
+// spread == 2 (long launches): the PROF kernel goes to side stream 2 behind the chroma patch kernels
+int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists, int spread)
 {
 #ifndef INTER_WARP_CTAS
 #define INTER_WARP_CTAS 7                                        // persistent: 7 CTAs fit an SM (shared memory)
@@ -697,7 +698,7 @@ int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &li
     const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
     inter_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count);
     VVC_LAUNCHED(ctx);
-    inter_warp_kernel<1><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count);
+    inter_warp_kernel<1><<<grid, kThreads, 0, spread == 2 ? ctx->side[2] : ctx->stream>>>(p, lists.coop, p.n, lists.count);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }
