@@ -11,6 +11,7 @@ EDGE_LEFT, EDGE_TOP, EDGE_RIGHT, EDGE_BOTTOM = 1, 2, 4, 8
 
 
 OPT_GENERIC_KERNELS = 1      # vvc_cuda_ctx_set_option()
+OPT_ALF_WIDE_MULTIPLY = 2
 
 
 class VVCCudaFrame(C.Structure):

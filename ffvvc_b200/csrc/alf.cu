@@ -26,6 +26,7 @@ struct AlfK {
     const VVCCudaALFCtb  *ctbs;
     const VVCCudaALFSets *sets;
     int        sets_per_frame;
+    int        wide_multiply;         // VVC_CUDA_OPT_ALF_WIDE_MULTIPLY: every block through the 32-bit-multiply path
 };
 
 constexpr int kThreads = 256;
@@ -37,7 +38,10 @@ struct AlfSmem {
     alignas(16) pel     luma[TH + 6][LP];
     alignas(16) pel     chroma[2][TH / 2 + 4][CP];
     alignas(16) ushort4 cell[TH / 2 + 2][TW / 2 + 2];
-    alignas(16) uint32_t coef[(TH / 4) * (TW / 4)][24];  // per tap: the coefficient as the IDP.2A word (f, 0, 0, f), then the clip value in both halves
+    // per 4x4 block: 12 coefficients as IDP.2A words (f, 0, 0, f), 12 clip values in both halves, and one word of class
+    // information for the wide-coefficient path (bit 0: some |f| == 128, bits 8..: class, bits 16..: transpose).  25 words
+    // per block: an odd pitch, so the blocks a warp reads side by side sit in different banks.
+    alignas(16) uint32_t coef[(TH / 4) * (TW / 4)][25];
 };
 
 struct ClampWin { int xlo, xhi, ylo, yhi; };
@@ -90,6 +94,45 @@ __constant__ uint8_t c_perm[4][12] = {
 };
 __constant__ uint8_t c_act[16] = { 0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4 };
 __constant__ uint8_t c_clip_shift[4] = { 0, 3, 5, 7 };
+
+// Tap geometry of the two diamonds (:102-113, :196-201): vertical reach (index into d[], 0 = same row) and column offset
+// of the first sample of each point-symmetric pair.
+__constant__ int8_t c_luma_tap[12][2]   = { {3, 0}, {2, 1}, {2, 0}, {2, -1}, {1, 2}, {1, 1}, {1, 0}, {1, -1}, {1, -2}, {0, 3}, {0, 2}, {0, 1} };
+__constant__ int8_t c_chroma_tap[6][2]  = { {2, 0}, {1, 1}, {1, 0}, {1, -1}, {0, 2}, {0, 1} };
+
+// One 4x1 strip with 32-bit multiplies: the path of coefficient sets that hold +128, which does not fit the signed byte
+// of the IDP.2A form (and the comparison path of VVC_CUDA_OPT_ALF_WIDE_MULTIPLY).  Rare, so written for few registers
+// (rolled loops, coefficients fetched per tap) and kept out of line: the packed path's registers and code are unaffected.
+// luma: info = the block's class word (sm.coef[..][24]); chroma: info = -1 - alt.
+__device__ __noinline__ uint2 alf_strip_wide(const pel *p0, int d1, int d2, int d3, bool near_vb, int bd,
+                                             const VVCCudaALFSets *sets, int set, int info)
+{
+    const bool chroma = info < 0;
+    const int cls = (info >> 8) & 0xff, tr = (info >> 16) & 3, alt = -1 - info;
+    const int16_t *ff;
+    const uint8_t *ci = nullptr;
+    if (chroma)        { ff = sets->chroma_coeff[alt]; ci = sets->chroma_clip_idx[alt]; }
+    else if (set < 16) { ff = vvct_alf_fix_filt_coeff[vvct_alf_class_to_filt_map[set][cls]]; }
+    else               { ff = sets->luma_coeff[set - 16][vvct_alf_aps_class_to_filt_map[cls]]; ci = sets->luma_clip_idx[set - 16][cls]; }
+    const int d[4] = { 0, d1, d2, d3 };
+    int sum[4] = { 0, 0, 0, 0 };
+#pragma unroll 1
+    for (int j = 0; j < (chroma ? 6 : 12); j++) {
+        const int s = chroma ? j : c_perm[tr][j];
+        const int f = ff[s], c = 1 << (bd - (ci ? c_clip_shift[ci[s]] : 0));
+        const int dy = d[chroma ? c_chroma_tap[j][0] : c_luma_tap[j][0]], dx = chroma ? c_chroma_tap[j][1] : c_luma_tap[j][1];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int cur = p0[i];
+            sum[i] += f * (d_clip3((int)p0[i + dy + dx] - cur, -c, c) + d_clip3((int)p0[i - dy - dx] - cur, -c, c));
+        }
+    }
+    unsigned res[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        res[i] = (unsigned)d_clip_pel(p0[i] + (near_vb ? (sum[i] + 512) >> 10 : (sum[i] + 64) >> 7), bd);
+    return make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
+}
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
@@ -178,10 +221,13 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
             else if (hi > 2 * lo) cls += (2 * hv_wins + 1) * 5;
             const int tr = d0_le_d1 * 2 + v_le_h;
 
-            // coefficients are 8-bit by syntax (AlfCoeff in -128..127): byte 0 feeds the first sample of a pair (IDP.2A.LO),
-            // byte 3 the second (IDP.2A.HI)
+            // Coefficients are -128..128 by syntax (alf_luma_coeff_abs 0..128, cbs_h266_syntax_template.c:2285, stored as
+            // +-abs in int16, vvc_ps.c:803-808).  -128..127 go into signed bytes: byte 0 feeds the first sample of a pair
+            // (IDP.2A.LO), byte 3 the second (IDP.2A.HI).  A block whose permuted set holds +128 is flagged and filtered by
+            // alf_strip_wide() with 32-bit multiplies.
             uint32_t *out = sm.coef[b];
             const int set = a.filt_set_idx_y;
+            int wide = 0;
             if (set < 16) {
                 const int16_t *f = vvct_alf_fix_filt_coeff[vvct_alf_class_to_filt_map[set][cls]];
 #pragma unroll
@@ -197,10 +243,12 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                 for (int j = 0; j < 12; j++) {
                     const int s = c_perm[tr][j];
                     const uint32_t fb = (uint32_t)f[s] & 0xff, cv = 1u << (bd - c_clip_shift[ci[s]]);
+                    wide |= f[s] > 127;
                     out[j]      = fb | (fb << 24);
                     out[12 + j] = cv | (cv << 16);
                 }
             }
+            out[24] = (uint32_t)(wide | p.wide_multiply) | ((uint32_t)cls << 8) | ((uint32_t)tr << 16);
         }
         __syncthreads();
     }
@@ -208,6 +256,7 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
     // ---- luma 7x7 diamond (:43-135), 4x1 strips ------------------------------------------------
     {
         pel *dplane = p.dst[0] + k * p.db[0];
+        bool any_wide = false;
         for (int s = tid; s < BX * TH; s += kThreads) {
             const int r = s / BX, c4 = s - r * BX;
             const int y = ty0 + r, x = tx0 + 4 * c4;
@@ -222,6 +271,10 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                 const int d1 = vb_reach(1, t, 4) * LP, d2 = vb_reach(2, t, 4) * LP, d3 = vb_reach(3, t, 4) * LP;
                 const bool near_vb = (t == -1 || t == 0);
                 const uint32_t *cf = sm.coef[(r >> 2) * BX + c4];
+                if (cf[24] & 1) {           // +128 in this block's set: left to the wide-multiply loop below
+                    any_wide = true;
+                    continue;
+                }
                 // The strip as two sample pairs in 16x2 arithmetic: clip3(-c, c, n - cur) = max(min(n + (-cur), c), -c) is
                 // VIADDMNMX + VIMNMX per pair, the two clipped differences add as VIADD.16x2, and IDP.2A multiplies the
                 // pair by the tap (exact 32-bit accumulate per sample).  wd[i] = samples (-4 + 2i, -3 + 2i) of a row.
@@ -285,6 +338,20 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
             }
             *reinterpret_cast<uint2 *>(dplane + (long long)y * p.dp[0] + x) = o;
         }
+        // strips of blocks whose coefficient set holds +128 (rare; no thread of most tiles ever gets here)
+        if (any_wide) {
+            for (int s = tid; s < BX * TH; s += kThreads) {
+                const int r = s / BX, c4 = s - r * BX;
+                const int y = ty0 + r, x = tx0 + 4 * c4;
+                const uint32_t info = sm.coef[(r >> 2) * BX + c4][24];
+                if (y >= p.h || x >= p.w || !(info & 1))
+                    continue;
+                const int t = (y - y0) - vb;
+                *reinterpret_cast<uint2 *>(dplane + (long long)y * p.dp[0] + x) =
+                    alf_strip_wide(&sm.luma[r + 3][8 + 4 * c4], vb_reach(1, t, 4) * LP, vb_reach(2, t, 4) * LP, vb_reach(3, t, 4) * LP,
+                                            t == -1 || t == 0, bd, sets, a.filt_set_idx_y, (int)info);
+            }
+        }
     }
 
     // ---- chroma 5x5 diamond (:137-221) + CC-ALF from the staged pre-ALF luma (:223-263) --------
@@ -310,31 +377,14 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                 const int d1 = vb_reach(1, t, 2) * CP, d2 = vb_reach(2, t, 2) * CP;
                 const bool near_vb = (t == -1 || t == 0);
                 const int alt = a.chroma_alt_idx[pc];
-                if (TW == 32) {
-                    // 32x32 CTBs keep the scalar form: the packed form below is bit-exact on every 64-wide tile case but
-                    // differs by one on some samples of 16-wide chroma tiles (cause not yet found), so it is not used here
-                    int f[6], c[6];
+                bool wide = p.wide_multiply;
 #pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        f[j] = sets->chroma_coeff[alt][j];
-                        c[j] = 1 << (bd - c_clip_shift[sets->chroma_clip_idx[alt][j]]);
-                    }
-#define PAIR_CLIP(cur, a_, b_, c_) (d_clip3((a_) - (cur), -(c_), (c_)) + d_clip3((b_) - (cur), -(c_), (c_)))
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const pel *q = p0 + j;
-                        const int cur = q[0];
-                        int sum = 0;
-                        sum += f[0] * PAIR_CLIP(cur, q[d2],     q[-d2],     c[0]);
-                        sum += f[1] * PAIR_CLIP(cur, q[d1 + 1], q[-d1 - 1], c[1]);
-                        sum += f[2] * PAIR_CLIP(cur, q[d1],     q[-d1],     c[2]);
-                        sum += f[3] * PAIR_CLIP(cur, q[d1 - 1], q[-d1 + 1], c[3]);
-                        sum += f[4] * PAIR_CLIP(cur, q[2],      q[-2],      c[4]);
-                        sum += f[5] * PAIR_CLIP(cur, q[1],      q[-1],      c[5]);
-                        sum = near_vb ? (sum + 512) >> 10 : (sum + 64) >> 7;
-                        val[j] = d_clip_pel(cur + sum, bd);
-                    }
-#undef PAIR_CLIP
+                for (int j = 0; j < 6; j++)
+                    wide |= sets->chroma_coeff[alt][j] > 127;
+                if (wide) {
+                    // 32-bit multiplies: sets holding +128 (alf_chroma_coeff_abs 0..128, cbs_h266_syntax_template.c:2314)
+                    const uint2 o = alf_strip_wide(p0, d1, d2, 0, near_vb, bd, sets, 0, -1 - alt);
+                    val[0] = o.x & 0xffff; val[1] = o.x >> 16; val[2] = o.y & 0xffff; val[3] = o.y >> 16;
                 } else {
                     // same 16x2 scheme as luma: one coefficient / clip word per tap for the whole CTB
                     uint32_t fw[6], cw[6];
@@ -447,6 +497,7 @@ extern "C" int vvc_cuda_alf_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, cons
     p.ctb_cols = ceil_div(p.w, 1 << p.ctb_log2);
     p.ctb_rows = ceil_div(p.h, 1 << p.ctb_log2);
     p.ctbs = ctbs; p.sets = sets; p.sets_per_frame = sets_per_frame;
+    p.wide_multiply = ctx->alf_wide_multiply;
 
     if (p.ctb_log2 >= 6) {
         dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, 32), src->batch);

@@ -81,8 +81,13 @@ def struct_planes(geom, seed=12345):
     return planes
 
 
-def alf_params(geom, seed=777, all_on=True):
-    """Per-CTB ALF parameters + filter sets, SURVEY.md 8(d) config 1 distributions."""
+def alf_params(geom, seed=777, all_on=True, coeffs="int8"):
+    """Per-CTB ALF parameters + filter sets, SURVEY.md 8(d) config 1 distributions.
+
+    coeffs: "int8" = checkasm's draw (-128..127, AlfCtbFiltSetIdxY 0..16; the golden fixtures depend on it);
+    "full" = the whole legal range -128..+128 (alf_luma_coeff_abs / alf_chroma_coeff_abs 0..128,
+    cbs_h266_syntax_template.c:2285,2314; +-abs stored by vvc_ps.c:803-808) in all 8 APS slots, AlfCtbFiltSetIdxY 0..23;
+    "max" = every tap +128 or -128."""
     rng = LCG(seed)
     n = geom.ctb_count * geom.batch
     ctbs = np.zeros(n, dtype=abi.ALF_CTB_DTYPE)
@@ -90,15 +95,34 @@ def alf_params(geom, seed=777, all_on=True):
         ctbs["ctb_flag"][:] = 1
     else:
         ctbs["ctb_flag"][:] = rng.below(n * 3, 2).reshape(n, 3)
-    ctbs["filt_set_idx_y"] = rng.below(n, 17)
+    ctbs["filt_set_idx_y"] = rng.below(n, 17 if coeffs == "int8" else 24)
+    if coeffs != "int8":        # every other CTB takes an APS slot, so that small pictures reach them too
+        ctbs["filt_set_idx_y"][::2] = 16 + ctbs["filt_set_idx_y"][::2] % 8
     ctbs["chroma_alt_idx"][:] = rng.below(n * 2, 8).reshape(n, 2)
     ctbs["cc_idc"][:] = rng.below(n * 2, 5).reshape(n, 2)
     sets = np.zeros(1, dtype=abi.ALF_SETS_DTYPE)
-    # APS luma: random int8-range coefficients (tests/checkasm/vvc_alf.c:55-59), clip idx rnd%4
-    sets["luma_coeff"][0] = (rng.below(8 * 25 * 12, 256) - 128).reshape(8, 25, 12)
-    sets["luma_clip_idx"][0] = rng.below(8 * 25 * 12, 4).reshape(8, 25, 12)
-    sets["chroma_coeff"][0] = (rng.below(8 * 6, 256) - 128).reshape(8, 6)
-    sets["chroma_clip_idx"][0] = rng.below(8 * 6, 4).reshape(8, 6)
+    if coeffs == "int8":
+        # APS luma: random int8-range coefficients (tests/checkasm/vvc_alf.c:55-59), clip idx rnd%4
+        sets["luma_coeff"][0] = (rng.below(8 * 25 * 12, 256) - 128).reshape(8, 25, 12)
+        sets["luma_clip_idx"][0] = rng.below(8 * 25 * 12, 4).reshape(8, 25, 12)
+        sets["chroma_coeff"][0] = (rng.below(8 * 6, 256) - 128).reshape(8, 6)
+        sets["chroma_clip_idx"][0] = rng.below(8 * 6, 4).reshape(8, 6)
+    else:
+        if coeffs == "full":
+            sets["luma_coeff"][0] = (rng.below(8 * 25 * 12, 257) - 128).reshape(8, 25, 12)
+            sets["chroma_coeff"][0] = (rng.below(8 * 6, 257) - 128).reshape(8, 6)
+            # a quarter of the filters get at least one +128 so the wide path is always exercised
+            hit = rng.below(8 * 25, 4).reshape(8, 25) == 0
+            tap = rng.below(8 * 25, 12).reshape(8, 25)
+            for a, b in zip(*np.nonzero(hit)):
+                sets["luma_coeff"][0][a, b, tap[a, b]] = 128
+            sets["chroma_coeff"][0][::2, rng.below(1, 6)[0]] = 128
+        else:
+            assert coeffs == "max"
+            sets["luma_coeff"][0] = (rng.below(8 * 25 * 12, 2) * 256 - 128).reshape(8, 25, 12)
+            sets["chroma_coeff"][0] = (rng.below(8 * 6, 2) * 256 - 128).reshape(8, 6)
+        sets["luma_clip_idx"][0] = rng.below(8 * 25 * 12, 4).reshape(8, 25, 12)
+        sets["chroma_clip_idx"][0] = rng.below(8 * 6, 4).reshape(8, 6)
     # CC-ALF coefficients are 0 or +-2^k, k <= 6 (vvc_ps.c:810-819)
     mag = rng.below(2 * 5 * 7, 8)
     sgn = rng.below(2 * 5 * 7, 2) * 2 - 1

@@ -60,6 +60,10 @@ const char *vvc_cuda_version(void);
 /* Options.  VVC_CUDA_OPT_GENERIC_KERNELS = 1 routes every stage through the generic kernels (any bit
  * depth / alignment) even where a specialised 10-bit kernel exists; both are CUDA, results identical. */
 #define VVC_CUDA_OPT_GENERIC_KERNELS 1
+/* VVC_CUDA_OPT_ALF_WIDE_MULTIPLY = 1 sends every ALF block through the 32-bit-multiply path that otherwise serves only
+ * coefficient sets holding +128 (the packed 16x2 / IDP.2A path carries coefficients -128..127); results identical, tests
+ * compare the two. */
+#define VVC_CUDA_OPT_ALF_WIDE_MULTIPLY 2
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
  * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs): lets foreign-language bindings verify their struct mirrors. */

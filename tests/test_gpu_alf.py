@@ -50,6 +50,41 @@ def test_alf_frame_bit_exact(ctx, w, h, ctb_log2, dist):
     util.assert_planes_equal(geom, got, want, "cuda vs oracle")
 
 
+@pytest.mark.parametrize("coeffs", ["full", "max"])
+@pytest.mark.parametrize("w,h,ctb_log2,bd", [(256, 128, 7, 10), (176, 144, 6, 10), (128, 64, 5, 10), (256, 128, 7, 12),
+                                             (1920, 1080, 7, 10)])
+def test_alf_full_coefficient_range(ctx, w, h, ctb_log2, bd, coeffs):
+    """Coefficients over the whole legal range -128..+128 (cbs_h266_syntax_template.c:2285,2314; +128 does not fit the
+    signed byte of the packed path) in every APS slot, AlfCtbFiltSetIdxY 0..23."""
+    geom = abi.FrameGeom(w, h, ctb_log2=ctb_log2, bit_depth=bd)
+    planes = (synth.uniform_planes if w < 1000 else synth.struct_planes)(geom, seed=w + h)
+    ctbs, sets = synth.alf_params(geom, seed=h + ctb_log2, coeffs=coeffs)
+    assert sets["luma_coeff"].max() == 128 and sets["chroma_coeff"].max() == 128
+    got = cuda_alf(ctx, geom, planes, ctbs, sets)
+    want = oracle_alf(geom, planes, ctbs, sets)
+    util.assert_planes_equal(geom, got, want, "cuda vs oracle")
+
+
+@pytest.mark.parametrize("w,h,ctb_log2,bd", [(128, 64, 5, 10), (160, 96, 5, 12), (256, 192, 5, 10), (176, 144, 6, 12),
+                                             (384, 256, 7, 10), (384, 256, 7, 12)])
+def test_alf_packed_vs_wide_multiply(ctx, w, h, ctb_log2, bd):
+    """The packed 16x2 / IDP.2A arithmetic against the 32-bit-multiply path of the same kernel (and the oracle), over
+    seeds: every clip index, the virtual-boundary rows, 10 and 12 bit, 16-wide chroma tiles (32x32 CTBs) included."""
+    geom = abi.FrameGeom(w, h, ctb_log2=ctb_log2, bit_depth=bd, batch=2)
+    for seed in range(6):
+        planes = (synth.uniform_planes if seed & 1 else synth.struct_planes)(geom, seed=100 + seed)
+        ctbs, sets = synth.alf_params(geom, seed=200 + seed, all_on=seed < 4)
+        ctbs["edges"] = synth.LCG(seed).below(len(ctbs), 16) if seed >= 2 else 0
+        packed = cuda_alf(ctx, geom, planes, ctbs, sets)
+        ctx.set_option(abi.OPT_ALF_WIDE_MULTIPLY, 1)
+        try:
+            wide = cuda_alf(ctx, geom, planes, ctbs, sets)
+        finally:
+            ctx.set_option(abi.OPT_ALF_WIDE_MULTIPLY, 0)
+        util.assert_planes_equal(geom, packed, wide, "packed vs wide multiply (seed %d)" % seed)
+        util.assert_planes_equal(geom, packed, oracle_alf(geom, planes, ctbs, sets), "cuda vs oracle (seed %d)" % seed)
+
+
 def test_alf_interior_edges_batch_ring(ctx):
     geom = abi.FrameGeom(384, 256, batch=3)
     planes = synth.struct_planes(geom, seed=99)

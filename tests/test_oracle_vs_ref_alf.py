@@ -47,3 +47,15 @@ def test_alf_1080p_frame():
     ctbs, sets = synth.alf_params(geom, seed=12345)
     out_o, out_r = run_both(geom, planes, ctbs, sets)
     util.assert_planes_equal(geom, out_o, out_r, "oracle vs reference")
+
+
+@pytest.mark.parametrize("coeffs", ["full", "max"])
+@pytest.mark.parametrize("w,h,ctb_log2,bd", [(256, 128, 7, 10), (176, 144, 6, 10), (128, 64, 5, 10), (256, 128, 7, 12)])
+def test_alf_full_coefficient_range(w, h, ctb_log2, bd, coeffs):
+    """Coefficients over the whole legal range -128..+128 (cbs_h266_syntax_template.c:2285,2314), every APS slot."""
+    geom = abi.FrameGeom(w, h, ctb_log2=ctb_log2, bit_depth=bd)
+    planes = synth.uniform_planes(geom, seed=w + h)
+    ctbs, sets = synth.alf_params(geom, seed=h + ctb_log2, coeffs=coeffs)
+    assert sets["luma_coeff"].max() == 128 and sets["chroma_coeff"].max() == 128 and ctbs["filt_set_idx_y"].max() > 16
+    out_o, out_r = run_both(geom, planes, ctbs, sets)
+    util.assert_planes_equal(geom, out_o, out_r, "oracle vs reference")
