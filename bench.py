@@ -221,6 +221,16 @@ def run_cpu(inp, steps, warmup, threads):
     return kind, inp.w * inp.h * threads * steps / total / 1e6, total / steps * 1e3
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -236,6 +246,8 @@ def main():
     ap.add_argument("--seed", type=int, default=12345, help="seed of the synthetic inputs (rank r uses seed + r)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against the reference C")
+    ap.add_argument("--quick", action="store_true", help="skip the one-picture-per-launch and the >1 s runs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -245,24 +257,28 @@ def main():
     workload = ("recon_4k: INTER (MC/bi/DMVR/BDOF/PROF/GPM) -> residual (dequant+LFNST+itx+add) -> inverse LMCS -> deblock V+H -> SAO -> "
                 "ALF/CC-ALF on %dx%d 10-bit 4:2:0, 100%% inter area, coded fraction 1.0") % (args.width, args.height)
 
-    oracle_so = os.path.join(ROOT, "oracle", "liboracle.so")
-    lfnst_set_of = None
-    if os.path.exists(oracle_so):                 # table accessor only (which LFNST set a mode maps to), not compute
-        olib = C.CDLL(oracle_so)
-        olib.vvco_lfnst_tr_set.argtypes = [C.c_int]
-        lfnst_set_of = olib.vvco_lfnst_tr_set
+    lfnst_set_of = synth.lfnst_set_of              # LFNST set of an intra mode, from the generated tables
+    # the same `config` in both arms: what is measured; how each arm runs it goes under "run"
+    config = {"workload": workload, "width": args.width, "height": args.height, "bit_depth": 10, "chroma_format": "4:2:0",
+              "coded_fraction": 1.0, "stages": STAGES,
+              "l2": "inputs larger than L2: every step streams a ring of pictures, references and coefficients several times the 126 MB L2, no flush needed",
+              "parallelism": "independent streams x%d, no collective" % args.gpus}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         inp = Inputs(args.width, args.height, seed=args.seed, distinct=2, lfnst_set_of=lfnst_set_of)
         kind, mpix, ms = run_cpu(inp, args.steps, max(args.warmup, 1), threads)
+        _, mpix1, ms1 = run_cpu(inp, 1, 0, 1)
         sample = "%d pictures per step (one %dx%d picture per host thread) of the same synthetic workload" % (threads, args.width, args.height)
         line = {
             "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u16", "data": "synthetic", "config": {"workload": workload, "cpu_threads": threads},
-            "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "dtype": "u16", "data": "synthetic", "config": config,
+            "run": {"cpu_threads": threads, "pictures_per_step": threads},
+            "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                             "one_thread": {"value": mpix1, "unit": UNIT, "ms_per_picture": ms1}, "cpu_model": cpu_model(),
+                             "simd": "C only: the reference's x86 assembly needs nasm, which this image lacks, so its AVX2 MC/SAO/ALF is not represented"},
             "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -318,45 +334,53 @@ def main():
     p_wp, p_prof, p_sets, p_lut, p_sl = up(inp.wp), up(inp.prof), up(inp.sets), up(inp.inv_lut), up(inp.scaling)
     n_ctb = g1.ctb_count
 
-    def sub_frame(df, k0):
+    def sub_frame(df, k0, n):
         f = abi.VVCCudaFrame()
         C.memmove(C.byref(f), C.byref(df.desc), C.sizeof(f))
         for c in range(3):
             f.data[c] = df.desc.data[c] + k0 * df.desc.batch_stride[c]
-        f.batch = group
+        f.batch = n
         return f
 
-    groups = []
-    for k0 in range(0, frames, group):
-        ks = list(range(k0, k0 + group))
-        pbs = np.concatenate([inp.records(k, frames, j) for j, k in enumerate(ks)])
-        tb_parts, co_parts, off = [], [], 0
-        for j, k in enumerate(ks):
-            t = inp.tbs[k % inp.distinct].copy()
-            t["pic"] = j
-            t["coeff_offset"] += off
-            off += len(inp.coeffs[k % inp.distinct])
-            tb_parts.append(t)
-            co_parts.append(inp.coeffs[k % inp.distinct])
-        tbs, coeffs = np.concatenate(tb_parts), np.concatenate(co_parts)
-        quant = np.concatenate([inp.quant[k % inp.distinct] for k in ks])
-        md = abi.VVCCudaDeblockMaps()
-        for d in range(2):
-            for c in range(3):
-                rows, pitch = abi.deblock_map_shape(g1, d, c)
-                arr = np.concatenate([inp.maps[k % inp.distinct][d][c] for k in ks])
-                md.edge[d][c] = up(arr)
-                md.pitch[d][c], md.rows[d][c], md.size[d][c] = pitch, rows, rows * pitch
-        groups.append(dict(
-            cur=sub_frame(cur, k0), out=sub_frame(out, k0), pbs=up(pbs), n_pbs=len(pbs), tbs=up(tbs), n_tbs=len(tbs),
-            coeffs=abi.coeffs_desc(up(coeffs), len(coeffs), abi.COEFF_DENSE32, up(quant), p_sl), md=md, sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
-            alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
+    def build_groups(group):
+        """Descriptors of the ring, `group` pictures (independent streams) per launch."""
+        groups = []
+        for k0 in range(0, frames, group):
+            ks = list(range(k0, k0 + group))
+            pbs = np.concatenate([inp.records(k, frames, j) for j, k in enumerate(ks)])
+            tb_parts, co_parts, off = [], [], 0
+            for j, k in enumerate(ks):
+                t = inp.tbs[k % inp.distinct].copy()
+                t["pic"] = j
+                t["coeff_offset"] += off
+                off += len(inp.coeffs[k % inp.distinct])
+                tb_parts.append(t)
+                co_parts.append(inp.coeffs[k % inp.distinct])
+            tbs, coeffs = np.concatenate(tb_parts), np.concatenate(co_parts)
+            quant = np.concatenate([inp.quant[k % inp.distinct] for k in ks])
+            md = abi.VVCCudaDeblockMaps()
+            for d in range(2):
+                for c in range(3):
+                    rows, pitch = abi.deblock_map_shape(g1, d, c)
+                    arr = np.concatenate([inp.maps[k % inp.distinct][d][c] for k in ks])
+                    md.edge[d][c] = up(arr)
+                    md.pitch[d][c], md.rows[d][c], md.size[d][c] = pitch, rows, rows * pitch
+            groups.append(dict(
+                cur=sub_frame(cur, k0, group), out=sub_frame(out, k0, group), ta=sub_frame(tmp_a, 0, group), tb=sub_frame(tmp_b, 0, group),
+                pbs=up(pbs), n_pbs=len(pbs), tbs=up(tbs), n_tbs=len(tbs),
+                coeffs=abi.coeffs_desc(up(coeffs), len(coeffs), abi.COEFF_DENSE32, up(quant), p_sl), md=md,
+                sao=up(np.concatenate([inp.sao[k % inp.distinct] for k in ks])),
+                alf=up(np.concatenate([inp.alf[k % inp.distinct] for k in ks]))))
+        return groups
+
+    groups = build_groups(group)
     # kernels per picture group: inter = 7 (classify, four thread-per-patch class kernels, two warp-per-record kernels),
     # residual = 4 (size binning, thread-per-block kernel for 2x2..4x4, warp-per-TB kernel, generic kernel over the
     # blocks those leave), every other stage 1
-    launches_per_step = len(groups) * (len(STAGES) + 9)
+    launches_per_group = len(STAGES) + 9
+    launches_per_step = len(groups) * launches_per_group
 
-    def step(events=None):
+    def step(events=None, groups=groups):
         for gi, g in enumerate(groups):
             ev = events[gi] if events is not None else None
             if ev: ev[0].record()
@@ -366,14 +390,31 @@ def main():
             if ev: ev[2].record()
             ctx.lmcs_frame(g["cur"], p_lut, None)
             if ev: ev[3].record()
-            ctx.deblock_frame(tmp_a.desc, g["cur"], g["md"], 1)
+            ctx.deblock_frame(g["ta"], g["cur"], g["md"], 1)
             if ev: ev[4].record()
-            ctx.deblock_frame(tmp_b.desc, tmp_a.desc, g["md"], 0)
+            ctx.deblock_frame(g["tb"], g["ta"], g["md"], 0)
             if ev: ev[5].record()
-            ctx.sao_frame(tmp_a.desc, tmp_b.desc, g["sao"])
+            ctx.sao_frame(g["ta"], g["tb"], g["sao"])
             if ev: ev[6].record()
-            ctx.alf_frame(g["out"], tmp_a.desc, g["alf"], p_sets, 0)
+            ctx.alf_frame(g["out"], g["ta"], g["alf"], p_sets, 0)
             if ev: ev[7].record()
+
+    def timed(n_steps, groups):
+        """n_steps passes over the ring, CUDA events on the context's stream; max over ranks."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(n_steps):
+            step(None, groups)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     def barrier():
         torch.cuda.synchronize()
@@ -443,6 +484,24 @@ def main():
         "algorithmic_bytes_per_launch": algo_bytes, "stages": per_stage,
         "chain": {"algorithmic_bytes_per_luma_px": CHAIN_ALGO_BYTES_PER_LUMA_PX, "achieved_gbs": chain_gbs, "frac": chain_gbs / peak},
     }
+
+    # ---- the same ring with ONE picture per launch (BASELINE config 5 as worded: one stream per GPU) and a run of
+    # ---- more than a second (the headline region is a burst of ~0.1 s) ----------------------------------
+    extra = {}
+    if not args.quick:
+        if group > 1:
+            g_one = build_groups(1)
+            step(None, g_one)
+            ms1 = timed(min(args.steps, 5), g_one)
+            extra["one_picture_per_launch"] = {"value": luma_px_per_step * min(args.steps, 5) * world / (ms1 * 1e-3) / 1e6, "unit": UNIT,
+                                               "ms_per_step": ms1 / min(args.steps, 5)}
+            del g_one
+        n_long = max(args.steps, int(np.ceil(1500.0 / (elapsed_ms / args.steps))))
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        ms_long = timed(n_long, groups)
+        extra["sustained"] = {"value": luma_px_per_step * n_long * world / (ms_long * 1e-3) / 1e6, "unit": UNIT, "steps": n_long,
+                              "seconds": ms_long * 1e-3, "clocks": sampler2.result()}
 
     # ---- e2e: pinned host buffers through vvc_cuda_recon_frame_host -----------------------------------
     e2e = None
@@ -516,6 +575,7 @@ def main():
             e_ms = float(t.item())
         e2e = {"value": luma_px_per_step * e_steps * world / (e_ms * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
+               "h2d_gbs_per_rank": h2d * e_steps / (e_ms * 1e-3) / 1e9, "d2h_gbs_per_rank": d2h * e_steps / (e_ms * 1e-3) / 1e9,
                "api": "vvc_cuda_recon_frame_host (pinned host reference pictures, records, quantised levels in the 16-bit window layout; output pictures copied back)"}
         # the same call with the DPB already in HBM (reference pictures are earlier outputs in a decoder): only the
         # per-picture records / coefficients / filter parameters go up, the output pictures come back
@@ -557,13 +617,48 @@ def main():
                 raise AssertionError("e2e result differs from device-resident result: plane %d, %d samples (per picture %s), first (pic %d, y %d, x %d) %d vs %d" % (
                     c, len(bad), per_pic, bad[0][0], bad[0][1], bad[0][2], he[tuple(bad[0])], de[tuple(bad[0])]))
 
+    # ---- parity gate at the benchmark's own size: the reference C (oracle/_ref, else the oracle port) reconstructs the
+    # ---- two distinct pictures of this rank's workload; every ring slot of the device-resident result, and of the
+    # ---- end-to-end result, must equal the picture of its content bit for bit ---------------------------
+    parity = None
+    if not args.no_parity:
+        kind_p, fns = cpu_lib()
+        want = [None] * inp.distinct
+
+        def ref_pic(i):
+            want[i] = [q.copy() for q in cpu_reconstruct(fns, inp, i, inp.ref_planes, [abi.alloc_planes(g1) for _ in range(3)])]
+
+        ts = [threading.Thread(target=ref_pic, args=(i,)) for i in range(inp.distinct)]
+        for t in ts: t.start()
+        for t in ts: t.join()
+        got = out.to_numpy()
+        bad = []
+        for c in range(3):
+            wv = g1.plane_wh(c)[0]
+            for k_ in range(frames):
+                ref_k = want[k_ % inp.distinct][c][0][:, :wv]
+                if not np.array_equal(got[c][k_][:, :wv], ref_k):
+                    bad.append(("device", c, k_, int((got[c][k_][:, :wv] != ref_k).sum())))
+                if e2e is not None and not np.array_equal(h_out[c].numpy().view(np.uint16)[k_][:, :wv], ref_k):
+                    bad.append(("e2e", c, k_, int((h_out[c].numpy().view(np.uint16)[k_][:, :wv] != ref_k).sum())))
+        parity = {"pictures": frames, "distinct": inp.distinct, "equal": not bad, "against": kind_p,
+                  "paths": ["device-resident"] + (["e2e host entry"] if e2e is not None else [])}
+        if bad:
+            sys.stderr.write("bench.py: PARITY FAILURE vs the %s C at %dx%d: (path, plane, ring slot, samples) %s\n" % (
+                kind_p, args.width, args.height, bad[:8]))
+            print(json.dumps({"metric": METRIC, "parity": parity, "error": "result differs from the reference C"}))
+            return 3
+
     # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind, mpix, ms = run_cpu(inp, steps=1, warmup=1, threads=threads)
+        _, mpix1, ms1 = run_cpu(inp, 1, 0, 1)
         cpu_baseline = {"value": mpix, "unit": UNIT, "cores": threads, "kind": kind,
                         "sample": "1 warm-up + 1 timed step x %d pictures (one %dx%d picture per host thread, all stages), same synthetic workload, %.0f ms" % (
-                            threads, args.width, args.height, ms)}
+                            threads, args.width, args.height, ms),
+                        "one_thread": {"value": mpix1, "unit": UNIT, "ms_per_picture": ms1}, "cpu_model": cpu_model(),
+                        "simd": "C only: the reference's x86 assembly needs nasm, which this image lacks, so its AVX2 MC/SAO/ALF is not represented"}
 
     if rank == 0:
         ring_mb = (3 * inp.frame_bytes() * frames + sum(len(c) for c in inp.coeffs) * 4 / inp.distinct * frames) / 1e6
@@ -571,12 +666,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16", "data": "synthetic",
-            "config": {"workload": workload, "pictures_per_step": frames, "pictures_per_launch": group,
-                       "l2": "inputs larger than L2: per step %d reference + %d reconstructed + %d output pictures and their coefficients = %.0f MB (> 126 MB), no flush needed" % (frames, frames, frames, ring_mb),
-                       "parallelism": "independent streams x%d, no collective" % world},
+            "config": config,
+            "run": {"pictures_per_step": frames, "pictures_per_launch": group, "ring_mb": ring_mb,
+                    "l2": "per step %d reference + %d reconstructed + %d output pictures and their coefficients = %.0f MB (> 126 MB)" % (frames, frames, frames, ring_mb)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "clocks": clocks,
+            "clocks": clocks, "parity": parity,
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

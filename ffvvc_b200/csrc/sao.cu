@@ -5,12 +5,19 @@
 //   sao_edge_filter      libavcodec/h26x/h2656_sao_template.c:50-79
 //   sao_edge_restore_0/1 libavcodec/h26x/h2656_sao_template.c:81-215
 //
-// B200 design: purely streaming.  A thread owns 8 consecutive samples (one 128-bit load/store) of
-// RPT consecutive rows and keeps a rolling 3-row window in registers; the left/right neighbour
-// samples of its 8-sample group come from the adjacent lanes by warp shuffle (only the two lanes
-// at the ends of a warp touch memory for them).  The reference reads its neighbours from a per-CTB
-// copy with a halo of saved pre-SAO lines; here the pre-SAO picture is simply read-only, which is
-// the same thing.  The per-CTB restore rules are evaluated only on CTB border samples.
+// B200 design: purely streaming, 16x2 packed arithmetic, CTB-uniform warps.
+//  * A warp works inside ONE CTB of one plane: its lanes tile the CTB's width in 8-sample groups (one 128-bit load /
+//    store each) and the remaining lane bits select row groups of RPT rows, so type / class / offsets are warp-uniform
+//    and no lane idles because its neighbour's CTB has another SAO type (a 256-sample-wide warp straddles two to four
+//    CTBs and ran with 18 of 32 lanes active).
+//  * Samples stay packed two to a register.  Edge: 1 + clamp(n - v, -1, 1) is one VIADDMNMX.RELU per neighbour, the
+//    category is their sum, the offset comes out of an 8-byte table with two PRMTs (sign-extending), and
+//    clip(v + offset) is one more VIADDMNMX.RELU: 8 instructions per sample pair.  Band: shift / mask / add / mask /
+//    min, then the same lookup and clip.
+//  * Left / right neighbours of an 8-sample group come from the adjacent lanes by shuffle; only the lanes at the CTB's
+//    sides touch memory for them.  The reference reads its neighbours from a per-CTB copy with a halo of saved pre-SAO
+//    lines; here the pre-SAO picture is simply read-only, which is the same thing.
+//  * The picture-border and restore rules (:81-215) are per-lane 8-bit masks, computed only in CTBs that have any.
 #include "common.cuh"
 
 namespace {
@@ -21,25 +28,22 @@ struct SaoK {
     int        sp[3], dp[3];
     long long  sb[3], db[3];
     int        pw[3], ph[3], hs[3], vs[3];
+    int        cta_start[4];        // first CTA of each plane inside a picture's share of the grid; [3] = CTAs per picture
     int        bd, ctb_log2, ctb_cols, ctb_rows, planes;
     const VVCCudaSAOCtb *ctbs;
 };
 
-constexpr int RPT = 4;          // rows per thread
-constexpr int WARPS = 8;        // warps per CTA, each on its own row group
+constexpr int RPT = 4;          // rows per lane
+constexpr int WARPS = 8;        // warps per CTA, each on its own rows
 
-struct Row10 { int v[10]; };    // samples x-1 .. x+8 of one row
+struct Row { uint32_t w[4]; uint32_t left, right; };     // 8 samples as 4 pairs; left = (., x-1) in the high half, right = (x+8, .) in the low half
 
-__device__ __forceinline__ Row10 load_row(const pel *plane, int pitch, int pw, int ph, int x, int y, int lane)
+__device__ __forceinline__ void load_row8(uint32_t w[4], const pel *row, int x, int pw)
 {
-    Row10 r;
-    y = min(max(y, 0), ph - 1);
-    const pel *row = plane + (long long)y * pitch;
-    unsigned w[4];
     if (x + 7 < pw) {
         const uint4 u = __ldg(reinterpret_cast<const uint4 *>(row + x));
         w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
-    } else {
+    } else {                                       // the last group of a plane whose width is not a multiple of 8
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const unsigned lo = x + 2 * e     < pw ? __ldg(row + x + 2 * e)     : 0;
@@ -47,156 +51,216 @@ __device__ __forceinline__ Row10 load_row(const pel *plane, int pitch, int pw, i
             w[e] = lo | (hi << 16);
         }
     }
+}
+
+__device__ __forceinline__ void store_row8(pel *row, int x, int pw, const uint32_t o[4])
+{
+    if (x + 7 < pw) {
+        *reinterpret_cast<uint4 *>(row + x) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        r.v[1 + 2 * e] = w[e] & 0xffff;
-        r.v[2 + 2 * e] = w[e] >> 16;
+        for (int i = 0; i < 8; i++)
+            if (x + i < pw)
+                row[x + i] = (pel)(o[i >> 1] >> ((i & 1) * 16));
     }
-    // neighbours across the 8-sample group: from the adjacent lanes, memory only at the warp ends
-    int left  = __shfl_up_sync(0xffffffffu, r.v[8], 1);
-    int right = __shfl_down_sync(0xffffffffu, r.v[1], 1);
-    if (lane == 0)
-        left = x > 0 ? __ldg(row + x - 1) : 0;
-    if (lane == 31)
-        right = x + 8 < pw ? __ldg(row + x + 8) : 0;
-    r.v[0] = left;
-    r.v[9] = right;
+}
+
+// a row with its two outer neighbours: from the adjacent lanes of the row group, from memory at the CTB's sides
+__device__ __forceinline__ Row load_row_nb(const pel *plane, int pitch, int pw, int ph, int x, int y, bool first, bool last)
+{
+    Row r;
+    y = min(max(y, 0), ph - 1);
+    const pel *row = plane + (long long)y * pitch;
+    load_row8(r.w, row, x, pw);
+    r.left  = __shfl_up_sync(0xffffffffu, r.w[3], 1);
+    r.right = __shfl_down_sync(0xffffffffu, r.w[0], 1);
+    if (first)
+        r.left = x > 0 ? (uint32_t)__ldg(row + x - 1) << 16 : 0;
+    if (last)
+        r.right = x + 8 < pw ? __ldg(row + x + 8) : 0;
     return r;
 }
 
-// byte (sel & 7) of {lo, hi} sign-extended to 32 bits: PTX prmt replicates the selected byte's sign where bit 3 of a
-// selector nibble is set (__byte_perm masks that bit)
-__device__ __forceinline__ int prmt_s8(unsigned lo, unsigned hi, unsigned sel)
+// offsets of both halves of a pair of table indices (0..7 each) as sign-extended 16-bit values: PTX prmt replicates
+// the selected byte's sign where bit 3 of a selector nibble is set
+__device__ __forceinline__ uint32_t lookup2(uint32_t tab_lo, uint32_t tab_hi, uint32_t idx2)
 {
-    int d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    const uint32_t n = idx2 * 0x11u + 0x00800080u;      // per half: (idx, idx | 8) in the low byte
+    uint32_t sel, d;
+    asm("prmt.b32 %0, %1, %1, 0x0020;" : "=r"(sel) : "r"(n));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(tab_lo), "r"(tab_hi), "r"(sel));
     return d;
 }
 
-__global__ void __launch_bounds__(32 * WARPS, 3) sao_kernel(const SaoK p)
+__device__ __forceinline__ uint32_t pack_bytes(int b0, int b1, int b2, int b3)
+{
+    return (uint32_t)(b0 & 0xff) | ((uint32_t)(b1 & 0xff) << 8) | ((uint32_t)(b2 & 0xff) << 16) | ((uint32_t)(b3 & 0xff) << 24);
+}
+
+// 8-bit mask -> the pairs' 16-bit lane masks
+__device__ __forceinline__ uint32_t pair_mask(unsigned m8, int i)
+{
+    return ((m8 >> (2 * i)) & 1 ? 0x0000ffffu : 0u) | ((m8 >> (2 * i + 1)) & 1 ? 0xffff0000u : 0u);
+}
+
+// samples x-1 / x+1 of pair i of a row
+__device__ __forceinline__ uint32_t left_of(const Row &r, int i)  { return __funnelshift_r(i ? r.w[i - 1] : r.left, r.w[i], 16); }
+__device__ __forceinline__ uint32_t right_of(const Row &r, int i) { return __funnelshift_r(r.w[i], i < 3 ? r.w[i + 1] : r.right, 16); }
+
+// One row of edge offset, class EO: neighbours a / b = left / right, above / below, above-left / below-right,
+// above-right / below-left (:54-59).
+template <int EO>
+__device__ __forceinline__ void edge_row(uint32_t o[4], const Row &above, const Row &cur, const Row &below,
+                                         uint32_t tab_lo, uint32_t tab_hi, uint32_t maxv2)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t a = EO == 0 ? left_of(cur, i) : EO == 1 ? above.w[i] : EO == 2 ? left_of(above, i) : right_of(above, i);
+        const uint32_t b = EO == 0 ? right_of(cur, i) : EO == 1 ? below.w[i] : EO == 2 ? right_of(below, i) : left_of(below, i);
+        const uint32_t v = cur.w[i], nv1 = __vsub2(0x00010001u, v);
+        const uint32_t cat = __viaddmin_s16x2_relu(a, nv1, 0x00020002u) + __viaddmin_s16x2_relu(b, nv1, 0x00020002u);
+        o[i] = __viaddmin_s16x2_relu(v, lookup2(tab_lo, tab_hi, cat), maxv2);
+    }
+}
+
+__global__ void __launch_bounds__(32 * WARPS, 4) sao_kernel(const SaoK p)
 {
     const int lane = threadIdx.x, warp = threadIdx.y;
-    const int c = blockIdx.z % p.planes, k = blockIdx.z / p.planes;
+    const int per_pic = p.cta_start[3];
+    const int k = blockIdx.x / per_pic;
+    int r = blockIdx.x - k * per_pic;
+    const int c = r >= p.cta_start[2] ? 2 : r >= p.cta_start[1] ? 1 : 0;
+    r -= p.cta_start[c];
+    const int cx = r % p.ctb_cols, chunk = (r / p.ctb_cols) * WARPS + warp;
+
     const int pw = p.pw[c], ph = p.ph[c];
-    const int x = (blockIdx.x * 32 + lane) * 8;
-    const int y0 = (blockIdx.y * WARPS + warp) * RPT;
-    if (y0 >= ph || (int)blockIdx.x * 256 >= pw)
-        return;                                    // whole warp leaves together
-    const bool live = x < pw;                      // dead lanes still take part in the shuffles
+    const int ctb_w = (1 << p.ctb_log2) >> p.hs[c], ctb_h = (1 << p.ctb_log2) >> p.vs[c];
+    const int lxl = p.ctb_log2 - p.hs[c] - 3;                  // log2 of the 8-sample groups across a CTB
+    const int groups = min(32 >> lxl, ctb_h / RPT);            // row groups of a warp (all inside one CTB row)
+    const int lx = lane & ((1 << lxl) - 1), g = lane >> lxl;
+    const int bx0 = cx * ctb_w, bw = min(ctb_w, pw - bx0);
+    const int x = bx0 + 8 * lx;
+    const int wy0 = chunk * RPT * groups;                      // first row of the warp
+    if (wy0 >= ph)
+        return;
+    const int y0 = wy0 + g * RPT;
+    const bool live = g < groups && 8 * lx < bw && y0 < ph;    // dead lanes still take part in the shuffles
+    const int xs = live ? x : bx0, ys = live ? y0 : wy0;
+    const int cy = wy0 / ctb_h;
+    const int by0 = cy * ctb_h, bh = min(ctb_h, ph - by0);
+
     const pel *src = p.src[c] + k * p.sb[c];
     pel *dst = p.dst[c] + k * p.db[c];
-    const int pitch = p.sp[c];
+    const int pitch = p.sp[c], dpitch = p.dp[c];
     const int bd = p.bd;
+    const uint32_t maxv2 = (uint32_t)((1 << bd) - 1) * 0x00010001u;
 
-    // per-CTB parameters of this 8-sample group (a group never straddles CTBs: CTB widths are multiples of 8)
-    const int ctb_w = (1 << p.ctb_log2) >> p.hs[c], ctb_h = (1 << p.ctb_log2) >> p.vs[c];
-    const int xs = live ? x : 0;
-    const int cx = xs / ctb_w;
-    const int bx0 = cx * ctb_w, bw = min(ctb_w, pw - bx0);
-
-    // The RPT rows of a thread start at a multiple of RPT, so they lie in one CTB: its parameters are read once.  The five
-    // edge offsets / four band offsets (6-bit magnitudes) become an 8-byte table indexed with PRMT (byte `idx`,
-    // sign-extended), instead of a chain of compares per sample.
-    const int cy = y0 / ctb_h;
-    const int by0 = cy * ctb_h, bh = min(ctb_h, ph - by0);
     const VVCCudaSAOCtb *sp = p.ctbs + ((long long)k * p.ctb_rows + cy) * p.ctb_cols + cx;
     const int type = sp->type_idx[c];
     int off[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) off[i] = sp->offset_val[c][i];
-    const int bp = sp->band_position[c], eo = sp->eo_class[c];
-    // edge: category 0..4 -> offset index {1,2,0,3,4} (edge_idx, :53); band: band 0..3 -> offsets 1..4, band >= 4 -> 0
-    const unsigned tab_lo = type == 1 ? ((off[1] & 0xff) | ((off[2] & 0xff) << 8) | ((off[3] & 0xff) << 16) | ((unsigned)(off[4] & 0xff) << 24))
-                                      : ((off[1] & 0xff) | ((off[2] & 0xff) << 8) | ((off[0] & 0xff) << 16) | ((unsigned)(off[3] & 0xff) << 24));
-    const unsigned tab_hi = type == 1 ? 0u : (unsigned)(off[4] & 0xff);
-#define SAO_LOOKUP(idx) prmt_s8(tab_lo, tab_hi, (unsigned)(idx) * 0x1111u + 0x8880u)
 
-    Row10 above, cur, below;
-    cur   = load_row(src, pitch, pw, ph, xs, y0 - 1, lane);
-    below = load_row(src, pitch, pw, ph, xs, y0, lane);
-    for (int r = 0; r < RPT; r++) {
-        const int y = y0 + r;
-        if (y >= ph)
-            break;                                 // warp-uniform
+    if (type == 1) {
+        // band (:24-46): band k = 0..3 from band_position on takes offset_val[k + 1], every other band 0
+        const uint32_t tab_lo = pack_bytes(off[1], off[2], off[3], off[4]), tab_hi = 0;
+        const uint32_t sub = (32u - sp->band_position[c]) * 0x00010001u;
+        const int sh = bd - 5;
+        if (live) {
+            for (int rr = 0; rr < RPT && ys + rr < ph; rr++) {
+                uint32_t w[4], o[4];
+                load_row8(w, src + (long long)(ys + rr) * pitch, xs, pw);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t band = (((w[i] >> sh) & 0x001f001fu) + sub) & 0x001f001fu;
+                    o[i] = __viaddmin_s16x2_relu(w[i], lookup2(tab_lo, tab_hi, __vminu2(band, 0x00040004u)), maxv2);
+                }
+                store_row8(dst + (long long)(ys + rr) * dpitch, xs, pw, o);
+            }
+        }
+        return;
+    }
+    if (type != 2) {
+        if (live) {
+            for (int rr = 0; rr < RPT && ys + rr < ph; rr++) {
+                uint32_t w[4];
+                load_row8(w, src + (long long)(ys + rr) * pitch, xs, pw);
+                store_row8(dst + (long long)(ys + rr) * dpitch, xs, pw, w);
+            }
+        }
+        return;
+    }
+
+    // ---- edge (:50-79).  s = 1 + clamp(n - v, -1, 1) per neighbour; s_a + s_b = 4 - (2 + sign(v - a) + sign(v - b)), so
+    // the table is edge_idx[] = {1, 2, 0, 3, 4} read backwards ----
+    const int eo = sp->eo_class[c];
+    const uint32_t tab_lo = pack_bytes(off[4], off[3], off[0], off[2]), tab_hi = pack_bytes(off[1], 0, 0, 0);
+    const uint32_t off0 = (uint32_t)(off[0] & 0xffff) * 0x00010001u;
+    const bool first = lx == 0, last = 8 * lx + 8 >= bw;
+
+    // CTB border rules (:81-215): which of them can fire in this CTB at all (warp-uniform)
+    const bool bl = cx == 0, bt = cy == 0, br = cx == p.ctb_cols - 1, bb = cy == p.ctb_rows - 1;
+    const bool not_v = eo != 1, not_h = eo != 0;
+    const int nf = sp->restore ? sp->no_filter : 0;
+    const bool rules = nf || (not_v && (bl || br)) || (not_h && (bt || bb));
+    const int init_x = not_v && bl, w1 = bw - (not_v && br);
+    const int init_y = not_h && bt, h1 = bh - (not_h && bb);
+    const bool dg0 = nf & 16, dg1 = nf & 32, dg2 = nf & 64, dg3 = nf & 128;
+    const int keep_ul = !dg0 && eo == 2 && !bl && !bt, keep_ur = !dg1 && eo == 3 && !bt && !br;
+    const int keep_lr = !dg2 && eo == 2 && !br && !bb, keep_ll = !dg3 && eo == 3 && !bl && !bb;
+    const int rx = xs - bx0;
+
+    Row above, cur, below;
+    cur   = load_row_nb(src, pitch, pw, ph, xs, ys - 1, first, last);
+    below = load_row_nb(src, pitch, pw, ph, xs, ys, first, last);
+    for (int rr = 0; rr < RPT; rr++) {
+        const int y = ys + rr;
+        if (wy0 + rr >= ph)
+            break;                                 // warp-uniform: row groups only add multiples of RPT, and ph is one too
         above = cur; cur = below;
-        below = load_row(src, pitch, pw, ph, xs, y + 1, lane);
-        if (!live)
-            continue;
+        below = load_row_nb(src, pitch, pw, ph, xs, y + 1, first, last);
 
-        int out[8];
-        if (type == 1) {
-            const int sh = bd - 5;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int v = cur.v[1 + i];
-                const int band = ((v >> sh) - bp) & 31;
-                out[i] = d_clip_pel(v + SAO_LOOKUP(min(band, 4)), bd);
-            }
-        } else if (type == 2) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int v = cur.v[1 + i];
-                int a, b;
-                if (eo == 0)      { a = cur.v[i];       b = cur.v[i + 2]; }
-                else if (eo == 1) { a = above.v[i + 1]; b = below.v[i + 1]; }
-                else if (eo == 2) { a = above.v[i];     b = below.v[i + 2]; }
-                else              { a = above.v[i + 2]; b = below.v[i]; }
-                const int cat = 2 + min(max(v - a, -1), 1) + min(max(v - b, -1), 1);
-                out[i] = d_clip_pel(v + SAO_LOOKUP(cat), bd);
-            }
-            // ---- CTB border rules (:81-215), only for groups that touch the CTB border ----
+        uint32_t o[4];
+        switch (eo) {
+        case 0:  edge_row<0>(o, above, cur, below, tab_lo, tab_hi, maxv2); break;
+        case 1:  edge_row<1>(o, above, cur, below, tab_lo, tab_hi, maxv2); break;
+        case 2:  edge_row<2>(o, above, cur, below, tab_lo, tab_hi, maxv2); break;
+        default: edge_row<3>(o, above, cur, below, tab_lo, tab_hi, maxv2); break;
+        }
+        if (rules) {
             const int ry = y - by0;
-            const int rx = x - bx0;
-            if (ry == 0 || ry >= bh - 2 || rx == 0 || rx + 8 >= bw) {
-                const bool bl = cx == 0, bt = cy == 0, br = cx == p.ctb_cols - 1, bb = cy == p.ctb_rows - 1;
-                const bool not_v = eo != 1, not_h = eo != 0;
-                const int nf = sp->no_filter;
-                const bool restore = sp->restore;
-                const int init_x = not_v && bl, w1 = bw - (not_v && br);
-                const int init_y = not_h && bt, h1 = bh - (not_h && bb);
-                const bool dg0 = nf & 16, dg1 = nf & 32, dg2 = nf & 64, dg3 = nf & 128;
-                const int keep_ul = !dg0 && eo == 2 && !bl && !bt, keep_ur = !dg1 && eo == 3 && !bt && !br;
-                const int keep_lr = !dg2 && eo == 2 && !br && !bb, keep_ll = !dg3 && eo == 3 && !bl && !bb;
+            unsigned zero = 0, keep = 0;
+            const bool zrow = not_h && ((bt && ry == 0) || (bb && ry == bh - 1));
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int px = rx + i;
-                    if (px >= bw)
-                        break;
-                    const int v = cur.v[1 + i];
-                    if ((not_v && ((bl && px == 0) || (br && px == bw - 1))) ||
-                        (not_h && ((bt && ry == 0) || (bb && ry == bh - 1))))
-                        out[i] = d_clip_pel(v + off[0], bd);
-                    if (restore) {
-                        bool keep = false;
-                        if ((nf & 1) && not_v && px == 0      && ry >= init_y + keep_ul && ry < h1 - keep_ll) keep = true;
-                        if ((nf & 2) && not_v && px == w1 - 1 && ry >= init_y + keep_ur && ry < h1 - keep_lr) keep = true;
-                        if ((nf & 4) && not_h && ry == 0      && px >= init_x + keep_ul && px < w1 - keep_ur) keep = true;
-                        if ((nf & 8) && not_h && ry == h1 - 1 && px >= init_x + keep_ll && px < w1 - keep_lr) keep = true;
-                        if (dg0 && eo == 2 && px == 0      && ry == 0)      keep = true;
-                        if (dg1 && eo == 3 && px == w1 - 1 && ry == 0)      keep = true;
-                        if (dg2 && eo == 2 && px == w1 - 1 && ry == h1 - 1) keep = true;
-                        if (dg3 && eo == 3 && px == 0      && ry == h1 - 1) keep = true;
-                        if (keep)
-                            out[i] = v;
-                    }
+            for (int i = 0; i < 8; i++) {
+                const int px = rx + i;
+                if (zrow || (not_v && ((bl && px == 0) || (br && px == bw - 1))))
+                    zero |= 1u << i;
+                bool kp = false;
+                if ((nf & 1) && not_v && px == 0      && ry >= init_y + keep_ul && ry < h1 - keep_ll) kp = true;
+                if ((nf & 2) && not_v && px == w1 - 1 && ry >= init_y + keep_ur && ry < h1 - keep_lr) kp = true;
+                if ((nf & 4) && not_h && ry == 0      && px >= init_x + keep_ul && px < w1 - keep_ur) kp = true;
+                if ((nf & 8) && not_h && ry == h1 - 1 && px >= init_x + keep_ll && px < w1 - keep_lr) kp = true;
+                if (dg0 && eo == 2 && px == 0      && ry == 0)      kp = true;
+                if (dg1 && eo == 3 && px == w1 - 1 && ry == 0)      kp = true;
+                if (dg2 && eo == 2 && px == w1 - 1 && ry == h1 - 1) kp = true;
+                if (dg3 && eo == 3 && px == 0      && ry == h1 - 1) kp = true;
+                if (kp)
+                    keep |= 1u << i;
+            }
+            if (zero | keep) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t v = cur.w[i];
+                    const uint32_t mz = pair_mask(zero, i), mk = pair_mask(keep, i);
+                    o[i] = (o[i] & ~mz) | (__viaddmin_s16x2_relu(v, off0, maxv2) & mz);
+                    o[i] = (o[i] & ~mk) | (v & mk);
                 }
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++) out[i] = cur.v[1 + i];
         }
-        pel *drow = dst + (long long)y * p.dp[c] + x;
-        if (x + 7 < pw) {
-            uint4 o;
-            o.x = out[0] | (out[1] << 16); o.y = out[2] | (out[3] << 16);
-            o.z = out[4] | (out[5] << 16); o.w = out[6] | (out[7] << 16);
-            *reinterpret_cast<uint4 *>(drow) = o;
-        } else {
-            for (int i = 0; x + i < pw; i++)
-                drow[i] = (pel)out[i];
-        }
+        if (live && y < ph)
+            store_row8(dst + (long long)y * dpitch, xs, pw, o);
     }
-#undef SAO_LOOKUP
 }
 
 }  // namespace
@@ -229,9 +293,18 @@ extern "C" int vvc_cuda_sao_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, cons
     p.ctb_cols = ceil_div(src->width, 1 << src->ctb_log2);
     p.ctb_rows = ceil_div(src->height, 1 << src->ctb_log2);
     p.ctbs = ctbs;
-    // the grid is sized for luma; chroma planes use its upper-left part and idle CTAs exit at once
-    dim3 grid(ceil_div(src->width, 256), ceil_div(src->height, WARPS * RPT), src->batch * p.planes);
-    sao_kernel<<<grid, dim3(32, WARPS), 0, ctx->stream>>>(p);
+    // a flat grid: per picture, the CTAs of plane 0, then 1, then 2; a CTA is one CTB column x WARPS warps of rows
+    int total = 0;
+    for (int c = 0; c < p.planes; c++) {
+        const int ctb_h = (1 << p.ctb_log2) >> p.vs[c], lxl = p.ctb_log2 - p.hs[c] - 3;
+        const int groups = (32 >> lxl) < ctb_h / RPT ? (32 >> lxl) : ctb_h / RPT;
+        p.cta_start[c] = total;
+        total += ceil_div(ceil_div(p.ph[c], RPT * groups), WARPS) * p.ctb_cols;
+    }
+    for (int c = p.planes; c < 4; c++)
+        p.cta_start[c] = total;
+    p.cta_start[3] = total;
+    sao_kernel<<<(unsigned)total * src->batch, dim3(32, WARPS), 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

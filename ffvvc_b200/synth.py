@@ -458,6 +458,12 @@ def lmcs_luts(bit_depth=10, seed=5):
 _TABLES = {}
 
 
+def lfnst_set_of(pred_mode_intra):
+    """LFNST transform set of an intra mode (wide angles < 0 -> set 1, vvc_itx_1d.c:711), read from the generated
+    tables: the callable tb_list() wants, without going through any library."""
+    return 1 if pred_mode_intra < 0 else int(spec_table("lfnst_tr_set_index")[pred_mode_intra])
+
+
 def spec_table(name):
     """One table of ffvvc_b200/csrc/vvc_tables.inc (generated H.266 constants) as a numpy array."""
     if not _TABLES:

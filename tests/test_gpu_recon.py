@@ -153,3 +153,32 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode):
     ctx.recon_frame_host(f_out, refs.desc, descs)
     got = [t.numpy().view(np.uint16) for t in h_out]
     util.assert_planes_equal(gr, got, want, "recon_frame_host with a device-resident DPB vs oracle chain")
+
+
+def test_recon_4k_bit_exact(ctx):
+    """The headline size: two 3840x2160 pictures through vvc_cuda_recon_frame (quantised levels, dequant() on the device,
+    stress mix of record kinds) against the oracle's stage-by-stage chain, every sample."""
+    from ffvvc_b200 import device
+    case = build(3840, 2160, 2, 41, "window_q")
+    gr = case["gr"]
+    want = oracle_chain(case)
+    keep = []
+
+    def up(a):
+        t, p = device.to_device(a)
+        keep.append(t)
+        return p
+
+    refs, cur, out = device.DeviceFrames(gr, planes=case["refs"]), device.DeviceFrames(gr), device.DeviceFrames(gr)
+    md = abi.deblock_maps_desc(gr, case["maps"], ptr_of=up)
+    d = abi.VVCCudaReconDesc()
+    d.pbs, d.n_pbs, d.wp, d.n_wp, d.prof, d.n_prof = up(case["pbs"]), len(case["pbs"]), up(case["wp"]), len(case["wp"]), up(case["prof"]), len(case["prof"])
+    d.log2_transform_range = 15
+    d.coeffs, d.n_coeffs, d.tbs, d.n_tbs = up(case["coeffs"]), len(case["coeffs"]), up(case["tbs"]), len(case["tbs"])
+    d.coeff_format, d.quant, d.scaling = case["fmt"], up(case["quant"]), up(case["sl"])
+    d.lmcs_inv_lut = up(case["inv"])
+    d.inloop.deblock = C.pointer(md)
+    d.inloop.sao, d.inloop.alf, d.inloop.alf_sets = up(case["sao"]), up(case["alf"]), up(case["sets"])
+    ctx.recon_frame(out.desc, cur.desc, refs.desc, d)
+    ctx.sync()
+    util.assert_planes_equal(gr, out.to_numpy(), want, "recon_frame 4K vs oracle chain")
