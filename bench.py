@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against the reference C")
+    ap.add_argument("--inter-tma", type=int, default=-1, help="VVC_CUDA_OPT_INTER_TMA (default: the library's)")
     ap.add_argument("--quick", action="store_true", help="skip the one-picture-per-launch and the >1 s runs")
     args = ap.parse_args()
 
@@ -313,6 +314,8 @@ def main():
     gring = abi.FrameGeom(args.width, args.height, batch=frames)
     ggrp = abi.FrameGeom(args.width, args.height, batch=group)
     ctx = lib.Context(local_rank)
+    if args.inter_tma >= 0:
+        ctx.set_option(abi.OPT_INTER_TMA, args.inter_tma)
     stream = ctx.torch_stream()
     torch.cuda.set_stream(stream)      # uploads, events and kernels all on the context's stream
 

@@ -18,6 +18,7 @@ struct VVCCudaCtx {
     uint64_t      launches;
     int           force_generic;        // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_GENERIC_KERNELS)
     int           alf_wide_multiply;    // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_ALF_WIDE_MULTIPLY)
+    int           inter_tma;            // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_INTER_TMA)
     bool          itx_packed;           // itx_warp.cu's packed transform matrices are built on this device
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;

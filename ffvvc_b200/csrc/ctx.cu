@@ -161,6 +161,7 @@ int vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value)
     switch (option) {
     case VVC_CUDA_OPT_GENERIC_KERNELS: ctx->force_generic = value != 0; return VVC_CUDA_OK;
     case VVC_CUDA_OPT_ALF_WIDE_MULTIPLY: ctx->alf_wide_multiply = value != 0; return VVC_CUDA_OK;
+    case VVC_CUDA_OPT_INTER_TMA: ctx->inter_tma = value != 0; return VVC_CUDA_OK;
     default: return VVC_CUDA_ERR_ARG;
     }
 }

@@ -605,7 +605,7 @@ extern "C" int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, co
         p.rp[c] = (int)(refs->stride[c] / 2);    p.dp[c] = (int)(dst->stride[c] / 2);
         p.rb[c] = refs->batch_stride[c] / 2;     p.db[c] = dst->batch_stride[c] / 2;
     }
-    p.w = dst->width; p.h = dst->height; p.bd = dst->bit_depth;
+    p.w = dst->width; p.h = dst->height; p.bd = dst->bit_depth; p.nref = refs->batch;
     p.pbs = pbs; p.n = n_pbs; p.wp = wp; p.prof = prof; p.dmvr_out = dmvr_out;
     if (p.bd == 10 && frame_vec_ok(dst) && frame_vec_ok(refs) && !ctx->force_generic) {
         InterLists lists;

@@ -8,7 +8,7 @@ struct InterK {
     pel       *dst[3];
     int        rp[3], dp[3];
     long long  rb[3], db[3];
-    int        w, h, bd, planes;
+    int        w, h, bd, planes, nref;      // nref: pictures in the reference ring
     const VVCCudaPB   *pbs;
     int                n;
     const VVCCudaWP   *wp;

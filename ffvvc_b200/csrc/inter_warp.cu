@@ -22,19 +22,61 @@
 //    samples it holds in registers and stores them transposed, so the vertical pass reads its column as
 //    two 128-bit shared loads and runs the same 8-outputs-per-lane code.
 //  * The bilinear DMVR prediction and the 25 SADs use 16x2 packed arithmetic (VIMNMX.U16x2, IDP.2A).
+#include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "inter_common.cuh"
 #include "tables.cuh"
 
 namespace {
+
+// ---- TMA staging of DMVR windows (KIND 0, TMA == 1) -----------------------------------------------------------
+// One tensor map describes the luma plane of the whole reference ring as a 3-D tensor (x, y, picture).  A warp's
+// elected lane asks for the (w + 7) x (h + 7) window of each list as one box (24 x 23 samples, the 16x16 case; smaller
+// records use its upper-left part) and the copy engine writes it densely into the warp's staging area while the warp is
+// still busy with the previous record; completion is a transaction count on the warp's own mbarrier.  Measured on B200
+// (tools/tma_probe2.cu): with 16-bit elements the innermost box coordinate must be a multiple of 8 (a 16-byte aligned
+// start), any other origin raises "illegal instruction" - so the box starts at the window's column rounded down to 8 and
+// is 32 samples wide (window of at most 23 + offset of at most 7), and the move into the padded window layout shifts
+// by the offset.  Out-of-picture reads would be zero-filled where the codec wants clamp-to-edge: records whose windows
+// leave the picture keep the clamped staging loop.
+constexpr int kBoxW = 32, kBoxH = 23, kBoxBytes = kBoxW * kBoxH * 2, kBoxSlot = 1536;   // slot: 128-byte multiple
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_box_3d(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
 
 constexpr int kWarps = 4, kThreads = kWarps * 32;
 constexpr int PWL = 15, WUL = 27 * PWL + 1;   // luma window: 27 rows x 15 words (30 samples); unit stride 406 words
 constexpr int PWC = 9, WUC = 15 * PWC;        // chroma window: 15 rows x 9 words (18 samples)
 constexpr int HPL = 24, HUL = 16 * HPL;       // transposed first-pass output: [col][row], luma
 constexpr int HPC = 16, HUC = 8 * HPC;        //                                            chroma
-constexpr int TP = 32, TU = 18 * TP;          // int16 tile: sample (x, y) at (y + 1) * TP + 8 + x, ring around it
-constexpr int DP = 24, DU = 20 * DP;          // DMVR bilinear tiles
-constexpr int GU = 256;                       // BDOF gradients: [y * 16 + x]
+constexpr int TP = 36, TU = 18 * TP;          // int16 tile: sample (x, y) at (y + 1) * TP + 8 + x, ring around it.  18-word rows: the
+                                              // lane-per-row passes (BDOF gradients) meet 16 different banks (14-way conflicts at 16 words)
+constexpr int DP = 26, DU = 20 * DP;          // DMVR bilinear tiles, 13-word rows (odd: lane-per-row stores, row-per-lane SAD loads)
+constexpr int GP = 20, GU = 16 * GP;          // BDOF gradients: [y * GP + x], 10-word rows
 
 struct UnitMC {
     int      woff, r0, c0;      // window of the unit: word offset, first row, first sample column
@@ -75,6 +117,8 @@ __device__ __forceinline__ uint32_t inv_rows(int d) { return d == 23 ? 2850u : d
 // 2 rows above and below), which equals clamping the coordinates to the unrefined block's window
 // (emulated_edge_dmvr, vvc_inter.c:60-89).  One out-of-line copy serves every caller (the kernel's code size
 // matters: warps sit in different phases and share the instruction cache).
+__device__ __noinline__ void stage_apron(uint32_t *win, int pw, int e, int cols, int rows, int sub, int group);
+
 __device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const pel *plane, int pitch, int W, int H,   //@region stage_core
                                          int wx0, int wy0, int cols, int rows, int sub, int group)
 {
@@ -102,6 +146,12 @@ __device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const p
     }
     if (!pad)
         return;
+    stage_apron(win, pw, e, cols, rows, sub, group);
+}
+
+// replicated apron of a DMVR window whose core is in place (2 samples each side, 2 rows above and below)
+__device__ __noinline__ void stage_apron(uint32_t *win, int pw, int e, int cols, int rows, int sub, int group)
+{
     __syncwarp();
     for (int r = sub; r < rows; r += group) {              // lane = core row
         uint16_t *row = reinterpret_cast<uint16_t *>(win) + (r + 2) * (2 * pw);
@@ -239,27 +289,89 @@ __device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, 
 
 // KIND 0: records with DMVR / BDOF and no PROF (always bi-predicted, never GPM): the uni, GPM and PROF paths are
 // compiled out.  KIND 1: the rest of the cooperative records (PROF), listed from the back of coop[].
-template <int KIND>
-__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, int cap, uint32_t *count)   //@region rec_load
+template <int TMA> struct TmaSmem { alignas(128) uint8_t box[kWarps][2][kBoxSlot]; uint64_t bar[kWarps]; };
+template <> struct TmaSmem<0> { };
+
+// Start the window copies of cooperative record `ci` if it is a DMVR record whose two unrefined windows lie inside the
+// picture (warp-uniform decision; lane 0 issues).  Returns whether the copies are in flight.
+template <int TMA>
+__device__ __forceinline__ int tma_prefetch(TmaSmem<TMA> &ts, const InterK &p, const uint32_t *__restrict__ coop, int ci,
+                                            const CUtensorMap *map, int warp, int lane)
+{
+    if constexpr (TMA) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p.pbs + __ldg(coop + ci));
+        const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+        const int x0 = r0 & 0xffff, y0 = r0 >> 16, w = r1 & 0xff, h = (r1 >> 8) & 0xff;
+        if (!((r2 >> 24) & VVC_CUDA_PB_DMVR) || !((r1 >> 16) & VVC_CUDA_PB_LUMA))
+            return 0;
+        int wx[2], wy[2];
+        bool inside = true;
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+            wx[l] = x0 + ((int)__ldg(q + 3 + 2 * l) >> 4) - 3;
+            wy[l] = y0 + ((int)__ldg(q + 4 + 2 * l) >> 4) - 3;
+            inside = inside && wx[l] >= 0 && wx[l] + w + 7 <= p.w && wy[l] >= 0 && wy[l] + h + 7 <= p.h;
+        }
+        if (!inside)
+            return 0;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the staging area was just read by the warp
+            mbar_expect_tx(&ts.bar[warp], 2 * kBoxBytes);
+            tma_box_3d(ts.box[warp][0], map, wx[0] & ~7, wy[0], (int)(r2 & 0xff), &ts.bar[warp]);
+            tma_box_3d(ts.box[warp][1], map, wx[1] & ~7, wy[1], (int)((r2 >> 8) & 0xff), &ts.bar[warp]);
+        }
+        return 1;
+    } else {
+        return 0;
+    }
+}
+
+// KIND 0: records with DMVR / BDOF and no PROF (always bi-predicted, never GPM): the uni, GPM and PROF paths are
+// compiled out.  KIND 1: the rest of the cooperative records (PROF), listed from the back of coop[].
+// TMA 1 (KIND 0 only): the DMVR windows of the NEXT record are fetched by the copy engine while this one is computed.
+template <int KIND, int TMA>
+__global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, int cap, uint32_t *count,   //@region rec_load
+                                                              const __grid_constant__ CUtensorMap tmap)
 {
     __shared__ WarpSmem sm[kWarps];
-    const int lane = threadIdx.x & 31;
-    WarpSmem &s = sm[threadIdx.x >> 5];
+    __shared__ TmaSmem<TMA> ts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem &s = sm[warp];
     const uint2 *lumaf = reinterpret_cast<const uint2 *>(&vvct_luma_mc_filters[0][0][0]);
     const uint32_t *chromaf = reinterpret_cast<const uint32_t *>(&vvct_chroma_mc_filters[0][0][0]);
+    if constexpr (TMA) {
+        if (lane == 0) {
+            mbar_init(&ts.bar[warp], 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     // Records are drawn from a counter (count[8 + KIND], zeroed with the list counts), two at a time: DMVR's early
     // termination and the per-record BDOF switch make their cost uneven, and with a fixed stride the launch lasted as
-    // long as its unluckiest warp.
+    // long as its unluckiest warp.  The draw runs one record ahead of the computation so that the next record's windows
+    // can be in flight.
     const int n_coop = (int)count[4 + KIND];
-    for (;;) {
-        int first = 0;
-        if (lane == 0)
-            first = (int)atomicAdd(count + 8 + KIND, 2u);
-        first = __shfl_sync(0xffffffffu, first, 0);
-        if (first >= n_coop)
-            break;
-    for (int ci = first; ci < min(first + 2, n_coop); ci++) {
+    int q_base = 0, q_k = 2, parity = 0;
+#define DRAW_NEXT()                                                                 \
+    do {                                                                            \
+        if (q_k == 2) {                                                             \
+            int f_ = 0;                                                             \
+            if (lane == 0)                                                          \
+                f_ = (int)atomicAdd(count + 8 + KIND, 2u);                          \
+            q_base = __shfl_sync(0xffffffffu, f_, 0);                               \
+            q_k = 0;                                                                \
+        }                                                                           \
+        nxt = q_base + q_k++;                                                       \
+        if (nxt >= n_coop)                                                          \
+            nxt = -1;                                                               \
+        nxt_tma = nxt >= 0 ? tma_prefetch<TMA>(ts, p, coop, KIND ? cap - 1 - nxt : nxt, &tmap, warp, lane) : 0;   \
+    } while (0)
+    int nxt, nxt_tma;
+    DRAW_NEXT();
+    while (nxt >= 0) {
+    {
+        const int ci = nxt, use_tma = nxt_tma;
         __syncwarp();
         const int ri = (int)__ldg(coop + (KIND ? cap - 1 - ci : ci));
         const Rec pb = load_rec(p.pbs + ri);
@@ -276,8 +388,25 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
 #define REF(l)    ((l) ? pb.ref[1] : pb.ref[0])
 
         // ---- DMVR: stage both unrefined windows, bilinear prediction, 25 SADs, refinement -------------
-        if (dmvr_luma) {   //@region dmvr_stage
-            {
+        if constexpr (TMA) if (use_tma) {   //@region dmvr_stage
+            // the copy engine has (or will have) put both windows into the staging area: move them into the padded
+            // window layout (core at sample column 2, no parity offset) and replicate the apron
+            mbar_wait(&ts.bar[warp], parity);
+            parity ^= 1;
+            const int l = lane >> 4, k = lane & 15, nw = (w + 8) >> 1;
+            if (k < nw) {
+                const int o = (pb.x0 + (MV0(l, 0) >> 4) - 3) & 7, sh = (o & 1) << 4;      // window column 0 inside the box
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(ts.box[warp][l]) + (o >> 1) + k;
+                uint32_t *dst = s.a.win + l * WUL + 2 * PWL + 1 + k;
+#pragma unroll 4
+                for (int r = 0; r < h + 7; r++, src += kBoxW / 2, dst += PWL)
+                    *dst = frc(src[0], src[1], sh);
+            }
+            stage_apron(s.a.win + l * WUL, PWL, 0, w + 7, h + 7, k, 16);
+        }
+        DRAW_NEXT();            // the staging area is free again: the next record's windows start now
+        if (dmvr_luma) {
+            if (!(TMA && use_tma)) {
                 const int l = lane >> 4;                    // lanes 0-15: list 0, lanes 16-31: list 1
                 stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h,
                             pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane & 15, 16);
@@ -290,7 +419,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 const int mx = MV0(l, 0) & 15, my = MV0(l, 1) & 15;
                 const int fx0 = vvct_dmvr_filters[mx][0], fx1 = vvct_dmvr_filters[mx][1];
                 const int fy0 = vvct_dmvr_filters[my][0], fy1 = vvct_dmvr_filters[my][1];
-                const int e = (pb.x0 + (MV0(l, 0) >> 4) - 3) & 1, c0 = 3 + e, sh = (c0 & 1) << 4;
+                const int e = (TMA && use_tma) ? 0 : (pb.x0 + (MV0(l, 0) >> 4) - 3) & 1, c0 = 3 + e, sh = (c0 & 1) << 4;
                 const int y = min(lane, h + 4);
                 const uint32_t *wp = s.a.win + l * WUL + (3 + y) * PWL + (c0 >> 1);
                 uint32_t hrow[10];
@@ -419,7 +548,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 UnitMC m;
                 m.woff = u * WUL;
                 if (dmvr) {
-                    const int e = (pb.x0 + (m0x >> 4) - 3) & 1;
+                    const int e = (TMA && use_tma) ? 0 : (pb.x0 + (m0x >> 4) - 3) & 1;
                     m.c0 = 2 + e + d_clip3((mvx >> 4) - (m0x >> 4), -2, 2);
                     m.r0 = 2 + d_clip3((mvy >> 4) - (m0y >> 4), -2, 2);
                 } else {
@@ -537,8 +666,8 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                     __syncwarp();                           // windows and first-pass rows are dead: reuse as gradient storage
                     if (lane < 2 * h) {
                         const int l = lane >= h, y = lane - l * h;
-                        uint32_t *g0 = reinterpret_cast<uint32_t *>(&s.b.grad[l * 2][y * 16]);
-                        uint32_t *g1 = reinterpret_cast<uint32_t *>(&s.b.grad[l * 2 + 1][y * 16]);
+                        uint32_t *g0 = reinterpret_cast<uint32_t *>(&s.b.grad[l * 2][y * GP]);
+                        uint32_t *g1 = reinterpret_cast<uint32_t *>(&s.b.grad[l * 2 + 1][y * GP]);
 #pragma unroll
                         for (int k = 0; k < 8; k++)
                             if (k < (w >> 1)) { g0[k] = gh[k]; g1[k] = gv[k]; }
@@ -552,7 +681,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
 #pragma unroll
                         for (int dx = -1; dx < 5; dx++) {
                             const int x = d_clip3(4 * bxi + dx, 0, w - 1);
-                            const int ti = (y + 1) * TP + 8 + x, gi = y * 16 + x;
+                            const int ti = (y + 1) * TP + 8 + x, gi = y * GP + x;
                             const int diff = (s.tile[0][ti] >> 4) - (s.tile[1][ti] >> 4);
                             const int th = (s.b.grad[0][gi] + s.b.grad[2][gi]) >> 1;
                             const int tv = (s.b.grad[1][gi] + s.b.grad[3][gi]) >> 1;
@@ -586,10 +715,10 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                         int a[4], b[4], o[4];
                         tile4(s, 0, x, y, a);
                         tile4(s, 1, x, y, b);
-                        const uint2 g0h = *reinterpret_cast<const uint2 *>(&s.b.grad[0][y * 16 + x]);
-                        const uint2 g0v = *reinterpret_cast<const uint2 *>(&s.b.grad[1][y * 16 + x]);
-                        const uint2 g1h = *reinterpret_cast<const uint2 *>(&s.b.grad[2][y * 16 + x]);
-                        const uint2 g1v = *reinterpret_cast<const uint2 *>(&s.b.grad[3][y * 16 + x]);
+                        const uint2 g0h = *reinterpret_cast<const uint2 *>(&s.b.grad[0][y * GP + x]);
+                        const uint2 g0v = *reinterpret_cast<const uint2 *>(&s.b.grad[1][y * GP + x]);
+                        const uint2 g1h = *reinterpret_cast<const uint2 *>(&s.b.grad[2][y * GP + x]);
+                        const uint2 g1v = *reinterpret_cast<const uint2 *>(&s.b.grad[3][y * GP + x]);
                         const int dh[4] = { lo16(g0h.x) - lo16(g1h.x), hi16(g0h.x) - hi16(g1h.x), lo16(g0h.y) - lo16(g1h.y), hi16(g0h.y) - hi16(g1h.y) };
                         const int dv[4] = { lo16(g0v.x) - lo16(g1v.x), hi16(g0v.x) - hi16(g1v.x), lo16(g0v.y) - lo16(g1v.y), hi16(g0v.y) - hi16(g1v.y) };
 #pragma unroll
@@ -684,9 +813,37 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
 #undef REF
     }
     }
+#undef DRAW_NEXT
 }
 
 }  // namespace
+
+// The luma plane of the reference ring as a 3-D tensor (x, y, picture) of 16-bit samples, box = one DMVR window.
+// cuTensorMapEncodeTiled is a host-side encoder in the driver library; it is fetched through the runtime so that the
+// library keeps linking against libcudart only.
+static int make_window_map(VVCCudaCtx *ctx, const InterK &p, CUtensorMap *map)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            return vvc_ctx_fail(ctx, VVC_CUDA_ERR_CUDA, "inter: cuTensorMapEncodeTiled is not available in this driver");
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[3] = { (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.nref };
+    const cuuint64_t strides[2] = { (cuuint64_t)p.rp[0] * 2, (cuuint64_t)p.rb[0] * 2 };
+    const cuuint32_t box[3] = { kBoxW, kBoxH, 1 }, estr[3] = { 1, 1, 1 };
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)p.ref[0], dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_CUDA, "inter: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VVC_CUDA_OK;
+}
 
 // spread == 2 (long launches): the PROF kernel goes to side stream 2 behind the chroma patch kernels
 int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &lists, int spread)
@@ -694,11 +851,24 @@ int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &li
 #ifndef INTER_WARP_CTAS
 #define INTER_WARP_CTAS 7                                        // persistent: 7 CTAs fit an SM (shared memory)
 #endif
+#ifndef INTER_WARP_CTAS_TMA
+#define INTER_WARP_CTAS_TMA 5                                    // with the staging area: 5
+#endif
     const int ctas = ceil_div(p.n, kWarps);
-    const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
-    inter_warp_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count);
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (ctx->inter_tma) {
+        if (make_window_map(ctx, p, &map))
+            return ctx->err;
+        const int grid = ctas < 148 * INTER_WARP_CTAS_TMA ? ctas : 148 * INTER_WARP_CTAS_TMA;
+        inter_warp_kernel<0, 1><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map);
+    } else {
+        const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
+        inter_warp_kernel<0, 0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map);
+    }
     VVC_LAUNCHED(ctx);
-    inter_warp_kernel<1><<<grid, kThreads, 0, spread == 2 ? ctx->side[2] : ctx->stream>>>(p, lists.coop, p.n, lists.count);
+    const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
+    inter_warp_kernel<1, 0><<<grid, kThreads, 0, spread == 2 ? ctx->side[2] : ctx->stream>>>(p, lists.coop, p.n, lists.count, map);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

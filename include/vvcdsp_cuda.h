@@ -64,6 +64,9 @@ const char *vvc_cuda_version(void);
  * coefficient sets holding +128 (the packed 16x2 / IDP.2A path carries coefficients -128..127); results identical, tests
  * compare the two. */
 #define VVC_CUDA_OPT_ALF_WIDE_MULTIPLY 2
+/* VVC_CUDA_OPT_INTER_TMA: 1 = the DMVR / BDOF records' reference windows are fetched by the copy engine (TMA box
+ * per window, one record ahead of the computation), 0 = staged by the warp's own loads.  Results identical. */
+#define VVC_CUDA_OPT_INTER_TMA 3
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
  * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs): lets foreign-language bindings verify their struct mirrors. */

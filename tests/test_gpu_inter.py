@@ -45,6 +45,24 @@ def test_inter_stage_bit_exact(ctx, w, h, seed, uniform, bd):
     assert np.array_equal(go[dm], oo[dm]), "DMVR outputs (refined vectors, min SAD, BDOF decision) differ"
 
 
+@pytest.mark.parametrize("tma", [0, 1])
+@pytest.mark.parametrize("w,h,seed,uniform", [(416, 240, 1, False), (136, 72, 5, True), (832, 480, 4, False), (1920, 1080, 6, False)])
+def test_inter_tma_staged_windows_bit_exact(ctx, w, h, seed, uniform, tma):
+    """VVC_CUDA_OPT_INTER_TMA on / off: DMVR windows fetched by the copy engine one record ahead (interior records) or
+    staged by the warp's own loads (always for records whose windows leave the picture); both against the oracle,
+    refined vectors included."""
+    gd, gr, refs, pbs, wp, prof = make_case(w, h, seed, mix=STRESS_MIX if seed != 6 else None, uniform=uniform)
+    ctx.set_option(abi.OPT_INTER_TMA, tma)
+    try:
+        gp, go = cuda_inter(ctx, gd, gr, refs, pbs, wp, prof)
+    finally:
+        ctx.set_option(abi.OPT_INTER_TMA, abi.INTER_TMA_DEFAULT)
+    od, oo = run_inter(util.oracle().vvco_inter_frame, gd, gr, refs, pbs, wp, prof)
+    util.assert_planes_equal(gd, gp, od, "cuda (tma=%d) vs oracle" % tma)
+    dm = (pbs["flags"] & abi.PB_DMVR) != 0
+    assert np.array_equal(go[dm], oo[dm])
+
+
 def test_inter_generic_kernel_matches(ctx):
     """The generic CTA-per-record kernel (any bit depth / alignment) and the 10-bit warp-per-record kernel agree."""
     gd, gr, refs, pbs, wp, prof = make_case(416, 240, 11, mix=STRESS_MIX)
