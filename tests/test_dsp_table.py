@@ -44,12 +44,27 @@ def test_hook_installs_the_documented_entries():
             for lw in range(7):
                 for lh in range(7):
                     assert bool(ptr(t.itx.itx[trh][trv][lw][lh])) == valid_cell(trh, trv, lw, lh), (trh, trv, lw, lh)
-    assert ptr(t.itx.transform_bdpcm) and ptr(t.itx.add_residual) and ptr(t.lmcs.filter)
-    # everything else keeps what the caller installed (here: nothing)
-    assert not ptr(t.itx.add_residual_joint) and not ptr(t.inter.avg) and not ptr(t.alf.classify) and not ptr(t.sao.band_filter[0])
-    for depth in (8, 12):
+    for depth in (10, 12):
         t = fresh_table(depth)
-        assert not ptr(t.lmcs.filter) and not ptr(t.itx.itx[0][0][2][2])
+        assert ptr(t.itx.transform_bdpcm) and ptr(t.itx.add_residual) and ptr(t.lmcs.filter)
+        assert ptr(t.itx.add_residual_joint) and ptr(t.itx.pred_residual_joint)
+        for ch in range(2):
+            for i in range(7):
+                for a in range(2):
+                    for b in range(2):
+                        assert ptr(t.inter.put[ch][i][a][b]) and ptr(t.inter.put_uni[ch][i][a][b]) and ptr(t.inter.put_uni_w[ch][i][a][b])
+        for name in ("avg", "w_avg", "put_ciip", "put_gpm", "fetch_samples", "bdof_fetch_samples", "prof_grad_filter", "apply_prof",
+                     "apply_prof_uni", "apply_prof_uni_w", "apply_bdof", "sad"):
+            assert ptr(getattr(t.inter, name)), name
+        assert all(ptr(t.inter.dmvr[a][b]) for a in range(2) for b in range(2))
+        assert all(ptr(t.sao.band_filter[i]) and ptr(t.sao.edge_filter[i]) for i in range(9))
+        assert ptr(t.alf.filter[0]) and ptr(t.alf.filter[1]) and ptr(t.alf.filter_cc) and ptr(t.alf.classify) and ptr(t.alf.recon_coeff_and_clip)
+        assert all(ptr(t.lf.filter_luma[d]) and ptr(t.lf.filter_chroma[d]) and ptr(t.lf.ladf_level[d]) for d in range(2))
+        # entries that take the decoder's VVCLocalContext, and the SAO restore pass (takes SAOParams), keep what the caller installed
+        assert not ptr(t.intra.intra_pred) and not ptr(t.intra.intra_cclm_pred) and not ptr(t.intra.lmcs_scale_chroma)
+        assert not ptr(t.sao.edge_restore[0])
+    t = fresh_table(8)                      # 8-bit pictures (pixel = uint8_t): nothing is installed
+    assert not ptr(t.lmcs.filter) and not ptr(t.itx.itx[0][0][2][2]) and not ptr(t.inter.avg)
 
 
 def test_reference_cells_are_the_cells_we_install():
