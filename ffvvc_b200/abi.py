@@ -313,6 +313,7 @@ class VVCCudaReconDesc(C.Structure):
         ("coeff_format", C.c_int32), ("ref_slots", C.c_uint32), ("quant", C.c_void_p), ("scaling", C.c_void_p),
         ("lmcs_inv_lut", C.c_void_p), ("lmcs_ctb_enable", C.c_void_p),
         ("inloop", VVCCudaInloopDesc),
+        ("arena", C.c_void_p), ("arena_bytes", C.c_size_t),
     ]
 
 
@@ -326,3 +327,44 @@ INTRA_PB_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("w", np.uint8)
 CIIP_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("w", np.uint8), ("h", np.uint8), ("c_idx", np.uint8),
                        ("pic", np.uint8), ("intra_weight", np.uint8), ("reserved", np.uint8, 3)])
 assert INTRA_PB_DTYPE.itemsize == 24 and CIIP_DTYPE.itemsize == 12
+
+
+def recon_arena(handle, geom1, alloc, *, pbs, wp, prof, tbs, coeffs, coeff_format, quant, scaling, inv_lut, maps, sao, alf, sets,
+                ref_slots=0, log2_transform_range=15):
+    """One picture's descriptors in ONE arena (vvc_cuda_recon_arena_size / _bind, include/vvcdsp_cuda.h): returns
+    (VVCCudaReconDesc, VVCCudaDeblockMaps, arena).  handle: the loaded library; geom1: FrameGeom of one picture;
+    alloc(nbytes) -> (object to keep alive, address) of 256-byte aligned (ideally pinned) host memory; maps[dir][c]:
+    (rows, pitch) DBK_EDGE arrays of this picture.  What the parser would write in place is copied here once."""
+    f = frame_desc(geom1, [0, 0, 0], [0, 0, 0], [0, 0, 0])
+    d, m = VVCCudaReconDesc(), VVCCudaDeblockMaps()
+    d.n_pbs, d.n_wp, d.n_prof, d.n_tbs, d.n_coeffs = len(pbs), len(wp), len(prof), len(tbs), len(coeffs)
+    d.coeff_format, d.log2_transform_range, d.ref_slots = coeff_format, log2_transform_range, ref_slots
+    for dr in range(2):
+        for c in range(3):
+            rows, pitch = deblock_map_shape(geom1, dr, c)
+            m.pitch[dr][c], m.rows[dr][c], m.size[dr][c] = pitch, rows, rows * pitch
+    d.inloop.deblock = C.pointer(m)
+    size = handle.vvc_cuda_recon_arena_size(C.byref(f), C.byref(d))
+    assert size > 0
+    keep, addr = alloc(size)
+    assert addr % 256 == 0
+    rc = handle.vvc_cuda_recon_arena_bind(C.byref(f), C.byref(d), C.byref(m), addr)
+    assert rc == 0, rc
+
+    def put(dst, a):
+        a = np.ascontiguousarray(a)
+        assert addr <= dst and dst + a.nbytes <= addr + size
+        C.memmove(dst, a.ctypes.data, a.nbytes)
+
+    put(d.pbs, pbs); put(d.wp, wp); put(d.prof, prof); put(d.tbs, tbs); put(d.coeffs, coeffs)
+    if quant is not None:
+        put(d.quant, quant); put(d.scaling, scaling)
+    else:
+        d.quant, d.scaling = None, None
+    put(d.lmcs_inv_lut, inv_lut)
+    d.lmcs_fwd_lut, d.lmcs_rects, d.lmcs_ctb_enable = None, None, None
+    for dr in range(2):
+        for c in range(3):
+            put(m.edge[dr][c], maps[dr][c])
+    put(d.inloop.sao, sao); put(d.inloop.alf, alf); put(d.inloop.alf_sets, sets)
+    return d, m, keep

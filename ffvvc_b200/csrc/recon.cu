@@ -46,41 +46,94 @@ static inline VVCCudaFrame one_picture(const VVCCudaFrame *f, int k)
     return o;
 }
 
-struct Carve {
-    uint8_t *at;
-    template <typename T> T *take(size_t n) { T *p = (T *)at; at += align_up(n * sizeof(T), 256); return p; }
-};
+// The arrays of one picture's descriptors in the order they are laid out - in a device slot, and in a caller's pinned
+// arena (vvc_cuda_recon_arena_bind), which is the same layout so that it goes up as ONE copy.  Every array takes at least
+// one element and is rounded up to 256 bytes.
+enum { IT_PBS, IT_WP, IT_PROF, IT_RECTS, IT_FWD, IT_INV, IT_COEFFS, IT_TBS, IT_QUANT, IT_SCALING, IT_CTB_EN,
+       IT_EDGE0, IT_SAO = IT_EDGE0 + 6, IT_ALF, IT_SETS, IT_COUNT };
 
-// Bytes one picture's descriptors take in a slot: must mirror the Carve::take() sequence of the upload below
-// exactly (every array takes at least one element, every take is rounded up to 256 bytes).
-size_t desc_bytes(const VVCCudaFrame *f, const VVCCudaReconDesc *d)
+struct Item { const void *host; size_t bytes; size_t off; };
+
+// Fills items[] (host pointer as the descriptor holds it, payload bytes, offset in the slot); returns the slot bytes
+// including the device-only refined-vector array at its end (*dmvr_off).
+size_t layout(const VVCCudaFrame *f, const VVCCudaReconDesc *d, Item items[IT_COUNT], size_t *dmvr_off)
 {
     const int planes = f->chroma_format_idc ? 3 : 1;
     const size_t n_ctb = (size_t)ceil_div(f->width, 1 << f->ctb_log2) * ceil_div(f->height, 1 << f->ctb_log2);
-    size_t n = 0;
-    auto take = [&n](size_t count, size_t elem) { n += align_up((count > 0 ? count : 1) * elem, 256); };
-    take(d->n_pbs > 0 ? d->n_pbs : 0, sizeof(VVCCudaPB));
-    take(d->n_wp > 0 ? d->n_wp : 0, sizeof(VVCCudaWP));
-    take(d->n_prof > 0 ? d->n_prof : 0, sizeof(VVCCudaProf));
-    take(d->n_pbs > 0 ? d->n_pbs : 0, sizeof(VVCCudaDmvrOut));
-    take(d->n_lmcs_rects > 0 ? d->n_lmcs_rects : 0, sizeof(VVCCudaRect));
-    take((size_t)1 << f->bit_depth, sizeof(uint16_t));
-    take((size_t)1 << f->bit_depth, sizeof(uint16_t));
-    take(d->n_coeffs, d->coeff_format == VVC_CUDA_COEFF_WINDOW16 ? sizeof(int16_t) : sizeof(int32_t));
-    take(d->n_tbs > 0 ? d->n_tbs : 0, sizeof(VVCCudaTB));
-    take(d->n_tbs > 0 ? d->n_tbs : 0, sizeof(VVCCudaTBQuant));
-    take(1, sizeof(VVCCudaScalingList));
-    take(n_ctb, sizeof(uint8_t));
+    const size_t lut = (size_t)2 << f->bit_depth;
+    const size_t npb = d->n_pbs > 0 ? d->n_pbs : 0, ntb = d->n_tbs > 0 ? d->n_tbs : 0;
+    const VVCCudaDeblockMaps *m = d->inloop.deblock;
+    for (int i = 0; i < IT_COUNT; i++) items[i] = Item{ nullptr, 0, 0 };
+    items[IT_PBS]     = Item{ d->pbs, npb * sizeof(VVCCudaPB), 0 };
+    items[IT_WP]      = Item{ d->wp, (size_t)(d->n_wp > 0 ? d->n_wp : 0) * sizeof(VVCCudaWP), 0 };
+    items[IT_PROF]    = Item{ d->prof, (size_t)(d->n_prof > 0 ? d->n_prof : 0) * sizeof(VVCCudaProf), 0 };
+    items[IT_RECTS]   = Item{ d->lmcs_rects, (size_t)(d->n_lmcs_rects > 0 ? d->n_lmcs_rects : 0) * sizeof(VVCCudaRect), 0 };
+    items[IT_FWD]     = Item{ d->lmcs_fwd_lut, lut, 0 };
+    items[IT_INV]     = Item{ d->lmcs_inv_lut, lut, 0 };
+    items[IT_COEFFS]  = Item{ d->coeffs, d->n_coeffs * (d->coeff_format == VVC_CUDA_COEFF_WINDOW16 ? sizeof(int16_t) : sizeof(int32_t)), 0 };
+    items[IT_TBS]     = Item{ d->tbs, ntb * sizeof(VVCCudaTB), 0 };
+    items[IT_QUANT]   = Item{ d->quant, ntb * sizeof(VVCCudaTBQuant), 0 };
+    items[IT_SCALING] = Item{ d->scaling, sizeof(VVCCudaScalingList), 0 };
+    items[IT_CTB_EN]  = Item{ d->lmcs_ctb_enable, n_ctb, 0 };
     for (int dir = 0; dir < 2; dir++)
-        for (int c = 0; c < planes; c++)
-            take(d->inloop.deblock->size[dir][c] > 0 ? d->inloop.deblock->size[dir][c] : 0, sizeof(VVCCudaDbkEdge));
-    take(n_ctb, sizeof(VVCCudaSAOCtb));
-    take(n_ctb, sizeof(VVCCudaALFCtb));
-    take(1, sizeof(VVCCudaALFSets));
-    return n + 256;
+        for (int c = 0; c < 3; c++)
+            items[IT_EDGE0 + dir * 3 + c] = Item{ m && c < planes ? m->edge[dir][c] : nullptr,
+                                                  m && c < planes && m->size[dir][c] > 0 ? (size_t)m->size[dir][c] * sizeof(VVCCudaDbkEdge) : 0, 0 };
+    items[IT_SAO]     = Item{ d->inloop.sao, n_ctb * sizeof(VVCCudaSAOCtb), 0 };
+    items[IT_ALF]     = Item{ d->inloop.alf, n_ctb * sizeof(VVCCudaALFCtb), 0 };
+    items[IT_SETS]    = Item{ d->inloop.alf_sets, sizeof(VVCCudaALFSets), 0 };
+    size_t n = 0;
+    for (int i = 0; i < IT_COUNT; i++) {
+        items[i].off = n;
+        n += align_up(items[i].bytes ? items[i].bytes : 1, 256);
+    }
+    *dmvr_off = n;
+    return n + align_up((npb ? npb : 1) * sizeof(VVCCudaDmvrOut), 256) + 256;
 }
 
 }  // namespace
+
+// ---- one pinned arena per picture --------------------------------------------------------------------------------
+// vvc_cuda_recon_arena_size(): bytes of the arena for a picture whose descriptor has its counts (n_pbs, n_wp, n_prof,
+// n_lmcs_rects, n_tbs, n_coeffs, coeff_format, inloop.deblock->size[][]) filled in.  vvc_cuda_recon_arena_bind(): points
+// every array of the descriptor (and of its VVCCudaDeblockMaps) into the arena, in the layout the device slot uses; the
+// caller - the parser - then writes its records straight through those pointers, and the host entry moves the picture's
+// descriptors with ONE cudaMemcpyAsync instead of one per array.
+extern "C" size_t vvc_cuda_recon_arena_size(const VVCCudaFrame *frame, const VVCCudaReconDesc *desc)
+{
+    if (!frame || !desc || !desc->inloop.deblock)
+        return 0;
+    Item it[IT_COUNT];
+    size_t dm;
+    layout(frame, desc, it, &dm);
+    return dm;                                   // the refined-vector array is device-only: not part of the arena
+}
+
+extern "C" int vvc_cuda_recon_arena_bind(const VVCCudaFrame *frame, VVCCudaReconDesc *desc, VVCCudaDeblockMaps *maps, void *arena)
+{
+    if (!frame || !desc || !maps || !arena || ((uintptr_t)arena & 255))
+        return VVC_CUDA_ERR_ARG;
+    desc->inloop.deblock = maps;
+    Item it[IT_COUNT];
+    size_t dm;
+    layout(frame, desc, it, &dm);
+    uint8_t *a = (uint8_t *)arena;
+    desc->pbs = (const VVCCudaPB *)(a + it[IT_PBS].off);           desc->wp = (const VVCCudaWP *)(a + it[IT_WP].off);
+    desc->prof = (const VVCCudaProf *)(a + it[IT_PROF].off);       desc->lmcs_rects = (const VVCCudaRect *)(a + it[IT_RECTS].off);
+    desc->lmcs_fwd_lut = (const uint16_t *)(a + it[IT_FWD].off);   desc->lmcs_inv_lut = (const uint16_t *)(a + it[IT_INV].off);
+    desc->coeffs = (int32_t *)(a + it[IT_COEFFS].off);             desc->tbs = (const VVCCudaTB *)(a + it[IT_TBS].off);
+    desc->quant = (const VVCCudaTBQuant *)(a + it[IT_QUANT].off);  desc->scaling = (const VVCCudaScalingList *)(a + it[IT_SCALING].off);
+    desc->lmcs_ctb_enable = a + it[IT_CTB_EN].off;
+    for (int dir = 0; dir < 2; dir++)
+        for (int c = 0; c < 3; c++)
+            maps->edge[dir][c] = (VVCCudaDbkEdge *)(a + it[IT_EDGE0 + dir * 3 + c].off);
+    desc->inloop.sao = (const VVCCudaSAOCtb *)(a + it[IT_SAO].off);
+    desc->inloop.alf = (const VVCCudaALFCtb *)(a + it[IT_ALF].off);
+    desc->inloop.alf_sets = (const VVCCudaALFSets *)(a + it[IT_SETS].off);
+    desc->arena = arena;
+    desc->arena_bytes = dm;
+    return VVC_CUDA_OK;
+}
 
 // Host entry.  Three streams: copy_in (H2D of picture k's descriptors), the context stream (kernels)
 // and copy_out (D2H of finished pictures); two descriptor slots and two picture slots rotate, events
@@ -107,7 +160,9 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
     const size_t psz = align_up(vvc_stage_frame_size(&out1), 256), rsz = align_up(vvc_stage_frame_size(refs), 256);
     size_t dsz = 0;
     for (int k = 0; k < out->batch; k++) {
-        const size_t n = desc_bytes(out, &descs[k]);
+        Item it[IT_COUNT];
+        size_t dm;
+        const size_t n = layout(out, &descs[k], it, &dm);
         dsz = n > dsz ? n : dsz;
     }
     // layout: [refs][cur x2][out x2][desc slot x2]
@@ -119,6 +174,7 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
     // host pictures are staged once per call.
     cudaPointerAttributes attr;
     const bool refs_on_device = cudaPointerGetAttributes(&attr, refs->data[0]) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    const bool out_on_device = cudaPointerGetAttributes(&attr, out->data[0]) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     cudaGetLastError();                                    // unregistered host memory reports an error on old drivers: not ours
     VVCCudaFrame drefs;
     if (refs_on_device)
@@ -153,8 +209,11 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
         const VVCCudaReconDesc *h = &descs[k];
         VVCCudaFrame dcur, dout;
         vvc_stage_frame_layout(&out1, base + rsz + sl * psz, &dcur);
-        vvc_stage_frame_layout(&out1, base + rsz + (2 + sl) * psz, &dout);
-        Carve cv = { base + rsz + 4 * psz + sl * dsz };
+        if (out_on_device)
+            dout = one_picture(out, k);                    // the output ring lives in HBM (it is the DPB of later pictures)
+        else
+            vvc_stage_frame_layout(&out1, base + rsz + (2 + sl) * psz, &dout);
+        uint8_t *slot = base + rsz + 4 * psz + sl * dsz;
         VVCCudaReconDesc dd = *h;
         VVCCudaDeblockMaps dm = *h->inloop.deblock;
         if (k >= 2) {
@@ -163,41 +222,36 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
         }
         if (upload_refs(h->ref_slots && refs->batch <= 32 ? (uint64_t)h->ref_slots : ~0ull))
             return ctx->err;
-#define UP(dst_ptr, src_ptr, type, count)                                                                             \
-        do {                                                                                                          \
-            type *dev_ = cv.take<type>((count) > 0 ? (count) : 1);                                                    \
-            if ((src_ptr) && (count) > 0)                                                                             \
-                VVC_TRY(ctx, cudaMemcpyAsync(dev_, (src_ptr), (size_t)(count) * sizeof(type), cudaMemcpyHostToDevice, cin)); \
-            dst_ptr = (src_ptr) ? dev_ : NULL;                                                                        \
-        } while (0)
-        UP(dd.pbs, h->pbs, VVCCudaPB, h->n_pbs);
-        UP(dd.wp, h->wp, VVCCudaWP, h->n_wp);
-        UP(dd.prof, h->prof, VVCCudaProf, h->n_prof);
-        VVCCudaDmvrOut *ddm = cv.take<VVCCudaDmvrOut>(h->n_pbs > 0 ? h->n_pbs : 1);
-        dd.dmvr_out = h->dmvr_out ? ddm : NULL;
-        UP(dd.lmcs_rects, h->lmcs_rects, VVCCudaRect, h->n_lmcs_rects);
-        UP(dd.lmcs_fwd_lut, h->lmcs_fwd_lut, uint16_t, 1 << out->bit_depth);
-        UP(dd.lmcs_inv_lut, h->lmcs_inv_lut, uint16_t, 1 << out->bit_depth);
-        if (h->coeff_format == VVC_CUDA_COEFF_WINDOW16) {
-            int16_t *dco = NULL;
-            UP(dco, (const int16_t *)h->coeffs, int16_t, (long long)h->n_coeffs);
-            dd.coeffs = (int32_t *)dco;
+        Item it[IT_COUNT];
+        size_t dmvr_off;
+        layout(out, h, it, &dmvr_off);
+        // A descriptor bound to an arena (vvc_cuda_recon_arena_bind) whose arrays still lie where the binding put them goes
+        // up as one copy; anything else array by array.
+        bool packed = h->arena && h->arena_bytes == dmvr_off;
+        for (int i = 0; packed && i < IT_COUNT; i++)
+            packed = !it[i].host || it[i].host == (const uint8_t *)h->arena + it[i].off;
+        if (packed) {
+            VVC_TRY(ctx, cudaMemcpyAsync(slot, h->arena, dmvr_off, cudaMemcpyHostToDevice, cin));
         } else {
-            UP(dd.coeffs, h->coeffs, int32_t, (long long)h->n_coeffs);
+            for (int i = 0; i < IT_COUNT; i++)
+                if (it[i].host && it[i].bytes)
+                    VVC_TRY(ctx, cudaMemcpyAsync(slot + it[i].off, it[i].host, it[i].bytes, cudaMemcpyHostToDevice, cin));
         }
-        UP(dd.tbs, h->tbs, VVCCudaTB, h->n_tbs);
-        UP(dd.quant, h->quant, VVCCudaTBQuant, h->n_tbs);
-        UP(dd.scaling, h->scaling, VVCCudaScalingList, 1);
-        UP(dd.lmcs_ctb_enable, h->lmcs_ctb_enable, uint8_t, n_ctb);
+#define DEV(i, type) (it[i].host ? (type)(slot + it[i].off) : (type)NULL)
+        dd.pbs = DEV(IT_PBS, const VVCCudaPB *);                dd.wp = DEV(IT_WP, const VVCCudaWP *);
+        dd.prof = DEV(IT_PROF, const VVCCudaProf *);            dd.lmcs_rects = DEV(IT_RECTS, const VVCCudaRect *);
+        dd.lmcs_fwd_lut = DEV(IT_FWD, const uint16_t *);        dd.lmcs_inv_lut = DEV(IT_INV, const uint16_t *);
+        dd.coeffs = DEV(IT_COEFFS, int32_t *);                  dd.tbs = DEV(IT_TBS, const VVCCudaTB *);
+        dd.quant = DEV(IT_QUANT, const VVCCudaTBQuant *);       dd.scaling = DEV(IT_SCALING, const VVCCudaScalingList *);
+        dd.lmcs_ctb_enable = DEV(IT_CTB_EN, const uint8_t *);
         for (int dir = 0; dir < 2; dir++)
             for (int c = 0; c < planes; c++)
-                UP(dm.edge[dir][c], h->inloop.deblock->edge[dir][c], VVCCudaDbkEdge, (long long)h->inloop.deblock->size[dir][c]);
-        UP(dd.inloop.sao, h->inloop.sao, VVCCudaSAOCtb, n_ctb);
-        UP(dd.inloop.alf, h->inloop.alf, VVCCudaALFCtb, n_ctb);
-        UP(dd.inloop.alf_sets, h->inloop.alf_sets, VVCCudaALFSets, 1);
-#undef UP
-        if (cv.at > base + rsz + 4 * psz + (size_t)(sl + 1) * dsz)
-            return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "recon_host: descriptor slot overflow (desc_bytes out of step with the upload)");
+                dm.edge[dir][c] = DEV(IT_EDGE0 + dir * 3 + c, VVCCudaDbkEdge *);
+        dd.inloop.sao = DEV(IT_SAO, const VVCCudaSAOCtb *);     dd.inloop.alf = DEV(IT_ALF, const VVCCudaALFCtb *);
+        dd.inloop.alf_sets = DEV(IT_SETS, const VVCCudaALFSets *);
+#undef DEV
+        VVCCudaDmvrOut *ddm = (VVCCudaDmvrOut *)(slot + dmvr_off);
+        dd.dmvr_out = h->dmvr_out ? ddm : NULL;
         dd.inloop.deblock = &dm;
         dd.inloop.alf_sets_per_frame = 0;
         VVC_TRY(ctx, cudaEventRecord(ctx->ev[1 + sl], cin));
@@ -209,7 +263,7 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
             return ctx->err;
         VVC_TRY(ctx, cudaEventRecord(ctx->ev[3 + sl], run));
         VVC_TRY(ctx, cudaStreamWaitEvent(cout, ctx->ev[3 + sl], 0));
-        {
+        if (!out_on_device) {
             const VVCCudaFrame hk = one_picture(out, k);
             cudaStream_t saved = ctx->stream;
             ctx->stream = cout;

@@ -79,6 +79,9 @@ def load():
     RP = C.POINTER(abi.VVCCudaReconDesc)
     lib.vvc_cuda_recon_frame.argtypes = [CTX, FP, FP, FP, RP]
     lib.vvc_cuda_recon_frame_host.argtypes = [CTX, FP, FP, RP]
+    lib.vvc_cuda_recon_arena_size.argtypes = [FP, RP]
+    lib.vvc_cuda_recon_arena_size.restype = C.c_size_t
+    lib.vvc_cuda_recon_arena_bind.argtypes = [FP, RP, C.POINTER(abi.VVCCudaDeblockMaps), C.c_void_p]
     lib.vvc_cuda_ctx_set_option.argtypes = [CTX, C.c_int, C.c_int]
     lib.vvc_cuda_intra_leaf_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p]
     lib.vvc_cuda_intra_leaf_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]

@@ -505,6 +505,10 @@ typedef struct VVCCudaReconDesc {
     const uint8_t     *lmcs_ctb_enable;
     /* DEBLOCK_V, DEBLOCK_H, SAO, ALF */
     VVCCudaInloopDesc  inloop;
+    /* _host entry: set by vvc_cuda_recon_arena_bind() - all arrays above live in this one (pinned) block, in the device
+     * slot's own layout, and go up as one copy.  NULL = arrays anywhere, one copy each. */
+    const void        *arena;
+    size_t             arena_bytes;
 } VVCCudaReconDesc;
 
 /* Device memory everywhere.  cur: the picture (ring) being reconstructed: prediction, residual and
@@ -517,6 +521,13 @@ int vvc_cuda_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCuda
  * reconstructed and picture k-2 is copied out.  refs: the DPB ring, either host memory (copied in once per
  * call) or device memory (a GPU-resident DPB, e.g. earlier outputs kept in HBM: used in place).  Returns when
  * all output pictures (and dmvr_out arrays) are in host memory. */
+/* One pinned arena per picture.  Fill in the descriptor's counts (n_pbs, n_wp, n_prof, n_lmcs_rects, n_tbs, n_coeffs,
+ * coeff_format) and maps->size[][] / pitch / rows, ask for the size, allocate (256-byte aligned, ideally pinned), bind:
+ * every array pointer of `desc` and `maps` then points into the arena and the caller writes its records through them.
+ * Optional arrays may be reset to NULL afterwards.  vvc_cuda_recon_frame_host() uploads a bound descriptor with a single
+ * copy.  `out` / `refs` of that entry may each be host or device memory (a device `out` ring stays in HBM: no copy back). */
+size_t vvc_cuda_recon_arena_size(const VVCCudaFrame *frame, const VVCCudaReconDesc *desc);
+int    vvc_cuda_recon_arena_bind(const VVCCudaFrame *frame, VVCCudaReconDesc *desc, VVCCudaDeblockMaps *maps, void *arena);
 int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
                               const VVCCudaReconDesc *descs);
 

@@ -182,3 +182,49 @@ def test_recon_4k_bit_exact(ctx):
     ctx.recon_frame(out.desc, cur.desc, refs.desc, d)
     ctx.sync()
     util.assert_planes_equal(gr, out.to_numpy(), want, "recon_frame 4K vs oracle chain")
+
+
+def test_recon_host_entry_arena_and_device_output(ctx):
+    """One pinned arena per picture (vvc_cuda_recon_arena_bind: a single upload per picture) and an output ring that stays
+    in HBM (device `out`): same pictures as the oracle chain."""
+    import torch
+    from ffvvc_b200 import device, lib
+    batch = 3
+    case = build(416, 240, batch, 51, "window_q")
+    g1, gr = case["g1"], case["gr"]
+    want = oracle_chain(case)
+    n_ctb = g1.ctb_count
+    keep = []
+
+    def alloc(n):
+        t = torch.empty(n + 256, dtype=torch.uint8).pin_memory()
+        keep.append(t)
+        return t, (t.data_ptr() + 255) & ~255
+
+    descs = (abi.VVCCudaReconDesc * batch)()
+    for k in range(batch):
+        pb = case["pbs"][case["pbs"]["pic"] == k].copy()
+        pb["pic"] = 0
+        of_k = case["tbs"]["pic"] == k
+        tb = case["tbs"][of_k].copy()
+        tb["pic"] = 0
+        lo = int(tb["coeff_offset"].min())
+        hi = int((tb["coeff_offset"].astype(np.int64) + tb["nzw"].astype(np.int64) * tb["nzh"].astype(np.int64)).max())
+        tb["coeff_offset"] -= lo
+        d, m, a = abi.recon_arena(lib.load(), g1, alloc, pbs=pb, wp=case["wp"], prof=case["prof"], tbs=tb, coeffs=case["coeffs"][lo:hi],
+                                  coeff_format=case["fmt"], quant=case["quant"][of_k], scaling=case["sl"], inv_lut=case["inv"],
+                                  maps=[[case["maps"][dr][c][k] for c in range(3)] for dr in range(2)],
+                                  sao=case["sao"][k * n_ctb:(k + 1) * n_ctb], alf=case["alf"][k * n_ctb:(k + 1) * n_ctb], sets=case["sets"])
+        keep += [m, a]
+        C.memmove(C.byref(descs[k]), C.byref(d), C.sizeof(d))
+        descs[k].inloop.deblock = C.pointer(m)
+    h_refs = [torch.from_numpy(p.view(np.int16)).pin_memory() for p in case["refs"]]
+    h_out = [torch.zeros_like(t).pin_memory() for t in h_refs]
+    f_refs = abi.frame_desc(gr, [t.data_ptr() for t in h_refs], [t.stride(1) * 2 for t in h_refs], [t.stride(0) * 2 for t in h_refs])
+    f_out = abi.frame_desc(gr, [t.data_ptr() for t in h_out], [t.stride(1) * 2 for t in h_out], [t.stride(0) * 2 for t in h_out])
+    ctx.recon_frame_host(f_out, f_refs, descs)
+    util.assert_planes_equal(gr, [t.numpy().view(np.uint16) for t in h_out], want, "arena-bound descriptors vs oracle chain")
+    d_out = device.DeviceFrames(gr)
+    ctx.recon_frame_host(d_out.desc, f_refs, descs)          # the output ring stays on the device
+    ctx.sync()
+    util.assert_planes_equal(gr, d_out.to_numpy(), want, "device-resident output ring vs oracle chain")
