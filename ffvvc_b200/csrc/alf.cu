@@ -39,7 +39,8 @@ struct AlfSmem {
     alignas(16) pel     chroma[2][TH / 2 + 4][CP];
     alignas(16) ushort4 cell[TH / 2 + 2][TW / 2 + 2];
     // per 4x4 block: 12 coefficients as IDP.2A words (f, 0, 0, f), 12 clip values in both halves, and one word of class
-    // information for the wide-coefficient path (bit 0: some |f| == 128, bits 8..: class, bits 16..: transpose).  25 words
+    // information (bit 0: some f == +128 -> wide path, bit 1: no clip can bind -> linear path, bits 8..: class, bits 16..:
+    // transpose, bits 20..31: sum of the coefficients).  25 words
     // per block: an odd pitch, so the blocks a warp reads side by side sit in different banks.
     alignas(16) uint32_t coef[(TH / 4) * (TW / 4)][25];
 };
@@ -103,12 +104,12 @@ __constant__ int8_t c_chroma_tap[6][2]  = { {2, 0}, {1, 1}, {1, 0}, {1, -1}, {0,
 // One 4x1 strip with 32-bit multiplies: the path of coefficient sets that hold +128, which does not fit the signed byte
 // of the IDP.2A form (and the comparison path of VVC_CUDA_OPT_ALF_WIDE_MULTIPLY).  Rare, so written for few registers
 // (rolled loops, coefficients fetched per tap) and kept out of line: the packed path's registers and code are unaffected.
-// luma: info = the block's class word (sm.coef[..][24]); chroma: info = -1 - alt.
+// luma: info = the block's class word (sm.coef[..][24]), alt = -1; chroma: alt = the CTB's alternative filter.
 __device__ __noinline__ uint2 alf_strip_wide(const pel *p0, int d1, int d2, int d3, bool near_vb, int bd,
-                                             const VVCCudaALFSets *sets, int set, int info)
+                                             const VVCCudaALFSets *sets, int set, uint32_t info, int alt)
 {
-    const bool chroma = info < 0;
-    const int cls = (info >> 8) & 0xff, tr = (info >> 16) & 3, alt = -1 - info;
+    const bool chroma = alt >= 0;
+    const int cls = (info >> 8) & 0xff, tr = (info >> 16) & 3;
     const int16_t *ff;
     const uint8_t *ci = nullptr;
     if (chroma)        { ff = sets->chroma_coeff[alt]; ci = sets->chroma_clip_idx[alt]; }
@@ -227,12 +228,13 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
             // alf_strip_wide() with 32-bit multiplies.
             uint32_t *out = sm.coef[b];
             const int set = a.filt_set_idx_y;
-            int wide = 0;
+            int wide = 0, clips = 0, fsum = 0;        // clips: some clip index other than 0 (a clip of 1 << bd never binds)
             if (set < 16) {
                 const int16_t *f = vvct_alf_fix_filt_coeff[vvct_alf_class_to_filt_map[set][cls]];
 #pragma unroll
                 for (int j = 0; j < 12; j++) {
                     const uint32_t fb = (uint32_t)f[c_perm[tr][j]] & 0xff, cv = 1u << bd;
+                    fsum += f[c_perm[tr][j]];
                     out[j]      = fb | (fb << 24);
                     out[12 + j] = cv | (cv << 16);
                 }
@@ -244,11 +246,13 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                     const int s = c_perm[tr][j];
                     const uint32_t fb = (uint32_t)f[s] & 0xff, cv = 1u << (bd - c_clip_shift[ci[s]]);
                     wide |= f[s] > 127;
+                    clips |= ci[s];
+                    fsum += f[s];
                     out[j]      = fb | (fb << 24);
                     out[12 + j] = cv | (cv << 16);
                 }
             }
-            out[24] = (uint32_t)(wide | p.wide_multiply) | ((uint32_t)cls << 8) | ((uint32_t)tr << 16);
+            out[24] = (uint32_t)(wide | p.wide_multiply) | (clips ? 0u : 2u) | ((uint32_t)cls << 8) | ((uint32_t)tr << 16) | ((uint32_t)fsum << 20);
         }
         __syncthreads();
     }
@@ -281,6 +285,7 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                 const uint2 c01 = *reinterpret_cast<const uint2 *>(p0);
                 const uint32_t ncur[2] = { __vneg2(c01.x), __vneg2(c01.y) };
                 int sum[4] = { 0, 0, 0, 0 };
+                const bool linear = cf[24] & 2;
 #define ALF_ROW(w, row, lo, hi)                                                        \
                 {                                                                      \
                     const pel *rp_ = (row);                                            \
@@ -298,6 +303,19 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                     const uint32_t fw_ = (fword), c2_ = (cword), nc2_ = (~c2_) + 0x00010001u;                                          \
                     ALF_PAIR(0, wp, wm, off) ALF_PAIR(1, wp, wm, off)                  \
                 }
+// the linear form: with every clip at 1 << bd no difference is ever clipped, so sum f (n1 - cur + n2 - cur) =
+// sum f (n1 + n2) - 2 cur sum f; one packed add and the two IDP.2A per tap and sample pair
+#define ALF_TAPL(k, wp, wm, off)                                                       \
+                {                                                                      \
+                    const uint32_t fw_ = cf[k];                                        \
+                    ALF_PAIRL(0, wp, wm, off) ALF_PAIRL(1, wp, wm, off)                \
+                }
+#define ALF_PAIRL(j_, wp, wm, off)                                                     \
+                    {                                                                  \
+                        const uint32_t s_ = ALF_AT(wp, 2 * (j_) + (off)) + ALF_AT(wm, 2 * (j_) - (off));                               \
+                        sum[2 * (j_)] = __dp2a_lo((int)s_, (int)fw_, sum[2 * (j_)]);  \
+                        sum[2 * (j_) + 1] = __dp2a_hi((int)s_, (int)fw_, sum[2 * (j_) + 1]);                                          \
+                    }
 #define ALF_PAIR(j_, wp, wm, off)                                                      \
                     {                                                                  \
                         const uint32_t a_ = __vmaxs2(__viaddmin_s16x2(ALF_AT(wp, 2 * (j_) + (off)), ncur[j_], c2_), nc2_);             \
@@ -306,6 +324,33 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                         sum[2 * (j_)] = __dp2a_lo((int)s_, (int)fw_, sum[2 * (j_)]);  \
                         sum[2 * (j_) + 1] = __dp2a_hi((int)s_, (int)fw_, sum[2 * (j_) + 1]);                                          \
                     }
+                const int cur[4] = { (int)(c01.x & 0xffff), (int)(c01.x >> 16), (int)(c01.y & 0xffff), (int)(c01.y >> 16) };
+                if (linear) {
+                    {
+                        uint32_t w0[6];
+                        ALF_ROW(w0, p0, 2, 2)
+                        ALF_TAPL(9, w0, w0, 3) ALF_TAPL(10, w0, w0, 2) ALF_TAPL(11, w0, w0, 1)
+                    }
+                    {
+                        uint32_t wp[6], wm[6];
+                        ALF_ROW(wp, p0 + d1, 1, 1) ALF_ROW(wm, p0 - d1, 1, 1)
+                        ALF_TAPL(4, wp, wm, 2) ALF_TAPL(5, wp, wm, 1) ALF_TAPL(6, wp, wm, 0) ALF_TAPL(7, wp, wm, -1) ALF_TAPL(8, wp, wm, -2)
+                    }
+                    {
+                        uint32_t wp[6], wm[6];
+                        ALF_ROW(wp, p0 + d2, 1, 1) ALF_ROW(wm, p0 - d2, 1, 1)
+                        ALF_TAPL(1, wp, wm, 1) ALF_TAPL(2, wp, wm, 0) ALF_TAPL(3, wp, wm, -1)
+                    }
+                    {
+                        uint32_t wp[6], wm[6];
+                        ALF_ROW(wp, p0 + d3, 0, 0) ALF_ROW(wm, p0 - d3, 0, 0)
+                        ALF_TAPL(0, wp, wm, 0)
+                    }
+                    const int fsum2 = 2 * ((int)cf[24] >> 20);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        sum[j] -= cur[j] * fsum2;
+                } else {
                 {
                     uint32_t w0[6];
                     ALF_ROW(w0, p0, 2, 2)
@@ -326,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                     ALF_ROW(wp, p0 + d3, 0, 0) ALF_ROW(wm, p0 - d3, 0, 0)
                     ALF_TAP(0, wp, wm, 0)
                 }
-                const int cur[4] = { (int)(c01.x & 0xffff), (int)(c01.x >> 16), (int)(c01.y & 0xffff), (int)(c01.y >> 16) };
+                }
                 unsigned res[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -349,7 +394,7 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                 const int t = (y - y0) - vb;
                 *reinterpret_cast<uint2 *>(dplane + (long long)y * p.dp[0] + x) =
                     alf_strip_wide(&sm.luma[r + 3][8 + 4 * c4], vb_reach(1, t, 4) * LP, vb_reach(2, t, 4) * LP, vb_reach(3, t, 4) * LP,
-                                            t == -1 || t == 0, bd, sets, a.filt_set_idx_y, (int)info);
+                                            t == -1 || t == 0, bd, sets, a.filt_set_idx_y, info, -1);
             }
         }
     }
@@ -383,7 +428,7 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
                     wide |= sets->chroma_coeff[alt][j] > 127;
                 if (wide) {
                     // 32-bit multiplies: sets holding +128 (alf_chroma_coeff_abs 0..128, cbs_h266_syntax_template.c:2314)
-                    const uint2 o = alf_strip_wide(p0, d1, d2, 0, near_vb, bd, sets, 0, -1 - alt);
+                    const uint2 o = alf_strip_wide(p0, d1, d2, 0, near_vb, bd, sets, 0, 0u, alt);
                     val[0] = o.x & 0xffff; val[1] = o.x >> 16; val[2] = o.y & 0xffff; val[3] = o.y >> 16;
                 } else {
                     // same 16x2 scheme as luma: one coefficient / clip word per tap for the whole CTB
@@ -452,6 +497,8 @@ __global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
 }
 
 #undef ALF_TAP
+#undef ALF_TAPL
+#undef ALF_PAIRL
 #undef ALF_TAPW
 #undef ALF_PAIR
 #undef ALF_AT
