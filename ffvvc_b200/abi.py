@@ -243,13 +243,21 @@ assert TB_QUANT_DTYPE.itemsize == 4 and SCALING_LIST_DTYPE.itemsize == 28 * 64 +
 
 class VVCCudaCoeffs(C.Structure):
     _fields_ = [("data", C.c_void_p), ("n", C.c_size_t), ("format", C.c_int32), ("reserved", C.c_int32),
-                ("quant", C.c_void_p), ("scaling", C.c_void_p)]
+                ("quant", C.c_void_p), ("scaling", C.c_void_p), ("lmcs_scales", C.c_void_p)]
 
 
-def coeffs_desc(data_ptr, n, fmt=COEFF_DENSE32, quant_ptr=None, scaling_ptr=None):
+def coeffs_desc(data_ptr, n, fmt=COEFF_DENSE32, quant_ptr=None, scaling_ptr=None, lmcs_scales_ptr=None):
     d = VVCCudaCoeffs()
-    d.data, d.n, d.format, d.quant, d.scaling = data_ptr, n, fmt, quant_ptr, scaling_ptr
+    d.data, d.n, d.format, d.quant, d.scaling, d.lmcs_scales = data_ptr, n, fmt, quant_ptr, scaling_ptr, lmcs_scales_ptr
     return d
+
+
+# LMCS chroma residual scaling: VPDU records and the VVCLMCS fields the derivation reads
+LMCS_VPDU_DTYPE = np.dtype([("x", np.uint16), ("y", np.uint16), ("avail_l", np.uint8), ("avail_t", np.uint8),
+                            ("pic", np.uint8), ("reserved", np.uint8)])
+LMCS_PARAMS_DTYPE = np.dtype([("pivot", np.uint16, (17,)), ("chroma_scale_coeff", np.uint16, (16,)),
+                              ("min_bin_idx", np.uint8), ("max_bin_idx", np.uint8)])
+assert LMCS_VPDU_DTYPE.itemsize == 8 and LMCS_PARAMS_DTYPE.itemsize == 68
 
 
 def pack_window16(tbs, coeffs):
@@ -314,6 +322,7 @@ class VVCCudaReconDesc(C.Structure):
         ("lmcs_inv_lut", C.c_void_p), ("lmcs_ctb_enable", C.c_void_p),
         ("inloop", VVCCudaInloopDesc),
         ("arena", C.c_void_p), ("arena_bytes", C.c_size_t),
+        ("lmcs_vpdus", C.c_void_p), ("lmcs_params", C.c_void_p), ("n_lmcs_vpdus", C.c_int32), ("n_luma_tbs", C.c_int32),
     ]
 
 
@@ -363,6 +372,7 @@ def recon_arena(handle, geom1, alloc, *, pbs, wp, prof, tbs, coeffs, coeff_forma
         d.quant, d.scaling = None, None
     put(d.lmcs_inv_lut, inv_lut)
     d.lmcs_fwd_lut, d.lmcs_rects, d.lmcs_ctb_enable = None, None, None
+    d.lmcs_vpdus, d.lmcs_params = None, None
     for dr in range(2):
         for c in range(3):
             put(m.edge[dr][c], maps[dr][c])

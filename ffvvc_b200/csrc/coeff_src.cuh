@@ -12,8 +12,15 @@ struct CoefSrc {
     const int16_t            *window;    // VVC_CUDA_COEFF_WINDOW16 (NULL otherwise)
     const VVCCudaTBQuant     *quant;     // NULL: already dequantised
     const VVCCudaScalingList *scaling;
+    const uint16_t           *lmcs_scales; // VVCCudaCoeffs.lmcs_scales: per-VPDU chroma residual scales or NULL
     int                       range, bd;
 };
+
+// VVCCudaTB.chroma_scale -> the scale lmcs_scale_chroma multiplies with (0: no scaling)
+__device__ __forceinline__ int tb_chroma_scale(const CoefSrc &s, int field)
+{
+    return !field ? 0 : s.lmcs_scales ? (int)__ldg(s.lmcs_scales + field - 1) : field;
+}
 
 // per-TB view
 struct TbCoef {

@@ -23,7 +23,7 @@ struct VVCCudaCtx {
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;
     void         *h_stage;  size_t h_stage_size;    // pinned
-    void         *d_scratch[3]; size_t d_scratch_size[3];   // [0],[1] intermediate pictures of chained stages, [2] inter task lists
+    void         *d_scratch[4]; size_t d_scratch_size[4];   // [0],[1] intermediate pictures of chained stages, [2] inter / residual task lists, [3] LMCS chroma scales
     cudaStream_t  copy_in, copy_out;                 // lazily created, *_host pipelines
     cudaStream_t  side[3];                           // lazily created: independent kernels of one stage run beside the context stream
     cudaEvent_t   fork_ev, join_ev[3];
@@ -53,6 +53,13 @@ __device__ __forceinline__ int d_clip_sbits(int v, int bits) { return min(max(v,
 __device__ __forceinline__ int d_clip_ubits(int v, int bits) { return min(max(v, 0), (1 << bits) - 1); }
 __device__ __forceinline__ int d_ilog2(unsigned v) { return v ? 31 - __clz(v) : 0; }   // av_log2
 __device__ __forceinline__ int d_sign(int v) { return (v > 0) - (v < 0); }
+// one residual through lmcs_scale_chroma (libavcodec/vvc/vvc_intra_template.c:431-448): av_clip_intp2(res, bit_depth),
+// magnitude * scale rounded at 11 bits, sign restored
+__device__ __forceinline__ int d_lmcs_scale(int res, int scale, int bd)
+{
+    const int c = d_clip_sbits(res, bd), m = (abs(c) * scale + (1 << 10)) >> 11;
+    return c > 0 ? m : -m;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -245,6 +245,13 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int ti, int *sC, 
         }
     } else {
         const int planes = (flags & VVC_CUDA_TB_JOINT) ? 2 : 1;
+        const int cscale = tb_chroma_scale(p.src, tb.chroma_scale);
+        // LMCS chroma residual scaling sits between the transform and add_residual (itransform, vvc_intra.c:468-475; the
+        // second plane of a joint block is derived first and scaled afterwards, :179-183)
+        auto res = [&](int r, int sign, int shift) -> int {
+            const int v = (r * sign) >> shift;
+            return cscale ? d_lmcs_scale(v, cscale, p.bd) : v;
+        };
         for (int pl = 0; pl < planes; pl++) {
             const int c = pl ? tb.joint_c_idx : tb.c_idx;
             pel *base = p.plane[c] + tb.pic * p.bstride[c] + (long long)tb.y0 * p.pitch[c] + tb.x0;
@@ -256,17 +263,17 @@ __device__ void process_tb(const ItxK &p, const VVCCudaTB &tb, int ti, int *sC, 
                     uint2 *d = reinterpret_cast<uint2 *>(base + (long long)y * p.pitch[c] + x);
                     const uint2 cur = *d;
                     const int *r = &sC[y * pitch + x];
-                    const int o0 = d_clip_pel((int)(cur.x & 0xffff) + ((r[0] * sign) >> shift), p.bd);
-                    const int o1 = d_clip_pel((int)(cur.x >> 16)    + ((r[1] * sign) >> shift), p.bd);
-                    const int o2 = d_clip_pel((int)(cur.y & 0xffff) + ((r[2] * sign) >> shift), p.bd);
-                    const int o3 = d_clip_pel((int)(cur.y >> 16)    + ((r[3] * sign) >> shift), p.bd);
+                    const int o0 = d_clip_pel((int)(cur.x & 0xffff) + res(r[0], sign, shift), p.bd);
+                    const int o1 = d_clip_pel((int)(cur.x >> 16)    + res(r[1], sign, shift), p.bd);
+                    const int o2 = d_clip_pel((int)(cur.y & 0xffff) + res(r[2], sign, shift), p.bd);
+                    const int o3 = d_clip_pel((int)(cur.y >> 16)    + res(r[3], sign, shift), p.bd);
                     *d = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
                 }
             } else {
                 for (int i = t; i < h * w; i += NT) {
                     const int y = i / w, x = i - y * w;
                     pel *d = base + (long long)y * p.pitch[c] + x;
-                    *d = (pel)d_clip_pel(*d + ((sC[y * pitch + x] * sign) >> shift), p.bd);
+                    *d = (pel)d_clip_pel(*d + res(sC[y * pitch + x], sign, shift), p.bd);
                 }
             }
         }
@@ -344,7 +351,7 @@ extern "C" int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, 
     }
     p.src.dense = (mode & 1) ? nullptr : (const int32_t *)co->data;
     p.src.window = (mode & 1) ? (const int16_t *)co->data : nullptr;
-    p.src.quant = co->quant; p.src.scaling = co->scaling;
+    p.src.quant = co->quant; p.src.scaling = co->scaling; p.src.lmcs_scales = co->lmcs_scales;
     p.src.range = log2_transform_range; p.src.bd = frame->bit_depth;
     p.store = (mode & 1) ? nullptr : (int32_t *)co->data;
     p.tbs = tbs; p.n_tbs = n_tbs; p.range = log2_transform_range; p.bd = frame->bit_depth;

@@ -188,6 +188,7 @@ struct Epi {
     int32_t *store;              // != NULL: residual written back as int32 [h][w]
     pel     *d0, *d1;            // picture samples of the TB's first row (d1: joint CbCr plane or NULL)
     int      pitch0, pitch1, sign, shift, w;
+    int      cscale;             // LMCS chroma residual scale (lmcs_scale_chroma, vvc_intra_template.c:431-448) or 0
 };
 
 // Pass 2: out[y][i] = (sum_x mid[y][x] * M[x][i] + 512) >> 10.  lane = (4 adjacent output columns, row group):
@@ -244,6 +245,17 @@ __device__ __forceinline__ void pass2(const WarpSmem<MODE> &s, int l2w, int h, c
                 a = dp2a_lo((int)in[2 * q], (int)m[c][q], dp2a_hi((int)in[2 * q + 1], (int)m[c][q], a));
             r[c] = (a + 512) >> 10;                         // shift = 5 + log2_transform_range - bit_depth
         }
+        int j[4];                                           // second plane of a joint CbCr block: derived before any scaling
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            j[c] = (r[c] * e.sign) >> e.shift;
+        if (e.cscale && !e.store) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                r[c] = d_lmcs_scale(r[c], e.cscale, 10);
+                j[c] = d_lmcs_scale(j[c], e.cscale, 10);
+            }
+        }
         if (e.store) {
             int32_t *o = e.store + y * e.w + c0;
             o[0] = r[0]; o[1] = r[1];
@@ -254,10 +266,8 @@ __device__ __forceinline__ void pass2(const WarpSmem<MODE> &s, int l2w, int h, c
             if (narrow) *reinterpret_cast<uint32_t *>(d0) = lo;
             else        *reinterpret_cast<uint2 *>(d0) = make_uint2(lo, hi);
             if (d1) {
-                const uint32_t jl = (uint32_t)d_clip_pel((int)(cur1.x & 0xffff) + ((r[0] * e.sign) >> e.shift), 10)
-                                  | ((uint32_t)d_clip_pel((int)(cur1.x >> 16) + ((r[1] * e.sign) >> e.shift), 10) << 16);
-                const uint32_t jh = (uint32_t)d_clip_pel((int)(cur1.y & 0xffff) + ((r[2] * e.sign) >> e.shift), 10)
-                                  | ((uint32_t)d_clip_pel((int)(cur1.y >> 16) + ((r[3] * e.sign) >> e.shift), 10) << 16);
+                const uint32_t jl = (uint32_t)d_clip_pel((int)(cur1.x & 0xffff) + j[0], 10) | ((uint32_t)d_clip_pel((int)(cur1.x >> 16) + j[1], 10) << 16);
+                const uint32_t jh = (uint32_t)d_clip_pel((int)(cur1.y & 0xffff) + j[2], 10) | ((uint32_t)d_clip_pel((int)(cur1.y >> 16) + j[3], 10) << 16);
                 if (narrow) *reinterpret_cast<uint32_t *>(d1) = jl;
                 else        *reinterpret_cast<uint2 *>(d1) = make_uint2(jl, jh);
             }
@@ -322,6 +332,7 @@ __global__ void __launch_bounds__(128) itx_tiny_kernel(const ItxW p)
     const int x0 = r1 & 0xffff, y0 = r1 >> 16, w = 1 << l2w, h = 1 << l2h;
     const int trh = r2 >> 24, trv = r3 & 0xff, nzw = (r3 >> 8) & 0xff, nzh = (r3 >> 16) & 0xff;
     const int jsign = (int8_t)((r4 >> 8) & 0xff), jshift = (r4 >> 16) & 0xff, jc = r4 >> 24, pic = r5 & 0xff;
+    const int cscale = tb_chroma_scale(p.src, (int)(r5 >> 16));
     const TbCoef tc = tb_coef<MODE>(p.src, ti, r0, l2w, l2h, nzw, nzh, false);
     const bool dc_only = trh == 0 && trv == 0 && nzw == 1 && nzh == 1 && w == h;
     const int rdv = dc_only ? 1 : inputs_read(trv, h, nzh);
@@ -372,6 +383,17 @@ __global__ void __launch_bounds__(128) itx_tiny_kernel(const ItxW p)
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 r[k] = (dp2a_lo((int)mid01[y], (int)wh[k], dp2a_hi((int)mid23[y], (int)wh[k], 0)) + 512) >> 10;
+            int j[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                j[k] = (r[k] * jsign) >> jshift;
+            if (cscale) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    r[k] = d_lmcs_scale(r[k], cscale, 10);
+                    j[k] = d_lmcs_scale(j[k], cscale, 10);
+                }
+            }
             auto add2 = [&](uint32_t cur, int a, int b) -> uint32_t {
                 return (uint32_t)d_clip_pel((int)(cur & 0xffff) + a, 10) | ((uint32_t)d_clip_pel((int)(cur >> 16) + b, 10) << 16);
             };
@@ -382,15 +404,14 @@ __global__ void __launch_bounds__(128) itx_tiny_kernel(const ItxW p)
                 if (d1) {
                     uint2 *u = reinterpret_cast<uint2 *>(d1 + y * pitch1);
                     const uint2 c1 = *u;
-                    *u = make_uint2(add2(c1.x, (r[0] * jsign) >> jshift, (r[1] * jsign) >> jshift),
-                                    add2(c1.y, (r[2] * jsign) >> jshift, (r[3] * jsign) >> jshift));
+                    *u = make_uint2(add2(c1.x, j[0], j[1]), add2(c1.y, j[2], j[3]));
                 }
             } else {
                 uint32_t *t = reinterpret_cast<uint32_t *>(d0 + y * pitch0);
                 *t = add2(*t, r[0], r[1]);
                 if (d1) {
                     uint32_t *u = reinterpret_cast<uint32_t *>(d1 + y * pitch1);
-                    *u = add2(*u, (r[0] * jsign) >> jshift, (r[1] * jsign) >> jshift);
+                    *u = add2(*u, j[0], j[1]);
                 }
             }
         }
@@ -537,6 +558,7 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
         e.pitch0 = SEL3(p.pitch, c_idx);
         e.d0 = SEL3(p.plane, c_idx) + pic * SEL3(p.bstride, c_idx) + (long long)y0 * e.pitch0 + x0;
         e.d1 = nullptr; e.pitch1 = 0; e.sign = jsign; e.shift = jshift;
+        e.cscale = tb_chroma_scale(p.src, (int)(r5 >> 16));
         if (flags & VVC_CUDA_TB_JOINT) {
             e.pitch1 = SEL3(p.pitch, jc);
             e.d1 = SEL3(p.plane, jc) + pic * SEL3(p.bstride, jc) + (long long)y0 * e.pitch1 + x0;
@@ -578,7 +600,7 @@ int vvc_itx_launch_warp(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCud
     const int mode = coef_mode(co);
     p.src.dense = (mode & 1) ? nullptr : (const int32_t *)co->data;
     p.src.window = (mode & 1) ? (const int16_t *)co->data : nullptr;
-    p.src.quant = co->quant; p.src.scaling = co->scaling; p.src.range = 15; p.src.bd = 10;
+    p.src.quant = co->quant; p.src.scaling = co->scaling; p.src.lmcs_scales = co->lmcs_scales; p.src.range = 15; p.src.bd = 10;
     p.store = (mode & 1) ? nullptr : (int32_t *)co->data;
     p.tbs = tbs; p.n_tbs = n_tbs; p.counts = scratch; p.lists = scratch + 16;
     *rest = p.lists + 4 * (size_t)n_tbs; *rest_count = p.counts + 4;

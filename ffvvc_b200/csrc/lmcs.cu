@@ -80,6 +80,41 @@ __global__ void __launch_bounds__(kThreads) lmcs_rects_kernel(pel *plane, int pi
     }
 }
 
+// lmcs_derive_chroma_scale (libavcodec/vvc/vvc_intra_template.c:389-428) for a list of VPDUs: one warp per VPDU sums the
+// reconstructed luma column left of it and the row above it (lmcs_sum_samples :377-387 repeats the last sample past the
+// picture edge, which is what the clamped index does), averages, and searches the pivots.
+__global__ void __launch_bounds__(kThreads) lmcs_chroma_scale_kernel(const pel *plane, int pitch, long long bstride, int w, int h,
+                                                                     int size, int bd, const VVCCudaLmcsVpdu *vpdus, int n,
+                                                                     const VVCCudaLmcsParams *lp, uint16_t *scales)
+{
+    const int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n)
+        return;
+    const VVCCudaLmcsVpdu v = vpdus[i];
+    const pel *pic = plane + v.pic * bstride;
+    int sum = 0, cnt = 0;
+    if (v.avail_l) {
+        for (int j = lane; j < size; j += 32)
+            sum += pic[(long long)min(v.y + j, h - 1) * pitch + v.x - 1];
+        cnt = size;
+    }
+    if (v.avail_t) {
+        for (int j = lane; j < size; j += 32)
+            sum += pic[(long long)(v.y - 1) * pitch + min(v.x + j, w - 1)];
+        cnt += size;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane)
+        return;
+    const int luma = cnt ? (sum + (cnt >> 1)) >> d_ilog2(cnt) : 1 << (bd - 1);
+    int k = lp->min_bin_idx;
+    while (k <= lp->max_bin_idx && luma >= lp->pivot[k + 1])
+        k++;
+    scales[i] = lp->chroma_scale_coeff[min(k, 15)];
+}
+
 // whole_rows: the CTB kernel walks rows with 128-bit accesses and needs the width to be a multiple of 8;
 // the rectangle kernel checks alignment per rectangle
 int check(VVCCudaCtx *ctx, const VVCCudaFrame *f, const void *lut, bool whole_rows)
@@ -120,6 +155,25 @@ extern "C" int vvc_cuda_lmcs_rects(VVCCudaCtx *ctx, const VVCCudaFrame *f, const
     const int grid = n_rects < 148 * 8 ? n_rects : 148 * 8;
     lmcs_rects_kernel<<<grid, kThreads, n * sizeof(unsigned), ctx->stream>>>(
         (pel *)f->data[0], (int)(f->stride[0] / 2), f->batch_stride[0] / 2, lut, n, rects, n_rects);
+    VVC_LAUNCHED(ctx);
+    return VVC_CUDA_OK;
+}
+
+extern "C" int vvc_cuda_lmcs_chroma_scale(VVCCudaCtx *ctx, const VVCCudaFrame *f, const VVCCudaLmcsVpdu *vpdus, int n,
+                                          const VVCCudaLmcsParams *params, uint16_t *scales)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!f || !vpdus || !params || !scales || n < 0)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "lmcs_chroma_scale: null argument");
+    if (f->bit_depth != 10 && f->bit_depth != 12)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "lmcs_chroma_scale: unsupported picture format");
+    if (!n)
+        return VVC_CUDA_OK;
+    const int ctb = 1 << f->ctb_log2;
+    lmcs_chroma_scale_kernel<<<ceil_div(n, kThreads / 32), kThreads, 0, ctx->stream>>>(
+        (const pel *)f->data[0], (int)(f->stride[0] / 2), f->batch_stride[0] / 2, f->width, f->height, ctb < 64 ? ctb : 64,
+        f->bit_depth, vpdus, n, params, scales);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

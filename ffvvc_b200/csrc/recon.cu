@@ -21,7 +21,25 @@ extern "C" int vvc_cuda_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *out, co
         memset(&co, 0, sizeof(co));
         co.data = d->coeffs; co.n = d->n_coeffs; co.format = d->coeff_format;
         co.quant = d->quant; co.scaling = d->scaling;
-        if (vvc_cuda_itx_frame_q(ctx, cur, &co, d->tbs, d->n_tbs, d->log2_transform_range))
+        if (d->n_lmcs_vpdus > 0) {
+            // chroma residual scaling: the luma blocks first, then the per-VPDU scales from the reconstructed (still mapped)
+            // luma, then the chroma blocks (lmcs_derive_chroma_scale, vvc_intra_template.c:389-428)
+            if (!d->lmcs_vpdus || !d->lmcs_params || d->n_luma_tbs < 0 || d->n_luma_tbs > d->n_tbs)
+                return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "recon: LMCS chroma scaling needs lmcs_vpdus, lmcs_params and 0 <= n_luma_tbs <= n_tbs");
+            uint16_t *scales = (uint16_t *)vvc_ctx_scratch(ctx, 3, (size_t)d->n_lmcs_vpdus * sizeof(uint16_t));
+            if (!scales)
+                return ctx->err;
+            if (d->n_luma_tbs > 0 && vvc_cuda_itx_frame_q(ctx, cur, &co, d->tbs, d->n_luma_tbs, d->log2_transform_range))
+                return ctx->err;
+            if (vvc_cuda_lmcs_chroma_scale(ctx, cur, d->lmcs_vpdus, d->n_lmcs_vpdus, d->lmcs_params, scales))
+                return ctx->err;
+            co.lmcs_scales = scales;
+            if (co.quant)
+                co.quant += d->n_luma_tbs;
+            if (d->n_tbs > d->n_luma_tbs &&
+                vvc_cuda_itx_frame_q(ctx, cur, &co, d->tbs + d->n_luma_tbs, d->n_tbs - d->n_luma_tbs, d->log2_transform_range))
+                return ctx->err;
+        } else if (vvc_cuda_itx_frame_q(ctx, cur, &co, d->tbs, d->n_tbs, d->log2_transform_range))
             return ctx->err;
     }
     if (d->lmcs_inv_lut && vvc_cuda_lmcs_frame(ctx, cur, d->lmcs_inv_lut, d->lmcs_ctb_enable))
@@ -50,7 +68,7 @@ static inline VVCCudaFrame one_picture(const VVCCudaFrame *f, int k)
 // arena (vvc_cuda_recon_arena_bind), which is the same layout so that it goes up as ONE copy.  Every array takes at least
 // one element and is rounded up to 256 bytes.
 enum { IT_PBS, IT_WP, IT_PROF, IT_RECTS, IT_FWD, IT_INV, IT_COEFFS, IT_TBS, IT_QUANT, IT_SCALING, IT_CTB_EN,
-       IT_EDGE0, IT_SAO = IT_EDGE0 + 6, IT_ALF, IT_SETS, IT_COUNT };
+       IT_EDGE0, IT_SAO = IT_EDGE0 + 6, IT_ALF, IT_SETS, IT_VPDUS, IT_LMCSP, IT_COUNT };
 
 struct Item { const void *host; size_t bytes; size_t off; };
 
@@ -82,6 +100,8 @@ size_t layout(const VVCCudaFrame *f, const VVCCudaReconDesc *d, Item items[IT_CO
     items[IT_SAO]     = Item{ d->inloop.sao, n_ctb * sizeof(VVCCudaSAOCtb), 0 };
     items[IT_ALF]     = Item{ d->inloop.alf, n_ctb * sizeof(VVCCudaALFCtb), 0 };
     items[IT_SETS]    = Item{ d->inloop.alf_sets, sizeof(VVCCudaALFSets), 0 };
+    items[IT_VPDUS]   = Item{ d->lmcs_vpdus, (size_t)(d->n_lmcs_vpdus > 0 ? d->n_lmcs_vpdus : 0) * sizeof(VVCCudaLmcsVpdu), 0 };
+    items[IT_LMCSP]   = Item{ d->lmcs_params, d->n_lmcs_vpdus > 0 ? sizeof(VVCCudaLmcsParams) : 0, 0 };
     size_t n = 0;
     for (int i = 0; i < IT_COUNT; i++) {
         items[i].off = n;
@@ -130,6 +150,8 @@ extern "C" int vvc_cuda_recon_arena_bind(const VVCCudaFrame *frame, VVCCudaRecon
     desc->inloop.sao = (const VVCCudaSAOCtb *)(a + it[IT_SAO].off);
     desc->inloop.alf = (const VVCCudaALFCtb *)(a + it[IT_ALF].off);
     desc->inloop.alf_sets = (const VVCCudaALFSets *)(a + it[IT_SETS].off);
+    desc->lmcs_vpdus = (const VVCCudaLmcsVpdu *)(a + it[IT_VPDUS].off);
+    desc->lmcs_params = (const VVCCudaLmcsParams *)(a + it[IT_LMCSP].off);
     desc->arena = arena;
     desc->arena_bytes = dm;
     return VVC_CUDA_OK;
@@ -249,6 +271,7 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
                 dm.edge[dir][c] = DEV(IT_EDGE0 + dir * 3 + c, VVCCudaDbkEdge *);
         dd.inloop.sao = DEV(IT_SAO, const VVCCudaSAOCtb *);     dd.inloop.alf = DEV(IT_ALF, const VVCCudaALFCtb *);
         dd.inloop.alf_sets = DEV(IT_SETS, const VVCCudaALFSets *);
+        dd.lmcs_vpdus = DEV(IT_VPDUS, const VVCCudaLmcsVpdu *); dd.lmcs_params = DEV(IT_LMCSP, const VVCCudaLmcsParams *);
 #undef DEV
         VVCCudaDmvrOut *ddm = (VVCCudaDmvrOut *)(slot + dmvr_off);
         dd.dmvr_out = h->dmvr_out ? ddm : NULL;

@@ -74,6 +74,7 @@ def load():
     lib.vvc_cuda_lmcs_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_lmcs_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_lmcs_rects.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, C.c_int]
+    lib.vvc_cuda_lmcs_chroma_scale.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_inter_frame.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vvc_cuda_inter_frame_host.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     RP = C.POINTER(abi.VVCCudaReconDesc)
@@ -193,6 +194,10 @@ class Context:
 
     def lmcs_frame_host(self, frame, lut_ptr, ctb_enable_ptr=None):
         self.check(self.lib.vvc_cuda_lmcs_frame_host(self.handle, C.byref(frame), lut_ptr, ctb_enable_ptr))
+
+    def lmcs_chroma_scale(self, frame, vpdus_ptr, n, params_ptr, scales_ptr):
+        """Per-VPDU chroma residual scales from the reconstructed luma (lmcs_derive_chroma_scale)."""
+        self.check(self.lib.vvc_cuda_lmcs_chroma_scale(self.handle, C.byref(frame), vpdus_ptr, n, params_ptr, scales_ptr))
 
     def inter_frame(self, dst, refs, pbs_ptr, n_pbs, wp_ptr, prof_ptr, dmvr_out_ptr=None):
         """Motion compensation (+ DMVR / BDOF / PROF / GPM / weighted prediction) of a record list."""

@@ -452,6 +452,52 @@ def lmcs_luts(bit_depth=10, seed=5):
     return fwd.astype(np.uint16), inv.astype(np.uint16)
 
 
+def lmcs_chroma(geom, tbs, seed=9, literal=False):
+    """LMCS chroma residual scaling inputs for a TB list (ph_chroma_residual_scale_flag pictures).
+
+    Returns (tbs2, order, vpdus, params, n_luma): the TB records reordered luma first (order = the permutation applied,
+    for per-TB side arrays), every 64x64 (min(CtbSizeY, 64)) VPDU of every picture with the availability of its left / top
+    neighbours (0 at the picture border, and at a random quarter of the CTB borders - a slice or tile boundary), VVCLMCS's
+    pivots / chroma_scale_coeff / bin range (shaped like vvc_ps.c derives them), and the number of luma blocks.  Chroma
+    blocks of more than 4 samples carry 1 + the index of the VPDU of their origin (literal=True: a scale itself)."""
+    rng = LCG(seed)
+    size = min(geom.ctb_size, 64)
+    cols, rows = (geom.width + size - 1) // size, (geom.height + size - 1) // size
+    n = cols * rows * geom.batch
+    v = np.zeros(n, dtype=abi.LMCS_VPDU_DTYPE)
+    idx = np.arange(n)
+    v["pic"] = idx // (cols * rows)
+    v["x"] = (idx % cols) * size
+    v["y"] = ((idx // cols) % rows) * size
+    cut = rng.below(2 * n, 4) == 0
+    ctb = geom.ctb_size
+    v["avail_l"] = (v["x"] > 0) & ~((v["x"] % ctb == 0) & cut[:n])
+    v["avail_t"] = (v["y"] > 0) & ~((v["y"] % ctb == 0) & cut[n:])
+    bd = geom.bit_depth
+    org = (1 << bd) // 16
+    p = np.zeros(1, dtype=abi.LMCS_PARAMS_DTYPE)
+    cw = org // 2 + rng.below(16, org)
+    cw[0] = cw[15] = 0
+    p["min_bin_idx"], p["max_bin_idx"] = 1, 14
+    cw = (cw * ((1 << bd) - 1) // max(int(cw.sum()), 1)).astype(np.int64)
+    p["pivot"][0] = np.concatenate([[0], np.cumsum(cw)])
+    p["chroma_scale_coeff"][0] = np.where(cw > 0, (org << 11) // np.maximum(cw + rng.below(16, 15).astype(np.int64) - 7, 1), 1 << 11)
+    order = np.argsort(tbs["c_idx"] > 0, kind="stable")
+    t2 = tbs[order].copy()
+    n_luma = int((t2["c_idx"] == 0).sum())
+    ch = (t2["c_idx"] > 0) & ((t2["log2_w"].astype(np.int64) + t2["log2_h"]) > 2)
+    sh_x, sh_y = geom.hshift, geom.vshift
+    vi = (t2["pic"].astype(np.int64) * rows + ((t2["y0"].astype(np.int64) << sh_y) // size)) * cols + ((t2["x0"].astype(np.int64) << sh_x) // size)
+    if literal:
+        lit = 256 + rng.below(len(t2), 16128)
+        lit[rng.below(len(t2), 16) == 0] = 65535
+        t2["chroma_scale"] = np.where(ch, lit, 0)
+    else:
+        assert n < 65535
+        t2["chroma_scale"] = np.where(ch, vi + 1, 0)
+    return t2, order, v, p, n_luma
+
+
 # ---------------------------------------------------------------------------------------------
 # Inter prediction inputs (SURVEY.md 8(d) config 4): a random-access-like motion field
 # ---------------------------------------------------------------------------------------------

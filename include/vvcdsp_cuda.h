@@ -69,7 +69,7 @@ const char *vvc_cuda_version(void);
 #define VVC_CUDA_OPT_INTER_TMA 3
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -256,7 +256,10 @@ typedef struct VVCCudaTB {
     uint8_t  joint_c_idx;
     uint8_t  pic;            /* picture of the ring this TB belongs to                                  */
     uint8_t  reserved;
-    uint16_t chroma_scale;   /* reserved for LMCS chroma residual scaling (0 = off)                     */
+    uint16_t chroma_scale;   /* LMCS chroma residual scaling (lmcs_scale_chroma, vvc_intra_template.c:431-448):
+                                0 = off; with VVCCudaCoeffs.lmcs_scales == NULL the scale itself
+                                (lmcs->chroma_scale_coeff[i]), else 1 + the index of this block's VPDU in that
+                                array (filled on the device by vvc_cuda_lmcs_chroma_scale)                 */
 } VVCCudaTB;                 /* 24 bytes */
 
 /* frame: prediction in, reconstruction out (in place - TBs are disjoint).  coeffs: dequantised
@@ -308,7 +311,27 @@ typedef struct VVCCudaCoeffs {
                                             (TransCoeffLevel) and the device runs dequant()                */
     const VVCCudaScalingList *scaling;   /* the picture's scaling list (fc->ps.sl); may be NULL when every
                                             sl_id is 0                                                     */
+    const uint16_t           *lmcs_scales; /* optional: per-VPDU chroma residual scales, see VVCCudaTB.chroma_scale */
 } VVCCudaCoeffs;
+
+/* LMCS chroma residual scaling, the derivation (replaces lmcs_derive_chroma_scale, vvc_intra_template.c:389-428): per
+ * 64x64 VPDU (min(CtbSizeY, 64)) the average of the reconstructed luma samples left of and above it - in the mapped
+ * domain, i.e. after the luma residual and BEFORE the inverse LMCS stage - picks the bin whose chroma_scale_coeff scales
+ * the chroma residuals of every CU that starts in the VPDU.  The luma blocks of a picture therefore go through the
+ * residual stage first, then this call, then the chroma blocks with VVCCudaCoeffs.lmcs_scales = scales. */
+typedef struct VVCCudaLmcsVpdu {
+    uint16_t x, y;            /* luma position of the VPDU (cu->x0 & ~(size - 1), cu->y0 & ~(size - 1))              */
+    uint8_t  avail_l, avail_t;/* ff_vvc_get_left_available / _top_available(lc, x, y, 1, 0) != 0                      */
+    uint8_t  pic, reserved;
+} VVCCudaLmcsVpdu;            /* 8 bytes */
+typedef struct VVCCudaLmcsParams {  /* of VVCLMCS, libavcodec/vvc/vvc_ps.h:192-202 */
+    uint16_t pivot[17];
+    uint16_t chroma_scale_coeff[16];
+    uint8_t  min_bin_idx, max_bin_idx;
+} VVCCudaLmcsParams;
+/* frame: the picture (ring) being reconstructed; vpdus, params, scales (n entries out): device memory */
+int vvc_cuda_lmcs_chroma_scale(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaLmcsVpdu *vpdus, int n,
+                               const VVCCudaLmcsParams *params, uint16_t *scales);
 
 /* Same stage as vvc_cuda_itx_frame.  VVC_CUDA_TB_STORE_RESIDUAL needs DENSE32. */
 int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *coeffs,
@@ -509,6 +532,12 @@ typedef struct VVCCudaReconDesc {
      * slot's own layout, and go up as one copy.  NULL = arrays anywhere, one copy each. */
     const void        *arena;
     size_t             arena_bytes;
+    /* LMCS chroma residual scaling (optional, ph_chroma_residual_scale_flag): with n_lmcs_vpdus > 0 the TB list holds its
+     * n_luma_tbs luma blocks first; the stage then runs luma residuals -> vvc_cuda_lmcs_chroma_scale over lmcs_vpdus ->
+     * chroma residuals, whose VVCCudaTB.chroma_scale is 1 + the index of the block's VPDU in lmcs_vpdus. */
+    const VVCCudaLmcsVpdu   *lmcs_vpdus;
+    const VVCCudaLmcsParams *lmcs_params;
+    int32_t            n_lmcs_vpdus, n_luma_tbs;
 } VVCCudaReconDesc;
 
 /* Device memory everywhere.  cur: the picture (ring) being reconstructed: prediction, residual and

@@ -48,6 +48,8 @@ static void ref_lfnst(int *c, int w, int h, int lfnst, int range)
     }
 }
 
+void vvcref_lmcs_scale_block(int *dst, const int *coeff, int w, int h, int scale, int bit_depth);      /* ref_glue_lmcs_chroma.c */
+
 void vvcref_itx_frame(const VVCCudaFrame *f, int32_t *coeffs, const VVCCudaTB *tbs, int n_tbs, int range)
 {
     const VVCDSPContext *dsp = vvcref_dsp(f->bit_depth);
@@ -71,6 +73,22 @@ void vvcref_itx_frame(const VVCCudaFrame *f, int32_t *coeffs, const VVCCudaTB *t
         }
         if (tb->flags & VVC_CUDA_TB_STORE_RESIDUAL)
             continue;
+        if (tb->chroma_scale) {
+            /* itransform() / add_residual_for_joint_coding_chroma with chroma_scale (vvc_intra.c:166-186, 468-475); the scale
+             * is the literal one of the record (the derivation is pinned separately, ref_glue_lmcs_chroma.c) */
+            static _Thread_local int temp[64 * 64];
+            uint8_t *plane = (uint8_t *)f->data[tb->c_idx] + tb->pic * f->batch_stride[tb->c_idx];
+            vvcref_lmcs_scale_block(temp, c, w, h, tb->chroma_scale, f->bit_depth);
+            dsp->itx.add_residual(plane + tb->y0 * f->stride[tb->c_idx] + tb->x0 * 2, temp, w, h, f->stride[tb->c_idx]);
+            if (tb->flags & VVC_CUDA_TB_JOINT) {
+                const int jc = tb->joint_c_idx;
+                uint8_t *pj = (uint8_t *)f->data[jc] + tb->pic * f->batch_stride[jc];
+                dsp->itx.pred_residual_joint(c, w, h, tb->joint_sign, tb->joint_shift);
+                vvcref_lmcs_scale_block(c, c, w, h, tb->chroma_scale, f->bit_depth);
+                dsp->itx.add_residual(pj + tb->y0 * f->stride[jc] + tb->x0 * 2, c, w, h, f->stride[jc]);
+            }
+            continue;
+        }
         {
             uint8_t *plane = (uint8_t *)f->data[tb->c_idx] + tb->pic * f->batch_stride[tb->c_idx];
             dsp->itx.add_residual(plane + tb->y0 * f->stride[tb->c_idx] + tb->x0 * 2, c, w, h, f->stride[tb->c_idx]);

@@ -184,6 +184,13 @@ static void dequant_tb(int *c, int log2_w, int log2_h, int ts, const VVCCudaTBQu
         }
 }
 
+/* one residual through lmcs_scale_chroma (libavcodec/vvc/vvc_intra_template.c:431-448) */
+static inline int lmcs_scale_one(int res, int scale, int bd)
+{
+    const int c = o_clip3(res, -(1 << bd), (1 << bd) - 1);
+    return c > 0 ? (c * scale + (1 << 10)) >> 11 : -((-c * scale + (1 << 10)) >> 11);
+}
+
 /* Residual stage on either coefficient layout, with optional dequantisation; order of itransform()
  * (vvc_intra.c:453-470): transform_bdpcm -> dequant -> LFNST -> inverse transform -> add_residual(_joint). */
 void vvco_itx_frame_q(const VVCCudaFrame *f, const VVCCudaCoeffs *co, const VVCCudaTB *tbs, int n_tbs, int range)
@@ -221,20 +228,24 @@ void vvco_itx_frame_q(const VVCCudaFrame *f, const VVCCudaCoeffs *co, const VVCC
         if (tb->flags & VVC_CUDA_TB_STORE_RESIDUAL)
             continue;
         {
+            /* LMCS chroma residual scaling between the transform and add_residual (itransform, vvc_intra.c:449-472) */
+            const int scale = !tb->chroma_scale ? 0 : co->lmcs_scales ? co->lmcs_scales[tb->chroma_scale - 1] : tb->chroma_scale;
             const OPlane pl = o_plane(f, tb->c_idx, tb->pic);
             for (int y = 0; y < h; y++)
                 for (int x = 0; x < w; x++) {
                     pel *d = &pl.p[(tb->y0 + y) * pl.pitch + tb->x0 + x];
-                    *d = (pel)o_clip_pel(*d + c[y * w + x], bd);
+                    *d = (pel)o_clip_pel(*d + (scale ? lmcs_scale_one(c[y * w + x], scale, bd) : c[y * w + x]), bd);
                 }
-        }
-        if (tb->flags & VVC_CUDA_TB_JOINT) {
-            const OPlane pl = o_plane(f, tb->joint_c_idx, tb->pic);
-            for (int y = 0; y < h; y++)
-                for (int x = 0; x < w; x++) {
-                    pel *d = &pl.p[(tb->y0 + y) * pl.pitch + tb->x0 + x];
-                    *d = (pel)o_clip_pel(*d + ((c[y * w + x] * tb->joint_sign) >> tb->joint_shift), bd);
-                }
+            if (tb->flags & VVC_CUDA_TB_JOINT) {
+                /* add_residual_for_joint_coding_chroma (:166-186): derive the second plane's residual, then scale it */
+                const OPlane pj = o_plane(f, tb->joint_c_idx, tb->pic);
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++) {
+                        pel *d = &pj.p[(tb->y0 + y) * pj.pitch + tb->x0 + x];
+                        const int r = (c[y * w + x] * tb->joint_sign) >> tb->joint_shift;
+                        *d = (pel)o_clip_pel(*d + (scale ? lmcs_scale_one(r, scale, bd) : r), bd);
+                    }
+            }
         }
     }
 }

@@ -32,3 +32,35 @@ void vvco_lmcs_rects(const VVCCudaFrame *f, const uint16_t *lut, const VVCCudaRe
         map_rect(&pl, rects[i].x, rects[i].y, rects[i].w, rects[i].h, lut);
     }
 }
+
+
+/* lmcs_derive_chroma_scale (libavcodec/vvc/vvc_intra_template.c:377-428) per VPDU: average of the reconstructed luma left
+ * of and above the VPDU (lmcs_sum_samples :377-387 replicates the last sample past the picture), bin search over the pivots */
+void vvco_lmcs_chroma_scale(const VVCCudaFrame *f, const VVCCudaLmcsVpdu *vpdus, int n, const VVCCudaLmcsParams *lp, uint16_t *scales)
+{
+    const int ctb = 1 << f->ctb_log2, size = ctb < 64 ? ctb : 64, bd = f->bit_depth;
+    for (int i = 0; i < n; i++) {
+        const VVCCudaLmcsVpdu *v = &vpdus[i];
+        const OPlane pl = o_plane(f, 0, v->pic);
+        int luma = 0, cnt = 0, k;
+        if (v->avail_l) {
+            const int avail = f->height - v->y, m = avail < size ? avail : size;
+            for (int j = 0; j < m; j++)
+                luma += pl.p[(v->y + j) * pl.pitch + v->x - 1];
+            luma += pl.p[(v->y + m - 1) * pl.pitch + v->x - 1] * (size - m);
+            cnt = size;
+        }
+        if (v->avail_t) {
+            const int avail = f->width - v->x, m = avail < size ? avail : size;
+            for (int j = 0; j < m; j++)
+                luma += pl.p[(v->y - 1) * pl.pitch + v->x + j];
+            luma += pl.p[(v->y - 1) * pl.pitch + v->x + m - 1] * (size - m);
+            cnt += size;
+        }
+        luma = cnt ? (luma + (cnt >> 1)) >> o_ilog2(cnt) : 1 << (bd - 1);
+        for (k = lp->min_bin_idx; k <= lp->max_bin_idx; k++)
+            if (luma < lp->pivot[k + 1])
+                break;
+        scales[i] = lp->chroma_scale_coeff[k < 15 ? k : 15];
+    }
+}

@@ -23,7 +23,7 @@ def ctx():
     c.close()
 
 
-def build(w, h, batch, seed, coeff_mode="dense"):
+def build(w, h, batch, seed, coeff_mode="dense", lmcs_chroma=False):
     g1 = abi.FrameGeom(w, h)
     gr = abi.FrameGeom(w, h, batch=batch)
     case = dict(g1=g1, gr=gr, refs=synth.struct_planes(gr, seed=seed))
@@ -34,6 +34,11 @@ def build(w, h, batch, seed, coeff_mode="dense"):
         case["tbs"], case["coeffs"] = abi.pack_window16(synth.tb_for_window(case["tbs"]), case["coeffs"])
         case["quant"], case["sl"] = synth.tb_quant(case["tbs"], seed=seed + 7, scaling=True)
         case["fmt"] = abi.COEFF_WINDOW16
+    case["vpdus"] = None
+    if lmcs_chroma:                     # ph_chroma_residual_scale_flag: luma blocks first, chroma blocks name their VPDU
+        case["tbs"], order, case["vpdus"], case["lmcs_params"], case["n_luma"] = synth.lmcs_chroma(gr, case["tbs"], seed=seed + 8)
+        if case["quant"] is not None:
+            case["quant"] = case["quant"][order].copy()
     _, case["inv"] = synth.lmcs_luts(10, seed=seed + 3)
     case["maps"] = synth.deblock_maps(gr, seed=seed + 4, qp_base=27, qp_span=16)
     case["sao"] = synth.sao_params(gr, seed=seed + 5)
@@ -49,7 +54,17 @@ def oracle_chain(case):
     co = case["coeffs"].copy()
     cd = abi.coeffs_desc(co.ctypes.data, co.size, case["fmt"], case["quant"].ctypes.data if case["quant"] is not None else None,
                          case["sl"].ctypes.data if case["sl"] is not None else None)
-    o.vvco_itx_frame_q(abi.frame_from_numpy(gr, cur), C.byref(cd), case["tbs"].ctypes.data, len(case["tbs"]), 15)
+    if case["vpdus"] is not None:
+        nl, vp = case["n_luma"], case["vpdus"]
+        scales = np.zeros(len(vp), np.uint16)
+        o.vvco_itx_frame_q(abi.frame_from_numpy(gr, cur), C.byref(cd), case["tbs"].ctypes.data, nl, 15)
+        o.vvco_lmcs_chroma_scale(abi.frame_from_numpy(gr, cur), vp.ctypes.data, len(vp), case["lmcs_params"].ctypes.data, scales.ctypes.data)
+        cd.lmcs_scales = scales.ctypes.data
+        if case["quant"] is not None:
+            cd.quant = case["quant"][nl:].ctypes.data
+        o.vvco_itx_frame_q(abi.frame_from_numpy(gr, cur), C.byref(cd), case["tbs"][nl:].ctypes.data, len(case["tbs"]) - nl, 15)
+    else:
+        o.vvco_itx_frame_q(abi.frame_from_numpy(gr, cur), C.byref(cd), case["tbs"].ctypes.data, len(case["tbs"]), 15)
     o.vvco_lmcs_frame(abi.frame_from_numpy(gr, cur), case["inv"].ctypes.data, None)
     md = abi.deblock_maps_desc(gr, case["maps"])
     a, b = abi.alloc_planes(gr), abi.alloc_planes(gr)
@@ -60,12 +75,13 @@ def oracle_chain(case):
     return b
 
 
-@pytest.mark.parametrize("w,h,batch,seed,coeff_mode", [(416, 240, 4, 31, "dense"), (256, 192, 5, 32, "dense"),
-                                                       (416, 240, 3, 33, "window_q")])
-def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode):
+@pytest.mark.parametrize("w,h,batch,seed,coeff_mode,lmcs_chroma", [(416, 240, 4, 31, "dense", False), (256, 192, 5, 32, "dense", False),
+                                                                   (416, 240, 3, 33, "window_q", False), (416, 240, 3, 34, "window_q", True),
+                                                                   (256, 192, 2, 35, "dense", True)])
+def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode, lmcs_chroma):
     import torch
     from ffvvc_b200 import device
-    case = build(w, h, batch, seed, coeff_mode)
+    case = build(w, h, batch, seed, coeff_mode, lmcs_chroma)
     g1, gr = case["g1"], case["gr"]
     want = oracle_chain(case)
     keep = []
@@ -86,6 +102,8 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode):
     if case["quant"] is not None:
         d.quant, d.scaling = up(case["quant"]), up(case["sl"])
     d.lmcs_inv_lut = up(case["inv"])
+    if lmcs_chroma:
+        d.lmcs_vpdus, d.n_lmcs_vpdus, d.lmcs_params, d.n_luma_tbs = up(case["vpdus"]), len(case["vpdus"]), up(case["lmcs_params"]), case["n_luma"]
     d.inloop.deblock = C.pointer(md)
     d.inloop.sao, d.inloop.alf, d.inloop.alf_sets = up(case["sao"]), up(case["alf"]), up(case["sets"])
     for _ in range(2):                      # in place: a second pass over the same ring must give the same pictures
@@ -140,6 +158,14 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode):
         if case["quant"] is not None:
             e.quant, e.scaling = pin(case["quant"][of_k]), pin(case["sl"])
         e.lmcs_inv_lut = pin(case["inv"])
+        if lmcs_chroma:                  # this picture's VPDUs; its chroma blocks index them from 1
+            vk = case["vpdus"]["pic"] == k
+            first = int(np.nonzero(vk)[0][0])
+            vp = case["vpdus"][vk].copy()
+            vp["pic"] = 0
+            tb["chroma_scale"] = np.where(tb["chroma_scale"] > 0, tb["chroma_scale"] - first, 0)
+            C.memmove(e.tbs, tb.ctypes.data, tb.nbytes)
+            e.lmcs_vpdus, e.n_lmcs_vpdus, e.lmcs_params, e.n_luma_tbs = pin(vp), len(vp), pin(case["lmcs_params"]), int((tb["c_idx"] == 0).sum())
         e.inloop.deblock = C.pointer(hmd)
         e.inloop.sao = pin(case["sao"][k * n_ctb:(k + 1) * n_ctb])
         e.inloop.alf = pin(case["alf"][k * n_ctb:(k + 1) * n_ctb])

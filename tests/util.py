@@ -56,6 +56,8 @@ def oracle():
         lib.vvco_lmcs_frame.restype = None
         lib.vvco_lmcs_rects.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int]
         lib.vvco_lmcs_rects.restype = None
+        lib.vvco_lmcs_chroma_scale.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.vvco_lmcs_chroma_scale.restype = None
         lib.vvco_inter_frame.argtypes = [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vvco_inter_frame.restype = None
         lib.vvco_intra_leaf_frame.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p]
@@ -94,6 +96,8 @@ def ref():
         lib.vvcref_lmcs_frame.restype = None
         lib.vvcref_lmcs_rects.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int]
         lib.vvcref_lmcs_rects.restype = None
+        lib.vvcref_lmcs_chroma_scale.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.vvcref_lmcs_chroma_scale.restype = None
         lib.vvcref_inter_frame.argtypes = [FP, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vvcref_inter_frame.restype = None
         lib.vvcref_intra_leaf_frame.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p]
