@@ -337,6 +337,16 @@ CIIP_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("w", np.uint8), ("
                        ("pic", np.uint8), ("intra_weight", np.uint8), ("reserved", np.uint8, 3)])
 assert INTRA_PB_DTYPE.itemsize == 24 and CIIP_DTYPE.itemsize == 12
 
+# full intra prediction (edge preparation on the device) and CCLM
+INTRA_KIND_PRED, INTRA_KIND_MIP, INTRA_KIND_CCLM = 0, 1, 2
+INTRA_F_ISP, INTRA_F_BDPCM, INTRA_F_MIP_TRANSP, INTRA_F_UP_LEFT = 1, 2, 4, 8
+INTRA_F_LUMA_AVAIL_T, INTRA_F_LUMA_AVAIL_L, INTRA_F_COLLOCATED = 16, 32, 64
+INTRA_BLK_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("w", np.uint8), ("h", np.uint8), ("c_idx", np.uint8),
+                            ("pic", np.uint8), ("kind", np.uint8), ("pred_mode", np.uint8), ("ref_idx", np.uint8),
+                            ("flags", np.uint8), ("cb_w", np.uint8), ("cb_h", np.uint8), ("avail_left", np.uint8),
+                            ("avail_top", np.uint8)])
+assert INTRA_BLK_DTYPE.itemsize == 16
+
 
 def recon_arena(handle, geom1, alloc, *, pbs, wp, prof, tbs, coeffs, coeff_format, quant, scaling, inv_lut, maps, sao, alf, sets,
                 ref_slots=0, log2_transform_range=15):

@@ -193,6 +193,7 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 18: return sizeof(VVCCudaCoeffs);
     case 19: return sizeof(VVCCudaLmcsVpdu);
     case 20: return sizeof(VVCCudaLmcsParams);
+    case 21: return sizeof(VVCCudaIntraBlk);
     default: return 0;
     }
 }

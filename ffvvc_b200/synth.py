@@ -775,6 +775,85 @@ def intra_list(geom, seed=606):
     return np.concatenate(recs), np.concatenate(edge_parts)
 
 
+def intra_blk_list(geom, seed=808, cell=256):
+    """Independent VVCCudaIntraBlk records for the function-level tests of intra_pred / intra_cclm_pred: one block per
+    cell x cell luma area, placed so that no block's reference samples (up to 2 * 64 + 3 to the right / below, 3 above /
+    left) touch another block, so the whole list is one wavefront.  Every mode (0..66, wide angles through the mapping),
+    reference line 0..2, ISP-shaped and BDPCM blocks, MIP, chroma blocks, the three CCLM modes; availability counts as
+    the reference's functions can return them at that position (picture / CTB borders, partial lines, nothing)."""
+    rng = LCG(seed)
+    hs, vs, ctb = geom.hshift, geom.vshift, geom.ctb_size
+    recs = []
+    cells = [(k, cx, cy) for k in range(geom.batch) for cy in range(0, geom.height, cell) for cx in range(0, geom.width, cell)]
+    n = len(cells)
+    R = lambda m: rng.below(n, m)
+    r_kind, r_ox, r_oy, r_lw, r_lh, r_mode, r_ref = R(16), R(16), R(16), R(5), R(5), R(1 << 16), R(6)
+    r_al, r_at, r_l, r_t, r_ul, r_isp, r_bd, r_tr, r_col = R(8), R(8), R(1 << 16), R(1 << 16), R(4), R(8), R(10), R(2), R(2)
+    for i, (k, cx, cy) in enumerate(cells):
+        kd = int(r_kind[i])
+        chroma = kd in (10, 11, 12, 13, 14, 15) and geom.chroma_format_idc
+        cclm = kd in (13, 14, 15) and geom.chroma_format_idc
+        mipk = kd in (8, 9)
+        ox = 0 if r_ox[i] == 0 else 4 + 4 * int(r_ox[i])        # luma offsets inside the cell: 0 or 8..64
+        oy = 0 if r_oy[i] == 0 else 4 + 4 * int(r_oy[i])
+        wl, hl = 4 << int(r_lw[i]), 4 << int(r_lh[i])            # luma size 4..64
+        if chroma:
+            wl, hl = max(wl, 8 << (hs - 1) if hs else 4), max(hl, 8 << (vs - 1) if vs else 4)
+        x0l, y0l = cx + ox, cy + oy
+        if x0l + wl > geom.width or y0l + hl > geom.height:
+            x0l, y0l = cx, cy
+            if x0l + wl > geom.width or y0l + hl > geom.height:
+                continue
+        sx, sy = (hs, vs) if chroma else (0, 0)
+        x, y, w, h = x0l >> sx, y0l >> sy, wl >> sx, hl >> sy
+        pw = geom.width >> sx
+        r = np.zeros(1, dtype=abi.INTRA_BLK_DTYPE)
+        r["x0"], r["y0"], r["w"], r["h"], r["pic"], r["cb_w"], r["cb_h"] = x, y, w, h, k, wl, hl
+        r["c_idx"] = (1 + int(r_mode[i]) % 2 if not cclm else 1) if chroma else 0
+        # availability the reference's functions can report here
+        max_y = min(geom.height, ((y0l >> geom.ctb_log2) + 1) << geom.ctb_log2) >> sy
+        max_x = min(geom.width, ((x0l >> geom.ctb_log2) + 1) << geom.ctb_log2) >> sx
+        left_max = max_y - y if x > 0 else 0
+        if x0l % ctb == 0:
+            L = 0 if (r_al[i] == 0 or x == 0) else left_max
+        else:
+            L = left_max if r_al[i] >= 3 else 0 if r_al[i] == 0 else 2 * (int(r_l[i]) % (left_max // 2 + 1))
+        if y == 0:
+            T = 0
+        elif y0l % ctb == 0:
+            T = 0 if r_at[i] == 0 else (pw - x) if r_at[i] >= 3 else 1 + int(r_t[i]) % (pw - x)
+        else:
+            T = (max_x - x) if r_at[i] >= 3 else 0 if r_at[i] == 0 else 2 * (int(r_t[i]) % ((max_x - x) // 2 + 1))
+        r["avail_left"], r["avail_top"] = min(L, 255), min(T, 255)
+        flags = abi.INTRA_F_UP_LEFT if (x > 0 and y > 0 and r_ul[i] != 0) else 0
+        if cclm:
+            r["kind"], r["pred_mode"] = abi.INTRA_KIND_CCLM, 81 + (kd - 13)
+            flags |= (abi.INTRA_F_LUMA_AVAIL_T if T > 0 else 0) | (abi.INTRA_F_LUMA_AVAIL_L if L > 0 else 0)
+            flags |= abi.INTRA_F_COLLOCATED if r_col[i] else 0
+        elif mipk:
+            size_id = 0 if (w == 4 and h == 4) else (1 if (w == 4 or h == 4 or (w == 8 and h == 8)) else 2)
+            r["kind"], r["pred_mode"] = abi.INTRA_KIND_MIP, int(r_mode[i]) % (16, 8, 6)[size_id]
+            flags |= abi.INTRA_F_MIP_TRANSP if r_tr[i] else 0
+        else:
+            m = int(r_mode[i]) % 80
+            r["pred_mode"] = m if m < 67 else (0, 1, 18, 50, 2, 34, 66, 0, 1, 18, 50, 0, 1)[m - 67]
+            if not chroma:
+                r["ref_idx"] = (0, 0, 0, 0, 1, 2)[int(r_ref[i])] if y0l % ctb else 0
+                if r_isp[i] == 0 and r["ref_idx"][0] == 0 and wl * hl >= 32:     # a sub-partition of a wl x hl coding block
+                    if r_tr[i] and hl >= 8:
+                        h = hl // (4 if hl >= 16 and wl * hl > 32 else 2)
+                    elif wl >= 8:
+                        w = wl // (4 if wl >= 16 and wl * hl > 32 else 2)
+                    else:
+                        h = hl // 2
+                    r["w"], r["h"] = w, h
+                    flags |= abi.INTRA_F_ISP
+            flags |= abi.INTRA_F_BDPCM if r_bd[i] == 0 else 0
+        r["flags"] = flags
+        recs.append(r)
+    return np.concatenate(recs)
+
+
 def ciip_list(geom, seed=707):
     """CIIP blocks on a random partition: every block of every plane with intra weight 1..3."""
     rng = LCG(seed)

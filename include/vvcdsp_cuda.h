@@ -69,7 +69,7 @@ const char *vvc_cuda_version(void);
 #define VVC_CUDA_OPT_INTER_TMA 3
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams, 21 VVCCudaIntraBlk): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -479,6 +479,56 @@ int vvc_cuda_intra_leaf_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const 
                               const uint16_t *edges);
 int vvc_cuda_intra_leaf_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraPB *pbs, int n_pbs,
                                    const uint16_t *edges, size_t n_edges);
+
+/* ------------------------------------------------------------------------------------------
+ * Full intra prediction: the table entries intra.intra_pred (vvc_intra_template.c:595-683 with
+ * prepare_intra_edge_params :467-592 and ref_filter :450-465) and intra.intra_cclm_pred (:29-375) on the device -
+ * reference-line gather from the reconstructed picture, substitution of unavailable samples, the [1 2 1] smoothing,
+ * the projected / extended part of the angular reference, wide-angle mode mapping (ff_vvc_wide_angle_mode_mapping,
+ * vvc_intra.c:693-715), the predictors, and the PDPC of planar / DC / H / V; CCLM: luma down-sampling, the four
+ * selected neighbour positions, min / max pairs, the a / b / k derivation and the linear predictor for Cb and Cr.
+ * What a record states about the decoder's CTU state is what ff_vvc_get_left_available / _top_available
+ * (vvc_intra.c:591-648) return with an unbounded target size - the callee takes min(target, that) - and
+ * lc->na.cand_up_left.  Blocks of one call must not depend on each other (one wavefront).
+ * ---------------------------------------------------------------------------------------- */
+#define VVC_CUDA_INTRA_KIND_PRED  0   /* intra_pred, regular modes 0..66                               */
+#define VVC_CUDA_INTRA_KIND_MIP   1   /* intra_pred, matrix-based (fc->tab.imf set)                    */
+#define VVC_CUDA_INTRA_KIND_CCLM  2   /* intra_cclm_pred: predicts Cb and Cr; pred_mode 81 / 82 / 83   */
+
+#define VVC_CUDA_INTRA_F_ISP          1   /* cu->isp_split_type != ISP_NO_SPLIT (luma)                 */
+#define VVC_CUDA_INTRA_F_BDPCM        2   /* cu->bdpcm_flag[c_idx]                                     */
+#define VVC_CUDA_INTRA_F_MIP_TRANSP   4   /* fc->tab.imtf                                              */
+#define VVC_CUDA_INTRA_F_UP_LEFT      8   /* lc->na.cand_up_left                                       */
+#define VVC_CUDA_INTRA_F_LUMA_AVAIL_T 16  /* CCLM: ff_vvc_get_top_available(lc, x0, y0, 1, 0) != 0     */
+#define VVC_CUDA_INTRA_F_LUMA_AVAIL_L 32  /* CCLM: ff_vvc_get_left_available(lc, x0, y0, 1, 0) != 0    */
+#define VVC_CUDA_INTRA_F_COLLOCATED   64  /* CCLM: sps_chroma_vertical_collocated_flag                 */
+
+typedef struct VVCCudaIntraBlk {
+    uint16_t x0, y0;          /* top-left sample in plane c_idx's own units (CCLM: chroma units)       */
+    uint8_t  w, h;            /* in the same units: 2..64 (4..64 for MIP)                              */
+    uint8_t  c_idx, pic;      /* CCLM: c_idx = 1 (both chroma planes are predicted)                    */
+    uint8_t  kind;            /* VVC_CUDA_INTRA_KIND_*                                                  */
+    uint8_t  pred_mode;       /* cu->intra_pred_mode_y / _c before wide-angle mapping; MIP: the mode id */
+    uint8_t  ref_idx;         /* cu->intra_luma_ref_idx (0 for chroma)                                 */
+    uint8_t  flags;           /* VVC_CUDA_INTRA_F_*                                                     */
+    uint8_t  cb_w, cb_h;      /* cu->cb_width / cb_height (luma samples; read for ISP blocks only)     */
+    uint8_t  avail_left;      /* ff_vvc_get_left_available(lc, x, y, 255, c_idx)                       */
+    uint8_t  avail_top;       /* ff_vvc_get_top_available(lc, x, y, 255, c_idx)                        */
+} VVCCudaIntraBlk;            /* 16 bytes */
+
+/* frame: the picture (ring) being reconstructed: reference samples are read from it, the prediction is written
+ * into it.  blks: device memory. */
+int vvc_cuda_intra_pred_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraBlk *blks, int n_blks);
+int vvc_cuda_intra_pred_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraBlk *blks, int n_blks);
+
+/* All-intra reconstruction of a picture (ring): prediction and residual alternate wavefront by wavefront.  The
+ * blocks and the transform blocks are sorted by wavefront; wave g owns blks[blk_end[g-1] .. blk_end[g]) and
+ * tbs[tb_end[g-1] .. tb_end[g]) (blk_end / tb_end: HOST arrays of n_waves running totals).  A block belongs to the
+ * first wavefront in which every block whose samples it reads (reference lines, CCLM's luma) has been reconstructed;
+ * its transform blocks belong to the same wavefront.  Everything else as vvc_cuda_intra_pred_frame / _itx_frame_q. */
+int vvc_cuda_intra_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraBlk *blks, const int32_t *blk_end,
+                               const VVCCudaCoeffs *coeffs, const VVCCudaTB *tbs, const int32_t *tb_end, int n_waves,
+                               int log2_transform_range);
 
 typedef struct VVCCudaCiip {
     uint16_t x0, y0;          /* in plane c_idx's own units */

@@ -44,3 +44,10 @@ size_t vvcref_dsp_sizeof(void)
 {
     return sizeof(VVCDSPContext);
 }
+
+/* vvc_intra.c calls ff_log2() without the header that defines it as a macro (libavutil/intmath.h), so the compiler
+ * emits a call: the function of that header (floor(log2(v)), v | 1) */
+int ff_log2(unsigned v)
+{
+    return 31 - __builtin_clz(v | 1);
+}

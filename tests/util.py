@@ -64,6 +64,10 @@ def oracle():
         lib.vvco_intra_leaf_frame.restype = None
         lib.vvco_ciip_frame.argtypes = [FP, FP, C.c_void_p, C.c_int]
         lib.vvco_ciip_frame.restype = None
+        lib.vvco_intra_pred_frame.argtypes = [FP, C.c_void_p, C.c_int]
+        lib.vvco_intra_pred_frame.restype = None
+        lib.vvco_intra_recon_frame.argtypes = [FP, C.c_void_p, C.c_void_p, C.POINTER(abi.VVCCudaCoeffs), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.vvco_intra_recon_frame.restype = None
         _oracle = lib
     return _oracle
 
@@ -104,6 +108,8 @@ def ref():
         lib.vvcref_intra_leaf_frame.restype = None
         lib.vvcref_ciip_frame.argtypes = [FP, FP, C.c_void_p, C.c_int]
         lib.vvcref_ciip_frame.restype = None
+        lib.vvcref_intra_pred_frame.argtypes = [FP, C.c_void_p, C.c_int]
+        lib.vvcref_intra_pred_frame.restype = None
         _ref = lib
     return _ref
 
