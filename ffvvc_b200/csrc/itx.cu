@@ -373,6 +373,35 @@ extern "C" int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, 
     return VVC_CUDA_OK;
 }
 
+// One launch of the generic kernel over a short list: the per-wavefront residual step of vvc_cuda_intra_recon_frame,
+// where the sort + three-kernel structure above would cost more launches than the blocks are worth.
+int vvc_itx_launch_short(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaCoeffs *co, const VVCCudaTB *tbs, int n_tbs, int range)
+{
+    if (!frame || !co || !co->data || !tbs || n_tbs <= 0)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: null argument");
+    if ((frame->bit_depth != 10 && frame->bit_depth != 12) || range < 15 || range > 20 ||
+        (co->format != VVC_CUDA_COEFF_DENSE32 && co->format != VVC_CUDA_COEFF_WINDOW16) || (co->format == VVC_CUDA_COEFF_WINDOW16 && range != 15) ||
+        !frame_vec_ok(frame))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: unsupported picture or coefficient format");
+    const int mode = coef_mode(co);
+    ItxK p;
+    for (int c = 0; c < 3; c++) {
+        p.plane[c] = (pel *)frame->data[c];
+        p.pitch[c] = (int)(frame->stride[c] / 2);
+        p.bstride[c] = frame->batch_stride[c] / 2;
+    }
+    p.src.dense = (mode & 1) ? nullptr : (const int32_t *)co->data;
+    p.src.window = (mode & 1) ? (const int16_t *)co->data : nullptr;
+    p.src.quant = co->quant; p.src.scaling = co->scaling; p.src.lmcs_scales = co->lmcs_scales;
+    p.src.range = range; p.src.bd = frame->bit_depth;
+    p.store = (mode & 1) ? nullptr : (int32_t *)co->data;
+    p.tbs = tbs; p.n_tbs = n_tbs; p.range = range; p.bd = frame->bit_depth;
+    p.list = p.list_count = NULL;
+    launch_generic(p, mode, ceil_div(n_tbs, TBS_PER_CTA), ctx->stream);
+    VVC_LAUNCHED(ctx);
+    return VVC_CUDA_OK;
+}
+
 extern "C" int vvc_cuda_itx_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int32_t *coeffs,
                                   const VVCCudaTB *tbs, int n_tbs, int log2_transform_range)
 {

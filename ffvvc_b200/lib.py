@@ -4,6 +4,8 @@ There is deliberately no fallback: if the CUDA library is missing or no device i
 importing callers get an exception.  PyTorch is used only to own device memory and streams.
 """
 import ctypes as C
+
+import numpy as np
 import os
 import re
 
@@ -86,6 +88,9 @@ def load():
     lib.vvc_cuda_ctx_set_option.argtypes = [CTX, C.c_int, C.c_int]
     lib.vvc_cuda_intra_leaf_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p]
     lib.vvc_cuda_intra_leaf_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.vvc_cuda_intra_pred_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int]
+    lib.vvc_cuda_intra_pred_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_int]
+    lib.vvc_cuda_intra_recon_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, CP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.vvc_cuda_ciip_frame.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int]
     lib.vvc_cuda_ciip_frame_host.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int]
     lib.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
@@ -221,6 +226,20 @@ class Context:
 
     def intra_leaf_frame_host(self, frame, pbs_ptr, n_pbs, edges_ptr, n_edges):
         self.check(self.lib.vvc_cuda_intra_leaf_frame_host(self.handle, C.byref(frame), pbs_ptr, n_pbs, edges_ptr, n_edges))
+
+    def intra_pred_frame(self, frame, blks_ptr, n_blks):
+        """intra_pred (reference lines prepared on the device) / intra_cclm_pred of one wavefront of blocks."""
+        self.check(self.lib.vvc_cuda_intra_pred_frame(self.handle, C.byref(frame), blks_ptr, n_blks))
+
+    def intra_pred_frame_host(self, frame, blks_ptr, n_blks):
+        self.check(self.lib.vvc_cuda_intra_pred_frame_host(self.handle, C.byref(frame), blks_ptr, n_blks))
+
+    def intra_recon_frame(self, frame, blks_ptr, blk_end, coeffs_desc, tbs_ptr, tb_end, log2_transform_range=15):
+        """All-intra reconstruction, prediction and residual alternating wavefront by wavefront (blk_end / tb_end: host
+        int32 arrays of running totals)."""
+        assert len(blk_end) == len(tb_end) and blk_end.dtype == tb_end.dtype == np.int32
+        self.check(self.lib.vvc_cuda_intra_recon_frame(self.handle, C.byref(frame), blks_ptr, blk_end.ctypes.data, C.byref(coeffs_desc),
+                                                       tbs_ptr, tb_end.ctypes.data, len(blk_end), log2_transform_range))
 
     def ciip_frame(self, dst, inter, blocks_ptr, n_blocks):
         """CIIP blend of the intra prediction in dst with the inter prediction picture."""

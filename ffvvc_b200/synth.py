@@ -854,6 +854,160 @@ def intra_blk_list(geom, seed=808, cell=256):
     return np.concatenate(recs)
 
 
+def _morton(x, y):
+    m = np.zeros_like(x, dtype=np.int64)
+    for b in range(12):
+        m |= ((x >> b) & 1).astype(np.int64) << (2 * b)
+        m |= ((y >> b) & 1).astype(np.int64) << (2 * b + 1)
+    return m
+
+
+def intra_picture(geom, seed=909):
+    """An all-intra picture ring for vvc_cuda_intra_recon_frame: the transform blocks of tb_list() double as coding units
+    (luma block + its two chroma blocks, 4:2:0), decoded CTU by CTU in raster order and in z-order inside a CTU.  Every
+    luma block gets a regular mode (0..66, MRL away from CTB tops), MIP or a BDPCM flag; the chroma pair either one CCLM
+    record (three modes) or two regular records.  Availability counts and flags are what that decoding order makes
+    available (a neighbour sample is available when its coding unit comes earlier, inside the limits of
+    ff_vvc_get_left_available / _top_available); a block's wave is one more than the latest wave among the blocks whose
+    samples it reads, chroma after its own luma.
+
+    Returns dict(blks, blk_end, tbs, tb_end, coeffs: sorted by wave; dec_blks, dec_blk_end, dec_tbs, dec_tb_end: the same
+    records in decoding order, one luma and one chroma step per coding unit - what a CPU decoder does)."""
+    assert geom.chroma_format_idc == 1 and geom.hshift == 1 and geom.vshift == 1
+    rng = LCG(seed)
+    tbs, coeffs = tb_list(geom, seed=seed + 1, extras=False)
+    keep = ~((tbs["c_idx"] > 0) & ((tbs["log2_w"] < 2) | (tbs["log2_h"] < 2)))        # no 2-wide chroma blocks in VVC intra
+    tbs = tbs[keep]
+    ctb, cl2 = geom.ctb_size, geom.ctb_log2
+    luma = np.nonzero(tbs["c_idx"] == 0)[0]
+    lx, ly = tbs["x0"][luma].astype(np.int64), tbs["y0"][luma].astype(np.int64)
+    key = (tbs["pic"][luma].astype(np.int64) << 40) | (((ly >> cl2) * geom.ctb_cols + (lx >> cl2)) << 24) | _morton(lx & (ctb - 1), ly & (ctb - 1))
+    luma = luma[np.argsort(key, kind="stable")]
+    # chroma TBs of a coding unit, by (pic, x, y)
+    chroma_of = {}
+    for i in np.nonzero(tbs["c_idx"] > 0)[0]:
+        chroma_of.setdefault((int(tbs["pic"][i]), int(tbs["x0"][i]), int(tbs["y0"][i])), []).append(int(i))
+    H, W = geom.height, geom.width
+    order = [np.full((geom.batch, H >> s, W >> s), -1, dtype=np.int64) for s in (0, 1)]
+    wave = [np.full((geom.batch, H >> s, W >> s), -1, dtype=np.int64) for s in (0, 1)]
+    n = len(luma)
+    R = lambda m: rng.below(n, m)
+    r_kind, r_mode, r_ref, r_bd, r_tr, r_ck, r_cm, r_col = R(10), R(1 << 16), R(6), R(12), R(2), R(5), R(1 << 16), R(2)
+    blks, blk_wave, tb_wave = [], [], np.zeros(len(tbs), dtype=np.int64)
+    dec_blks, dec_blk_end, dec_tb_idx, dec_tb_end = [], [], [], []
+
+    def avail(ch, k, o, x, y, x0l, y0l):
+        """(left count, top count, up-left) of the block at plane position (x, y) of plane type ch"""
+        sh = ch
+        om = order[ch][k]
+        ph, pw = om.shape
+        max_y = min(H, ((y0l >> cl2) + 1) << cl2) >> sh
+        max_x = min(W, ((x0l >> cl2) + 1) << cl2) >> sh
+        L = T = 0
+        if x > 0:
+            col = om[y:max_y, x - 1]
+            ok = (col >= 0) & (col < o)
+            L = int(len(ok) if ok.all() else np.argmin(ok))
+        if y > 0:
+            row = om[y - 1, x:(pw if y0l % ctb == 0 else max_x)]
+            ok = (row >= 0) & (row < o)
+            T = int(len(ok) if ok.all() else np.argmin(ok))
+        ul = x > 0 and y > 0 and 0 <= om[y - 1, x - 1] < o
+        return min(L, 255), min(T, 255), ul
+
+    def deps(ch, k, x, y, w, h):
+        """latest wave among the samples the block at (x, y, w, h) of plane type ch may read"""
+        wm = wave[ch][k]
+        ya, xa = max(y - 3, 0), max(x - 3, 0)
+        m = -1
+        if y > 0:
+            m = max(m, int(wm[ya:y, xa:x + 2 * w + 4].max()))
+        if x > 0:
+            m = max(m, int(wm[ya:y + 2 * h + 4, xa:x].max()))
+        return m
+
+    for j, ti in enumerate(luma):
+        t = tbs[ti]
+        k, x0, y0, w, h = int(t["pic"]), int(t["x0"]), int(t["y0"]), 1 << int(t["log2_w"]), 1 << int(t["log2_h"])
+        o = j
+        # ---- luma block ----
+        r = np.zeros(1, dtype=abi.INTRA_BLK_DTYPE)
+        r["x0"], r["y0"], r["w"], r["h"], r["pic"], r["cb_w"], r["cb_h"] = x0, y0, w, h, k, w, h
+        L, T, ul = avail(0, k, o, x0, y0, x0, y0)
+        r["avail_left"], r["avail_top"] = L, T
+        flags = abi.INTRA_F_UP_LEFT if ul else 0
+        if r_kind[j] < 2:
+            size_id = 0 if (w == 4 and h == 4) else (1 if (w == 4 or h == 4 or (w == 8 and h == 8)) else 2)
+            r["kind"], r["pred_mode"] = abi.INTRA_KIND_MIP, int(r_mode[j]) % (16, 8, 6)[size_id]
+            flags |= abi.INTRA_F_MIP_TRANSP if r_tr[j] else 0
+        else:
+            m = int(r_mode[j]) % 75
+            r["pred_mode"] = m if m < 67 else (0, 1, 18, 50, 0, 1, 34, 66)[m - 67]
+            r["ref_idx"] = (0, 0, 0, 0, 1, 2)[int(r_ref[j])] if y0 % ctb else 0
+            flags |= abi.INTRA_F_BDPCM if r_bd[j] == 0 else 0
+        r["flags"] = flags
+        wl = deps(0, k, x0, y0, w, h) + 1
+        order[0][k, y0:y0 + h, x0:x0 + w] = o
+        wave[0][k, y0:y0 + h, x0:x0 + w] = wl
+        blks.append(r); blk_wave.append(wl)
+        tb_wave[ti] = wl
+        dec_blks.append(r); dec_blk_end.append(len(dec_blks)); dec_tb_idx.append(ti); dec_tb_end.append(len(dec_tb_idx))
+        # ---- its chroma blocks ----
+        ctbs = chroma_of.get((k, x0 >> 1, y0 >> 1), [])
+        if w < 8 or h < 8:
+            assert not ctbs
+            continue
+        x, y, cw, chh = x0 >> 1, y0 >> 1, w >> 1, h >> 1
+        L, T, ul = avail(1, k, o, x, y, x0, y0)
+        wc = max(deps(1, k, x, y, cw, chh), wl) + 1
+        recs = []
+        if r_ck[j] < 2:
+            q = np.zeros(1, dtype=abi.INTRA_BLK_DTYPE)
+            q["x0"], q["y0"], q["w"], q["h"], q["pic"], q["c_idx"], q["cb_w"], q["cb_h"] = x, y, cw, chh, k, 1, w, h
+            q["kind"], q["pred_mode"] = abi.INTRA_KIND_CCLM, 81 + int(r_cm[j]) % 3
+            q["avail_left"], q["avail_top"] = L, T
+            lo = order[0][k]
+            at = y0 > 0 and 0 <= lo[y0 - 1, x0] < o
+            al = x0 > 0 and 0 <= lo[y0, x0 - 1] < o
+            q["flags"] = (abi.INTRA_F_UP_LEFT if ul else 0) | (abi.INTRA_F_LUMA_AVAIL_T if at else 0) | (abi.INTRA_F_LUMA_AVAIL_L if al else 0) | \
+                         (abi.INTRA_F_COLLOCATED if r_col[j] else 0)
+            # the luma it reads: above / left of the coding unit as far as the T / L modes reach, and the unit itself
+            lw_ = wave[0][k]
+            ya, xa = max(y0 - 3, 0), max(x0 - 3, 0)
+            m = wl
+            if y0 > 0:
+                m = max(m, int(lw_[ya:y0, xa:x0 + 2 * w + 4].max()))
+            if x0 > 0:
+                m = max(m, int(lw_[ya:y0 + 2 * h + 4, xa:x0].max()))
+            wc = max(wc, m + 1)
+            recs.append(q)
+        else:
+            m = int(r_cm[j]) % 75
+            pm = m if m < 67 else (0, 1, 18, 50, 0, 1, 34, 66)[m - 67]
+            for c in (1, 2):
+                q = np.zeros(1, dtype=abi.INTRA_BLK_DTYPE)
+                q["x0"], q["y0"], q["w"], q["h"], q["pic"], q["c_idx"], q["cb_w"], q["cb_h"] = x, y, cw, chh, k, c, w, h
+                q["pred_mode"], q["avail_left"], q["avail_top"], q["flags"] = pm, L, T, abi.INTRA_F_UP_LEFT if ul else 0
+                recs.append(q)
+        order[1][k, y:y + chh, x:x + cw] = o
+        wave[1][k, y:y + chh, x:x + cw] = wc
+        for q in recs:
+            blks.append(q); blk_wave.append(wc); dec_blks.append(q)
+        dec_blk_end.append(len(dec_blks))
+        for ci in ctbs:
+            tb_wave[ci] = wc
+            dec_tb_idx.append(ci)
+        dec_tb_end.append(len(dec_tb_idx))
+    blks = np.concatenate(blks)
+    blk_wave = np.array(blk_wave)
+    n_waves = int(max(blk_wave.max(), tb_wave.max())) + 1
+    bo, to = np.argsort(blk_wave, kind="stable"), np.argsort(tb_wave, kind="stable")
+    return dict(blks=blks[bo], blk_end=np.cumsum(np.bincount(blk_wave, minlength=n_waves)).astype(np.int32),
+                tbs=tbs[to], tb_end=np.cumsum(np.bincount(tb_wave, minlength=n_waves)).astype(np.int32), coeffs=coeffs,
+                dec_blks=np.concatenate(dec_blks), dec_blk_end=np.array(dec_blk_end, dtype=np.int32),
+                dec_tbs=tbs[np.array(dec_tb_idx)], dec_tb_end=np.array(dec_tb_end, dtype=np.int32), n_waves=n_waves)
+
+
 def ciip_list(geom, seed=707):
     """CIIP blocks on a random partition: every block of every plane with intra weight 1..3."""
     rng = LCG(seed)

@@ -1,0 +1,88 @@
+"""GPU parity: full intra prediction (reference lines prepared on the device, wide-angle mapping, every predictor, PDPC,
+MIP), CCLM, and the all-intra reconstruction by wavefronts - vs the oracle, through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ffvvc_b200 import abi, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from ffvvc_b200 import lib
+    c = lib.Context(0)
+    with torch.cuda.stream(c.torch_stream()):
+        yield c
+    c.close()
+
+
+@pytest.mark.parametrize("w,h,batch,bd,ctb_log2,seed", [(2048, 1536, 6, 10, 7, 1), (1920, 1080, 8, 10, 7, 2), (1024, 768, 16, 12, 6, 3),
+                                                        (1280, 720, 16, 10, 5, 4), (3840, 2160, 2, 10, 7, 5)])
+def test_intra_pred_and_cclm_bit_exact(ctx, w, h, batch, bd, ctb_log2, seed):
+    from ffvvc_b200 import device
+    geom = abi.FrameGeom(w, h, batch=batch, bit_depth=bd, ctb_log2=ctb_log2)
+    planes = synth.uniform_planes(geom, seed=seed + 20)
+    blks = synth.intra_blk_list(geom, seed=seed)
+    want = [a.copy() for a in planes]
+    util.oracle().vvco_intra_pred_frame(abi.frame_from_numpy(geom, want), blks.ctypes.data, len(blks))
+    fr = device.DeviceFrames(geom, planes=planes)
+    t, p = device.to_device(blks)
+    ctx.intra_pred_frame(fr.desc, p, len(blks))
+    ctx.sync()
+    got = fr.to_numpy()
+    for c in range(3):
+        bad = np.argwhere(util.visible(geom, got)[c] != util.visible(geom, want)[c]) if hasattr(util, "visible") else []
+        if len(bad):
+            k, y, x = bad[0]
+            hit = blks[(blks["pic"] == k) & ((blks["c_idx"] == c) | ((blks["kind"] == 2) & (c > 0))) &
+                       (blks["x0"] <= x) & (x < blks["x0"] + blks["w"].astype(int)) & (blks["y0"] <= y) & (y < blks["y0"] + blks["h"].astype(int))]
+            raise AssertionError("plane %d differs at pic %d (%d, %d): cuda %d oracle %d, record %s" % (c, k, x, y, got[c][k, y, x], want[c][k, y, x], hit))
+    util.assert_planes_equal(geom, got, want, "cuda vs oracle")
+    if w == 1920:
+        host = [a.copy() for a in planes]
+        ctx.intra_pred_frame_host(abi.frame_from_numpy(geom, host), blks.ctypes.data, len(blks))
+        util.assert_planes_equal(geom, host, want, "host entry vs oracle")
+
+
+@pytest.mark.parametrize("w,h,batch,seed,mode", [(416, 240, 2, 3, "dense"), (256, 192, 3, 4, "window_q"), (832, 480, 1, 5, "dense")])
+def test_all_intra_pictures_by_wavefronts_bit_exact(ctx, w, h, batch, seed, mode):
+    """prediction and residual alternating wavefront by wavefront on the GPU vs the oracle walking the same blocks in
+    decoding order (luma step, chroma step per coding unit)"""
+    from ffvvc_b200 import device
+    geom = abi.FrameGeom(w, h, batch=batch)
+    case = synth.intra_picture(geom, seed=seed)
+    planes = abi.alloc_planes(geom, fill=512)
+    fmt, coeffs = abi.COEFF_DENSE32, case["coeffs"]
+    quant = dq = sl = None
+    tbs, dtbs = case["tbs"], case["dec_tbs"]
+    if mode == "window_q":
+        # one packing for both orders: pack in decoding order, then carry the new offsets over to the wave order
+        dtbs, coeffs = abi.pack_window16(synth.tb_for_window(dtbs), coeffs)
+        dq, sl = synth.tb_quant(dtbs, seed=seed + 7, scaling=True)
+        key = lambda t: (t["pic"].astype(np.int64) << 40) | (t["c_idx"].astype(np.int64) << 36) | (t["y0"].astype(np.int64) << 16) | t["x0"]
+        pos = {int(k): i for i, k in enumerate(key(dtbs))}
+        idx = np.array([pos[int(k)] for k in key(tbs)])
+        tbs, quant = dtbs[idx], dq[idx]
+        fmt = abi.COEFF_WINDOW16
+    want = [a.copy() for a in planes]
+    co = coeffs.copy()
+    cd = abi.coeffs_desc(co.ctypes.data, co.size, fmt, dq.ctypes.data if dq is not None else None, sl.ctypes.data if sl is not None else None)
+    util.oracle().vvco_intra_recon_frame(abi.frame_from_numpy(geom, want), case["dec_blks"].ctypes.data, case["dec_blk_end"].ctypes.data,
+                                         C.byref(cd), dtbs.ctypes.data, case["dec_tb_end"].ctypes.data, len(case["dec_blk_end"]), 15)
+    fr = device.DeviceFrames(geom, planes=planes)
+    keep = [device.to_device(a) for a in (case["blks"], coeffs, tbs)]
+    pq = psl = None
+    if quant is not None:
+        keep += [device.to_device(quant), device.to_device(sl)]
+        pq, psl = keep[-2][1], keep[-1][1]
+    before = ctx.launches()
+    ctx.intra_recon_frame(fr.desc, keep[0][1], case["blk_end"], abi.coeffs_desc(keep[1][1], coeffs.size, fmt, pq, psl), keep[2][1], case["tb_end"], 15)
+    ctx.sync()
+    assert ctx.launches() - before <= 2 * case["n_waves"]
+    util.assert_planes_equal(geom, fr.to_numpy(), want, "wavefronts on the GPU vs decoding order on the CPU")
+    assert case["n_waves"] > 20 and (case["blks"]["kind"] == 2).any() and (case["blks"]["kind"] == 1).any()
