@@ -80,9 +80,9 @@ def test_all_intra_pictures_by_wavefronts_bit_exact(ctx, w, h, batch, seed, mode
     if quant is not None:
         keep += [device.to_device(quant), device.to_device(sl)]
         pq, psl = keep[-2][1], keep[-1][1]
-    before = ctx.launches()
+    before = ctx.launches
     ctx.intra_recon_frame(fr.desc, keep[0][1], case["blk_end"], abi.coeffs_desc(keep[1][1], coeffs.size, fmt, pq, psl), keep[2][1], case["tb_end"], 15)
     ctx.sync()
-    assert ctx.launches() - before <= 2 * case["n_waves"]
+    assert ctx.launches - before <= 2 * case["n_waves"]
     util.assert_planes_equal(geom, fr.to_numpy(), want, "wavefronts on the GPU vs decoding order on the CPU")
     assert case["n_waves"] > 20 and (case["blks"]["kind"] == 2).any() and (case["blks"]["kind"] == 1).any()
