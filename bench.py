@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against the reference C")
     ap.add_argument("--inter-tma", type=int, default=-1, help="VVC_CUDA_OPT_INTER_TMA (default: the library's)")
+    ap.add_argument("--ref-pad", type=int, default=0, help="VVC_CUDA_OPT_REF_PAD: margin of replicated samples around the device-resident DPB ring")
     ap.add_argument("--quick", action="store_true", help="skip the one-picture-per-launch and the >1 s runs")
     args = ap.parse_args()
 
@@ -322,7 +323,10 @@ def main():
     # ---- device-resident rings --------------------------------------------------------------------
     reps = frames // inp.distinct + 1
     ring_planes = [np.ascontiguousarray(np.concatenate([p] * reps)[:frames]) for p in inp.ref_planes]
-    refs = device.DeviceFrames(gring, device=dev, planes=ring_planes)       # DPB ring (frames pictures > L2)
+    refs = device.DeviceFrames(gring, device=dev, planes=ring_planes, pad=args.ref_pad)       # DPB ring (frames pictures > L2)
+    if args.ref_pad:
+        ctx.pad_frame(refs.desc, args.ref_pad)
+        ctx.set_option(abi.OPT_REF_PAD, args.ref_pad)
     cur = device.DeviceFrames(gring, device=dev)
     out = device.DeviceFrames(gring, device=dev)
     tmp_a = device.DeviceFrames(ggrp, device=dev)

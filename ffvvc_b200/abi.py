@@ -13,6 +13,7 @@ EDGE_LEFT, EDGE_TOP, EDGE_RIGHT, EDGE_BOTTOM = 1, 2, 4, 8
 OPT_GENERIC_KERNELS = 1      # vvc_cuda_ctx_set_option()
 OPT_ALF_WIDE_MULTIPLY = 2
 OPT_INTER_TMA = 3
+OPT_REF_PAD = 4
 INTER_TMA_DEFAULT = 0       # what vvc_cuda_ctx_create() starts with
 
 

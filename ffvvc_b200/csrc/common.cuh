@@ -19,6 +19,7 @@ struct VVCCudaCtx {
     int           force_generic;        // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_GENERIC_KERNELS)
     int           alf_wide_multiply;    // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_ALF_WIDE_MULTIPLY)
     int           inter_tma;            // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_INTER_TMA)
+    int           ref_pad;              // vvc_cuda_ctx_set_option(VVC_CUDA_OPT_REF_PAD): replicated luma samples around the reference planes
     bool          itx_packed;           // itx_warp.cu's packed transform matrices are built on this device
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;
@@ -42,6 +43,13 @@ void *vvc_ctx_scratch(VVCCudaCtx *ctx, int slot, size_t bytes);
 // the tail of one fills with the next instead of draining the machine between launches.
 int   vvc_ctx_fork(VVCCudaCtx *ctx, int n);
 int   vvc_ctx_join(VVCCudaCtx *ctx, int n);
+
+// The *_host entries stage host reference pictures without margins: VVC_CUDA_OPT_REF_PAD does not apply to them.
+struct VVCRefPadOff {
+    VVCCudaCtx *ctx; int saved;
+    explicit VVCRefPadOff(VVCCudaCtx *c, bool off) : ctx(c), saved(c->ref_pad) { if (off) c->ref_pad = 0; }
+    ~VVCRefPadOff() { ctx->ref_pad = saved; }
+};
 
 #define VVC_TRY(ctx, call)  do { if (vvc_ctx_check((ctx), (call), #call)) return (ctx)->err; } while (0)
 #define VVC_LAUNCHED(ctx)   do { (ctx)->launches++; if (vvc_ctx_check((ctx), cudaGetLastError(), "kernel launch")) return (ctx)->err; } while (0)

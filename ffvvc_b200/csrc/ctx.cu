@@ -162,6 +162,11 @@ int vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value)
     case VVC_CUDA_OPT_GENERIC_KERNELS: ctx->force_generic = value != 0; return VVC_CUDA_OK;
     case VVC_CUDA_OPT_ALF_WIDE_MULTIPLY: ctx->alf_wide_multiply = value != 0; return VVC_CUDA_OK;
     case VVC_CUDA_OPT_INTER_TMA: ctx->inter_tma = value != 0; return VVC_CUDA_OK;
+    case VVC_CUDA_OPT_REF_PAD:
+        if (value < 0 || (value & 15) || value > 1024)       // 16: the chroma planes stay 16-byte aligned
+            return VVC_CUDA_ERR_ARG;
+        ctx->ref_pad = value;
+        return VVC_CUDA_OK;
     default: return VVC_CUDA_ERR_ARG;
     }
 }

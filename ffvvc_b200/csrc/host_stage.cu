@@ -58,3 +58,50 @@ int vvc_stage_frame_d2h(VVCCudaCtx *ctx, const VVCCudaFrame *host, const VVCCuda
 {
     return copy_frame(ctx, host, dev, cudaMemcpyDeviceToHost);
 }
+
+// ---- pre-padded reference planes (VVC_CUDA_OPT_REF_PAD) ------------------------------------------------------------
+// What the reference fabricates per block when a motion vector points outside the picture (ff_emulated_edge_mc through
+// emulated_edge, libavcodec/vvc/vvc_inter.c:33-58: every coordinate clamped to the picture) is stored once per picture
+// instead: a margin of replicated samples around every plane.  One thread per margin sample; the interior is not touched.
+namespace {
+
+__global__ void __launch_bounds__(256) pad_frame_kernel(pel *plane, int pitch, long long bstride, int w, int h, int mx, int my)
+{
+    pel *pic = plane + blockIdx.y * bstride;
+    const int W = w + 2 * mx;
+    // margin samples in row-major order of the padded plane: my full rows above, then (left, right) strips of the h picture
+    // rows, then my full rows below
+    const long long top = (long long)my * W, sides = (long long)h * 2 * mx, total = 2 * top + sides;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        int x, y;
+        if (i < top)              { y = (int)(i / W) - my;              x = (int)(i % W) - mx; }
+        else if (i < top + sides) { const long long j = i - top; y = (int)(j / (2 * mx)); const int k = (int)(j % (2 * mx)); x = k < mx ? k - mx : w + k - mx; }
+        else                      { const long long j = i - top - sides; y = h + (int)(j / W); x = (int)(j % W) - mx; }
+        pic[(long long)y * pitch + x] = pic[(long long)min(max(y, 0), h - 1) * pitch + min(max(x, 0), w - 1)];
+    }
+}
+
+}  // namespace
+
+extern "C" int vvc_cuda_pad_frame(VVCCudaCtx *ctx, const VVCCudaFrame *f, int pad)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!f || pad < 0 || (pad & 3))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "pad_frame: null frame or a margin that is not a multiple of 4");
+    if (!pad)
+        return VVC_CUDA_OK;
+    const int planes = f->chroma_format_idc ? 3 : 1;
+    for (int c = 0; c < planes; c++) {
+        const int w = c ? f->width >> f->hshift : f->width, h = c ? f->height >> f->vshift : f->height;
+        const int mx = c ? pad >> f->hshift : pad, my = c ? pad >> f->vshift : pad;
+        if (f->stride[c] / 2 < w + 2 * mx)
+            return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "pad_frame: the row pitch of plane %d leaves no room for a margin of %d", c, mx);
+        const long long total = 2ll * my * (w + 2 * mx) + 2ll * mx * h;
+        const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        pad_frame_kernel<<<dim3(grid, f->batch), 256, 0, ctx->stream>>>((pel *)f->data[c], (int)(f->stride[c] / 2), f->batch_stride[c] / 2,
+                                                                        w, h, mx, my);
+        VVC_LAUNCHED(ctx);
+    }
+    return VVC_CUDA_OK;
+}

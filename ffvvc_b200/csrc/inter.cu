@@ -606,6 +606,7 @@ extern "C" int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, co
         p.rb[c] = refs->batch_stride[c] / 2;     p.db[c] = dst->batch_stride[c] / 2;
     }
     p.w = dst->width; p.h = dst->height; p.bd = dst->bit_depth; p.nref = refs->batch;
+    p.margin = ctx->ref_pad;
     p.pbs = pbs; p.n = n_pbs; p.wp = wp; p.prof = prof; p.dmvr_out = dmvr_out;
     if (p.bd == 10 && frame_vec_ok(dst) && frame_vec_ok(refs) && !ctx->force_generic) {
         InterLists lists;
@@ -651,6 +652,7 @@ extern "C" int vvc_cuda_inter_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ds
         return ctx->err;
     if (!dst || !refs || (n_pbs > 0 && !pbs))
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "inter_host: null argument");
+    const VVCRefPadOff pad_guard(ctx, true);               // staged host references carry no margins
     const size_t dsz = align_up(vvc_stage_frame_size(dst), 256), rsz = align_up(vvc_stage_frame_size(refs), 256);
     const size_t psz = align_up((size_t)n_pbs * sizeof(VVCCudaPB), 256);
     const size_t wsz = align_up((size_t)(n_wp > 0 ? n_wp : 1) * sizeof(VVCCudaWP), 256);

@@ -9,6 +9,7 @@ struct InterK {
     int        rp[3], dp[3];
     long long  rb[3], db[3];
     int        w, h, bd, planes, nref;      // nref: pictures in the reference ring
+    int        margin;                      // replicated luma samples around every reference plane (VVC_CUDA_OPT_REF_PAD; chroma: half)
     const VVCCudaPB   *pbs;
     int                n;
     const VVCCudaWP   *wp;

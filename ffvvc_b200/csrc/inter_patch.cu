@@ -56,14 +56,15 @@ struct Blend { int w0, w1, off, sh, ox; };
 // gives per-sample GPM weights (w0 = g, w1 = 8 - g; first sample's address, steps gsx / gsy, columns clamped
 // to cmax).
 template <int TAPS, bool KEEP, bool BI>
-__device__ __forceinline__ void mc_patch(const pel *plane, int pitch, int W, int H, int x, int y, int nrows,
+__device__ __forceinline__ void mc_patch(const pel *plane, int pitch, int W, int H, int margin, int x, int y, int nrows,
                                          uint32_t hf0, uint32_t hf1, uint32_t vf0, uint32_t vf1, int shh, int shv,
                                          uint32_t keep[16], const Blend &k, const uint8_t *gw, int gsx, int gsy, int cmax,
                                          pel *d, int dpitch, bool two_words)
 {
     constexpr int B = TAPS / 2 - 1, NW = TAPS == 8 ? 6 : 4, NR = 8 + TAPS - 1;
     const int e = (x - B) & 1, bx = x - B - e, sh = e << 4, y0 = y - B;
-    const bool inside = bx >= 0 && bx + 2 * NW <= W && y0 >= 0 && y0 + nrows + TAPS - 1 <= H;
+    // pre-padded reference planes (margin > 0) hold the clamped samples themselves: the plain loads may reach into the margin
+    const bool inside = bx >= -margin && bx + 2 * NW <= W + margin && y0 >= -margin && y0 + nrows + TAPS - 1 <= H + margin;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (long long)y0 * pitch + bx);
     const int wpitch = pitch >> 1;
     uint32_t P[NR - 1][4];
@@ -207,9 +208,10 @@ __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, con
                     continue;
                 const int mx = (int)__ldg(q + 3 + 2 * l), my = (int)__ldg(q + 4 + 2 * l);
                 const int xx = x0 + (mx >> 4), yy = y0 + (my >> 4);
-                border |= xx - 4 < 0 || xx + w + 5 > p.w || yy - 3 < 0 || yy + h + 4 > p.h;
+                const int m = p.margin, mc = p.margin >> 1;
+                border |= xx - 4 < -m || xx + w + 5 > p.w + m || yy - 3 < -m || yy + h + 4 > p.h + m;
                 const int xc = (x0 >> 1) + (mx >> 5), yc = (y0 >> 1) + (my >> 5);
-                border |= xc - 2 < 0 || xc + (w >> 1) + 6 > (p.w >> 1) || yc - 1 < 0 || yc + (h >> 1) + 2 > (p.h >> 1);
+                border |= xc - 2 < -mc || xc + (w >> 1) + 6 > (p.w >> 1) + mc || yc - 1 < -mc || yc + (h >> 1) + 2 > (p.h >> 1) + mc;
             }
         }
     }
@@ -281,7 +283,7 @@ __device__ __forceinline__ void luma_task(const InterK &p, const Rec &pb, int pi
     pel *d = p.dst[0] + pb.pic * p.db[0] + (long long)(pb.y0 + oy) * p.dp[0] + pb.x0 + ox;
     const uint8_t *gw = gpm ? wt + oy * pb.gsy + ox * pb.gsx : nullptr;
     uint32_t keep[16];
-#define LUMA_ARGS(l) p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, pb.x0 + ox + (MV0(l, 0) >> 4), pb.y0 + oy + (MV0(l, 1) >> 4), nrows, \
+#define LUMA_ARGS(l) p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, p.margin, pb.x0 + ox + (MV0(l, 0) >> 4), pb.y0 + oy + (MV0(l, 1) >> 4), nrows, \
         (MV0(l, 0) & 15) ? fh.x : 0x01000000u, (MV0(l, 0) & 15) ? fh.y : 0u, \
         (MV0(l, 1) & 15) ? fv.x : ((MV0(l, 0) & 15) ? 0x01000000u : 0x10000000u), (MV0(l, 1) & 15) ? fv.y : 0u, \
         (MV0(l, 0) & 15) ? 2 : 0, (MV0(l, 1) & 15) ? ((MV0(l, 0) & 15) ? 6 : 2) : 0
@@ -323,7 +325,7 @@ __device__ __forceinline__ void chroma_task(const InterK &p, const Rec &pb, int 
     const uint8_t *gw = gpm ? wt + ox * 2 * pb.gsx : nullptr;
     const int cmax = bw - 1 - ox > 3 ? 3 : bw - 1 - ox;
     uint32_t keep[16];
-#define CHROMA_ARGS(l) rplane + REF(l) * rb, rp, p.w >> 1, p.h >> 1, x0 + ox + (MV0(l, 0) >> 5), y0 + (MV0(l, 1) >> 5), bh, \
+#define CHROMA_ARGS(l) rplane + REF(l) * rb, rp, p.w >> 1, p.h >> 1, p.margin >> 1, x0 + ox + (MV0(l, 0) >> 5), y0 + (MV0(l, 1) >> 5), bh, \
         (MV0(l, 0) & 31) ? chromaf[MV0(l, 0) & 31] : 0x00000100u, 0u, \
         (MV0(l, 1) & 31) ? chromaf[MV0(l, 1) & 31] : ((MV0(l, 0) & 31) ? 0x00000100u : 0x00001000u), 0u, \
         (MV0(l, 0) & 31) ? 2 : 0, (MV0(l, 1) & 31) ? ((MV0(l, 0) & 31) ? 6 : 2) : 0

@@ -119,14 +119,14 @@ __device__ __forceinline__ uint32_t inv_rows(int d) { return d == 23 ? 2850u : d
 // matters: warps sit in different phases and share the instruction cache).
 __device__ __noinline__ void stage_apron(uint32_t *win, int pw, int e, int cols, int rows, int sub, int group);
 
-__device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const pel *plane, int pitch, int W, int H,   //@region stage_core
+__device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const pel *plane, int pitch, int W, int H, int margin,   //@region stage_core
                                          int wx0, int wy0, int cols, int rows, int sub, int group)
 {
     const int e = wx0 & 1, bx = wx0 - e, nw = (cols + e + 1) >> 1;
     const int lk = nw > 8 ? 4 : 3;
     const int k = sub & ((1 << lk) - 1), rsub = sub >> lk, rstep = group >> lk;
     if (k < nw) {
-        const bool inside = bx >= 0 && bx + 2 * nw <= W && wy0 >= 0 && wy0 + rows <= H;
+        const bool inside = bx >= -margin && bx + 2 * nw <= W + margin && wy0 >= -margin && wy0 + rows <= H + margin;   // margin: pre-padded planes
         uint32_t *dst = win + (2 * pad + rsub) * pw + pad + k;
         const int dstep = rstep * pw;
         if (inside) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
         if (dmvr_luma) {
             if (!(TMA && use_tma)) {
                 const int l = lane >> 4;                    // lanes 0-15: list 0, lanes 16-31: list 1
-                stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h,
+                stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, p.margin,
                             pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane & 15, 16);
             }
             __syncwarp();
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                     s.um[lane] = m;
                 if (!dmvr_luma) {
                     const int i = bi ? lane >> 4 : 0, li = bi ? i : lx;
-                    stage_units(s.a.win + i * WUL, PWL, 0, p.ref[0] + REF(li) * p.rb[0], p.rp[0], p.w, p.h,
+                    stage_units(s.a.win + i * WUL, PWL, 0, p.ref[0] + REF(li) * p.rb[0], p.rp[0], p.w, p.h, p.margin,
                                 pb.x0 + (MVR(li, 0) >> 4) - 3, pb.y0 + (MVR(li, 1) >> 4) - 3, w + 7, h + 7,
                                 bi ? lane & 15 : lane, bi ? 16 : 32);
                 }
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 const int u = bi ? lane >> 3 : lane >> 4;
                 const int list = bi ? (u & 1) : lx, pc = bi ? (u >> 1) : u;
                 const pel *plane = (pc ? p.ref[2] + REF(list) * p.rb[2] : p.ref[1] + REF(list) * p.rb[1]);
-                stage_units(s.a.win + u * WUC, PWC, dmvr ? 1 : 0, plane, pc ? p.rp[2] : p.rp[1], pw, ph,
+                stage_units(s.a.win + u * WUC, PWC, dmvr ? 1 : 0, plane, pc ? p.rp[2] : p.rp[1], pw, ph, p.margin >> 1,
                             x0 + ((dmvr ? MV0(list, 0) : MVR(list, 0)) >> 5) - 1, y0 + ((dmvr ? MV0(list, 1) : MVR(list, 1)) >> 5) - 1,
                             bw + 3, bh + 3, bi ? lane & 7 : lane & 15, bi ? 8 : 16);
             }

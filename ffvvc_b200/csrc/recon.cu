@@ -198,6 +198,7 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
     const bool refs_on_device = cudaPointerGetAttributes(&attr, refs->data[0]) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     const bool out_on_device = cudaPointerGetAttributes(&attr, out->data[0]) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     cudaGetLastError();                                    // unregistered host memory reports an error on old drivers: not ours
+    const VVCRefPadOff pad_guard(ctx, !refs_on_device);    // staged host references carry no margins
     VVCCudaFrame drefs;
     if (refs_on_device)
         drefs = *refs;

@@ -86,6 +86,7 @@ def load():
     lib.vvc_cuda_recon_arena_size.restype = C.c_size_t
     lib.vvc_cuda_recon_arena_bind.argtypes = [FP, RP, C.POINTER(abi.VVCCudaDeblockMaps), C.c_void_p]
     lib.vvc_cuda_ctx_set_option.argtypes = [CTX, C.c_int, C.c_int]
+    lib.vvc_cuda_pad_frame.argtypes = [CTX, FP, C.c_int]
     lib.vvc_cuda_intra_leaf_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p]
     lib.vvc_cuda_intra_leaf_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.vvc_cuda_intra_pred_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int]
@@ -199,6 +200,10 @@ class Context:
 
     def lmcs_frame_host(self, frame, lut_ptr, ctb_enable_ptr=None):
         self.check(self.lib.vvc_cuda_lmcs_frame_host(self.handle, C.byref(frame), lut_ptr, ctb_enable_ptr))
+
+    def pad_frame(self, frame, pad):
+        """Replicate the border samples of every plane into its margin (the pre-padded DPB format)."""
+        self.check(self.lib.vvc_cuda_pad_frame(self.handle, C.byref(frame), pad))
 
     def lmcs_chroma_scale(self, frame, vpdus_ptr, n, params_ptr, scales_ptr):
         """Per-VPDU chroma residual scales from the reconstructed luma (lmcs_derive_chroma_scale)."""

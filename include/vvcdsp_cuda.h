@@ -67,6 +67,13 @@ const char *vvc_cuda_version(void);
 /* VVC_CUDA_OPT_INTER_TMA: 1 = the DMVR / BDOF records' reference windows are fetched by the copy engine (TMA box
  * per window, one record ahead of the computation), 0 = staged by the warp's own loads.  Results identical. */
 #define VVC_CUDA_OPT_INTER_TMA 3
+/* VVC_CUDA_OPT_REF_PAD = n (a multiple of 16, 0 = off): the reference rings handed to the inter / reconstruction entries
+ * are PRE-PADDED - every plane carries n replicated luma samples (n / 2 chroma samples) on all four sides, as
+ * vvc_cuda_pad_frame() leaves them (data[] still points at sample (0, 0); stride[] spans the margins).  Those samples are
+ * what ff_emulated_edge_mc / emulated_edge (libavcodec/vvc/vvc_inter.c:33-58) would fabricate per block, so windows that
+ * stay inside the margin take the plain load path; vectors that point further out keep the clamped path.  Results are
+ * identical with and without the option. */
+#define VVC_CUDA_OPT_REF_PAD 4
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
  * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams, 21 VVCCudaIntraBlk): lets foreign-language bindings verify their struct mirrors. */
@@ -98,6 +105,12 @@ typedef struct VVCCudaFrame {
 #define VVC_CUDA_EDGE_TOP     2
 #define VVC_CUDA_EDGE_RIGHT   4
 #define VVC_CUDA_EDGE_BOTTOM  8
+
+/* Replicates the border samples of every plane of every picture of the ring into a margin of `pad` luma samples
+ * (pad >> hshift / vshift for chroma): sample (x, y) outside the plane becomes sample (clip(x), clip(y)).  The planes
+ * must have been allocated with that margin around them.  A decoder calls it once per output picture that will be used
+ * as a reference (the DPB format of VVC_CUDA_OPT_REF_PAD). */
+int vvc_cuda_pad_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, int pad);
 
 /* ------------------------------------------------------------------------------------------
  * ALF stage (replaces ff_vvc_alf_filter, libavcodec/vvc/vvc_filter.c:1254-1319, and the table

@@ -63,6 +63,37 @@ def test_inter_tma_staged_windows_bit_exact(ctx, w, h, seed, uniform, tma):
     assert np.array_equal(go[dm], oo[dm])
 
 
+@pytest.mark.parametrize("pad", [16, 64, 128])
+@pytest.mark.parametrize("w,h,seed,uniform", [(416, 240, 1, False), (136, 72, 5, True), (832, 480, 4, False), (1920, 1080, 6, False)])
+def test_inter_pre_padded_reference_planes_bit_exact(ctx, w, h, seed, uniform, pad):
+    """VVC_CUDA_OPT_REF_PAD: a DPB ring with a margin of replicated samples (vvc_cuda_pad_frame) gives the pictures of the
+    per-block edge emulation; vectors that leave the margin still take the clamped path.  The margin itself must be the
+    replicated border."""
+    from ffvvc_b200 import device
+    gd, gr, refs, pbs, wp, prof = make_case(w, h, seed, mix=STRESS_MIX if seed != 6 else None, uniform=uniform)
+    dst = device.DeviceFrames(gd, planes=abi.alloc_planes(gd, fill=77))
+    ref = device.DeviceFrames(gr, planes=refs, pad=pad)
+    ctx.pad_frame(ref.desc, pad)
+    full = ref.to_numpy(with_margin=True)
+    for c in range(3):
+        mx, my = ref.margin[c]
+        pw, ph = gr.plane_wh(c)
+        ys = np.clip(np.arange(-my, ph + my), 0, ph - 1)
+        xs = np.clip(np.arange(-mx, pw + mx), 0, pw - 1)
+        assert np.array_equal(full[c][:, :, :pw + 2 * mx], refs[c][:, ys][:, :, xs]), "margin of plane %d" % c
+    keep = [device.to_device(a) for a in (pbs, wp, prof, np.zeros(len(pbs), dtype=abi.DMVR_OUT_DTYPE))]
+    ctx.set_option(abi.OPT_REF_PAD, pad)
+    try:
+        ctx.inter_frame(dst.desc, ref.desc, keep[0][1], len(pbs), keep[1][1], keep[2][1], keep[3][1])
+        ctx.sync()
+    finally:
+        ctx.set_option(abi.OPT_REF_PAD, 0)
+    od, oo = run_inter(util.oracle().vvco_inter_frame, gd, gr, refs, pbs, wp, prof)
+    util.assert_planes_equal(gd, dst.to_numpy(), od, "pre-padded references (margin %d) vs oracle" % pad)
+    dm = (pbs["flags"] & abi.PB_DMVR) != 0
+    assert np.array_equal(keep[3][0].cpu().numpy().view(abi.DMVR_OUT_DTYPE)[dm], oo[dm])
+
+
 def test_inter_generic_kernel_matches(ctx):
     """The generic CTA-per-record kernel (any bit depth / alignment) and the 10-bit warp-per-record kernel agree."""
     gd, gr, refs, pbs, wp, prof = make_case(416, 240, 11, mix=STRESS_MIX)
