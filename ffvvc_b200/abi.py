@@ -169,6 +169,26 @@ assert DBK_EDGE_DTYPE.itemsize == C.sizeof(VVCCudaDbkEdge) == 4
 assert SAO_CTB_DTYPE.itemsize == C.sizeof(VVCCudaSAOCtb) == 42
 
 
+# deblocking parameters on the device: transform-unit / motion / CTB records (include/vvcdsp_cuda.h)
+DBK_TU_LUMA, DBK_TU_CHROMA = 1, 2
+DBK_CBF_Y, DBK_CBF_CB, DBK_CBF_CR, DBK_JOINT, DBK_BDPCM_Y, DBK_BDPCM_C = 1, 2, 4, 8, 16, 32
+DBK_CU_SUBBLOCK = 1
+DBK_TU_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("log2_w", np.uint8), ("log2_h", np.uint8), ("planes", np.uint8),
+                         ("flags", np.uint8), ("qp", np.int8, (3,)), ("cu_flags", np.uint8), ("cu_dx", np.uint8), ("cu_dy", np.uint8),
+                         ("cb_log2_w", np.uint8), ("cb_log2_h", np.uint8), ("pic", np.uint8), ("reserved", np.uint8, (3,))])
+DBK_MVF_DTYPE = np.dtype([("x0", np.uint16), ("y0", np.uint16), ("w4", np.uint8), ("h4", np.uint8), ("pred_flag", np.uint8),
+                          ("ciip_flag", np.uint8), ("ref_pic", np.int16, (2,)), ("mv", np.int32, (2, 2)), ("pic", np.uint8),
+                          ("reserved", np.uint8, (3,))])
+DBK_CTB_DTYPE = np.dtype([("beta_offset", np.int8, (3,)), ("tc_offset", np.int8, (3,)), ("no_left", np.uint8), ("no_top", np.uint8)])
+assert DBK_TU_DTYPE.itemsize == 20 and DBK_MVF_DTYPE.itemsize == 32 and DBK_CTB_DTYPE.itemsize == 8
+
+
+class VVCCudaDbkParams(C.Structure):
+    _fields_ = [("qp_bd_offset", C.c_int32), ("ladf_enabled", C.c_int32), ("num_ladf_intervals", C.c_int32),
+                ("ladf_lowest_interval_qp_offset", C.c_int32), ("ladf_qp_offset", C.c_int32 * 4),
+                ("ladf_interval_lower_bound", C.c_int32 * 5)]
+
+
 def deblock_map_shape(geom, direction, c):
     """(rows, pitch) of the edge map for plane c; direction 1 = vertical edges, 0 = horizontal."""
     w, h = geom.plane_wh(c)

@@ -199,6 +199,10 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 19: return sizeof(VVCCudaLmcsVpdu);
     case 20: return sizeof(VVCCudaLmcsParams);
     case 21: return sizeof(VVCCudaIntraBlk);
+    case 22: return sizeof(VVCCudaDbkTU);
+    case 23: return sizeof(VVCCudaDbkMvf);
+    case 24: return sizeof(VVCCudaDbkCtb);
+    case 25: return sizeof(VVCCudaDbkParams);
     default: return 0;
     }
 }

@@ -619,7 +619,7 @@ extern "C" int vvc_cuda_inter_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, co
 #ifndef INTER_LONG_SPREAD
 #define INTER_LONG_SPREAD 1         // long launches move the small kernels (chroma classes, PROF) to a side stream: inter 2.77 -> 2.65 ms per 16 pictures (tools/sweep_long_spread.sh)
 #endif
-        const bool spread = p.n < 200000;
+        const bool spread = p.n < 200000 || INTER_LONG_SPREAD == 3;     // 3 (experiment): every class kernel on its own stream at any size
         if (spread) {
             if (vvc_ctx_fork(ctx, 3))
                 return ctx->err;

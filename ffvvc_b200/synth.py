@@ -236,6 +236,108 @@ def deblock_maps(geom, seed=4242, qp_base=22, qp_span=21):
     return out
 
 
+def deblock_side_info(geom, seed=515, ladf=True):
+    """What the parser knows about a picture ring, as the list inputs of vvc_cuda_deblock_params_frame: coding units on a
+    random partition (intra / inter / CIIP / sub-block motion), each cut into one, two or four transform units with random
+    coded flags, joint CbCr, BDPCM, per-unit QPs; motion rectangles with vectors from a small palette plus jitter so that
+    neighbours differ by less and by more than half a sample, different reference pictures, uni / bi; per-CTB beta / tc
+    offsets and unfilterable tile borders; LADF intervals.  Returns (tus, mvfs, ctbs, VVCCudaDbkParams)."""
+    rng = LCG(seed)
+    tus, mvfs = [], []
+    for k in range(geom.batch):
+        lw, lh = tb_partition(geom, rng, stop_p=0.4)
+        uh, uw = lw.shape
+        uy, ux = np.mgrid[0:uh, 0:uw]
+        origin = ((ux * 4) % (1 << lw) == 0) & ((uy * 4) % (1 << lh) == 0)
+        x0, y0, l2w, l2h = ux[origin] * 4, uy[origin] * 4, lw[origin], lh[origin]
+        inside = (x0 + (1 << l2w) <= geom.width) & (y0 + (1 << l2h) <= geom.height)
+        # blocks that stick out of the picture are re-cut into 4x4 units (every unit of the picture belongs to a block)
+        out = ~inside
+        ex, ey = [], []
+        for bx, by, bw, bh in zip(x0[out], y0[out], l2w[out], l2h[out]):
+            for yy in range(by, min(by + (1 << bh), geom.height), 4):
+                for xx in range(bx, min(bx + (1 << bw), geom.width), 4):
+                    ex.append(xx); ey.append(yy)
+        x0 = np.concatenate([x0[inside], np.array(ex, dtype=np.int64)])
+        y0 = np.concatenate([y0[inside], np.array(ey, dtype=np.int64)])
+        l2w = np.concatenate([l2w[inside], np.full(len(ex), 2, dtype=np.int64)])
+        l2h = np.concatenate([l2h[inside], np.full(len(ex), 2, dtype=np.int64)])
+        n = len(x0)
+        R = lambda m: rng.below(n, m)
+        kind, split, sb_r, pal, jit, prd, refa, refb, qpd, bdp = R(100), R(8), R(100), R(6), R(1 << 16), R(3), R(3), R(3), R(7), R(20)
+        cbf = rng.below(4 * n, 8).reshape(n, 4)
+        palette = np.array([[0, 0], [37, -12], [-150, 64], [8, 8], [1024, -700], [-5, 3]])
+        for i in range(n):
+            x, y, w, h = int(x0[i]), int(y0[i]), 1 << int(l2w[i]), 1 << int(l2h[i])
+            intra = kind[i] < 20
+            ciip = (not intra) and kind[i] < 26 and w * h >= 64
+            sb = (not intra) and (not ciip) and sb_r[i] < 20 and w >= 8 and h >= 8
+            qp_y = 27 + int(qpd[i]) - 3
+            # transform units: the whole block, two halves or four quarters
+            cuts = [(0, 0, w, h)]
+            if split[i] == 0 and w >= 8:
+                cuts = [(0, 0, w // 2, h), (w // 2, 0, w // 2, h)]
+            elif split[i] == 1 and h >= 8:
+                cuts = [(0, 0, w, h // 2), (0, h // 2, w, h // 2)]
+            elif split[i] == 2 and w >= 8 and h >= 8:
+                cuts = [(0, 0, w // 2, h // 2), (w // 2, 0, w // 2, h // 2), (0, h // 2, w // 2, h // 2), (w // 2, h // 2, w // 2, h // 2)]
+            elif split[i] == 3 and w >= 16:        # a quarter and three quarters (SBT-like), offsets that are not multiples of 8
+                cuts = [(0, 0, w // 4, h), (w // 4, 0, 3 * w // 4, h)] if w // 4 >= 4 else cuts
+            for j, (dx, dy, tw, th) in enumerate(cuts):
+                parts = [(dx, dy, tw, th)]
+                if tw & (tw - 1):                   # 3/4 of a power of two: two records of power-of-two width
+                    parts = [(dx, dy, tw * 2 // 3, th), (dx + tw * 2 // 3, dy, tw // 3, th)]
+                for (px, py, pw, ph) in parts:
+                    t = np.zeros(1, dtype=abi.DBK_TU_DTYPE)
+                    t["x0"], t["y0"], t["log2_w"], t["log2_h"], t["pic"] = x + px, y + py, pw.bit_length() - 1, ph.bit_length() - 1, k
+                    t["planes"] = abi.DBK_TU_LUMA | (abi.DBK_TU_CHROMA if geom.chroma_format_idc else 0)
+                    f = int(cbf[i, j % 4])
+                    fl = (abi.DBK_CBF_Y if f & 1 else 0) | (abi.DBK_CBF_CB if f & 2 else 0) | (abi.DBK_CBF_CR if f & 4 else 0)
+                    if f == 6 and bdp[i] < 4:
+                        fl |= abi.DBK_JOINT
+                    if intra and bdp[i] == 0:
+                        fl |= abi.DBK_BDPCM_Y | abi.DBK_BDPCM_C
+                    t["flags"] = fl
+                    t["qp"][0] = (qp_y, qp_y + 12 + (j % 3) - 1, qp_y + 12 - (j % 2))
+                    t["cu_flags"] = abi.DBK_CU_SUBBLOCK if sb else 0
+                    t["cu_dx"], t["cu_dy"], t["cb_log2_w"], t["cb_log2_h"] = px // 4, py // 4, int(l2w[i]), int(l2h[i])
+                    tus.append(t)
+            # motion
+            base = palette[int(pal[i])]
+            pf = 0 if intra else int(prd[i]) + 1
+            def rec(rx, ry, rw, rh, mv0, mv1):
+                m = np.zeros(1, dtype=abi.DBK_MVF_DTYPE)
+                m["x0"], m["y0"], m["w4"], m["h4"], m["pred_flag"], m["ciip_flag"], m["pic"] = rx, ry, rw // 4, rh // 4, pf, int(ciip), k
+                m["ref_pic"][0] = (int(refa[i]), int(refb[i]))
+                m["mv"][0] = (mv0, mv1)
+                mvfs.append(m)
+            j0 = np.array([int(jit[i]) % 13 - 6, (int(jit[i]) >> 4) % 13 - 6])
+            if sb:
+                for sy in range(0, h, 4):
+                    for sx in range(0, w, 4):
+                        d = np.array([5 * (sx // 4), -5 * (sy // 4)])
+                        rec(x + sx, y + sy, 4, 4, base + j0 + d, base - j0 + 2 * d)
+            else:
+                rec(x, y, w, h, base + j0, base - j0 if pal[i] & 1 else base + j0)
+    ctbs = np.zeros(geom.ctb_count * geom.batch, dtype=abi.DBK_CTB_DTYPE)
+    nc = len(ctbs)
+    ctbs["beta_offset"] = (rng.below(nc * 3, 25) - 12).reshape(nc, 3)
+    ctbs["tc_offset"] = (rng.below(nc * 3, 25) - 12).reshape(nc, 3)
+    ctbs["no_left"] = rng.below(nc, 8) == 0
+    ctbs["no_top"] = rng.below(nc, 8) == 0
+    p = abi.VVCCudaDbkParams()
+    p.qp_bd_offset = 6 * (geom.bit_depth - 8)
+    p.ladf_enabled = int(ladf)
+    p.num_ladf_intervals = 4
+    p.ladf_lowest_interval_qp_offset = -2
+    bounds = (0, 1 << (geom.bit_depth - 2), 1 << (geom.bit_depth - 1), 3 << (geom.bit_depth - 2), 0)
+    for i in range(4):
+        p.ladf_qp_offset[i] = (3, -1, 2, 0)[i]
+    for i in range(5):
+        p.ladf_interval_lower_bound[i] = bounds[i]
+    return np.concatenate(tus), np.concatenate(mvfs), ctbs, p
+
+
 def sao_params(geom, seed=99, with_restore=False):
     """Per-CTB SAO parameters, SURVEY.md 8(d) config 2: type rnd%3, band position rnd%32,
     eo rnd%4, offsets rnd % (1 << (bd-5)) with the edge-class signs (+,+,-,-) the parser applies

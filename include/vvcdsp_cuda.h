@@ -76,7 +76,7 @@ const char *vvc_cuda_version(void);
 #define VVC_CUDA_OPT_REF_PAD 4
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams, 21 VVCCudaIntraBlk): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams, 21 VVCCudaIntraBlk, 22 VVCCudaDbkTU, 23 VVCCudaDbkMvf, 24 VVCCudaDbkCtb, 25 VVCCudaDbkParams): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -190,6 +190,73 @@ int vvc_cuda_deblock_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCu
 /* both passes: src -> tmp (vertical) -> dst (horizontal) */
 int vvc_cuda_deblock_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,
                                 const VVCCudaDeblockMaps *maps);
+
+/* ------------------------------------------------------------------------------------------
+ * Deblocking parameters on the device: boundary strengths, maximum filter lengths and the QP -> beta / tc mapping with
+ * the luma-adaptive offset (replaces vvc_deblock_bs with its luma / chroma / sub-block passes and boundary_strength,
+ * derive_max_filter_length_luma, max_filter_length_chroma, get_qp_y / get_qp_c, TC_CALC and the per-edge part of
+ * ff_vvc_deblock_vertical / _horizontal, libavcodec/vvc/vvc_filter.c:308-1003, and lf.ladf_level,
+ * vvc_filter_template.c:788-804).  Input is what the parser knows per transform unit and per motion rectangle - the
+ * content of the reference's per-4x4 side tables (fc->tab.tb_pos_x0 / tb_width / tu_coded_flag / pcmf / qp / cb_pos_x /
+ * cb_width / msf / iaf / mvf) in list form; the device scatters it into those tables and fills the VVCCudaDeblockMaps of
+ * one direction, which vvc_cuda_deblock_frame then consumes.  4:2:0 and 4:0:0.
+ * ---------------------------------------------------------------------------------------- */
+#define VVC_CUDA_DBK_TU_LUMA      1   /* planes: the unit has a luma transform block (single tree, dual-tree luma)   */
+#define VVC_CUDA_DBK_TU_CHROMA    2   /* planes: it has chroma transform blocks (single tree, dual-tree chroma)      */
+#define VVC_CUDA_DBK_CBF_Y        1   /* flags: tu_y_coded_flag / tu_cb_coded_flag / tu_cr_coded_flag                */
+#define VVC_CUDA_DBK_CBF_CB       2
+#define VVC_CUDA_DBK_CBF_CR       4
+#define VVC_CUDA_DBK_JOINT        8   /* tu_joint_cbcr_residual_flag                                                 */
+#define VVC_CUDA_DBK_BDPCM_Y      16  /* fc->tab.pcmf[LUMA] (set for BDPCM blocks, vvc_ctu.c:1246-1247)              */
+#define VVC_CUDA_DBK_BDPCM_C      32  /* fc->tab.pcmf[CHROMA]                                                        */
+#define VVC_CUDA_DBK_CU_SUBBLOCK  1   /* cu_flags: merge_subblock_flag | inter_affine_flag (fc->tab.msf / iaf)       */
+
+typedef struct VVCCudaDbkTU {
+    uint16_t x0, y0;              /* luma position of the transform unit                                         */
+    uint8_t  log2_w, log2_h;      /* luma size (4..64); the chroma blocks are that shifted by the subsampling    */
+    uint8_t  planes;              /* VVC_CUDA_DBK_TU_*                                                            */
+    uint8_t  flags;               /* VVC_CUDA_DBK_CBF_* | JOINT | BDPCM_*                                          */
+    int8_t   qp[3];               /* fc->tab.qp[LUMA / CB / CR] at this unit (ff_vvc_get_qPy, get_qPc)            */
+    uint8_t  cu_flags;            /* VVC_CUDA_DBK_CU_*                                                            */
+    uint8_t  cu_dx, cu_dy;        /* (x0 - CbPosX) >> 2, (y0 - CbPosY) >> 2: where the unit sits in its coding block */
+    uint8_t  cb_log2_w, cb_log2_h;/* CbWidth, CbHeight of the luma coding block                                   */
+    uint8_t  pic, reserved[3];
+} VVCCudaDbkTU;                   /* 20 bytes */
+
+/* motion of a rectangle of 4x4 units, as ff_vvc_set_mvf / ff_vvc_set_intra_mvf leave it in fc->tab.mvf */
+typedef struct VVCCudaDbkMvf {
+    uint16_t x0, y0;              /* luma position                                                              */
+    uint8_t  w4, h4;              /* size in 4-sample units                                                     */
+    uint8_t  pred_flag;           /* PF_INTRA 0, PF_L0 1, PF_L1 2, PF_BI 3                                       */
+    uint8_t  ciip_flag;
+    int16_t  ref_pic[2];          /* identity of the picture each list refers to (rpl[l].list[ref_idx[l]]: a POC  */
+                                  /* or DPB slot number - only compared for equality)                            */
+    int32_t  mv[2][2];            /* [list][x, y], 1/16 sample                                                  */
+    uint8_t  pic, reserved[3];
+} VVCCudaDbkMvf;                  /* 32 bytes */
+
+typedef struct VVCCudaDbkCtb {    /* per CTB, raster order, per picture                                         */
+    int8_t  beta_offset[3];       /* DBParams (vvc_ctu.h), per plane                                             */
+    int8_t  tc_offset[3];
+    uint8_t no_left, no_top;      /* the CTB's left / upper border is a slice or tile border that must not be filtered
+                                     across (vvc_filter.c:498-506)                                               */
+} VVCCudaDbkCtb;                  /* 8 bytes */
+
+typedef struct VVCCudaDbkParams { /* host memory                                                                 */
+    int32_t  qp_bd_offset;
+    int32_t  ladf_enabled;        /* sps_ladf_enabled_flag                                                       */
+    int32_t  num_ladf_intervals;  /* sps->num_ladf_intervals (2..5)                                              */
+    int32_t  ladf_lowest_interval_qp_offset;
+    int32_t  ladf_qp_offset[4];   /* sps_ladf_qp_offset[]                                                        */
+    int32_t  ladf_interval_lower_bound[5];
+} VVCCudaDbkParams;
+
+/* frame: the picture the pass of direction `dir` will read (luma levels for LADF: the V pass reads the reconstructed
+ * picture, the H pass the output of the V pass).  tus, mvfs, ctbs: device memory, covering the whole ring.  maps: host
+ * struct whose edge[dir][*] device arrays (sized by pitch / rows / size as for vvc_cuda_deblock_frame) are filled. */
+int vvc_cuda_deblock_params_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaDbkTU *tus, int n_tus,
+                                  const VVCCudaDbkMvf *mvfs, int n_mvfs, const VVCCudaDbkCtb *ctbs,
+                                  const VVCCudaDbkParams *params, const VVCCudaDeblockMaps *maps, int dir);
 
 /* ------------------------------------------------------------------------------------------
  * SAO stage (replaces ff_vvc_sao_filter, libavcodec/vvc/vvc_filter.c:154-298, and the table

@@ -45,6 +45,8 @@ def oracle():
         lib.vvco_deblock_frame.restype = None
         lib.vvco_sao_frame.argtypes = [FP, FP, C.c_void_p]
         lib.vvco_sao_frame.restype = None
+        lib.vvco_deblock_params_frame.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(abi.VVCCudaDbkParams), MP, C.c_int]
+        lib.vvco_deblock_params_frame.restype = None
         lib.vvco_itx_frame.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.vvco_itx_frame.restype = None
         lib.vvco_itx_frame_q.argtypes = [FP, C.POINTER(abi.VVCCudaCoeffs), C.c_void_p, C.c_int, C.c_int]
@@ -92,6 +94,8 @@ def ref():
         lib.vvcref_deblock_frame.restype = None
         lib.vvcref_sao_frame.argtypes = [FP, FP, C.c_void_p]
         lib.vvcref_sao_frame.restype = None
+        lib.vvcref_deblock_params_filter.argtypes = [FP, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(abi.VVCCudaDbkParams)]
+        lib.vvcref_deblock_params_filter.restype = None
         lib.vvcref_itx_frame.argtypes = [FP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.vvcref_itx_frame.restype = None
         lib.vvcref_dequant_tb.argtypes = [C.c_void_p] + [C.c_int] * 20 + [C.c_void_p]
