@@ -63,6 +63,8 @@ def load():
     MP = C.POINTER(abi.VVCCudaDeblockMaps)
     lib.vvc_cuda_deblock_frame.argtypes = [CTX, FP, FP, MP, C.c_int]
     lib.vvc_cuda_deblock_frame_host.argtypes = [CTX, FP, FP, MP]
+    lib.vvc_cuda_deblock_params_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                  C.POINTER(abi.VVCCudaDbkParams), MP, C.c_int]
     lib.vvc_cuda_sao_frame.argtypes = [CTX, FP, FP, C.c_void_p]
     lib.vvc_cuda_sao_frame_host.argtypes = [CTX, FP, FP, C.c_void_p]
     IP = C.POINTER(abi.VVCCudaInloopDesc)
@@ -167,6 +169,11 @@ class Context:
 
     def deblock_frame_host(self, dst, src, maps):
         self.check(self.lib.vvc_cuda_deblock_frame_host(self.handle, C.byref(dst), C.byref(src), C.byref(maps)))
+
+    def deblock_params_frame(self, frame, tus_ptr, n_tus, mvfs_ptr, n_mvfs, ctbs_ptr, params, maps, direction):
+        """Boundary strengths, filter lengths, beta / tc (LADF from `frame`) of one direction into the maps' device arrays."""
+        self.check(self.lib.vvc_cuda_deblock_params_frame(self.handle, C.byref(frame), tus_ptr, n_tus, mvfs_ptr, n_mvfs, ctbs_ptr,
+                                                          C.byref(params), C.byref(maps), direction))
 
     def sao_frame(self, dst, src, ctbs_ptr):
         self.check(self.lib.vvc_cuda_sao_frame(self.handle, C.byref(dst), C.byref(src), ctbs_ptr))
