@@ -214,11 +214,17 @@ def deblock_maps_desc(geom, arrays, ptr_of=lambda a: a.ctypes.data):
     return m
 
 
+class VVCCudaDbkSide(C.Structure):
+    _fields_ = [("tus", C.c_void_p), ("mvfs", C.c_void_p), ("ctbs", C.c_void_p), ("params", C.POINTER(VVCCudaDbkParams)),
+                ("n_tus", C.c_int32), ("n_mvfs", C.c_int32)]
+
+
 class VVCCudaInloopDesc(C.Structure):
     _fields_ = [
         ("deblock", C.POINTER(VVCCudaDeblockMaps)),
         ("sao", C.c_void_p), ("alf", C.c_void_p), ("alf_sets", C.c_void_p),
         ("alf_sets_per_frame", C.c_int32), ("reserved", C.c_int32),
+        ("dbk_side", C.POINTER(VVCCudaDbkSide)),
     ]
 
 

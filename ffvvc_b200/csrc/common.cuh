@@ -24,7 +24,7 @@ struct VVCCudaCtx {
     // staging for the *_host entries and the per-call table shims
     void         *d_stage;  size_t d_stage_size;
     void         *h_stage;  size_t h_stage_size;    // pinned
-    void         *d_scratch[5]; size_t d_scratch_size[5];   // [0],[1] intermediate pictures of chained stages, [2] inter / residual task lists, [3] LMCS chroma scales, [4] deblocking side tables
+    void         *d_scratch[6]; size_t d_scratch_size[6];   // [0],[1] intermediate pictures of chained stages, [2] inter / residual task lists, [3] LMCS chroma scales, [4] deblocking side tables, [5] derived deblocking maps
     cudaStream_t  copy_in, copy_out;                 // lazily created, *_host pipelines
     cudaStream_t  side[3];                           // lazily created: independent kernels of one stage run beside the context stream
     cudaEvent_t   fork_ev, join_ev[3];

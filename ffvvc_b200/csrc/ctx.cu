@@ -131,7 +131,7 @@ void vvc_cuda_ctx_destroy(VVCCudaCtx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    for (int i = 0; i < 5; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+    for (int i = 0; i < 6; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->fork_ev) {
         cudaEventDestroy(ctx->fork_ev);
         for (int i = 0; i < 3; i++) { cudaStreamSynchronize(ctx->side[i]); cudaStreamDestroy(ctx->side[i]); cudaEventDestroy(ctx->join_ev[i]); }
@@ -203,6 +203,7 @@ extern "C" size_t vvc_cuda_abi_sizeof(int which)
     case 23: return sizeof(VVCCudaDbkMvf);
     case 24: return sizeof(VVCCudaDbkCtb);
     case 25: return sizeof(VVCCudaDbkParams);
+    case 26: return sizeof(VVCCudaDbkSide);
     default: return 0;
     }
 }

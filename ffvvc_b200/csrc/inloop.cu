@@ -29,7 +29,7 @@ extern "C" int vvc_cuda_inloop_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, c
 {
     if (ctx->err)
         return ctx->err;
-    if (!dst || !src || !desc || !desc->deblock || !desc->sao || !desc->alf || !desc->alf_sets)
+    if (!dst || !src || !desc || (!desc->deblock && !desc->dbk_side) || !desc->sao || !desc->alf || !desc->alf_sets)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "inloop: null argument");
     const size_t fsz = align_up(vvc_stage_frame_size(src), 256);
     void *s0 = vvc_ctx_scratch(ctx, 0, fsz), *s1 = vvc_ctx_scratch(ctx, 1, fsz);
@@ -38,8 +38,38 @@ extern "C" int vvc_cuda_inloop_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, c
     VVCCudaFrame a, b;
     vvc_stage_frame_layout(src, s0, &a);
     vvc_stage_frame_layout(src, s1, &b);
-    if (vvc_cuda_deblock_frame(ctx, &a, src, desc->deblock, 1)) return ctx->err;
-    if (vvc_cuda_deblock_frame(ctx, &b, &a, desc->deblock, 0))  return ctx->err;
+    if (desc->dbk_side) {
+        // parameters derived here: strengths, lengths, beta / tc of a pass from the lists and - for LADF - the pass's input
+        const VVCCudaDbkSide *sd = desc->dbk_side;
+        const int planes = src->chroma_format_idc ? 3 : 1;
+        VVCCudaDeblockMaps m;
+        memset(&m, 0, sizeof(m));
+        size_t total = 0;
+        for (int d = 0; d < 2; d++)
+            for (int c = 0; c < planes; c++) {
+                const int pw = c ? src->width >> src->hshift : src->width, ph = c ? src->height >> src->vshift : src->height;
+                const int grid = c ? 8 : 4, seg = c ? 4 >> (d ? src->vshift : src->hshift) : 4;
+                m.rows[d][c] = d ? ceil_div(ph, seg) : ceil_div(ph, grid);
+                m.pitch[d][c] = d ? ceil_div(pw, grid) : ceil_div(pw, seg);
+                m.size[d][c] = (int64_t)m.rows[d][c] * m.pitch[d][c];
+                total += align_up((size_t)m.size[d][c] * src->batch * sizeof(VVCCudaDbkEdge), 256);
+            }
+        uint8_t *at = (uint8_t *)vvc_ctx_scratch(ctx, 5, total);
+        if (!at)
+            return ctx->err;
+        for (int d = 0; d < 2; d++)
+            for (int c = 0; c < planes; c++) {
+                m.edge[d][c] = (const VVCCudaDbkEdge *)at;
+                at += align_up((size_t)m.size[d][c] * src->batch * sizeof(VVCCudaDbkEdge), 256);
+            }
+        if (vvc_cuda_deblock_params_frame(ctx, src, sd->tus, sd->n_tus, sd->mvfs, sd->n_mvfs, sd->ctbs, sd->params, &m, 1)) return ctx->err;
+        if (vvc_cuda_deblock_frame(ctx, &a, src, &m, 1)) return ctx->err;
+        if (vvc_cuda_deblock_params_frame(ctx, &a, sd->tus, sd->n_tus, sd->mvfs, sd->n_mvfs, sd->ctbs, sd->params, &m, 0)) return ctx->err;
+        if (vvc_cuda_deblock_frame(ctx, &b, &a, &m, 0)) return ctx->err;
+    } else {
+        if (vvc_cuda_deblock_frame(ctx, &a, src, desc->deblock, 1)) return ctx->err;
+        if (vvc_cuda_deblock_frame(ctx, &b, &a, desc->deblock, 0))  return ctx->err;
+    }
     if (vvc_cuda_sao_frame(ctx, &a, &b, desc->sao))             return ctx->err;
     return vvc_cuda_alf_frame(ctx, dst, &a, desc->alf, desc->alf_sets, desc->alf_sets_per_frame);
 }

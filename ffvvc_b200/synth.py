@@ -262,6 +262,14 @@ def deblock_side_info(geom, seed=515, ladf=True):
         y0 = np.concatenate([y0[inside], np.array(ey, dtype=np.int64)])
         l2w = np.concatenate([l2w[inside], np.full(len(ex), 2, dtype=np.int64)])
         l2h = np.concatenate([l2h[inside], np.full(len(ex), 2, dtype=np.int64)])
+        # a coding block never exceeds the CTB
+        while (l2w > geom.ctb_log2).any() or (l2h > geom.ctb_log2).any():
+            big_w = l2w > geom.ctb_log2
+            x0 = np.concatenate([x0, x0[big_w] + (1 << (l2w[big_w] - 1))]); y0 = np.concatenate([y0, y0[big_w]])
+            l2h = np.concatenate([l2h, l2h[big_w]]); l2w = np.concatenate([np.where(big_w, l2w - 1, l2w), l2w[big_w] - 1])
+            big_h = l2h > geom.ctb_log2
+            x0 = np.concatenate([x0, x0[big_h]]); y0 = np.concatenate([y0, y0[big_h] + (1 << (l2h[big_h] - 1))])
+            l2w = np.concatenate([l2w, l2w[big_h]]); l2h = np.concatenate([np.where(big_h, l2h - 1, l2h), l2h[big_h] - 1])
         n = len(x0)
         R = lambda m: rng.below(n, m)
         kind, split, sb_r, pal, jit, prd, refa, refb, qpd, bdp = R(100), R(8), R(100), R(6), R(1 << 16), R(3), R(3), R(3), R(7), R(20)

@@ -76,7 +76,7 @@ const char *vvc_cuda_version(void);
 #define VVC_CUDA_OPT_REF_PAD 4
 int         vvc_cuda_ctx_set_option(VVCCudaCtx *ctx, int option, int value);
 /* sizeof() of descriptor `which` as compiled into the library (0 VVCCudaFrame, 1 VVCCudaALFCtb,
- * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams, 21 VVCCudaIntraBlk, 22 VVCCudaDbkTU, 23 VVCCudaDbkMvf, 24 VVCCudaDbkCtb, 25 VVCCudaDbkParams): lets foreign-language bindings verify their struct mirrors. */
+ * 2 VVCCudaALFSets, 3 VVCCudaDbkEdge, 4 VVCCudaDeblockMaps, 5 VVCCudaSAOCtb, 6 VVCCudaInloopDesc, 7 VVCCudaTB, 8 VVCCudaPB, 9 VVCCudaWP, 10 VVCCudaProf, 11 VVCCudaDmvrOut, 12 VVCCudaRect, 13 VVCCudaReconDesc, 14 VVCCudaIntraPB, 15 VVCCudaCiip, 16 VVCCudaTBQuant, 17 VVCCudaScalingList, 18 VVCCudaCoeffs, 19 VVCCudaLmcsVpdu, 20 VVCCudaLmcsParams, 21 VVCCudaIntraBlk, 22 VVCCudaDbkTU, 23 VVCCudaDbkMvf, 24 VVCCudaDbkCtb, 25 VVCCudaDbkParams, 26 VVCCudaDbkSide): lets foreign-language bindings verify their struct mirrors. */
 size_t      vvc_cuda_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -287,6 +287,15 @@ int vvc_cuda_sao_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCC
  * which its dependency scores allow - SURVEY.md 3.3).  Intermediate pictures live in the
  * context's scratch area.
  * ---------------------------------------------------------------------------------------- */
+/* the list inputs of vvc_cuda_deblock_params_frame for a picture ring (host struct, device arrays) */
+typedef struct VVCCudaDbkSide {
+    const VVCCudaDbkTU     *tus;
+    const VVCCudaDbkMvf    *mvfs;
+    const VVCCudaDbkCtb    *ctbs;
+    const VVCCudaDbkParams *params;       /* host memory */
+    int32_t                 n_tus, n_mvfs;
+} VVCCudaDbkSide;
+
 typedef struct VVCCudaInloopDesc {
     const VVCCudaDeblockMaps *deblock;        /* host struct; its arrays follow the entry's memory space */
     const VVCCudaSAOCtb      *sao;
@@ -294,6 +303,9 @@ typedef struct VVCCudaInloopDesc {
     const VVCCudaALFSets     *alf_sets;
     int32_t                   alf_sets_per_frame;
     int32_t                   reserved;
+    const VVCCudaDbkSide     *dbk_side;       /* device entries only, optional: the deblocking parameters are derived on
+                                                 the device (vvc_cuda_deblock_params_frame before each pass, maps in the
+                                                 context's scratch area) and `deblock` is not read                     */
 } VVCCudaInloopDesc;
 
 int vvc_cuda_inloop_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src,

@@ -24,7 +24,7 @@ def test_descriptor_sizes_match_the_header():
             14: abi.INTRA_PB_DTYPE.itemsize, 15: abi.CIIP_DTYPE.itemsize,
             16: abi.TB_QUANT_DTYPE.itemsize, 17: abi.SCALING_LIST_DTYPE.itemsize, 18: C.sizeof(abi.VVCCudaCoeffs),
             19: abi.LMCS_VPDU_DTYPE.itemsize, 20: abi.LMCS_PARAMS_DTYPE.itemsize, 21: abi.INTRA_BLK_DTYPE.itemsize, 22: abi.DBK_TU_DTYPE.itemsize,
-            23: abi.DBK_MVF_DTYPE.itemsize, 24: abi.DBK_CTB_DTYPE.itemsize, 25: C.sizeof(abi.VVCCudaDbkParams)}
+            23: abi.DBK_MVF_DTYPE.itemsize, 24: abi.DBK_CTB_DTYPE.itemsize, 25: C.sizeof(abi.VVCCudaDbkParams), 26: C.sizeof(abi.VVCCudaDbkSide)}
     for which, size in want.items():
         assert handle.vvc_cuda_abi_sizeof(which) == size, which
 

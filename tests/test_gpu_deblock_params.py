@@ -56,3 +56,28 @@ def test_parameters_and_filtered_pictures_bit_exact(ctx, w, h, batch, seed, bd, 
             bad = np.argwhere(got != want_maps[d][c])
             assert not len(bad), "map dir %d plane %d differs at %s: cuda %s oracle %s" % (d, c, bad[0], got[tuple(bad[0])], want_maps[d][c][tuple(bad[0])])
     util.assert_planes_equal(geom, out.to_numpy(), want, "derived on the device + deblocked vs oracle")
+
+
+def test_inloop_chain_with_parameters_derived_on_the_device(ctx):
+    """vvc_cuda_inloop_frame with VVCCudaInloopDesc.dbk_side instead of precomputed maps: deblock V / H with the parameters
+    derived before each pass, then SAO and ALF - against the oracle's chain"""
+    from ffvvc_b200 import device
+    geom = abi.FrameGeom(416, 240, batch=2)
+    planes = smooth_planes(geom, 77)
+    tus, mvfs, ctbs, prm = synth.deblock_side_info(geom, seed=9, ladf=True)
+    sao = synth.sao_params(geom, seed=3)
+    alf, sets = synth.alf_params(geom, seed=4)
+    o = util.oracle()
+    deblocked, _ = derive_and_filter(oracle_params, geom, planes, tus, mvfs, ctbs, prm)
+    a, want = abi.alloc_planes(geom), abi.alloc_planes(geom)
+    o.vvco_sao_frame(abi.frame_from_numpy(geom, a), abi.frame_from_numpy(geom, deblocked), sao.ctypes.data)
+    o.vvco_alf_frame(abi.frame_from_numpy(geom, want), abi.frame_from_numpy(geom, a), alf.ctypes.data, sets.ctypes.data, 0)
+    src, dst = device.DeviceFrames(geom, planes=planes), device.DeviceFrames(geom)
+    keep = [device.to_device(x) for x in (tus, mvfs, ctbs, sao, alf, sets)]
+    side = abi.VVCCudaDbkSide()
+    side.tus, side.mvfs, side.ctbs, side.params, side.n_tus, side.n_mvfs = keep[0][1], keep[1][1], keep[2][1], C.pointer(prm), len(tus), len(mvfs)
+    d = abi.VVCCudaInloopDesc()
+    d.sao, d.alf, d.alf_sets, d.dbk_side = keep[3][1], keep[4][1], keep[5][1], C.pointer(side)
+    ctx.inloop_frame(dst.desc, src.desc, d)
+    ctx.sync()
+    util.assert_planes_equal(geom, dst.to_numpy(), want, "in-loop chain, parameters derived on the device")
