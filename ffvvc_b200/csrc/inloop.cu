@@ -143,6 +143,7 @@ extern "C" int vvc_cuda_inloop_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *d
         VVC_TRY(ctx, cudaStreamWaitEvent(run, in_done, 0));
         VVCCudaDeblockMaps km = one_picture_maps(&dm, k);
         VVCCudaInloopDesc kd;
+        memset(&kd, 0, sizeof(kd));
         kd.deblock = &km;
         kd.sao = dsao + (size_t)k * n_ctb;
         kd.alf = dalf + (size_t)k * n_ctb;
