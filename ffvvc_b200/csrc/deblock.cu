@@ -35,36 +35,43 @@ struct DbkK {
 
 constexpr int kThreads = 256;
 
-#define AT(base, k) ((base)[(k) * xs])
+#define AT(base, k) ((base)[(k) * XS])
+#ifndef DBK_LINE_UNROLL
+#define DBK_LINE_UNROLL 1
+#endif
 
-__device__ __forceinline__ int curv(const pel *l, int xs, int a, int b, int c)
-{
-    return abs((int)AT(l, a) - 2 * (int)AT(l, b) + (int)AT(l, c));
-}
-
-// One line of a luma segment.  seg_in points at Q0 of line 0 of the segment in the unfiltered tile,
-// seg_out at the same sample of the output tile.
-__device__ __forceinline__ void luma_line(const pel *seg_in, pel *seg_out, int xs, int ys, int line,
-                                          int tc_in, int beta_in, int lp, int lq, int hor_ctu_edge, int bd)
+// One luma segment (4 lines across one edge) by one thread: the 4 + 4 samples next to the edge of all four lines are
+// loaded once, the segment's decisions (vvc_loop_filter_luma :546-631 takes them from lines 0 and 3) are made once, and
+// the lines are filtered from registers.  in / out: Q0 of line 0 in the unfiltered / output tile; XS / YS: sample strides
+// across / along the edge.
+template <int XS, int YS>
+__device__ __forceinline__ void luma_segment(const pel *__restrict__ in, pel *__restrict__ out, int tc_in, int beta_in,
+                                             int lp, int lq, int hor_ctu_edge, int bd)
 {
     const int tc = tc_in << (bd - 10), beta = beta_in << (bd - 8);
     if (!tc)
         return;
-    const pel *l0 = seg_in, *l3 = seg_in + 3 * ys;
-    const pel *in = seg_in + line * ys;
-    pel *out = seg_out + line * ys;
-
-    const int dp0 = curv(l0, xs, -3, -2, -1), dq0 = curv(l0, xs, 2, 1, 0);
-    const int dp3 = curv(l3, xs, -3, -2, -1), dq3 = curv(l3, xs, 2, 1, 0);
+    // lines 0 and 3 decide for the segment: v0 / v3[k + 4], k = -4 .. 3 (P3 .. P0, Q0 .. Q3)
+    int v0[8], v3[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v0[k] = in[(k - 4) * XS];
+        v3[k] = in[3 * YS + (k - 4) * XS];
+    }
+#define CURV(v, a, b, c) abs(v[(a) + 4] - 2 * v[(b) + 4] + v[(c) + 4])
+    const int dp0 = CURV(v0, -3, -2, -1), dq0 = CURV(v0, 2, 1, 0), dp3 = CURV(v3, -3, -2, -1), dq3 = CURV(v3, 2, 1, 0);
+#undef CURV
     const int d0 = dp0 + dq0, d3 = dp3 + dq3;
     const int tc25 = (tc * 5 + 1) >> 1;
     const bool big_p = lp > 3 && !hor_ctu_edge, big_q = lq > 3;
 
     if (big_p || big_q) {
-        const int dp0l = big_p ? (dp0 + curv(l0, xs, -6, -5, -4) + 1) >> 1 : dp0;
-        const int dq0l = big_q ? (dq0 + curv(l0, xs, 5, 4, 3) + 1) >> 1 : dq0;
-        const int dp3l = big_p ? (dp3 + curv(l3, xs, -6, -5, -4) + 1) >> 1 : dp3;
-        const int dq3l = big_q ? (dq3 + curv(l3, xs, 5, 4, 3) + 1) >> 1 : dq3;
+        const pel *l0 = in, *l3 = in + 3 * YS;
+        auto curv = [&](const pel *l, int a, int b, int c) { return abs((int)AT(l, a) - 2 * (int)AT(l, b) + (int)AT(l, c)); };
+        const int dp0l = big_p ? (dp0 + curv(l0, -6, -5, -4) + 1) >> 1 : dp0;
+        const int dq0l = big_q ? (dq0 + curv(l0, 5, 4, 3) + 1) >> 1 : dq0;
+        const int dp3l = big_p ? (dp3 + curv(l3, -6, -5, -4) + 1) >> 1 : dp3;
+        const int dq3l = big_q ? (dq3 + curv(l3, 5, 4, 3) + 1) >> 1 : dq3;
         const int d0l = dp0l + dq0l, d3l = dp3l + dq3l;
         lp = big_p ? lp : 3;          // sticky for the normal decision below (:591-592)
         lq = big_q ? lq : 3;
@@ -85,43 +92,48 @@ __device__ __forceinline__ void luma_line(const pel *seg_in, pel *seg_out, int x
             if (sp0 + sq0 < b53 && abs(AT(l0, -1) - AT(l0, 0)) < tc25 &&
                 sp3 + sq3 < b53 && abs(AT(l3, -1) - AT(l3, 0)) < tc25 &&
                 (d0l << 1) < b4 && (d3l << 1) < b4) {
-                // ---- long filter (:466-544): bilinear pull towards the middle value m ----
-                int p[8], q[8];
+                // ---- long filter (:466-544): bilinear pull towards the middle value m, line by line ----
+                const int w0p = lp == 3 ? 53 : lp == 5 ? 58 : 59, wsp = lp == 3 ? 21 : lp == 5 ? 13 : 9, ksp = lp == 3 ? 2 : 1;
+                const int w0q = lq == 3 ? 53 : lq == 5 ? 58 : 59, wsq = lq == 3 ? 21 : lq == 5 ? 13 : 9, ksq = lq == 3 ? 2 : 1;
+#pragma unroll 1
+                for (int line = 0; line < 4; line++) {
+                    const pel *li = in + line * YS;
+                    pel *lo = out + line * YS;
+                    int p[8], q[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) { p[i] = AT(in, -1 - i); q[i] = AT(in, i); }
-                int m;
-                if (lp == 5 && lq == 5)
-                    m = (p[4] + p[3] + 2 * (p[2] + p[1] + p[0] + q[0] + q[1] + q[2]) + q[3] + q[4] + 8) >> 4;
-                else if (lp == lq)
-                    m = (p[6] + p[5] + p[4] + p[3] + p[2] + p[1] + 2 * (p[0] + q[0]) + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + 8) >> 4;
-                else if (lp + lq == 12)
-                    m = (p[5] + p[4] + p[3] + p[2] + 2 * (p[1] + p[0] + q[0] + q[1]) + q[2] + q[3] + q[4] + q[5] + 8) >> 4;
-                else if (lp + lq == 8)
-                    m = (p[3] + p[2] + p[1] + p[0] + q[0] + q[1] + q[2] + q[3] + 4) >> 3;
-                else if (lq == 7)
-                    m = (2 * (p[2] + p[1] + p[0] + q[0]) + p[0] + p[1] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + 8) >> 4;
-                else
-                    m = (p[6] + p[5] + p[4] + p[3] + p[2] + p[1] + 2 * (q[2] + q[1] + q[0] + p[0]) + q[0] + q[1] + 8) >> 4;
-                // tap weights 3:{53,32,11} 5:{58,45,32,19,6} 7:{59,50,41,32,23,14,5}; tc scale 6,(5),4,(3),2,(1,1)
-                {
-                    const int w0 = lp == 3 ? 53 : lp == 5 ? 58 : 59, ws = lp == 3 ? 21 : lp == 5 ? 13 : 9, ks = lp == 3 ? 2 : 1;
-                    const int ref = (p[lp] + p[lp - 1] + 1) >> 1;
+                    for (int i = 0; i < 8; i++) { p[i] = AT(li, -1 - i); q[i] = AT(li, i); }
+                    int m;
+                    if (lp == 5 && lq == 5)
+                        m = (p[4] + p[3] + 2 * (p[2] + p[1] + p[0] + q[0] + q[1] + q[2]) + q[3] + q[4] + 8) >> 4;
+                    else if (lp == lq)
+                        m = (p[6] + p[5] + p[4] + p[3] + p[2] + p[1] + 2 * (p[0] + q[0]) + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + 8) >> 4;
+                    else if (lp + lq == 12)
+                        m = (p[5] + p[4] + p[3] + p[2] + 2 * (p[1] + p[0] + q[0] + q[1]) + q[2] + q[3] + q[4] + q[5] + 8) >> 4;
+                    else if (lp + lq == 8)
+                        m = (p[3] + p[2] + p[1] + p[0] + q[0] + q[1] + q[2] + q[3] + 4) >> 3;
+                    else if (lq == 7)
+                        m = (2 * (p[2] + p[1] + p[0] + q[0]) + p[0] + p[1] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + 8) >> 4;
+                    else
+                        m = (p[6] + p[5] + p[4] + p[3] + p[2] + p[1] + 2 * (q[2] + q[1] + q[0] + p[0]) + q[0] + q[1] + 8) >> 4;
+                    // tap weights 3:{53,32,11} 5:{58,45,32,19,6} 7:{59,50,41,32,23,14,5}; tc scale 6,(5),4,(3),2,(1,1)
+                    {
+                        const int ref = lp == 3 ? (p[3] + p[2] + 1) >> 1 : lp == 5 ? (p[5] + p[4] + 1) >> 1 : (p[7] + p[6] + 1) >> 1;
 #pragma unroll
-                    for (int i = 0; i < 7; i++)
-                        if (i < lp) {
-                            const int w = w0 - ws * i, lim = (tc * max(6 - ks * i, 1)) >> 1;
-                            AT(out, -1 - i) = (pel)(p[i] + d_clip3(((m * w + ref * (64 - w) + 32) >> 6) - p[i], -lim, lim));
-                        }
-                }
-                {
-                    const int w0 = lq == 3 ? 53 : lq == 5 ? 58 : 59, ws = lq == 3 ? 21 : lq == 5 ? 13 : 9, ks = lq == 3 ? 2 : 1;
-                    const int ref = (q[lq] + q[lq - 1] + 1) >> 1;
+                        for (int i = 0; i < 7; i++)
+                            if (i < lp) {
+                                const int w = w0p - wsp * i, lim = (tc * max(6 - ksp * i, 1)) >> 1;
+                                AT(lo, -1 - i) = (pel)(p[i] + d_clip3(((m * w + ref * (64 - w) + 32) >> 6) - p[i], -lim, lim));
+                            }
+                    }
+                    {
+                        const int ref = lq == 3 ? (q[3] + q[2] + 1) >> 1 : lq == 5 ? (q[5] + q[4] + 1) >> 1 : (q[7] + q[6] + 1) >> 1;
 #pragma unroll
-                    for (int i = 0; i < 7; i++)
-                        if (i < lq) {
-                            const int w = w0 - ws * i, lim = (tc * max(6 - ks * i, 1)) >> 1;
-                            AT(out, i) = (pel)(q[i] + d_clip3(((m * w + ref * (64 - w) + 32) >> 6) - q[i], -lim, lim));
-                        }
+                        for (int i = 0; i < 7; i++)
+                            if (i < lq) {
+                                const int w = w0q - wsq * i, lim = (tc * max(6 - ksq * i, 1)) >> 1;
+                                AT(lo, i) = (pel)(q[i] + d_clip3(((m * w + ref * (64 - w) + 32) >> 6) - q[i], -lim, lim));
+                            }
+                    }
                 }
                 return;
             }
@@ -129,54 +141,62 @@ __device__ __forceinline__ void luma_line(const pel *seg_in, pel *seg_out, int x
     }
     if (d0 + d3 >= beta)
         return;
-    const int p3 = AT(in, -4), p2 = AT(in, -3), p1 = AT(in, -2), p0 = AT(in, -1);
-    const int q0 = AT(in, 0), q1 = AT(in, 1), q2 = AT(in, 2), q3 = AT(in, 3);
-    if (lp > 2 && lq > 2 &&
-        abs(AT(l0, -4) - AT(l0, -1)) + abs(AT(l0, 3) - AT(l0, 0)) < (beta >> 3) && abs(AT(l0, -1) - AT(l0, 0)) < tc25 &&
-        abs(AT(l3, -4) - AT(l3, -1)) + abs(AT(l3, 3) - AT(l3, 0)) < (beta >> 3) && abs(AT(l3, -1) - AT(l3, 0)) < tc25 &&
-        (d0 << 1) < (beta >> 2) && (d3 << 1) < (beta >> 2)) {
-        AT(out, -1) = (pel)(p0 + d_clip3(((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3) - p0, -3 * tc, 3 * tc));
-        AT(out, -2) = (pel)(p1 + d_clip3(((p2 + p1 + p0 + q0 + 2) >> 2) - p1, -2 * tc, 2 * tc));
-        AT(out, -3) = (pel)(p2 + d_clip3(((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3) - p2, -tc, tc));
-        AT(out, 0)  = (pel)(q0 + d_clip3(((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3) - q0, -3 * tc, 3 * tc));
-        AT(out, 1)  = (pel)(q1 + d_clip3(((p0 + q0 + q1 + q2 + 2) >> 2) - q1, -2 * tc, 2 * tc));
-        AT(out, 2)  = (pel)(q2 + d_clip3(((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3) - q2, -tc, tc));
-    } else {
-        int np = 1, nq = 1;
-        if (lp > 1 && lq > 1) {
-            const int side = (beta + (beta >> 1)) >> 3;
-            if (dp0 + dp3 < side) np = 2;
-            if (dq0 + dq3 < side) nq = 2;
-        }
-        int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
-        if (abs(delta) < 10 * tc) {
-            const int half = tc >> 1;
-            delta = d_clip3(delta, -tc, tc);
-            AT(out, -1) = (pel)d_clip_pel(p0 + delta, bd);
-            AT(out, 0)  = (pel)d_clip_pel(q0 - delta, bd);
-            if (np > 1)
-                AT(out, -2) = (pel)d_clip_pel(p1 + d_clip3((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -half, half), bd);
-            if (nq > 1)
-                AT(out, 1)  = (pel)d_clip_pel(q1 + d_clip3((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -half, half), bd);
+    const bool strong = lp > 2 && lq > 2 &&
+        abs(v0[0] - v0[3]) + abs(v0[7] - v0[4]) < (beta >> 3) && abs(v0[3] - v0[4]) < tc25 &&
+        abs(v3[0] - v3[3]) + abs(v3[7] - v3[4]) < (beta >> 3) && abs(v3[3] - v3[4]) < tc25 &&
+        (d0 << 1) < (beta >> 2) && (d3 << 1) < (beta >> 2);
+    int np = 1, nq = 1;
+    if (!strong && lp > 1 && lq > 1) {
+        const int side = (beta + (beta >> 1)) >> 3;
+        if (dp0 + dp3 < side) np = 2;
+        if (dq0 + dq3 < side) nq = 2;
+    }
+#pragma unroll 1
+    for (int line = 0; line < 4; line++) {
+        const pel *li = in + line * YS;
+        pel *lo = out + line * YS;
+        const int p2 = AT(li, -3), p1 = AT(li, -2), p0 = AT(li, -1), q0 = AT(li, 0), q1 = AT(li, 1), q2 = AT(li, 2);
+        if (strong) {
+            const int p3 = AT(li, -4), q3 = AT(li, 3);
+            AT(lo, -1) = (pel)(p0 + d_clip3(((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3) - p0, -3 * tc, 3 * tc));
+            AT(lo, -2) = (pel)(p1 + d_clip3(((p2 + p1 + p0 + q0 + 2) >> 2) - p1, -2 * tc, 2 * tc));
+            AT(lo, -3) = (pel)(p2 + d_clip3(((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3) - p2, -tc, tc));
+            AT(lo, 0)  = (pel)(q0 + d_clip3(((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3) - q0, -3 * tc, 3 * tc));
+            AT(lo, 1)  = (pel)(q1 + d_clip3(((p0 + q0 + q1 + q2 + 2) >> 2) - q1, -2 * tc, 2 * tc));
+            AT(lo, 2)  = (pel)(q2 + d_clip3(((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3) - q2, -tc, tc));
+        } else {
+            int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+            if (abs(delta) < 10 * tc) {
+                const int half = tc >> 1;
+                delta = d_clip3(delta, -tc, tc);
+                AT(lo, -1) = (pel)d_clip_pel(p0 + delta, bd);
+                AT(lo, 0)  = (pel)d_clip_pel(q0 - delta, bd);
+                if (np > 1)
+                    AT(lo, -2) = (pel)d_clip_pel(p1 + d_clip3((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -half, half), bd);
+                if (nq > 1)
+                    AT(lo, 1)  = (pel)d_clip_pel(q1 + d_clip3((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -half, half), bd);
+            }
         }
     }
 }
 
-// One line of a chroma segment of `lines` lines (2 when the edge direction is subsampled, else 4).
-__device__ __forceinline__ void chroma_line(const pel *seg_in, pel *seg_out, int xs, int ys, int line, int lines,
-                                            int tc_in, int beta_in, int lp, int lq, int bd)
+// One chroma segment of `lines` lines (2 when the edge direction is subsampled, else 4) by one thread.
+template <int XS, int YS>
+__device__ __forceinline__ void chroma_segment(const pel *__restrict__ in, pel *__restrict__ out, int lines,
+                                               int tc_in, int beta_in, int lp, int lq, int bd)
 {
     const int tc = tc_in << (bd - 10), beta = beta_in << (bd - 8);
     if (!tc || !lp || !lq)
         return;
     if (lq == 3) {
-        const pel *l0 = seg_in, *l1 = seg_in + (lines == 2 ? 1 : 3) * ys;
+        const pel *l0 = in, *l1 = in + (lines == 2 ? 1 : 3) * YS;
+        auto curv = [&](const pel *l, int a, int b, int c) { return abs((int)AT(l, a) - 2 * (int)AT(l, b) + (int)AT(l, c)); };
         const int tc25 = (tc * 5 + 1) >> 1;
         const bool one = lp == 1;
         const int p0 = AT(l0, -1), p1 = AT(l0, -2), p2 = one ? p1 : AT(l0, -3), p3 = one ? p1 : AT(l0, -4);
         const int n0 = AT(l1, -1), n1 = AT(l1, -2), n2 = one ? n1 : AT(l1, -3), n3 = one ? n1 : AT(l1, -4);
-        const int d0 = abs(p2 - 2 * p1 + p0) + curv(l0, xs, 2, 1, 0);
-        const int d1 = abs(n2 - 2 * n1 + n0) + curv(l1, xs, 2, 1, 0);
+        const int d0 = abs(p2 - 2 * p1 + p0) + curv(l0, 2, 1, 0);
+        const int d1 = abs(n2 - 2 * n1 + n0) + curv(l1, 2, 1, 0);
         bool strong = false;
         if (d0 + d1 < beta) {
             const bool ok0 = (d0 << 1) < (beta >> 2) && abs(p3 - p0) + abs(AT(l0, 0) - AT(l0, 3)) < (beta >> 3) && abs(p0 - AT(l0, 0)) < tc25;
@@ -186,26 +206,30 @@ __device__ __forceinline__ void chroma_line(const pel *seg_in, pel *seg_out, int
         if (!strong)
             lp = lq = 1;
     }
-    const pel *in = seg_in + line * ys;
-    pel *out = seg_out + line * ys;
-    const int p3 = AT(in, -4), p2 = AT(in, -3), p1 = AT(in, -2), p0 = AT(in, -1);
-    const int q0 = AT(in, 0), q1 = AT(in, 1), q2 = AT(in, 2), q3 = AT(in, 3);
-    if (lq == 3) {
-        if (lp == 3) {
-            AT(out, -1) = (pel)d_clip3((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3, p0 - tc, p0 + tc);
-            AT(out, -2) = (pel)d_clip3((2 * p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3, p1 - tc, p1 + tc);
-            AT(out, -3) = (pel)d_clip3((3 * p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3, p2 - tc, p2 + tc);
-            AT(out, 0)  = (pel)d_clip3((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3, q0 - tc, q0 + tc);
+#pragma unroll 1
+    for (int line = 0; line < lines; line++) {
+        const pel *li = in + line * YS;
+        pel *lo = out + line * YS;
+        const int p1 = AT(li, -2), p0 = AT(li, -1), q0 = AT(li, 0), q1 = AT(li, 1);
+        if (lq == 3) {
+            const int q2 = AT(li, 2), q3 = AT(li, 3);
+            if (lp == 3) {
+                const int p3 = AT(li, -4), p2 = AT(li, -3);
+                AT(lo, -1) = (pel)d_clip3((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3, p0 - tc, p0 + tc);
+                AT(lo, -2) = (pel)d_clip3((2 * p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3, p1 - tc, p1 + tc);
+                AT(lo, -3) = (pel)d_clip3((3 * p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3, p2 - tc, p2 + tc);
+                AT(lo, 0)  = (pel)d_clip3((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3, q0 - tc, q0 + tc);
+            } else {
+                AT(lo, -1) = (pel)d_clip3((3 * p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3, p0 - tc, p0 + tc);
+                AT(lo, 0)  = (pel)d_clip3((2 * p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3, q0 - tc, q0 + tc);
+            }
+            AT(lo, 1) = (pel)d_clip3((p1 + p0 + q0 + 2 * q1 + q2 + 2 * q3 + 4) >> 3, q1 - tc, q1 + tc);
+            AT(lo, 2) = (pel)d_clip3((p0 + q0 + q1 + 2 * q2 + 3 * q3 + 4) >> 3, q2 - tc, q2 + tc);
         } else {
-            AT(out, -1) = (pel)d_clip3((3 * p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3, p0 - tc, p0 + tc);
-            AT(out, 0)  = (pel)d_clip3((2 * p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3, q0 - tc, q0 + tc);
+            const int delta = d_clip3((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
+            AT(lo, -1) = (pel)d_clip_pel(p0 + delta, bd);
+            AT(lo, 0)  = (pel)d_clip_pel(q0 - delta, bd);
         }
-        AT(out, 1) = (pel)d_clip3((p1 + p0 + q0 + 2 * q1 + q2 + 2 * q3 + 4) >> 3, q1 - tc, q1 + tc);
-        AT(out, 2) = (pel)d_clip3((p0 + q0 + q1 + 2 * q2 + 3 * q3 + 4) >> 3, q2 - tc, q2 + tc);
-    } else {
-        const int delta = d_clip3((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
-        AT(out, -1) = (pel)d_clip_pel(p0 + delta, bd);
-        AT(out, 0)  = (pel)d_clip_pel(q0 - delta, bd);
     }
 }
 
@@ -223,8 +247,17 @@ struct DbkTile {
     static constexpr int ROWS = TH + 2 * AY;
 };
 
+#ifndef DBK_MIN_CTAS
+#define DBK_MIN_CTAS 8               // resident CTAs per SM the kernel is compiled for: full occupancy at 32 registers (tools/sweep_dbk2.sh: 4 / 5 / 6 / 7-8 -> V 0.62 / 0.53 / 0.47 / 0.40 ms per 16 pictures; the pass is latency bound)
+#endif
 template <bool VERT>
-__global__ void __launch_bounds__(kThreads) deblock_kernel(const DbkK p)
+__global__ void
+#if DBK_MIN_CTAS > 0
+__launch_bounds__(kThreads, DBK_MIN_CTAS)
+#else
+__launch_bounds__(kThreads)
+#endif
+deblock_kernel(const DbkK p)
 {
     using T = DbkTile<VERT>;
     constexpr int TW = T::TW, TH = T::TH, AX = T::AX, AY = T::AY, PITCH = T::PITCH, ROWS = T::ROWS;
@@ -271,7 +304,7 @@ __global__ void __launch_bounds__(kThreads) deblock_kernel(const DbkK p)
     }
     __syncthreads();
 
-    // ---- filter: one thread per (edge, line) ----
+    // ---- filter: one thread per edge segment (4 luma lines; 2 or 4 chroma lines) ----
     const bool chroma = c != 0;
     const int grid = chroma ? 8 : 4;
     const int shift = chroma ? (VERT ? p.vs[c] : p.hs[c]) : 0;
@@ -279,29 +312,31 @@ __global__ void __launch_bounds__(kThreads) deblock_kernel(const DbkK p)
     constexpr int ALONG = VERT ? TH : TW;                    // tile extent along the edges
     constexpr int ACROSS = VERT ? TW : TH;
     const int n_edges = ACROSS / grid + 1;                   // both tile borders included
+    const int n_segs = ALONG / seg;
     const VVCCudaDbkEdge *map = p.map[c] + k * p.msize[c];
     const int ctb_mask = (1 << p.ctb_log2) - 1;
     constexpr int xs = VERT ? 1 : PITCH, ys = VERT ? PITCH : 1;
 
-    for (int it = tid; it < n_edges * ALONG; it += kThreads) {
-        const int e = it / ALONG, a = it - e * ALONG;        // a: position along the edge inside the tile
+    // VERT: consecutive lanes take consecutive edges of one row of segments (their samples are 4 or 8 columns apart: the
+    // 32 lanes of a load touch 32 different banks); !VERT: consecutive lanes take consecutive segments of one edge
+    for (int it = tid; it < n_edges * n_segs; it += kThreads) {
+        const int e = VERT ? it % n_edges : it / n_segs, sg = VERT ? it / n_edges : it - e * n_segs;
         const int pos = (VERT ? tx0 : ty0) + e * grid;       // edge coordinate in the plane
-        const int along = (VERT ? ty0 : tx0) + a;
+        const int a0 = sg * seg, along = (VERT ? ty0 : tx0) + a0;
         if (pos == 0 || pos >= (VERT ? pw : ph) || along >= (VERT ? ph : pw))
             continue;
-        const int sidx = along / seg, line = along - sidx * seg;
+        const int sidx = along / seg;
         const VVCCudaDbkEdge ed = VERT ? map[(long long)sidx * p.mpitch[c] + pos / grid]
                                        : map[(long long)(pos / grid) * p.mpitch[c] + sidx];
         if (!ed.tc)
             continue;
         // Q0 of line 0 of this segment inside the tile
-        const int a0 = a - line;
         const int off = VERT ? (a0 + AY) * PITCH + (e * grid + AX) : (e * grid + AY) * PITCH + (a0 + AX);
         if (!chroma) {
             const int ctu_edge = !VERT && !(pos & ctb_mask);
-            luma_line(s_in + off, s_out + off, xs, ys, line, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, ctu_edge, p.bd);
+            luma_segment<xs, ys>(s_in + off, s_out + off, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, ctu_edge, p.bd);
         } else {
-            chroma_line(s_in + off, s_out + off, xs, ys, line, seg, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, p.bd);
+            chroma_segment<xs, ys>(s_in + off, s_out + off, seg, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, p.bd);
         }
     }
     __syncthreads();
