@@ -248,7 +248,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate against the reference C")
     ap.add_argument("--inter-tma", type=int, default=-1, help="VVC_CUDA_OPT_INTER_TMA (default: the library's)")
-    ap.add_argument("--ref-pad", type=int, default=0, help="VVC_CUDA_OPT_REF_PAD: margin of replicated samples around the device-resident DPB ring")
+    ap.add_argument("--ref-pad", type=int, default=128, help="VVC_CUDA_OPT_REF_PAD: margin of replicated samples around the device-resident DPB ring")
     ap.add_argument("--quick", action="store_true", help="skip the one-picture-per-launch and the >1 s runs")
     args = ap.parse_args()
 
@@ -752,6 +752,8 @@ def main():
             "dtype": "u16", "data": "synthetic",
             "config": config,
             "run": {"pictures_per_step": frames, "pictures_per_launch": group, "ring_mb": ring_mb,
+                    "dpb": ("device-resident DPB ring pre-padded with %d replicated samples per side (vvc_cuda_pad_frame, VVC_CUDA_OPT_REF_PAD; "
+                            "host reference pictures of the e2e figure are staged without margins)" % args.ref_pad) if args.ref_pad else "device-resident DPB ring, no margins",
                     "l2": "per step %d reference + %d reconstructed + %d output pictures and their coefficients = %.0f MB (> 126 MB)" % (frames, frames, frames, ring_mb)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
             "clocks": clocks, "parity": parity,
