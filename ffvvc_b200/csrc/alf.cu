@@ -135,8 +135,17 @@ __device__ __noinline__ uint2 alf_strip_wide(const pel *p0, int d1, int d2, int 
     return make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
 }
 
+#ifndef ALF_MIN_CTAS
+#define ALF_MIN_CTAS 0               // resident CTAs per SM the kernel is compiled for (0: the compiler's choice; tools/sweep_alf_occ.sh)
+#endif
 template <int TW, int TH>
-__global__ void __launch_bounds__(kThreads) alf_frame_kernel(const AlfK p)
+__global__ void
+#if ALF_MIN_CTAS > 0
+__launch_bounds__(kThreads, ALF_MIN_CTAS)
+#else
+__launch_bounds__(kThreads)
+#endif
+alf_frame_kernel(const AlfK p)
 {
     using SM = AlfSmem<TW, TH>;
     __shared__ SM sm;

@@ -109,8 +109,18 @@ template <int MODE>
 struct __align__(16) WarpSmem {
     short mid[64 * P2];          // pass-1 output: [row][input of pass 2]
     short lf[8 * 8];             // LFNST output window [row][col]
-    short win[(MODE & 2) ? 32 * 32 : 8];   // dequantised input window [row][col] (pitch 32) when dequant() runs here
+    short win[32 * 32];          // dequantised input window [row][col] (pitch 32) when dequant() runs here (MODE & 2)
 };
+
+// Park area of a block with LMCS chroma residual scaling: int32 [h][w], h, w <= 32 (chroma blocks), the last 4 KB of the
+// warp's shared memory - mid-stage rows 40.. (pass 2 of such a block reads rows below 32), the LFNST window and the
+// dequantised window, all dead once pass 1 is done.
+template <int MODE>
+__device__ __forceinline__ int32_t *park_of(WarpSmem<MODE> &s)
+{
+    static_assert(sizeof(WarpSmem<MODE>) >= 4096 + 32 * P2 * sizeof(short), "park area overlaps live mid-stage rows");
+    return reinterpret_cast<int32_t *>(reinterpret_cast<char *>(&s) + sizeof(WarpSmem<MODE>) - 4096);
+}
 
 __constant__ uint8_t c_diag4_x[16] = { 0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 1, 2, 3, 2, 3, 3 };
 __constant__ uint8_t c_diag4_y[16] = { 0, 1, 0, 2, 1, 0, 3, 2, 1, 0, 3, 2, 1, 3, 2, 3 };
@@ -188,7 +198,6 @@ struct Epi {
     int32_t *store;              // != NULL: residual written back as int32 [h][w]
     pel     *d0, *d1;            // picture samples of the TB's first row (d1: joint CbCr plane or NULL)
     int      pitch0, pitch1, sign, shift, w;
-    int      cscale;             // LMCS chroma residual scale (lmcs_scale_chroma, vvc_intra_template.c:431-448) or 0
 };
 
 // Pass 2: out[y][i] = (sum_x mid[y][x] * M[x][i] + 512) >> 10.  lane = (4 adjacent output columns, row group):
@@ -245,17 +254,6 @@ __device__ __forceinline__ void pass2(const WarpSmem<MODE> &s, int l2w, int h, c
                 a = dp2a_lo((int)in[2 * q], (int)m[c][q], dp2a_hi((int)in[2 * q + 1], (int)m[c][q], a));
             r[c] = (a + 512) >> 10;                         // shift = 5 + log2_transform_range - bit_depth
         }
-        int j[4];                                           // second plane of a joint CbCr block: derived before any scaling
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            j[c] = (r[c] * e.sign) >> e.shift;
-        if (e.cscale && !e.store) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                r[c] = d_lmcs_scale(r[c], e.cscale, 10);
-                j[c] = d_lmcs_scale(j[c], e.cscale, 10);
-            }
-        }
         if (e.store) {
             int32_t *o = e.store + y * e.w + c0;
             o[0] = r[0]; o[1] = r[1];
@@ -266,13 +264,35 @@ __device__ __forceinline__ void pass2(const WarpSmem<MODE> &s, int l2w, int h, c
             if (narrow) *reinterpret_cast<uint32_t *>(d0) = lo;
             else        *reinterpret_cast<uint2 *>(d0) = make_uint2(lo, hi);
             if (d1) {
-                const uint32_t jl = (uint32_t)d_clip_pel((int)(cur1.x & 0xffff) + j[0], 10) | ((uint32_t)d_clip_pel((int)(cur1.x >> 16) + j[1], 10) << 16);
-                const uint32_t jh = (uint32_t)d_clip_pel((int)(cur1.y & 0xffff) + j[2], 10) | ((uint32_t)d_clip_pel((int)(cur1.y >> 16) + j[3], 10) << 16);
+                const uint32_t jl = (uint32_t)d_clip_pel((int)(cur1.x & 0xffff) + ((r[0] * e.sign) >> e.shift), 10)
+                                  | ((uint32_t)d_clip_pel((int)(cur1.x >> 16) + ((r[1] * e.sign) >> e.shift), 10) << 16);
+                const uint32_t jh = (uint32_t)d_clip_pel((int)(cur1.y & 0xffff) + ((r[2] * e.sign) >> e.shift), 10)
+                                  | ((uint32_t)d_clip_pel((int)(cur1.y >> 16) + ((r[3] * e.sign) >> e.shift), 10) << 16);
                 if (narrow) *reinterpret_cast<uint32_t *>(d1) = jl;
                 else        *reinterpret_cast<uint2 *>(d1) = make_uint2(jl, jh);
             }
         }
         cur0 = nxt0; cur1 = nxt1;
+    }
+}
+
+// Epilogue of a block with LMCS chroma residual scaling (lmcs_scale_chroma between the transform and add_residual,
+// itransform vvc_intra.c:468-475; the second plane of a joint block is derived first and scaled afterwards, :179-183), from
+// the residuals pass 2 parked in shared memory (through its residual-store path: Epi.store pointing at the warp's own
+// park area, so the common path carries no extra instruction).  Luma blocks and pictures without
+// ph_chroma_residual_scale_flag never come here.
+__device__ __noinline__ void scaled_epilogue(const int32_t *park, int w, int h, int scale, pel *d0, int pitch0, pel *d1, int pitch1,
+                                             int sign, int shift, int lane)
+{
+    const int lw = 31 - __clz(w);
+    for (int i = lane; i < w * h; i += 32) {
+        const int y = i >> lw, x = i & (w - 1), r = park[i];
+        pel *p = d0 + (long long)y * pitch0 + x;
+        *p = (pel)d_clip_pel(*p + d_lmcs_scale(r, scale, 10), 10);
+        if (d1) {
+            pel *q = d1 + (long long)y * pitch1 + x;
+            *q = (pel)d_clip_pel(*q + d_lmcs_scale((r * sign) >> shift, scale, 10), 10);
+        }
     }
 }
 
@@ -297,8 +317,8 @@ __global__ void __launch_bounds__(256) itx_sort_kernel(const ItxW p)
         const uint32_t *q = reinterpret_cast<const uint32_t *>(p.tbs + ti);
         const uint32_t r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3);
         const int l2w = r2 & 0xff, l2h = (r2 >> 8) & 0xff, flags = r3 >> 24, lfnst = __ldg(q + 4) & 0xff;
-        if (!eligible(l2w, l2h, flags, r1 & 0xffff)) cls = 4;
-        else if (l2w <= 2 && l2h <= 2 && !lfnst && !(flags & VVC_CUDA_TB_STORE_RESIDUAL)) cls = 5;
+        if (!eligible(l2w, l2h, flags, r1 & 0xffff) || ((__ldg(q + 5) >> 16) && (l2w > 5 || l2h > 5))) cls = 4;   // (scaled 4:4:4 chroma blocks above 32: no room to park)
+        else if (l2w <= 2 && l2h <= 2 && !lfnst && !(flags & VVC_CUDA_TB_STORE_RESIDUAL) && !(__ldg(q + 5) >> 16)) cls = 5;   // (not with LMCS chroma scaling)
         else cls = l2w + l2h >= 12 ? 0 : l2w + l2h == 11 ? 1 : l2w + l2h == 10 ? 2 : 3;
     }
 #pragma unroll
@@ -332,7 +352,6 @@ __global__ void __launch_bounds__(128) itx_tiny_kernel(const ItxW p)
     const int x0 = r1 & 0xffff, y0 = r1 >> 16, w = 1 << l2w, h = 1 << l2h;
     const int trh = r2 >> 24, trv = r3 & 0xff, nzw = (r3 >> 8) & 0xff, nzh = (r3 >> 16) & 0xff;
     const int jsign = (int8_t)((r4 >> 8) & 0xff), jshift = (r4 >> 16) & 0xff, jc = r4 >> 24, pic = r5 & 0xff;
-    const int cscale = tb_chroma_scale(p.src, (int)(r5 >> 16));
     const TbCoef tc = tb_coef<MODE>(p.src, ti, r0, l2w, l2h, nzw, nzh, false);
     const bool dc_only = trh == 0 && trv == 0 && nzw == 1 && nzh == 1 && w == h;
     const int rdv = dc_only ? 1 : inputs_read(trv, h, nzh);
@@ -383,17 +402,6 @@ __global__ void __launch_bounds__(128) itx_tiny_kernel(const ItxW p)
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 r[k] = (dp2a_lo((int)mid01[y], (int)wh[k], dp2a_hi((int)mid23[y], (int)wh[k], 0)) + 512) >> 10;
-            int j[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                j[k] = (r[k] * jsign) >> jshift;
-            if (cscale) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    r[k] = d_lmcs_scale(r[k], cscale, 10);
-                    j[k] = d_lmcs_scale(j[k], cscale, 10);
-                }
-            }
             auto add2 = [&](uint32_t cur, int a, int b) -> uint32_t {
                 return (uint32_t)d_clip_pel((int)(cur & 0xffff) + a, 10) | ((uint32_t)d_clip_pel((int)(cur >> 16) + b, 10) << 16);
             };
@@ -404,14 +412,15 @@ __global__ void __launch_bounds__(128) itx_tiny_kernel(const ItxW p)
                 if (d1) {
                     uint2 *u = reinterpret_cast<uint2 *>(d1 + y * pitch1);
                     const uint2 c1 = *u;
-                    *u = make_uint2(add2(c1.x, j[0], j[1]), add2(c1.y, j[2], j[3]));
+                    *u = make_uint2(add2(c1.x, (r[0] * jsign) >> jshift, (r[1] * jsign) >> jshift),
+                                    add2(c1.y, (r[2] * jsign) >> jshift, (r[3] * jsign) >> jshift));
                 }
             } else {
                 uint32_t *t = reinterpret_cast<uint32_t *>(d0 + y * pitch0);
                 *t = add2(*t, r[0], r[1]);
                 if (d1) {
                     uint32_t *u = reinterpret_cast<uint32_t *>(d1 + y * pitch1);
-                    *u = add2(*u, j[0], j[1]);
+                    *u = add2(*u, (r[0] * jsign) >> jshift, (r[1] * jsign) >> jshift);
                 }
             }
         }
@@ -558,7 +567,9 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
         e.pitch0 = SEL3(p.pitch, c_idx);
         e.d0 = SEL3(p.plane, c_idx) + pic * SEL3(p.bstride, c_idx) + (long long)y0 * e.pitch0 + x0;
         e.d1 = nullptr; e.pitch1 = 0; e.sign = jsign; e.shift = jshift;
-        e.cscale = tb_chroma_scale(p.src, (int)(r5 >> 16));
+        const int cscale = e.store ? 0 : tb_chroma_scale(p.src, (int)(r5 >> 16));
+        if (cscale)                 // pass 2 "stores" the residual of a scaled block into the warp's park area
+            e.store = park_of(s);
         if (flags & VVC_CUDA_TB_JOINT) {
             e.pitch1 = SEL3(p.pitch, jc);
             e.d1 = SEL3(p.plane, jc) + pic * SEL3(p.bstride, jc) + (long long)y0 * e.pitch1 + x0;
@@ -572,6 +583,10 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
             case 16: pass2<16, MODE>(s, l2w, h, wpt, e, lane); break;
             default: pass2<32, MODE>(s, l2w, h, wpt, e, lane); break;
             }
+        }
+        if (cscale) {
+            __syncwarp();
+            scaled_epilogue(park_of(s), w, h, cscale, e.d0, e.pitch0, e.d1, e.pitch1, jsign, jshift, lane);
         }
     }
     }
