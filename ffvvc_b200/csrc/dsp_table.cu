@@ -14,12 +14,26 @@ VVCCudaCtx *g_ctx;
 int g_err;
 char g_msg[256] = "ok";
 
+// The entries return void like the reference's, so a failure cannot travel up the call: it is latched for
+// ff_vvc_dsp_cuda_last_error(), reported once on stderr, and - with VVC_CUDA_TABLE_ABORT=1 in the environment - aborts the
+// process, so that a decoder cannot run on over blocks that were never reconstructed.
 void latch(int code, const char *msg)
 {
     if (!g_err) {
         g_err = code;
         snprintf(g_msg, sizeof(g_msg), "%s", msg);
+        fprintf(stderr, "CUDA table error %d: %s\n", code, g_msg);
+        const char *ab = getenv("VVC_CUDA_TABLE_ABORT");
+        if (ab && atoi(ab))
+            abort();
     }
+}
+
+// a staged copy of a table entry: failures go through the context's sticky error (and from there into the latch)
+void copy(VVCCudaCtx *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+    if (!ctx->err)
+        vvc_ctx_check(ctx, cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream), "cudaMemcpyAsync (table entry)");
 }
 
 // called with g_mu held
@@ -70,10 +84,10 @@ void itx_call(int trh, int trv, int lw, int lh, int *coeffs, size_t nzw, size_t 
     const VVCCudaFrame f = dummy_frame(base, (int)bd);
     VVCCudaTB *dtb = (VVCCudaTB *)(base + 4096);
     int32_t *dco = (int32_t *)(base + 4096 + 256);
-    cudaMemcpyAsync(dtb, &tb, sizeof(tb), cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(dco, coeffs, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    copy(ctx, dtb, &tb, sizeof(tb), cudaMemcpyHostToDevice);
+    copy(ctx, dco, coeffs, n * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (!vvc_cuda_itx_frame(ctx, &f, dco, dtb, 1, (int)range)) {
-        cudaMemcpyAsync(coeffs, dco, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        copy(ctx, coeffs, dco, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
         vvc_cuda_sync(ctx);
     }
     finish(ctx);
@@ -149,10 +163,10 @@ void bdpcm_entry(int *coeffs, int width, int height, int vertical, int log2_tran
     const VVCCudaFrame f = dummy_frame(base, 10);
     VVCCudaTB *dtb = (VVCCudaTB *)(base + 4096);
     int32_t *dco = (int32_t *)(base + 4096 + 256);
-    cudaMemcpyAsync(dtb, &tb, sizeof(tb), cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(dco, coeffs, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    copy(ctx, dtb, &tb, sizeof(tb), cudaMemcpyHostToDevice);
+    copy(ctx, dco, coeffs, n * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (!vvc_cuda_itx_frame(ctx, &f, dco, dtb, 1, log2_transform_range)) {
-        cudaMemcpyAsync(coeffs, dco, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        copy(ctx, coeffs, dco, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
         vvc_cuda_sync(ctx);
     }
     finish(ctx);
@@ -205,8 +219,8 @@ void lmcs_entry(uint8_t *dst, ptrdiff_t dst_stride, int width, int height, const
     memset(&r, 0, sizeof(r));
     r.w = (uint16_t)width; r.h = (uint16_t)height;
     if (!vvc_stage_frame_h2d(ctx, &d, &f)) {
-        cudaMemcpyAsync(dlut, lut, lsz, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(drect, &r, sizeof(r), cudaMemcpyHostToDevice, ctx->stream);
+        copy(ctx, dlut, lut, lsz, cudaMemcpyHostToDevice);
+        copy(ctx, drect, &r, sizeof(r), cudaMemcpyHostToDevice);
         if (!vvc_cuda_lmcs_rects(ctx, &d, dlut, drect, 1) && !vvc_stage_frame_d2h(ctx, &f, &d))
             vvc_cuda_sync(ctx);
     }
@@ -637,6 +651,51 @@ void pred_residual_joint_entry(int *buf, int w, int h, int c_sign, int shift)
     c.done();
 }
 
+// ---- intra leaf predictors (vvc_intra_template.c:686-1000): pred_planar / pred_dc / pred_v / pred_h / pred_angular_v /
+// pred_angular_h / pred_mip through intra_leaf_kernel.  top / left point into IntraEdgeParams' arrays (6 * MAX_TB_SIZE + 5
+// samples with the pointer MAX_TB_SIZE + 3 in, vvcdsp.c:200-207): the range [-67, +200) around each pointer covers every
+// sample any predictor reads and lies inside those arrays.  stride is in SAMPLES, as the reference passes it. ----
+template <int BD>
+void intra_leaf_call(int kind, uint8_t *src, const uint8_t *top, const uint8_t *left, int w, int h, ptrdiff_t stride,
+                     int c_idx, int mode, int ref_idx, int filter_flag, int flags)
+{
+    constexpr int EB = 67, EN = EB + 200;
+    Call c((size_t)w * h * 2 + 2 * EN * 2 + 1024);
+    if (c.bad) return c.done();
+    pel *blk = c.take<pel>((size_t)w * h);
+    uint16_t *edges = c.take<uint16_t>(2 * EN);
+    VVCCudaIntraPB *dpb = c.take<VVCCudaIntraPB>(1);
+    if (top)  c.up(edges, (const uint16_t *)top - EB, EN * 2);
+    if (left) c.up(edges + EN, (const uint16_t *)left - EB, EN * 2);
+    VVCCudaIntraPB pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.w = (uint8_t)w; pb.h = (uint8_t)h; pb.c_idx = (uint8_t)c_idx; pb.kind = (uint8_t)kind; pb.mode = (int8_t)mode;
+    pb.ref_idx = (uint8_t)ref_idx; pb.filter_flag = (uint8_t)filter_flag; pb.flags = (uint8_t)flags;
+    pb.top = EB; pb.left = EN + EB;
+    c.up(dpb, &pb, sizeof(pb));
+    VVCCudaFrame f;                       // the block as a picture of its own; c_idx only selects luma / chroma arithmetic
+    memset(&f, 0, sizeof(f));
+    f.width = w; f.height = h; f.bit_depth = BD; f.ctb_log2 = 7; f.batch = 1; f.chroma_format_idc = 3;
+    for (int p = 0; p < 3; p++) { f.data[p] = blk; f.stride[p] = w * 2; f.batch_stride[p] = (ptrdiff_t)w * h * 2; }
+    if (!c.bad && !vvc_cuda_intra_leaf_frame(c.ctx, &f, dpb, 1, edges))
+        c.dn2d(src, stride * 2, blk, w * 2, w * 2, h);
+    c.done();
+}
+template <int BD> void pred_planar_entry(uint8_t *src, const uint8_t *top, const uint8_t *left, int w, int h, ptrdiff_t stride)
+{ intra_leaf_call<BD>(VVC_CUDA_INTRA_PLANAR, src, top, left, w, h, stride, 0, 0, 0, 0, 0); }
+template <int BD> void pred_dc_entry(uint8_t *src, const uint8_t *top, const uint8_t *left, int w, int h, ptrdiff_t stride)
+{ intra_leaf_call<BD>(VVC_CUDA_INTRA_DC, src, top, left, w, h, stride, 0, 0, 0, 0, 0); }
+template <int BD> void pred_v_entry(uint8_t *src, const uint8_t *top, int w, int h, ptrdiff_t stride)
+{ intra_leaf_call<BD>(VVC_CUDA_INTRA_VERT, src, top, nullptr, w, h, stride, 0, 0, 0, 0, 0); }
+template <int BD> void pred_h_entry(uint8_t *src, const uint8_t *left, int w, int h, ptrdiff_t stride)
+{ intra_leaf_call<BD>(VVC_CUDA_INTRA_HORZ, src, nullptr, left, w, h, stride, 0, 0, 0, 0, 0); }
+template <int BD> void pred_mip_entry(uint8_t *src, const uint8_t *top, const uint8_t *left, int w, int h, ptrdiff_t stride, int mode_id, int is_transpose)
+{ intra_leaf_call<BD>(VVC_CUDA_INTRA_MIP, src, top, left, w, h, stride, 0, mode_id, 0, 0, is_transpose ? VVC_CUDA_INTRA_MIP_TRANSPOSED : 0); }
+template <int BD, int V> void pred_angular_entry(uint8_t *src, const uint8_t *top, const uint8_t *left, int w, int h, ptrdiff_t stride,
+                                                  int c_idx, int mode, int ref_idx, int filter_flag, int need_pdpc)
+{ intra_leaf_call<BD>(V ? VVC_CUDA_INTRA_ANGULAR_V : VVC_CUDA_INTRA_ANGULAR_H, src, top, left, w, h, stride, c_idx, mode, ref_idx, filter_flag,
+                      need_pdpc ? VVC_CUDA_INTRA_PDPC : 0); }
+
 template <int BD>
 void install_blocks(VVCDSPContext *c)
 {
@@ -670,6 +729,10 @@ void install_blocks(VVCDSPContext *c)
     c->lf.filter_luma[0] = lf_luma_entry<BD, 0>;     c->lf.filter_luma[1] = lf_luma_entry<BD, 1>;
     c->lf.filter_chroma[0] = lf_chroma_entry<BD, 0>; c->lf.filter_chroma[1] = lf_chroma_entry<BD, 1>;
     c->lf.ladf_level[0] = ladf_entry<0>;             c->lf.ladf_level[1] = ladf_entry<1>;
+    c->intra.pred_planar = pred_planar_entry<BD>;  c->intra.pred_dc = pred_dc_entry<BD>;
+    c->intra.pred_v = pred_v_entry<BD>;            c->intra.pred_h = pred_h_entry<BD>;
+    c->intra.pred_mip = pred_mip_entry<BD>;
+    c->intra.pred_angular_v = pred_angular_entry<BD, 1>;  c->intra.pred_angular_h = pred_angular_entry<BD, 0>;
     c->itx.add_residual_joint = add_residual_joint_entry<BD>;
     c->itx.pred_residual_joint = pred_residual_joint_entry;
 }

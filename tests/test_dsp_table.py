@@ -61,7 +61,7 @@ def test_hook_installs_the_documented_entries():
         assert ptr(t.alf.filter[0]) and ptr(t.alf.filter[1]) and ptr(t.alf.filter_cc) and ptr(t.alf.classify) and ptr(t.alf.recon_coeff_and_clip)
         assert all(ptr(t.lf.filter_luma[d]) and ptr(t.lf.filter_chroma[d]) and ptr(t.lf.ladf_level[d]) for d in range(2))
         # entries that take the decoder's VVCLocalContext, and the SAO restore pass (takes SAOParams), keep what the caller installed
-        assert not ptr(t.intra.intra_pred) and not ptr(t.intra.intra_cclm_pred) and not ptr(t.intra.lmcs_scale_chroma)
+        assert not ptr(t.intra.intra_pred) and not ptr(t.intra.intra_cclm_pred) and not ptr(t.intra.lmcs_scale_chroma)   # these take VVCLocalContext*
         assert not ptr(t.sao.edge_restore[0])
     t = fresh_table(8)                      # 8-bit pictures (pixel = uint8_t): nothing is installed
     assert not ptr(t.lmcs.filter) and not ptr(t.itx.itx[0][0][2][2]) and not ptr(t.inter.avg)

@@ -269,3 +269,46 @@ def test_joint_residuals(tables):
             pic = rng.pix((h + 1) * (w + 4), bd)
             both(o.itx.add_residual_joint, r.itx.add_residual_joint, [pic, res], lambda f, p, q: f(p8(p), q.ctypes.data_as(ip), w, h, (w + 4) * 2, sign, shift))
             both(o.itx.pred_residual_joint, r.itx.pred_residual_joint, [res], lambda f, q: f(q.ctypes.data_as(ip), w, h, sign, shift))
+
+
+def test_intra_leaf_predictors(tables):
+    """intra.pred_planar / pred_dc / pred_v / pred_h / pred_angular_v / pred_angular_h / pred_mip with the edge pointers
+    IntraEdgeParams carries: arrays of 6 * 64 + 5 samples, pointer 67 in (vvcdsp.c:200-207); stride in samples."""
+    bd, o, r = tables
+    rng = R(11)
+    S, OFF = 80, 67
+    sizes = [4, 8, 16, 32, 64]
+    checked = 0
+    for it in range(160):
+        w, h = sizes[rng.one(5)], sizes[rng.one(5)]
+        top, left = rng.pix(389, bd), rng.pix(389, bd)
+        pic = rng.pix((h + 2) * S, bd)
+        pt, pl = lambda a: p8(a, OFF * 2), lambda a: p8(a, OFF * 2)
+        kind = it % 7
+        if kind == 0:
+            both(o.intra.pred_planar, r.intra.pred_planar, [pic, top, left], lambda f, p, t, l: f(p8(p, 2 * (S + 4)), pt(t), pl(l), w, h, S))
+        elif kind == 1:
+            both(o.intra.pred_dc, r.intra.pred_dc, [pic, top, left], lambda f, p, t, l: f(p8(p, 2 * (S + 4)), pt(t), pl(l), w, h, S))
+        elif kind == 2:
+            both(o.intra.pred_v, r.intra.pred_v, [pic, top], lambda f, p, t: f(p8(p, 2 * (S + 4)), pt(t), w, h, S))
+        elif kind == 3:
+            both(o.intra.pred_h, r.intra.pred_h, [pic, left], lambda f, p, l: f(p8(p, 2 * (S + 4)), pl(l), w, h, S))
+        elif kind == 4:
+            size_id = 0 if (w == 4 and h == 4) else (1 if (w == 4 or h == 4 or (w == 8 and h == 8)) else 2)
+            mode, tr = rng.one((16, 8, 6)[size_id]), rng.one(2)
+            both(o.intra.pred_mip, r.intra.pred_mip, [pic, top, left], lambda f, p, t, l: f(p8(p, 2 * (S + 4)), pt(t), pl(l), w, h, S, mode, tr))
+        else:
+            vertical = kind == 5
+            c_idx = rng.one(3)
+            mode = (34 + rng.one(47)) if vertical else (-14 + rng.one(48))
+            mode = {50: 51, 0: 2, 1: 3, 18: 19}.get(mode, mode)
+            ref_idx = 0 if c_idx else rng.one(3)
+            flt = rng.one(2)
+            pdpc = 0
+            if w >= 4 and h >= 4 and not ref_idx and not (18 < mode < 50) and rng.one(4):
+                ns, _ = synth.intra_nscale(w, h, mode)
+                pdpc = int(ns >= 0)
+            fo, fr = (o.intra.pred_angular_v, r.intra.pred_angular_v) if vertical else (o.intra.pred_angular_h, r.intra.pred_angular_h)
+            both(fo, fr, [pic, top, left], lambda f, p, t, l: f(p8(p, 2 * (S + 4)), pt(t), pl(l), w, h, S, c_idx, mode, ref_idx, flt, pdpc))
+        checked += 1
+    assert checked == 160

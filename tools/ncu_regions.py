@@ -11,12 +11,19 @@ import sys
 import tempfile
 
 rep, obj, srcpath, nrec = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+kernel = sys.argv[5] if len(sys.argv) > 5 else None      # optional ncu --kernel-name filter for reports with several kernels
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + (["--kernel-name", kernel] if kernel else []),
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
 h = rows[hdr]
 ii = h.index("Instructions Executed")
-recs = [(int(r[0], 16), int(r[ii] or 0)) for r in rows[hdr + 1:] if r and r[0]]
+recs = []
+for r in rows[hdr + 1:]:
+    if r and r[0] == "Kernel Name":          # several launches: the first one only
+        break
+    if r and r[0] and len(r) > ii:
+        recs.append((int(r[0], 16), int(r[ii] or 0)))
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=td, check=True, capture_output=True)
     dis = subprocess.run(["nvdisasm", "--print-line-info", glob.glob(td + "/*.cubin")[0]], capture_output=True, text=True).stdout
