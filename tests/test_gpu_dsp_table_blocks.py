@@ -300,9 +300,14 @@ def test_intra_leaf_predictors(tables):
         else:
             vertical = kind == 5
             c_idx = rng.one(3)
-            mode = (34 + rng.one(47)) if vertical else (-14 + rng.one(48))
-            mode = {50: 51, 0: 2, 1: 3, 18: 19}.get(mode, mode)
             ref_idx = 0 if c_idx else rng.one(3)
+            while True:         # a (mode, shape) pair whose reads stay inside the arrays, as every pair the decoder produces does
+                mode = (34 + rng.one(47)) if vertical else (-14 + rng.one(48))
+                mode = {50: 51, 0: 2, 1: 3, 18: 19}.get(mode, mode)
+                along, across = (w, h) if vertical else (h, w)
+                reach = (((across + 1 + ref_idx) * abs(synth.intra_angle(mode))) >> 5) + ref_idx + 6
+                if along + reach < 190 and reach < 60:
+                    break
             flt = rng.one(2)
             pdpc = 0
             if w >= 4 and h >= 4 and not ref_idx and not (18 < mode < 50) and rng.one(4):
