@@ -581,6 +581,10 @@ int check(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *refs)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "inter: dst/ref geometry differs (reference scaling is not supported)");
     if (dst->chroma_format_idc && (dst->hshift != 1 || dst->vshift != 1))
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "inter: only 4:0:0 and 4:2:0 are accelerated");
+    // VVCCudaPB.pic and .ref[] are 8-bit: a larger ring cannot be addressed by the records
+    if (dst->batch > 256 || refs->batch > 256)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "inter: rings of more than 256 pictures (%d destination, %d reference) cannot be addressed by the 8-bit picture fields of the records",
+                            dst->batch, refs->batch);
     return 0;
 }
 

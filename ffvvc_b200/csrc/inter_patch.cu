@@ -366,7 +366,7 @@ int vvc_inter_launch_classify(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
 {
     // scratch: [count: 64 bytes][luma: 8 n][chroma: 4 n][coop: n][luma border: 8 n][chroma border: 4 n] words
     const size_t n = (size_t)p.n;
-    uint32_t *base = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + 25 * n * sizeof(uint32_t));
+    uint32_t *base = (uint32_t *)vvc_ctx_scratch(ctx, 2, 64 + 25 * n * sizeof(uint32_t) + n * sizeof(VVCCudaDmvrOut));     // + refined vectors of the split DMVR kernels
     if (!base)
         return ctx->err;
     ls->count = base;

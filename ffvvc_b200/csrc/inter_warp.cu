@@ -22,6 +22,7 @@
 //    samples it holds in registers and stores them transposed, so the vertical pass reads its column as
 //    two 128-bit shared loads and runs the same 8-outputs-per-lane code.
 //  * The bilinear DMVR prediction and the 25 SADs use 16x2 packed arithmetic (VIMNMX.U16x2, IDP.2A).
+#include <type_traits>
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "inter_common.cuh"
 #include "tables.cuh"
@@ -103,6 +104,14 @@ struct __align__(16) WarpSmem {
     UnitMC um[4];
     int    sad[25];
     int    vxy[16][2];
+};
+
+// what the DMVR search alone needs (PHASE 1): both windows, the bilinear tiles, the 25 SADs - 5.4 KB instead of 7.7 KB per
+// warp, so that more of its CTAs fit an SM
+struct __align__(16) SearchSmem {
+    struct { uint32_t win[2 * WUL]; } a;
+    short dm[2][DU];
+    int   sad[25];
 };
 
 // (t * inv_rows(d)) >> 16 == t / d for t < 128; d is a window row count: 23, 15, 11 (luma), 11, 7, 5 (chroma)
@@ -329,14 +338,18 @@ __device__ __forceinline__ int tma_prefetch(TmaSmem<TMA> &ts, const InterK &p, c
 // KIND 0: records with DMVR / BDOF and no PROF (always bi-predicted, never GPM): the uni, GPM and PROF paths are
 // compiled out.  KIND 1: the rest of the cooperative records (PROF), listed from the back of coop[].
 // TMA 1 (KIND 0 only): the DMVR windows of the NEXT record are fetched by the copy engine while this one is computed.
-template <int KIND, int TMA>
+// PHASE (KIND 0 only): 0 = the whole record in one kernel; 1 = the DMVR search alone (window staging, bilinear, SADs, decision),
+// refined vectors and the BDOF switch go to `refined`; 2 = everything after it, reading them back.  Splitting halves the
+// code each kernel's warps run through (the one-kernel form spends 38 % of its stall samples waiting for instructions).
+template <int KIND, int TMA, int PHASE>
 __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, const uint32_t *__restrict__ coop, int cap, uint32_t *count,   //@region rec_load
-                                                              const __grid_constant__ CUtensorMap tmap)
+                                                              const __grid_constant__ CUtensorMap tmap, VVCCudaDmvrOut *__restrict__ refined)
 {
-    __shared__ WarpSmem sm[kWarps];
+    using SM = typename std::conditional<PHASE == 1, SearchSmem, WarpSmem>::type;
+    __shared__ SM sm[kWarps];
     __shared__ TmaSmem<TMA> ts;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem &s = sm[warp];
+    SM &s = sm[warp];
     const uint2 *lumaf = reinterpret_cast<const uint2 *>(&vvct_luma_mc_filters[0][0][0]);
     const uint32_t *chromaf = reinterpret_cast<const uint32_t *>(&vvct_chroma_mc_filters[0][0][0]);
     if constexpr (TMA) {
@@ -358,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
         if (q_k == 2) {                                                             \
             int f_ = 0;                                                             \
             if (lane == 0)                                                          \
-                f_ = (int)atomicAdd(count + 8 + KIND, 2u);                          \
+                f_ = (int)atomicAdd(count + (PHASE == 1 ? 14 : 8 + KIND), 2u);      \
             q_base = __shfl_sync(0xffffffffu, f_, 0);                               \
             q_k = 0;                                                                \
         }                                                                           \
@@ -405,7 +418,20 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
             stage_apron(s.a.win + l * WUL, PWL, 0, w + 7, h + 7, k, 16);
         }
         DRAW_NEXT();            // the staging area is free again: the next record's windows start now
-        if (dmvr_luma) {
+        if (PHASE == 1 && !dmvr_luma)
+            continue;
+        if (PHASE == 2 && dmvr_luma) {
+            // the search ran in its own kernel: windows again (the final motion compensation reads the same clamped windows),
+            // refined vectors and BDOF switch from its output
+            const int l = lane >> 4;
+            stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, p.margin,
+                        pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane & 15, 16);
+            const int *r = reinterpret_cast<const int *>(refined + ri);
+            mvr[0][0] = r[0]; mvr[0][1] = r[1]; mvr[1][0] = r[2]; mvr[1][1] = r[3];
+            bdof = r[5];
+            __syncwarp();
+        }
+        if (PHASE != 2 && dmvr_luma) {
             if (!(TMA && use_tma)) {
                 const int l = lane >> 4;                    // lanes 0-15: list 0, lanes 16-31: list 1
                 stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, p.margin,
@@ -523,15 +549,19 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 }
                 if (min_sad < 2 * w * h)
                     bdof = 0;
-                if (p.dmvr_out && lane == 0) {
+                if ((p.dmvr_out || PHASE == 1) && lane == 0) {
                     VVCCudaDmvrOut o;
                     o.mv[0][0] = mvr[0][0]; o.mv[0][1] = mvr[0][1]; o.mv[1][0] = mvr[1][0]; o.mv[1][1] = mvr[1][1];
                     o.min_sad = min_sad; o.bdof_applied = bdof;
-                    p.dmvr_out[ri] = o;
+                    if (p.dmvr_out)
+                        p.dmvr_out[ri] = o;
+                    if (PHASE == 1)
+                        refined[ri] = o;
                 }
             }
             __syncwarp();
         }
+        if constexpr (PHASE != 1) {
         const bool do_bdof = bdof && !gpm;   //@region luma_setup
         pel *dstp[3];
 #pragma unroll
@@ -808,6 +838,7 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
                 *reinterpret_cast<uint32_t *>(d) = pack16(o[0], o[1]);
             }
         }
+        }       // PHASE != 1
 #undef MVR
 #undef MV0
 #undef REF
@@ -851,24 +882,37 @@ int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &li
 #ifndef INTER_WARP_CTAS
 #define INTER_WARP_CTAS 7                                        // persistent: 7 CTAs fit an SM (shared memory)
 #endif
+#ifndef INTER_WARP_SPLIT
+#define INTER_WARP_SPLIT 1                                       // DMVR search and the rest of a record as two kernels (tools/sweep_split.sh: inter 2.41 -> 2.31 ms per 16 pictures)
+#endif
+#ifndef INTER_WARP_CTAS_SEARCH
+#define INTER_WARP_CTAS_SEARCH 9                                 // 22.8 KB of shared memory per CTA
+#endif
 #ifndef INTER_WARP_CTAS_TMA
 #define INTER_WARP_CTAS_TMA 5                                    // with the staging area: 5
 #endif
     const int ctas = ceil_div(p.n, kWarps);
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
+    VVCCudaDmvrOut *refined = reinterpret_cast<VVCCudaDmvrOut *>(lists.count + 16 + 25 * (size_t)p.n);      // behind the lists
     if (ctx->inter_tma) {
         if (make_window_map(ctx, p, &map))
             return ctx->err;
         const int grid = ctas < 148 * INTER_WARP_CTAS_TMA ? ctas : 148 * INTER_WARP_CTAS_TMA;
-        inter_warp_kernel<0, 1><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map);
+        inter_warp_kernel<0, 1, 0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map, refined);
+    } else if (INTER_WARP_SPLIT) {
+        const int g1 = ctas < 148 * INTER_WARP_CTAS_SEARCH ? ctas : 148 * INTER_WARP_CTAS_SEARCH;
+        inter_warp_kernel<0, 0, 1><<<g1, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map, refined);
+        VVC_LAUNCHED(ctx);
+        const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
+        inter_warp_kernel<0, 0, 2><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map, refined);
     } else {
         const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
-        inter_warp_kernel<0, 0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map);
+        inter_warp_kernel<0, 0, 0><<<grid, kThreads, 0, ctx->stream>>>(p, lists.coop, p.n, lists.count, map, refined);
     }
     VVC_LAUNCHED(ctx);
     const int grid = ctas < 148 * INTER_WARP_CTAS ? ctas : 148 * INTER_WARP_CTAS;
-    inter_warp_kernel<1, 0><<<grid, kThreads, 0, spread == 2 ? ctx->side[2] : ctx->stream>>>(p, lists.coop, p.n, lists.count, map);
+    inter_warp_kernel<1, 0, 0><<<grid, kThreads, 0, spread == 2 ? ctx->side[2] : ctx->stream>>>(p, lists.coop, p.n, lists.count, map, refined);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

@@ -340,6 +340,8 @@ extern "C" int vvc_cuda_itx_frame_q(VVCCudaCtx *ctx, const VVCCudaFrame *frame, 
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: the 16-bit window layout needs log2_transform_range 15");
     if (!frame_vec_ok(frame))
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: planes and strides must be 16-byte aligned");
+    if (frame->batch > 256)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "itx: a ring of %d pictures cannot be addressed by the 8-bit picture field of the records", frame->batch);
     if (!n_tbs)
         return VVC_CUDA_OK;
     const int mode = coef_mode(co);

@@ -639,7 +639,7 @@ int vvc_cuda_ciip_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVC
 /* ------------------------------------------------------------------------------------------
  * Whole-picture reconstruction: INTER -> RECON (residual) -> LMCS -> DEBLOCK_V -> DEBLOCK_H -> SAO ->
  * ALF, the reference's per-CTU stage list (libavcodec/vvc/vvc_thread.c:41-51) run stage by stage
- * over the picture (7 stage calls; 20 kernel launches for a 10-bit 4:2:0 picture, + 1 when forward-LMCS rectangles are given).
+ * over the picture (7 stage calls; 17 kernel launches for a 10-bit 4:2:0 picture ring: inter 8, residual 4, the other stages 1 each; + 1 when forward-LMCS rectangles are given).
  * ---------------------------------------------------------------------------------------- */
 typedef struct VVCCudaReconDesc {
     /* INTER */
