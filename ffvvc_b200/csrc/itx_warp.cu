@@ -32,7 +32,10 @@ __device__ __forceinline__ uint2 ldg_nc(const uint2 *p) { uint2 v; asm("ld.globa
 __device__ __forceinline__ uint32_t ldg_nc(const uint32_t *p) { uint32_t v; asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
 constexpr int kWarps = 4, kThreads = kWarps * 32;
-constexpr int P2 = 40;                        // pitch (int16) of the mid-stage rows: 32 inputs + pad, 16-byte multiple
+#ifndef ITX_MID_PITCH
+#define ITX_MID_PITCH 40
+#endif
+constexpr int P2 = ITX_MID_PITCH;             // pitch (int16) of the mid-stage rows: 32 inputs + pad, 16-byte multiple
 
 struct ItxW {
     pel       *plane[3];

@@ -123,7 +123,10 @@ __device__ __forceinline__ void edge_row(uint32_t o[4], const Row &above, const 
     }
 }
 
-__global__ void __launch_bounds__(32 * WARPS, 4) sao_kernel(const SaoK p)
+#ifndef SAO_MIN_CTAS
+#define SAO_MIN_CTAS 8               // resident CTAs (of 8 warps) per SM the kernel is compiled for: full occupancy at 32 registers (tools/sweep_sao_occ.sh: 3 / 4 / 5 / 6 / 8 -> 0.32 / 0.257 / 0.236 / 0.244 / 0.216 ms per 16 pictures)
+#endif
+__global__ void __launch_bounds__(32 * WARPS, SAO_MIN_CTAS) sao_kernel(const SaoK p)
 {
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int per_pic = p.cta_start[3];
