@@ -434,8 +434,14 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
         if (PHASE != 2 && dmvr_luma) {
             if (!(TMA && use_tma)) {
                 const int l = lane >> 4;                    // lanes 0-15: list 0, lanes 16-31: list 1
-                stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, p.margin,
-                            pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane & 15, 16);
+                if (PHASE == 1)
+                    // the search alone reads rows 1 .. h + 5 of the window (bilinear taps at -2 .. h + 2) and never its apron:
+                    // the same placement as below, two rows and the apron passes fewer
+                    stage_units(s.a.win + l * WUL + 3 * PWL + 1, PWL, 0, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, p.margin,
+                                pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 2, w + 7, h + 5, lane & 15, 16);
+                else
+                    stage_units(s.a.win + l * WUL, PWL, 1, p.ref[0] + REF(l) * p.rb[0], p.rp[0], p.w, p.h, p.margin,
+                                pb.x0 + (MV0(l, 0) >> 4) - 3, pb.y0 + (MV0(l, 1) >> 4) - 3, w + 7, h + 7, lane & 15, 16);
             }
             __syncwarp();
             // bilinear (dmvr / dmvr_h / dmvr_v / dmvr_hv, vvc_inter_template.c:324-409) on sample pairs; lane = row
