@@ -69,6 +69,13 @@ __device__ __forceinline__ void tma_box_3d(void *dst, const CUtensorMap *map, in
                  :: "r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef INTER_STAGE_UNROLL
+#define INTER_STAGE_UNROLL 4             // window rows a lane requests before it stores the first one
+#endif
+constexpr int kStageUnroll = INTER_STAGE_UNROLL;
+#ifndef INTER_WARP_PREFETCH
+#define INTER_WARP_PREFETCH 0            // measured slower (tools/sweep_prefetch2.sh: inter 2.285 -> 2.381 ms per 16 pictures)
+#endif
 constexpr int kWarps = 4, kThreads = kWarps * 32;
 constexpr int PWL = 15, WUL = 27 * PWL + 1;   // luma window: 27 rows x 15 words (30 samples); unit stride 406 words
 constexpr int PWC = 9, WUC = 15 * PWC;        // chroma window: 15 rows x 9 words (18 samples)
@@ -141,7 +148,7 @@ __device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const p
         if (inside) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (long long)(wy0 + rsub) * pitch + bx) + k;
             const int sstep = rstep * (pitch >> 1);
-#pragma unroll 4
+#pragma unroll kStageUnroll
             for (int r = rsub; r < rows; r += rstep, src += sstep, dst += dstep)
                 *dst = __ldg(src);
         } else {
@@ -296,6 +303,41 @@ __device__ __forceinline__ void fetch_ring(WarpSmem &s, int ui, int bw, int bh, 
     }
 }
 
+// The reference windows of the NEXT record of a warp (bi-predicted record of the DMVR / BDOF list) asked into L2 while the
+// current one is computed: the staging loop's first use of its loads was where a quarter of the main kernel's stall
+// samples sat (the reference ring of a 16-picture launch is three times the L2, so every window comes from DRAM).
+// One row per lane and list, both ends of the row (a row may straddle two lines); coordinates clamped into the plane.
+__device__ __noinline__ void prefetch_windows(const InterK &p, const uint32_t *__restrict__ coop, int ci, int lane)
+{
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p.pbs + __ldg(coop + ci));
+    const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2);
+    const int x0 = r0 & 0xffff, y0 = r0 >> 16, w = r1 & 0xff, h = (r1 >> 8) & 0xff;
+    const int l = lane >> 4, k = lane & 15;
+    const int mx = (int)__ldg(q + 3 + 2 * l), my = (int)__ldg(q + 4 + 2 * l), ref = l ? (r2 >> 8) & 0xff : r2 & 0xff;
+    {
+        const pel *plane = p.ref[0] + ref * p.rb[0];
+        const int xa = d_clip3(x0 + (mx >> 4) - 3, 0, p.w - 1), xb = d_clip3(x0 + (mx >> 4) + w + 3, 0, p.w - 1), ya = y0 + (my >> 4) - 3;
+#pragma unroll
+        for (int r = k; r < 23; r += 16)
+            if (r < h + 7) {
+                const pel *row = plane + (long long)d_clip3(ya + r, 0, p.h - 1) * p.rp[0];
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(row + xa));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(row + xb));
+            }
+    }
+    if (p.planes == 3) {
+        // chroma: lanes 0-7 / 8-15 of a list take Cb / Cr, rows k and k + 8 of the (h / 2 + 3)-row window (one line per row)
+        const int pc = (k >> 3) + 1, kk = k & 7, pw = p.w >> 1, ph = p.h >> 1;
+        const pel *plane = (pc == 1 ? p.ref[1] + ref * p.rb[1] : p.ref[2] + ref * p.rb[2]);
+        const int pitch = pc == 1 ? p.rp[1] : p.rp[2];
+        const int xa = d_clip3((x0 >> 1) + (mx >> 5) - 1, 0, pw - 1), ya = (y0 >> 1) + (my >> 5) - 1;
+#pragma unroll
+        for (int r = kk; r < 11; r += 8)
+            if (r < (h >> 1) + 3)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(plane + (long long)d_clip3(ya + r, 0, ph - 1) * pitch + xa));
+    }
+}
+
 // KIND 0: records with DMVR / BDOF and no PROF (always bi-predicted, never GPM): the uni, GPM and PROF paths are
 // compiled out.  KIND 1: the rest of the cooperative records (PROF), listed from the back of coop[].
 template <int TMA> struct TmaSmem { alignas(128) uint8_t box[kWarps][2][kBoxSlot]; uint64_t bar[kWarps]; };
@@ -379,6 +421,8 @@ __global__ void __launch_bounds__(kThreads) inter_warp_kernel(const InterK p, co
         if (nxt >= n_coop)                                                          \
             nxt = -1;                                                               \
         nxt_tma = nxt >= 0 ? tma_prefetch<TMA>(ts, p, coop, KIND ? cap - 1 - nxt : nxt, &tmap, warp, lane) : 0;   \
+        if (INTER_WARP_PREFETCH && KIND == 0 && !TMA && nxt >= 0)                   \
+            prefetch_windows(p, coop, nxt, lane);                                   \
     } while (0)
     int nxt, nxt_tma;
     DRAW_NEXT();
