@@ -69,6 +69,11 @@ __device__ __forceinline__ Rec load_rec(const VVCCudaPB *pb)
 }
 
 __device__ __forceinline__ uint32_t frc(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_rc(lo, hi, sh); }
+// The same instructions as CUDA's __dp2a_lo / __dp2a_hi / __funnelshift_rc, which the headers declare `asm volatile`: pure
+// functions of their operands, so the compiler may interleave independent chains, hoist and merge them (INTER_PLAIN_ASM).
+__device__ __forceinline__ int nv_dp2a_lo(int a, int b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int nv_dp2a_hi(int a, int b, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t nv_frc(uint32_t lo, uint32_t hi, int sh) { uint32_t d; asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sh)); return d; }
 __device__ __forceinline__ int lo16(uint32_t v) { return (short)(v & 0xffff); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)v >> 16; }
 __device__ __forceinline__ uint32_t pack16(int a, int b) { return (uint32_t)(a & 0xffff) | ((uint32_t)b << 16); }

@@ -14,6 +14,15 @@
 #include "inter_common.cuh"
 #include "tables.cuh"
 
+#ifndef INTER_PLAIN_ASM
+#define INTER_PLAIN_ASM 1
+#endif
+#if INTER_PLAIN_ASM
+#define __dp2a_lo nv_dp2a_lo
+#define __dp2a_hi nv_dp2a_hi
+#define __funnelshift_rc nv_frc
+#endif
+
 namespace {
 
 constexpr int kThreads = 128;

@@ -382,7 +382,7 @@ def sao_params(geom, seed=99, with_restore=False):
 # Residual stage inputs (coefficient/nz distributions of
 # tests/checkasm/vvc_itx.c:25-75)
 # ---------------------------------------------------------------------------------------------
-def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True):
+def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True, square=False):
     """Tile every picture of the ring with transform blocks (luma + both chroma planes).
 
     Returns (tbs, coeffs): TB_DTYPE records and the dense int32 coefficient buffer.
@@ -393,6 +393,8 @@ def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True):
     recs = []
     for k in range(geom.batch):
         lw, lh = tb_partition(geom, rng, stop_p=0.45)
+        if square:                       # a quadtree: every block cut into squares of its shorter side
+            lw = lh = np.minimum(lw, lh)
         uh, uw = lw.shape
         uy, ux = np.mgrid[0:uh, 0:uw]
         origin = ((ux * 4) % (1 << lw) == 0) & ((uy * 4) % (1 << lh) == 0)
@@ -985,7 +987,10 @@ def intra_picture(geom, seed=909):
     records in decoding order, one luma and one chroma step per coding unit - what a CPU decoder does)."""
     assert geom.chroma_format_idc == 1 and geom.hshift == 1 and geom.vshift == 1
     rng = LCG(seed)
-    tbs, coeffs = tb_list(geom, seed=seed + 1, extras=False)
+    # square blocks: the z-order of their origins is then the decoding order of a quadtree, in which everything left of a
+    # block over its whole height and above it over its whole width comes earlier (with rectangles the z-order of origins
+    # is not the order of any partition tree: a block could then read samples that are only written later)
+    tbs, coeffs = tb_list(geom, seed=seed + 1, extras=False, square=True)
     keep = ~((tbs["c_idx"] > 0) & ((tbs["log2_w"] < 2) | (tbs["log2_h"] < 2)))        # no 2-wide chroma blocks in VVC intra
     tbs = tbs[keep]
     ctb, cl2 = geom.ctb_size, geom.ctb_log2

@@ -49,7 +49,7 @@ def test_intra_pred_and_cclm_bit_exact(ctx, w, h, batch, bd, ctb_log2, seed):
         util.assert_planes_equal(geom, host, want, "host entry vs oracle")
 
 
-@pytest.mark.parametrize("w,h,batch,seed,mode", [(416, 240, 2, 3, "dense"), (256, 192, 3, 4, "window_q"), (832, 480, 1, 5, "dense")])
+@pytest.mark.parametrize("w,h,batch,seed,mode", [(416, 240, 2, 3, "dense"), (256, 192, 3, 4, "window_q"), (832, 480, 1, 5, "dense"), (1920, 1080, 1, 11, "dense")])
 def test_all_intra_pictures_by_wavefronts_bit_exact(ctx, w, h, batch, seed, mode):
     """prediction and residual alternating wavefront by wavefront on the GPU vs the oracle walking the same blocks in
     decoding order (luma step, chroma step per coding unit)"""
