@@ -14,11 +14,18 @@
 // product, then the two separable up-sampling passes.  The float in the reference's inverse-angle derivation
 // is an exact integer expression for the 30 angles that occur ((32768 + a) / (2 a), checked by the tests).
 #include "common.cuh"
+#include "coeff_src.cuh"
 #include "tables.cuh"
 
 namespace {
 
 constexpr int kThreads = 128;
+
+#include "itx_generic.cuh"        // process_tb: the residual step of the dependency-driven kernel below
+
+// A picture sample another CTA may have written during this launch (the dependency-driven kernel): read through L2, the
+// SM's own L1 may hold the line from before the sample was final.  The wave-by-wave kernels read plainly.
+template <bool CG> __device__ __forceinline__ int ld_pel(const pel *q) { return CG ? (int)__ldcg(q) : (int)*q; }
 
 struct IntraK {
     pel       *plane[3];
@@ -255,6 +262,7 @@ __device__ __forceinline__ bool smoothing_mode(int m)
     return m == -14 || m == -12 || m == -10 || m == -6 || m == 0 || m == 2 || m == 34 || m == 66 || m == 72 || m == 76 || m == 78 || m == 80;
 }
 
+template <bool CG>
 __device__ void cclm_block(const PredK &p, const VVCCudaIntraBlk &b, CclmShared &cs)
 {
     const int tid = threadIdx.x, bd = p.bd, hs = p.hs, vs = p.vs, w = b.w, h = b.h, x = b.x0, y = b.y0;
@@ -264,7 +272,7 @@ __device__ void cclm_block(const PredK &p, const VVCCudaIntraBlk &b, CclmShared 
     const pel *Y = p.plane[0] + b.pic * p.bstride[0];
     const int yp = p.pitch[0], cp = p.pitch[1];
     pel *C0 = p.plane[1] + b.pic * p.bstride[1], *C1 = p.plane[2] + b.pic * p.bstride[2];
-    auto L = [&](int xx, int yy) -> int { return Y[(long long)yy * yp + xx]; };
+    auto L = [&](int xx, int yy) -> int { return ld_pel<CG>(Y + (long long)yy * yp + xx); };
     if (!at && !al) {
         for (int idx = tid; idx < w * h; idx += kThreads) {
             const int i = idx / w, j = idx - i * w;
@@ -313,8 +321,8 @@ __device__ void cclm_block(const PredK &p, const VVCCudaIntraBlk &b, CclmShared 
                     v = (L(xl, y0 - 1) + 2 * L(lx, y0 - 1) + L(lx + 1, y0 - 1) + 2) >> 2;
                 }
             }
-            cs.sel[1][tid] = C0[(long long)(y - 1) * cp + x + pos];
-            cs.sel[2][tid] = C1[(long long)(y - 1) * cp + x + pos];
+            cs.sel[1][tid] = ld_pel<CG>(C0 + (long long)(y - 1) * cp + x + pos);
+            cs.sel[2][tid] = ld_pel<CG>(C1 + (long long)(y - 1) * cp + x + pos);
         } else {                                               // left (:141-166)
             if (!hs && !vs) {
                 v = L(x0 - al, y0 + pos);
@@ -324,8 +332,8 @@ __device__ void cclm_block(const PredK &p, const VVCCudaIntraBlk &b, CclmShared 
                 else if (colloc) v = (L(xl, ly) + L(lx, (pos || at) ? ly - 1 : ly) + 4 * L(lx, ly) + L(lx + 1, ly) + L(lx, ly + 1) + 4) >> 3;
                 else             v = (L(xl, ly) + L(xl, ly + 1) + 2 * L(lx, ly) + 2 * L(lx, ly + 1) + L(lx + 1, ly) + L(lx + 1, ly + 1) + 4) >> 3;
             }
-            cs.sel[1][tid] = C0[(long long)(y + pos) * cp + x - 1];
-            cs.sel[2][tid] = C1[(long long)(y + pos) * cp + x - 1];
+            cs.sel[1][tid] = ld_pel<CG>(C0 + (long long)(y + pos) * cp + x - 1);
+            cs.sel[2][tid] = ld_pel<CG>(C1 + (long long)(y + pos) * cp + x - 1);
         }
         cs.sel[0][tid] = v;
     }
@@ -376,117 +384,248 @@ __device__ void cclm_block(const PredK &p, const VVCCudaIntraBlk &b, CclmShared 
     }
 }
 
+// One record by the whole CTA (the caller has synchronised: shared memory is free).
+template <bool CG>
+__device__ void predict_record(const PredK &p, const VVCCudaIntraBlk &b, LeafScratch &sc, CclmShared &cs, uint16_t (*s_line)[E_LEN])
+{
+    const int tid = threadIdx.x, bd = p.bd;
+    if (b.kind == VVC_CUDA_INTRA_KIND_CCLM) {
+        cclm_block<CG>(p, b, cs);
+        return;
+    }
+    const int c_idx = b.c_idx, w = b.w, h = b.h, x0 = b.x0, y0 = b.y0;
+    const int pitch = SEL3(p.pitch, c_idx);
+    const pel *pic = SEL3(p.plane, c_idx) + b.pic * SEL3(p.bstride, c_idx);
+    const bool is_mip = b.kind == VVC_CUDA_INTRA_KIND_MIP, isp = (b.flags & VVC_CUDA_INTRA_F_ISP) && !c_idx;
+    const int ref_idx = c_idx ? 0 : b.ref_idx, rl = -1 - ref_idx;
+    int mode = 0;
+    if (!is_mip) {                                     // ff_vvc_wide_angle_mode_mapping
+        const int nw = isp ? b.cb_w : w, nh = isp ? b.cb_h : h;
+        const int ratio = abs(d_ilog2(nw) - d_ilog2(nh));
+        const int hi = ratio > 1 ? 8 + 2 * ratio : 8, lo = ratio > 1 ? 60 - 2 * ratio : 60;
+        mode = b.pred_mode;
+        if (nw > nh && mode >= 2 && mode < hi)         mode += 65;
+        else if (nh > nw && mode <= 66 && mode > lo)   mode -= 67;
+    }
+    const bool non_angular = mode == 0 || mode == 1 || mode == 18 || mode == 50;
+    int angle = 0, inv_angle = 0;
+    if (!is_mip && !non_angular) {
+        angle = pred_angle(mode);
+        inv_angle = angle > 0 ? (32768 + angle) / (2 * angle) : -((32768 - angle) / (-2 * angle));
+    }
+    bool pdpc = false;                                 // ff_vvc_need_pdpc
+    if (!is_mip && w >= 4 && h >= 4 && !ref_idx && !(b.flags & VVC_CUDA_INTRA_F_BDPCM)) {
+        if (non_angular)                  pdpc = true;
+        else if (mode > 18 && mode < 50)  pdpc = false;
+        else                              pdpc = min(2, d_ilog2(mode >= 50 ? h : w) - d_ilog2(3 * inv_angle - 2) + 8) >= 0;
+    }
+    const bool rff = !is_mip && smoothing_mode(mode);
+    const bool smooth = rff && !ref_idx && w * h > 32 && !c_idx && !(b.flags & VVC_CUDA_INTRA_F_ISP);
+    int n_left, n_top, refw = 0, refh = 0;
+    if (is_mip || mode == 0)  { n_left = h + 1 + smooth; n_top = w + 1 + smooth; }
+    else if (mode == 1)       { n_left = h; n_top = w; }
+    else if (mode == 50)      { n_left = pdpc ? h : 1; n_top = w; }
+    else if (mode == 18)      { n_left = h; n_top = pdpc ? w : 1; }
+    else {
+        refw = isp ? b.cb_w + w : 2 * w;
+        refh = isp ? b.cb_h + h : 2 * h;
+        n_top = refw; n_left = refh;
+    }
+    const int got_l = min(n_left, (int)b.avail_left), got_t = min(n_top, (int)b.avail_top);
+    const bool up_left = b.flags & VVC_CUDA_INTRA_F_UP_LEFT;
+    auto PIC = [&](int xx, int yy) -> int { return ld_pel<CG>(pic + (long long)(y0 + yy) * pitch + x0 + xx); };
+    // what the corner samples (negative indices) hold when the up-left block is not available
+    const int corner = got_l ? PIC(rl, 0) : got_t ? PIC(0, rl) : 1 << (bd - 1);
+    uint16_t *left = s_line[0] + E_NEG, *top = s_line[1] + E_NEG;
+    for (int i = rl + tid; i < n_left; i += kThreads)
+        left[i] = (uint16_t)(i < 0 ? (up_left ? PIC(rl, i) : corner)
+                                   : i < got_l ? PIC(rl, i) : got_l ? PIC(rl, got_l - 1) : (up_left ? PIC(rl, -1) : corner));
+    for (int i = rl + tid; i < n_top; i += kThreads)
+        top[i] = (uint16_t)(i < 0 ? (up_left ? PIC(i, rl) : corner)
+                                  : i < got_t ? PIC(i, rl) : got_t ? PIC(got_t - 1, rl) : (up_left ? PIC(-1, rl) : corner));
+    __syncthreads();
+    if (smooth) {                                      // ref_filter: [1 2 1], the angular modes keep their last sample
+        const int keep_last = !(is_mip || mode == 0);
+        uint16_t *fl = s_line[2] + E_NEG, *ft = s_line[3] + E_NEG;
+        for (int i = tid - 1; i < n_left; i += kThreads)
+            fl[i] = (uint16_t)(i < 0 ? (left[0] + 2 * left[-1] + top[0] + 2) >> 2
+                                     : (keep_last && i == n_left - 1) ? left[i] : (left[i - 1] + 2 * left[i] + left[i + 1] + 2) >> 2);
+        for (int i = tid - 1; i < n_top; i += kThreads)
+            ft[i] = (uint16_t)(i < 0 ? (left[0] + 2 * left[-1] + top[0] + 2) >> 2
+                                     : (keep_last && i == n_top - 1) ? top[i] : (top[i - 1] + 2 * top[i] + top[i + 1] + 2) >> 2);
+        __syncthreads();
+        left = fl; top = ft;
+    }
+    Leaf lf;
+    lf.w = w; lf.h = h; lf.c_idx = c_idx; lf.ref_idx = ref_idx; lf.filter_flag = 0; lf.flags = 0; lf.pdpc4 = 0;
+    if (is_mip) {
+        lf.kind = VVC_CUDA_INTRA_MIP; lf.mode = b.pred_mode;
+        lf.flags = (b.flags & VVC_CUDA_INTRA_F_MIP_TRANSP) ? VVC_CUDA_INTRA_MIP_TRANSPOSED : 0;
+    } else {
+        lf.kind = mode == 0 ? VVC_CUDA_INTRA_PLANAR : mode == 1 ? VVC_CUDA_INTRA_DC : mode == 50 ? VVC_CUDA_INTRA_VERT
+                : mode == 18 ? VVC_CUDA_INTRA_HORZ : mode >= 34 ? VVC_CUDA_INTRA_ANGULAR_V : VVC_CUDA_INTRA_ANGULAR_H;
+        lf.mode = mode;
+        lf.flags = (pdpc && !non_angular) ? VVC_CUDA_INTRA_PDPC : 0;
+        lf.pdpc4 = pdpc && non_angular;
+        if (mode != 0 && mode != 1 && !c_idx && !(rff || ref_idx || (b.flags & VVC_CUDA_INTRA_F_ISP))) {
+            const int dist = min(abs(mode - 50), abs(mode - 18)), ntbs = (d_ilog2(w) + d_ilog2(h)) >> 1;
+            lf.filter_flag = dist > (ntbs == 2 ? 24 : ntbs == 3 ? 14 : ntbs == 4 ? 2 : 0);
+        }
+        if (!non_angular) {
+            // the main reference beyond the fetched samples: projected from the other line (negative angles) or the
+            // last sample repeated (positive angles)
+            const bool vertical = mode >= 34;
+            uint16_t *mainr = vertical ? top : left;
+            const uint16_t *side = vertical ? left : top;
+            const int n_main = vertical ? refw : refh, across = vertical ? h : w, along = vertical ? w : h;
+            if (angle < 0) {
+                for (int k = -across + tid; k < 0; k += kThreads)
+                    mainr[k - (ref_idx + 1)] = side[-1 - ref_idx + min((k * inv_angle + 256) >> 9, across)];
+            } else {
+                const int last = n_main + max(1, along / across) * ref_idx + 1;
+                for (int i = n_main + tid; i <= last; i += kThreads)
+                    mainr[i] = mainr[n_main - 1];
+            }
+            __syncthreads();
+        }
+    }
+    pel *dst = SEL3(p.plane, c_idx) + b.pic * SEL3(p.bstride, c_idx) + (long long)y0 * pitch + x0;
+    leaf_predict(lf, top, left, dst, pitch, bd, sc);
+}
+
 __global__ void __launch_bounds__(kThreads) intra_pred_kernel(const PredK p)
 {
     __shared__ LeafScratch sc;
     __shared__ CclmShared cs;
     __shared__ uint16_t s_line[4][E_LEN];                  // raw left, raw top, smoothed left, smoothed top
-    const int tid = threadIdx.x, bd = p.bd;
     for (int ri = blockIdx.x; ri < p.n; ri += gridDim.x) {
         const VVCCudaIntraBlk b = p.blks[ri];
         __syncthreads();                                   // previous record is done with shared memory
-        if (b.kind == VVC_CUDA_INTRA_KIND_CCLM) {
-            cclm_block(p, b, cs);
-            continue;
+        predict_record<false>(p, b, sc, cs, s_line);
+    }
+}
+
+// ---- all-intra reconstruction driven by dependencies, one launch per picture ring ---------------------------------------
+// The host lists the steps of a decoder in decoding order - per coding unit a luma step and a chroma step, each "predict
+// these blocks, then add the residual of these transform blocks" (what predict_intra + itransform do per TU,
+// vvc_intra.c:233-281, 432-478).  Persistent CTAs draw steps from a counter in that order.  Before predicting a block a
+// CTA waits until the 4x4 units holding the samples the block may read - the availability counts of its record, i.e. what
+// the reference's reconstructed-area list answers - are marked done in a per-picture progress map; after the residual it
+// fences and marks its own units.  Every unit a step waits for belongs to an earlier step, and every drawn step is held by
+// a resident CTA (the grid never exceeds what the device keeps resident), so the earliest unfinished step can always
+// run: no deadlock, no global barrier, and the critical path is the dependency chain itself (about a thousand steps for
+// a 1080p picture) instead of two kernel launches per wavefront.  Samples written by other CTAs are read through L2.
+struct DagK {
+    PredK          pk;
+    ItxK           ik;
+    const int32_t *blk_end, *tb_end;    // running totals per step (device memory)
+    int            n_steps;
+    uint32_t      *counter;             // [0] next step, [1] error flag
+    uint8_t       *done[2];             // progress maps per plane type (luma, chroma), [batch][uh][uw] of 4x4 luma units
+    int            uw, uh;
+};
+
+constexpr unsigned kSpinLimit = 1u << 24;     // polls (with back-off) before a step gives up: malformed availability counts
+
+// wait until the units [ux0, ux1) x [uy0, uy1) of map `m` are done; returns false when the watchdog fires
+__device__ __forceinline__ bool wait_units(const DagK &d, const uint8_t *m, int ux0, int uy0, int ux1, int uy1)
+{
+    ux0 = max(ux0, 0); uy0 = max(uy0, 0); ux1 = min(ux1, d.uw); uy1 = min(uy1, d.uh);
+    const int nx = ux1 - ux0, n = nx > 0 && uy1 > uy0 ? nx * (uy1 - uy0) : 0;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const volatile uint8_t *f = m + (size_t)(uy0 + i / nx) * d.uw + ux0 + i % nx;
+        unsigned spins = 0;
+        while (!*f) {
+            __nanosleep(64);
+            if (++spins > kSpinLimit || *reinterpret_cast<volatile uint32_t *>(d.counter + 1)) {
+                atomicExch(d.counter + 1, 1u);
+                return false;
+            }
         }
-        const int c_idx = b.c_idx, w = b.w, h = b.h, x0 = b.x0, y0 = b.y0;
-        const int pitch = SEL3(p.pitch, c_idx);
-        const pel *pic = SEL3(p.plane, c_idx) + b.pic * SEL3(p.bstride, c_idx);
-        const bool is_mip = b.kind == VVC_CUDA_INTRA_KIND_MIP, isp = (b.flags & VVC_CUDA_INTRA_F_ISP) && !c_idx;
-        const int ref_idx = c_idx ? 0 : b.ref_idx, rl = -1 - ref_idx;
-        int mode = 0;
-        if (!is_mip) {                                     // ff_vvc_wide_angle_mode_mapping
-            const int nw = isp ? b.cb_w : w, nh = isp ? b.cb_h : h;
-            const int ratio = abs(d_ilog2(nw) - d_ilog2(nh));
-            const int hi = ratio > 1 ? 8 + 2 * ratio : 8, lo = ratio > 1 ? 60 - 2 * ratio : 60;
-            mode = b.pred_mode;
-            if (nw > nh && mode >= 2 && mode < hi)         mode += 65;
-            else if (nh > nw && mode <= 66 && mode > lo)   mode -= 67;
+    }
+    return true;
+}
+
+__device__ bool wait_for(const DagK &d, const VVCCudaIntraBlk &b)
+{
+    const int hs = d.pk.hs, vs = d.pk.vs;
+    const size_t pic = (size_t)b.pic * d.uw * d.uh;
+    const int ch = b.c_idx > 0;
+    const int sx = ch ? hs : 0, sy = ch ? vs : 0;                    // plane sample -> luma sample
+    const uint8_t *m = d.done[ch] + pic;
+    // samples of the block's own plane type: left column, top row, corner - as far as the record calls them available
+    const int x = b.x0, y = b.y0;
+    const int nl = min((int)b.avail_left, 2 * 64 + 2), nt = min((int)b.avail_top, 2 * 64 + 2);
+    bool ok = true;
+    if (nl > 0) ok &= wait_units(d, m, ((x - 1) << sx) >> 2, (y << sy) >> 2, (((x - 1) << sx) >> 2) + 1, (((y + nl - 1) << sy) >> 2) + 1);
+    if (nt > 0) ok &= wait_units(d, m, (x << sx) >> 2, ((y - 1) << sy) >> 2, (((x + nt - 1) << sx) >> 2) + 1, (((y - 1) << sy) >> 2) + 1);
+    if ((b.flags & VVC_CUDA_INTRA_F_UP_LEFT) && x > 0 && y > 0)
+        ok &= wait_units(d, m, ((x - 1) << sx) >> 2, ((y - 1) << sy) >> 2, (((x - 1) << sx) >> 2) + 1, (((y - 1) << sy) >> 2) + 1);
+    if (b.kind == VVC_CUDA_INTRA_KIND_CCLM) {
+        // the luma it reads: the coding unit's own luma, and the neighbouring luma rows / columns its flags call available
+        const uint8_t *ml = d.done[0] + pic;
+        const int x0 = x << hs, y0 = y << vs, wl = b.w << hs, hl = b.h << vs;
+        const bool at = b.flags & VVC_CUDA_INTRA_F_LUMA_AVAIL_T, al = b.flags & VVC_CUDA_INTRA_F_LUMA_AVAIL_L;
+        ok &= wait_units(d, ml, x0 >> 2, y0 >> 2, (x0 + wl + 3) >> 2, (y0 + hl + 3) >> 2);
+        if (al) {
+            const int rows = max(hl, min(b.h + min((int)b.w, (int)b.h), (int)b.avail_left) << vs);
+            ok &= wait_units(d, ml, (x0 - 1) >> 2, y0 >> 2, ((x0 - 1) >> 2) + 1, (y0 + rows + 3) >> 2);
         }
-        const bool non_angular = mode == 0 || mode == 1 || mode == 18 || mode == 50;
-        int angle = 0, inv_angle = 0;
-        if (!is_mip && !non_angular) {
-            angle = pred_angle(mode);
-            inv_angle = angle > 0 ? (32768 + angle) / (2 * angle) : -((32768 - angle) / (-2 * angle));
+        if (at) {
+            const int cols = max(wl, min(b.w + min((int)b.w, (int)b.h), (int)b.avail_top) << hs);
+            ok &= wait_units(d, ml, x0 >> 2, (y0 - 1) >> 2, (x0 + cols + 3) >> 2, ((y0 - 1) >> 2) + 1);
         }
-        bool pdpc = false;                                 // ff_vvc_need_pdpc
-        if (!is_mip && w >= 4 && h >= 4 && !ref_idx && !(b.flags & VVC_CUDA_INTRA_F_BDPCM)) {
-            if (non_angular)                  pdpc = true;
-            else if (mode > 18 && mode < 50)  pdpc = false;
-            else                              pdpc = min(2, d_ilog2(mode >= 50 ? h : w) - d_ilog2(3 * inv_angle - 2) + 8) >= 0;
-        }
-        const bool rff = !is_mip && smoothing_mode(mode);
-        const bool smooth = rff && !ref_idx && w * h > 32 && !c_idx && !(b.flags & VVC_CUDA_INTRA_F_ISP);
-        int n_left, n_top, refw = 0, refh = 0;
-        if (is_mip || mode == 0)  { n_left = h + 1 + smooth; n_top = w + 1 + smooth; }
-        else if (mode == 1)       { n_left = h; n_top = w; }
-        else if (mode == 50)      { n_left = pdpc ? h : 1; n_top = w; }
-        else if (mode == 18)      { n_left = h; n_top = pdpc ? w : 1; }
-        else {
-            refw = isp ? b.cb_w + w : 2 * w;
-            refh = isp ? b.cb_h + h : 2 * h;
-            n_top = refw; n_left = refh;
-        }
-        const int got_l = min(n_left, (int)b.avail_left), got_t = min(n_top, (int)b.avail_top);
-        const bool up_left = b.flags & VVC_CUDA_INTRA_F_UP_LEFT;
-        auto PIC = [&](int xx, int yy) -> int { return pic[(long long)(y0 + yy) * pitch + x0 + xx]; };
-        // what the corner samples (negative indices) hold when the up-left block is not available
-        const int corner = got_l ? PIC(rl, 0) : got_t ? PIC(0, rl) : 1 << (bd - 1);
-        uint16_t *left = s_line[0] + E_NEG, *top = s_line[1] + E_NEG;
-        for (int i = rl + tid; i < n_left; i += kThreads)
-            left[i] = (uint16_t)(i < 0 ? (up_left ? PIC(rl, i) : corner)
-                                       : i < got_l ? PIC(rl, i) : got_l ? PIC(rl, got_l - 1) : (up_left ? PIC(rl, -1) : corner));
-        for (int i = rl + tid; i < n_top; i += kThreads)
-            top[i] = (uint16_t)(i < 0 ? (up_left ? PIC(i, rl) : corner)
-                                      : i < got_t ? PIC(i, rl) : got_t ? PIC(got_t - 1, rl) : (up_left ? PIC(-1, rl) : corner));
+        if (al && at)
+            ok &= wait_units(d, ml, (x0 - 1) >> 2, (y0 - 1) >> 2, ((x0 - 1) >> 2) + 1, ((y0 - 1) >> 2) + 1);
+    }
+    return ok;
+}
+
+__device__ __forceinline__ void mark_done(const DagK &d, const VVCCudaIntraBlk &b)
+{
+    const int ch = b.c_idx > 0, sx = ch ? d.pk.hs : 0, sy = ch ? d.pk.vs : 0;
+    uint8_t *m = d.done[ch] + (size_t)b.pic * d.uw * d.uh;
+    const int ux0 = (b.x0 << sx) >> 2, uy0 = (b.y0 << sy) >> 2;
+    const int ux1 = min((((b.x0 + b.w) << sx) + 3) >> 2, d.uw), uy1 = min((((b.y0 + b.h) << sy) + 3) >> 2, d.uh), nx = ux1 - ux0;
+    for (int i = threadIdx.x; i < nx * (uy1 - uy0); i += kThreads)
+        *reinterpret_cast<volatile uint8_t *>(m + (size_t)(uy0 + i / nx) * d.uw + ux0 + i % nx) = 1;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) intra_dag_kernel(const DagK d)
+{
+    __shared__ LeafScratch sc;
+    __shared__ CclmShared cs;
+    __shared__ uint16_t s_line[4][E_LEN];
+    __shared__ alignas(16) int s_buf[2 * 64 * 65];
+    __shared__ int s_step;
+    for (;;) {
         __syncthreads();
-        if (smooth) {                                      // ref_filter: [1 2 1], the angular modes keep their last sample
-            const int keep_last = !(is_mip || mode == 0);
-            uint16_t *fl = s_line[2] + E_NEG, *ft = s_line[3] + E_NEG;
-            for (int i = tid - 1; i < n_left; i += kThreads)
-                fl[i] = (uint16_t)(i < 0 ? (left[0] + 2 * left[-1] + top[0] + 2) >> 2
-                                         : (keep_last && i == n_left - 1) ? left[i] : (left[i - 1] + 2 * left[i] + left[i + 1] + 2) >> 2);
-            for (int i = tid - 1; i < n_top; i += kThreads)
-                ft[i] = (uint16_t)(i < 0 ? (left[0] + 2 * left[-1] + top[0] + 2) >> 2
-                                         : (keep_last && i == n_top - 1) ? top[i] : (top[i - 1] + 2 * top[i] + top[i + 1] + 2) >> 2);
+        if (threadIdx.x == 0)
+            s_step = (int)atomicAdd(d.counter, 1u);
+        __syncthreads();
+        const int step = s_step;
+        if (step >= d.n_steps)
+            return;
+        const int b0 = step ? __ldg(d.blk_end + step - 1) : 0, b1 = __ldg(d.blk_end + step);
+        const int t0 = step ? __ldg(d.tb_end + step - 1) : 0, t1 = __ldg(d.tb_end + step);
+        for (int bi = b0; bi < b1; bi++) {
+            const VVCCudaIntraBlk b = d.pk.blks[bi];
+            const bool ok = wait_for(d, b);
+            __threadfence();                                   // the flags were seen: the samples behind them are next
+            if (!__syncthreads_and(ok))
+                return;                                        // watchdog: the error flag is set, every CTA leaves at its next poll
+            predict_record<true>(d.pk, b, sc, cs, s_line);
             __syncthreads();
-            left = fl; top = ft;
         }
-        Leaf lf;
-        lf.w = w; lf.h = h; lf.c_idx = c_idx; lf.ref_idx = ref_idx; lf.filter_flag = 0; lf.flags = 0; lf.pdpc4 = 0;
-        if (is_mip) {
-            lf.kind = VVC_CUDA_INTRA_MIP; lf.mode = b.pred_mode;
-            lf.flags = (b.flags & VVC_CUDA_INTRA_F_MIP_TRANSP) ? VVC_CUDA_INTRA_MIP_TRANSPOSED : 0;
-        } else {
-            lf.kind = mode == 0 ? VVC_CUDA_INTRA_PLANAR : mode == 1 ? VVC_CUDA_INTRA_DC : mode == 50 ? VVC_CUDA_INTRA_VERT
-                    : mode == 18 ? VVC_CUDA_INTRA_HORZ : mode >= 34 ? VVC_CUDA_INTRA_ANGULAR_V : VVC_CUDA_INTRA_ANGULAR_H;
-            lf.mode = mode;
-            lf.flags = (pdpc && !non_angular) ? VVC_CUDA_INTRA_PDPC : 0;
-            lf.pdpc4 = pdpc && non_angular;
-            if (mode != 0 && mode != 1 && !c_idx && !(rff || ref_idx || (b.flags & VVC_CUDA_INTRA_F_ISP))) {
-                const int dist = min(abs(mode - 50), abs(mode - 18)), ntbs = (d_ilog2(w) + d_ilog2(h)) >> 1;
-                lf.filter_flag = dist > (ntbs == 2 ? 24 : ntbs == 3 ? 14 : ntbs == 4 ? 2 : 0);
-            }
-            if (!non_angular) {
-                // the main reference beyond the fetched samples: projected from the other line (negative angles) or the
-                // last sample repeated (positive angles)
-                const bool vertical = mode >= 34;
-                uint16_t *mainr = vertical ? top : left;
-                const uint16_t *side = vertical ? left : top;
-                const int n_main = vertical ? refw : refh, across = vertical ? h : w, along = vertical ? w : h;
-                if (angle < 0) {
-                    for (int k = -across + tid; k < 0; k += kThreads)
-                        mainr[k - (ref_idx + 1)] = side[-1 - ref_idx + min((k * inv_angle + 256) >> 9, across)];
-                } else {
-                    const int last = n_main + max(1, along / across) * ref_idx + 1;
-                    for (int i = n_main + tid; i <= last; i += kThreads)
-                        mainr[i] = mainr[n_main - 1];
-                }
-                __syncthreads();
-            }
+        for (int ti = t0; ti < t1; ti++) {
+            const VVCCudaTB tb = d.ik.tbs[ti];
+            process_tb<kThreads, MODE>(d.ik, tb, ti, s_buf, s_buf + 64 * 65, threadIdx.x);
         }
-        pel *dst = SEL3(p.plane, c_idx) + b.pic * SEL3(p.bstride, c_idx) + (long long)y0 * pitch + x0;
-        leaf_predict(lf, top, left, dst, pitch, bd, sc);
+        __threadfence();                                       // this step's samples before its flags
+        __syncthreads();
+        for (int bi = b0; bi < b1; bi++)
+            mark_done(d, d.pk.blks[bi]);
     }
 }
 
@@ -658,6 +797,69 @@ extern "C" int vvc_cuda_intra_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *f
         }
         b0 = blk_end[g]; t0 = tb_end[g];
     }
+    return VVC_CUDA_OK;
+}
+
+extern "C" int vvc_cuda_intra_recon_frame_ordered(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraBlk *blks,
+                                                  const int32_t *blk_end, const VVCCudaCoeffs *co, const VVCCudaTB *tbs,
+                                                  const int32_t *tb_end, int n_steps, int n_blks, int n_tbs, int range)
+{
+    if (ctx->err)
+        return ctx->err;
+    if (!blk_end || !tb_end || n_steps < 0 || n_blks < 0 || n_tbs < 0 || (n_tbs > 0 && (!co || !co->data || !tbs)))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "intra_recon_ordered: null argument");
+    if (intra_pred_check(ctx, frame, blks, n_blks))
+        return ctx->err;
+    if (n_tbs > 0 && (range < 15 || range > 20 || (co->format != VVC_CUDA_COEFF_DENSE32 && co->format != VVC_CUDA_COEFF_WINDOW16) ||
+                      (co->format == VVC_CUDA_COEFF_WINDOW16 && range != 15) || !frame_vec_ok(frame)))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "intra_recon_ordered: unsupported picture or coefficient format");
+    if ((frame->width & 3) || (frame->height & 3))
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "intra_recon_ordered: picture size must be a multiple of 4");
+    if (!n_steps)
+        return VVC_CUDA_OK;
+    DagK d;
+    for (int c = 0; c < 3; c++) {
+        d.pk.plane[c] = d.ik.plane[c] = (pel *)frame->data[c];
+        d.pk.pitch[c] = d.ik.pitch[c] = (int)(frame->stride[c] / 2);
+        d.pk.bstride[c] = d.ik.bstride[c] = frame->batch_stride[c] / 2;
+    }
+    d.pk.bd = frame->bit_depth; d.pk.hs = frame->hshift; d.pk.vs = frame->vshift; d.pk.ctb_log2 = frame->ctb_log2;
+    d.pk.blks = blks; d.pk.n = n_blks;
+    const int mode = n_tbs > 0 ? coef_mode(co) : 0;
+    memset(&d.ik.src, 0, sizeof(d.ik.src));
+    if (n_tbs > 0) {
+        d.ik.src.dense = (mode & 1) ? nullptr : (const int32_t *)co->data;
+        d.ik.src.window = (mode & 1) ? (const int16_t *)co->data : nullptr;
+        d.ik.src.quant = co->quant; d.ik.src.scaling = co->scaling; d.ik.src.lmcs_scales = co->lmcs_scales;
+    }
+    d.ik.src.range = range; d.ik.src.bd = frame->bit_depth;
+    d.ik.store = (n_tbs > 0 && !(mode & 1)) ? (int32_t *)co->data : nullptr;
+    d.ik.tbs = tbs; d.ik.n_tbs = n_tbs; d.ik.range = range; d.ik.bd = frame->bit_depth;
+    d.ik.list = d.ik.list_count = NULL;
+    d.blk_end = blk_end; d.tb_end = tb_end; d.n_steps = n_steps;
+    d.uw = frame->width >> 2; d.uh = frame->height >> 2;
+    const size_t map = (size_t)d.uw * d.uh * frame->batch;
+    uint8_t *scratch = (uint8_t *)vvc_ctx_scratch(ctx, 4, 256 + 2 * map);
+    if (!scratch)
+        return ctx->err;
+    d.counter = (uint32_t *)scratch; d.done[0] = scratch + 256; d.done[1] = scratch + 256 + map;
+    VVC_TRY(ctx, cudaMemsetAsync(scratch, 0, 256 + 2 * map, ctx->stream));
+    // persistent grid: never more CTAs than the device keeps resident (a waiting CTA must not block one that has not started)
+    void (*kern)(const DagK) = mode == 0 ? intra_dag_kernel<0> : mode == 1 ? intra_dag_kernel<1> : mode == 2 ? intra_dag_kernel<2> : intra_dag_kernel<3>;
+    int per_sm = 0, sms = 0;
+    VVC_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+    VVC_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (per_sm < 1)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_CUDA, "intra_recon_ordered: the kernel does not fit an SM");
+    const int grid = n_steps < per_sm * sms ? n_steps : per_sm * sms;
+    kern<<<grid, kThreads, 0, ctx->stream>>>(d);
+    VVC_LAUNCHED(ctx);
+    // a fired watchdog (availability counts that name samples of later steps) must not pass silently
+    uint32_t flag = 0;
+    VVC_TRY(ctx, cudaMemcpyAsync(&flag, d.counter + 1, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    VVC_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "intra_recon_ordered: a step waited for samples that no earlier step reconstructs (availability counts / step order)");
     return VVC_CUDA_OK;
 }
 

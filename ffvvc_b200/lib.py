@@ -94,6 +94,7 @@ def load():
     lib.vvc_cuda_intra_pred_frame.argtypes = [CTX, FP, C.c_void_p, C.c_int]
     lib.vvc_cuda_intra_pred_frame_host.argtypes = [CTX, FP, C.c_void_p, C.c_int]
     lib.vvc_cuda_intra_recon_frame.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, CP, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.vvc_cuda_intra_recon_frame_ordered.argtypes = [CTX, FP, C.c_void_p, C.c_void_p, CP, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.vvc_cuda_ciip_frame.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int]
     lib.vvc_cuda_ciip_frame_host.argtypes = [CTX, FP, FP, C.c_void_p, C.c_int]
     lib.vvc_cuda_abi_sizeof.argtypes = [C.c_int]
@@ -252,6 +253,11 @@ class Context:
         assert len(blk_end) == len(tb_end) and blk_end.dtype == tb_end.dtype == np.int32
         self.check(self.lib.vvc_cuda_intra_recon_frame(self.handle, C.byref(frame), blks_ptr, blk_end.ctypes.data, C.byref(coeffs_desc),
                                                        tbs_ptr, tb_end.ctypes.data, len(blk_end), log2_transform_range))
+
+    def intra_recon_frame_ordered(self, frame, blks_ptr, blk_end_ptr, coeffs_desc, tbs_ptr, tb_end_ptr, n_steps, n_blks, n_tbs, log2_transform_range=15):
+        """All-intra reconstruction in one launch: steps in decoding order, dependencies resolved on the device."""
+        self.check(self.lib.vvc_cuda_intra_recon_frame_ordered(self.handle, C.byref(frame), blks_ptr, blk_end_ptr, C.byref(coeffs_desc), tbs_ptr,
+                                                               tb_end_ptr, n_steps, n_blks, n_tbs, log2_transform_range))
 
     def ciip_frame(self, dst, inter, blocks_ptr, n_blocks):
         """CIIP blend of the intra prediction in dst with the inter prediction picture."""

@@ -622,6 +622,16 @@ int vvc_cuda_intra_recon_frame(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const
                                const VVCCudaCoeffs *coeffs, const VVCCudaTB *tbs, const int32_t *tb_end, int n_waves,
                                int log2_transform_range);
 
+/* The same reconstruction driven by dependencies on the device, ONE launch per picture ring: the steps of a decoder in
+ * decoding order (per coding unit a luma step and a chroma step; step s predicts blks[blk_end[s-1] .. blk_end[s]) and then
+ * adds the residual of tbs[tb_end[s-1] .. tb_end[s])), blk_end / tb_end in DEVICE memory.  Persistent CTAs draw the steps
+ * in order and wait, per block, for exactly the neighbouring samples its availability counts name (a progress map of 4x4
+ * units), so no wave numbers are needed.  Returns after the launch has finished (the call checks the kernel's watchdog:
+ * VVC_CUDA_ERR_ARG when a step names samples no earlier step reconstructs). */
+int vvc_cuda_intra_recon_frame_ordered(VVCCudaCtx *ctx, const VVCCudaFrame *frame, const VVCCudaIntraBlk *blks, const int32_t *blk_end,
+                                       const VVCCudaCoeffs *coeffs, const VVCCudaTB *tbs, const int32_t *tb_end, int n_steps,
+                                       int n_blks, int n_tbs, int log2_transform_range);
+
 typedef struct VVCCudaCiip {
     uint16_t x0, y0;          /* in plane c_idx's own units */
     uint8_t  w, h, c_idx, pic;

@@ -86,3 +86,57 @@ def test_all_intra_pictures_by_wavefronts_bit_exact(ctx, w, h, batch, seed, mode
     assert ctx.launches - before <= 2 * case["n_waves"]
     util.assert_planes_equal(geom, fr.to_numpy(), want, "wavefronts on the GPU vs decoding order on the CPU")
     assert case["n_waves"] > 20 and (case["blks"]["kind"] == 2).any() and (case["blks"]["kind"] == 1).any()
+
+
+@pytest.mark.parametrize("w,h,batch,seed,mode", [(416, 240, 2, 3, "dense"), (256, 192, 3, 4, "window_q"), (832, 480, 1, 5, "dense"), (1920, 1080, 2, 11, "dense")])
+def test_all_intra_pictures_one_launch_dependencies_on_the_device(ctx, w, h, batch, seed, mode):
+    """vvc_cuda_intra_recon_frame_ordered: the decoder's steps in decoding order, ONE launch, every block waiting on the
+    progress map for exactly the samples its availability counts name - vs the oracle walking the same steps"""
+    from ffvvc_b200 import device
+    geom = abi.FrameGeom(w, h, batch=batch)
+    case = synth.intra_picture(geom, seed=seed)
+    planes = abi.alloc_planes(geom, fill=512)
+    fmt, coeffs, dtbs = abi.COEFF_DENSE32, case["coeffs"], case["dec_tbs"]
+    dq = sl = None
+    if mode == "window_q":
+        dtbs, coeffs = abi.pack_window16(synth.tb_for_window(dtbs), coeffs)
+        dq, sl = synth.tb_quant(dtbs, seed=seed + 7, scaling=True)
+        fmt = abi.COEFF_WINDOW16
+    want = [a.copy() for a in planes]
+    co = coeffs.copy()
+    cd = abi.coeffs_desc(co.ctypes.data, co.size, fmt, dq.ctypes.data if dq is not None else None, sl.ctypes.data if sl is not None else None)
+    util.oracle().vvco_intra_recon_frame(abi.frame_from_numpy(geom, want), case["dec_blks"].ctypes.data, case["dec_blk_end"].ctypes.data,
+                                         C.byref(cd), dtbs.ctypes.data, case["dec_tb_end"].ctypes.data, len(case["dec_blk_end"]), 15)
+    fr = device.DeviceFrames(geom, planes=planes)
+    keep = [device.to_device(a) for a in (case["dec_blks"], case["dec_blk_end"], coeffs, dtbs, case["dec_tb_end"])]
+    pq = psl = None
+    if dq is not None:
+        keep += [device.to_device(dq), device.to_device(sl)]
+        pq, psl = keep[-2][1], keep[-1][1]
+    before = ctx.launches
+    ctx.intra_recon_frame_ordered(fr.desc, keep[0][1], keep[1][1], abi.coeffs_desc(keep[2][1], coeffs.size, fmt, pq, psl), keep[3][1], keep[4][1],
+                                  len(case["dec_blk_end"]), len(case["dec_blks"]), len(dtbs), 15)
+    ctx.sync()
+    assert ctx.launches - before == 1
+    util.assert_planes_equal(geom, fr.to_numpy(), want, "one launch, dependencies on the device vs decoding order on the CPU")
+
+
+def test_ordered_entry_reports_unsatisfiable_dependencies(ctx):
+    """a block that calls samples of a LATER step available can never be served: the kernel's watchdog ends the launch and
+    the entry returns an error instead of hanging"""
+    from ffvvc_b200 import device, lib
+    geom = abi.FrameGeom(64, 64)
+    blks = np.zeros(2, dtype=abi.INTRA_BLK_DTYPE)
+    blks["x0"], blks["y0"], blks["w"], blks["h"], blks["pred_mode"] = (0, 8), (0, 0), 8, 8, 1
+    blks["cb_w"], blks["cb_h"] = 8, 8
+    blks["avail_left"] = (8, 0)              # block 0 at x = 0 claims a left neighbour; units left of x = 0 do not exist -> clamped away
+    blks[0]["x0"], blks[0]["avail_left"] = 16, 8        # block 0 at x = 16 waits for x = 12..15, which only block 1 (a later step, at x = 8) reconstructs
+    blk_end, tb_end = np.array([1, 2], np.int32), np.array([0, 0], np.int32)
+    c = lib.Context(0)
+    try:
+        fr = device.DeviceFrames(geom, planes=abi.alloc_planes(geom, fill=512))
+        keep = [device.to_device(a) for a in (blks, blk_end, tb_end)]
+        with pytest.raises(lib.VVCCudaError):
+            c.intra_recon_frame_ordered(fr.desc, keep[0][1], keep[1][1], abi.coeffs_desc(None, 0), None, keep[2][1], 2, 2, 0, 15)
+    finally:
+        c.close()
