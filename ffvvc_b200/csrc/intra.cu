@@ -13,6 +13,7 @@
 // a linear function of the row.  MIP goes through shared memory: reduced boundary, 16/64-sample matrix
 // product, then the two separable up-sampling passes.  The float in the reference's inverse-angle derivation
 // is an exact integer expression for the 30 angles that occur ((32768 + a) / (2 a), checked by the tests).
+#include <stdlib.h>
 #include "common.cuh"
 #include "coeff_src.cuh"
 #include "tables.cuh"
@@ -555,7 +556,10 @@ __device__ bool wait_for(const DagK &d, const VVCCudaIntraBlk &b)
     const uint8_t *m = d.done[ch] + pic;
     // samples of the block's own plane type: left column, top row, corner - as far as the record calls them available
     const int x = b.x0, y = b.y0;
-    const int nl = min((int)b.avail_left, 2 * 64 + 2), nt = min((int)b.avail_top, 2 * 64 + 2);
+    // ... and no further than any predictor reaches (2 w, or cb_w + w for an ISP part, + 2 for planar with smoothing), so
+    // that step orders other than the decoding order stay free of waits on samples the block never reads
+    const int nl = min((int)b.avail_left, max(2 * b.h, (b.cb_h >> sy) + b.h) + 2);
+    const int nt = min((int)b.avail_top, max(2 * b.w, (b.cb_w >> sx) + b.w) + 2);
     bool ok = true;
     if (nl > 0) ok &= wait_units(d, m, ((x - 1) << sx) >> 2, (y << sy) >> 2, (((x - 1) << sx) >> 2) + 1, (((y + nl - 1) << sy) >> 2) + 1);
     if (nt > 0) ok &= wait_units(d, m, (x << sx) >> 2, ((y - 1) << sy) >> 2, (((x + nt - 1) << sx) >> 2) + 1, (((y - 1) << sy) >> 2) + 1);
@@ -577,6 +581,11 @@ __device__ bool wait_for(const DagK &d, const VVCCudaIntraBlk &b)
         }
         if (al && at)
             ok &= wait_units(d, ml, (x0 - 1) >> 2, (y0 - 1) >> 2, ((x0 - 1) >> 2) + 1, ((y0 - 1) >> 2) + 1);
+        // INTRA_LT_CCLM picks its chroma neighbours by the LUMA flags (w above, h to the left: cclm_get_select_pos :68-71)
+        if (b.pred_mode == 81) {
+            if (al && nl < b.h) ok &= wait_units(d, m, ((x - 1) << sx) >> 2, (y << sy) >> 2, (((x - 1) << sx) >> 2) + 1, (((y + b.h - 1) << sy) >> 2) + 1);
+            if (at && nt < b.w) ok &= wait_units(d, m, (x << sx) >> 2, ((y - 1) << sy) >> 2, (((x + b.w - 1) << sx) >> 2) + 1, (((y - 1) << sy) >> 2) + 1);
+        }
     }
     return ok;
 }
@@ -609,6 +618,15 @@ __global__ void __launch_bounds__(kThreads) intra_dag_kernel(const DagK d)
             return;
         const int b0 = step ? __ldg(d.blk_end + step - 1) : 0, b1 = __ldg(d.blk_end + step);
         const int t0 = step ? __ldg(d.tb_end + step - 1) : 0, t1 = __ldg(d.tb_end + step);
+        // the step is on the pictures' critical path from the moment its neighbours are done: bring its coefficients from
+        // HBM into L2 while it waits for them
+        for (int ti = t0; ti < t1; ti++) {
+            const VVCCudaTB tb = d.ik.tbs[ti];
+            const char *c = (MODE & 1) ? (const char *)(d.ik.src.window + tb.coeff_offset) : (const char *)(d.ik.src.dense + tb.coeff_offset);
+            const int bytes = (MODE & 1) ? tb.nzw * tb.nzh * 2 : (tb.nzh << tb.log2_w) * 4;
+            for (int o = threadIdx.x * 128; o < bytes; o += kThreads * 128)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(c + o));
+        }
         for (int bi = b0; bi < b1; bi++) {
             const VVCCudaIntraBlk b = d.pk.blks[bi];
             const bool ok = wait_for(d, b);
@@ -851,7 +869,9 @@ extern "C" int vvc_cuda_intra_recon_frame_ordered(VVCCudaCtx *ctx, const VVCCuda
     VVC_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (per_sm < 1)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_CUDA, "intra_recon_ordered: the kernel does not fit an SM");
-    const int grid = n_steps < per_sm * sms ? n_steps : per_sm * sms;
+    int grid = n_steps < per_sm * sms ? n_steps : per_sm * sms;
+    if (const char *g = getenv("VVC_CUDA_INTRA_GRID"))     // debugging aid: fewer CTAs (1 = strictly sequential in decoding order)
+        grid = atoi(g) > 0 && atoi(g) < grid ? atoi(g) : grid;
     kern<<<grid, kThreads, 0, ctx->stream>>>(d);
     VVC_LAUNCHED(ctx);
     // a fired watchdog (availability counts that name samples of later steps) must not pass silently

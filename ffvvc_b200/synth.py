@@ -382,7 +382,7 @@ def sao_params(geom, seed=99, with_restore=False):
 # Residual stage inputs (coefficient/nz distributions of
 # tests/checkasm/vvc_itx.c:25-75)
 # ---------------------------------------------------------------------------------------------
-def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True, square=False):
+def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True, square=False, min_log2=2):
     """Tile every picture of the ring with transform blocks (luma + both chroma planes).
 
     Returns (tbs, coeffs): TB_DTYPE records and the dense int32 coefficient buffer.
@@ -394,7 +394,7 @@ def tb_list(geom, seed=31337, lfnst_set_of=None, extras=True, saturate=True, squ
     for k in range(geom.batch):
         lw, lh = tb_partition(geom, rng, stop_p=0.45)
         if square:                       # a quadtree: every block cut into squares of its shorter side
-            lw = lh = np.minimum(lw, lh)
+            lw = lh = np.maximum(np.minimum(lw, lh), min_log2)
         uh, uw = lw.shape
         uy, ux = np.mgrid[0:uh, 0:uw]
         origin = ((ux * 4) % (1 << lw) == 0) & ((uy * 4) % (1 << lh) == 0)
@@ -990,7 +990,9 @@ def intra_picture(geom, seed=909):
     # square blocks: the z-order of their origins is then the decoding order of a quadtree, in which everything left of a
     # block over its whole height and above it over its whole width comes earlier (with rectangles the z-order of origins
     # is not the order of any partition tree: a block could then read samples that are only written later)
-    tbs, coeffs = tb_list(geom, seed=seed + 1, extras=False, square=True)
+    # ... of at least 8x8 luma samples, so that every coding unit has chroma blocks (as in a stream, where the chroma of
+    # smaller luma blocks is coded with their 8x8 parent): no chroma sample stays unreconstructed next to a block that reads it
+    tbs, coeffs = tb_list(geom, seed=seed + 1, extras=False, square=True, min_log2=3)
     keep = ~((tbs["c_idx"] > 0) & ((tbs["log2_w"] < 2) | (tbs["log2_h"] < 2)))        # no 2-wide chroma blocks in VVC intra
     tbs = tbs[keep]
     ctb, cl2 = geom.ctb_size, geom.ctb_log2
@@ -1009,7 +1011,7 @@ def intra_picture(geom, seed=909):
     R = lambda m: rng.below(n, m)
     r_kind, r_mode, r_ref, r_bd, r_tr, r_ck, r_cm, r_col = R(10), R(1 << 16), R(6), R(12), R(2), R(5), R(1 << 16), R(2)
     blks, blk_wave, tb_wave = [], [], np.zeros(len(tbs), dtype=np.int64)
-    dec_blks, dec_blk_end, dec_tb_idx, dec_tb_end = [], [], [], []
+    dec_blks, dec_blk_end, dec_tb_idx, dec_tb_end, dec_wave, dec_ctu = [], [], [], [], [], []
 
     def avail(ch, k, o, x, y, x0l, y0l):
         """(left count, top count, up-left) of the block at plane position (x, y) of plane type ch"""
@@ -1067,6 +1069,7 @@ def intra_picture(geom, seed=909):
         blks.append(r); blk_wave.append(wl)
         tb_wave[ti] = wl
         dec_blks.append(r); dec_blk_end.append(len(dec_blks)); dec_tb_idx.append(ti); dec_tb_end.append(len(dec_tb_idx))
+        dec_wave.append(wl); dec_ctu.append((k, x0 // ctb, y0 // ctb))
         # ---- its chroma blocks ----
         ctbs = chroma_of.get((k, x0 >> 1, y0 >> 1), [])
         if w < 8 or h < 8:
@@ -1113,6 +1116,7 @@ def intra_picture(geom, seed=909):
             tb_wave[ci] = wc
             dec_tb_idx.append(ci)
         dec_tb_end.append(len(dec_tb_idx))
+        dec_wave.append(wc); dec_ctu.append((k, x0 // ctb, y0 // ctb))
     blks = np.concatenate(blks)
     blk_wave = np.array(blk_wave)
     n_waves = int(max(blk_wave.max(), tb_wave.max())) + 1
@@ -1120,7 +1124,34 @@ def intra_picture(geom, seed=909):
     return dict(blks=blks[bo], blk_end=np.cumsum(np.bincount(blk_wave, minlength=n_waves)).astype(np.int32),
                 tbs=tbs[to], tb_end=np.cumsum(np.bincount(tb_wave, minlength=n_waves)).astype(np.int32), coeffs=coeffs,
                 dec_blks=np.concatenate(dec_blks), dec_blk_end=np.array(dec_blk_end, dtype=np.int32),
-                dec_tbs=tbs[np.array(dec_tb_idx)], dec_tb_end=np.array(dec_tb_end, dtype=np.int32), n_waves=n_waves)
+                dec_tbs=tbs[np.array(dec_tb_idx)], dec_tb_end=np.array(dec_tb_end, dtype=np.int32), n_waves=n_waves,
+                dec_wave=np.array(dec_wave, dtype=np.int64), dec_ctu=np.array(dec_ctu, dtype=np.int64))
+
+
+def intra_step_order(case, how):
+    """The steps of intra_picture() in another legal order for vvc_cuda_intra_recon_frame_ordered (every step after the steps
+    whose samples it reads): "decode" = as decoded, picture after picture; "ctu_wavefront" = by CTU anti-diagonal x + 2 y
+    (the order of wavefront parallel processing, which a decoder knows without analysing blocks), pictures interleaved;
+    "block_wave" = by the block's own wave.  Returns (blks, blk_end, tbs, tb_end)."""
+    n = len(case["dec_blk_end"])
+    if how == "decode":
+        perm = np.arange(n)
+    elif how == "ctu_wavefront":
+        k, cx, cy = case["dec_ctu"].T
+        perm = np.lexsort((np.arange(n), k, cx + 2 * cy))
+    elif how == "block_wave":
+        perm = np.argsort(case["dec_wave"], kind="stable")
+    else:
+        raise ValueError(how)
+
+    def gather(items, ends):
+        starts = np.concatenate(([0], ends[:-1])).astype(np.int64)
+        lens = (ends - starts)[perm]
+        idx = np.repeat(starts[perm] - np.concatenate(([0], np.cumsum(lens)[:-1])), lens) + np.arange(int(lens.sum()))
+        return items[idx], np.cumsum(lens).astype(np.int32)
+    blks, blk_end = gather(case["dec_blks"], case["dec_blk_end"])
+    tbs, tb_end = gather(case["dec_tbs"], case["dec_tb_end"])
+    return blks, blk_end, tbs, tb_end
 
 
 def ciip_list(geom, seed=707):

@@ -121,16 +121,40 @@ def test_all_intra_pictures_one_launch_dependencies_on_the_device(ctx, w, h, bat
     util.assert_planes_equal(geom, fr.to_numpy(), want, "one launch, dependencies on the device vs decoding order on the CPU")
 
 
+@pytest.mark.parametrize("how", ["ctu_wavefront", "block_wave"])
+@pytest.mark.parametrize("w,h,batch,seed", [(416, 240, 3, 21), (832, 480, 2, 22)])
+def test_one_launch_other_legal_step_orders(ctx, w, h, batch, seed, how):
+    """the same steps by CTU anti-diagonal (the wavefront-parallel order, pictures interleaved) and by block wave: other legal
+    orders give the same pictures as the decoding order on the CPU"""
+    from ffvvc_b200 import device
+    geom = abi.FrameGeom(w, h, batch=batch)
+    case = synth.intra_picture(geom, seed=seed)
+    planes = abi.alloc_planes(geom, fill=512)
+    want = [a.copy() for a in planes]
+    co = case["coeffs"].copy()
+    cd = abi.coeffs_desc(co.ctypes.data, co.size)
+    util.oracle().vvco_intra_recon_frame(abi.frame_from_numpy(geom, want), case["dec_blks"].ctypes.data, case["dec_blk_end"].ctypes.data,
+                                         C.byref(cd), case["dec_tbs"].ctypes.data, case["dec_tb_end"].ctypes.data, len(case["dec_blk_end"]), 15)
+    blks, blk_end, tbs, tb_end = synth.intra_step_order(case, how)
+    assert not np.array_equal(blks, case["dec_blks"])
+    fr = device.DeviceFrames(geom, planes=planes)
+    keep = [device.to_device(a) for a in (blks, blk_end, case["coeffs"], tbs, tb_end)]
+    ctx.intra_recon_frame_ordered(fr.desc, keep[0][1], keep[1][1], abi.coeffs_desc(keep[2][1], case["coeffs"].size), keep[3][1], keep[4][1],
+                                  len(blk_end), len(blks), len(tbs), 15)
+    ctx.sync()
+    util.assert_planes_equal(geom, fr.to_numpy(), want, "one launch, steps in %s order vs decoding order on the CPU" % how)
+
+
 def test_ordered_entry_reports_unsatisfiable_dependencies(ctx):
-    """a block that calls samples of a LATER step available can never be served: the kernel's watchdog ends the launch and
-    the entry returns an error instead of hanging"""
+    """a block that calls samples available which no step reconstructs can never be served: the kernel's watchdog ends the
+    launch and the entry returns an error instead of hanging"""
     from ffvvc_b200 import device, lib
     geom = abi.FrameGeom(64, 64)
     blks = np.zeros(2, dtype=abi.INTRA_BLK_DTYPE)
-    blks["x0"], blks["y0"], blks["w"], blks["h"], blks["pred_mode"] = (0, 8), (0, 0), 8, 8, 1
+    blks["x0"], blks["y0"], blks["w"], blks["h"], blks["pred_mode"] = (0, 32), (0, 0), 8, 8, 1
     blks["cb_w"], blks["cb_h"] = 8, 8
     blks["avail_left"] = (8, 0)              # block 0 at x = 0 claims a left neighbour; units left of x = 0 do not exist -> clamped away
-    blks[0]["x0"], blks[0]["avail_left"] = 16, 8        # block 0 at x = 16 waits for x = 12..15, which only block 1 (a later step, at x = 8) reconstructs
+    blks[0]["x0"], blks[0]["avail_left"] = 16, 8        # block 0 at x = 16 waits for x = 12..15, which no step reconstructs
     blk_end, tb_end = np.array([1, 2], np.int32), np.array([0, 0], np.int32)
     c = lib.Context(0)
     try:

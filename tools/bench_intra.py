@@ -53,28 +53,33 @@ for _ in range(5):
     ctx.sync()
     times.append(a.elapsed_time(b))
 ms = float(np.median(times))
-# the same pictures in ONE launch, dependencies resolved on the device (steps in decoding order)
-keep2 = [device.to_device(a) for a in (case["dec_blks"], case["dec_blk_end"], case["dec_tbs"], case["dec_tb_end"])]
-n_steps = len(case["dec_blk_end"])
-fr3 = device.DeviceFrames(geom, planes=planes)
-ctx.intra_recon_frame_ordered(fr3.desc, keep2[0][1], keep2[1][1], dcd, keep2[2][1], keep2[3][1], n_steps, len(case["dec_blks"]), len(case["dec_tbs"]), 15)
-got3 = fr3.to_numpy()
-equal3 = all(np.array_equal(got3[c][:, :, :geom.plane_wh(c)[0]], want[c][:, :, :geom.plane_wh(c)[0]]) for c in range(3))
-times3 = []
-for _ in range(5):
-    fr4 = device.DeviceFrames(geom, planes=planes)
-    ctx.sync()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    ctx.intra_recon_frame_ordered(fr4.desc, keep2[0][1], keep2[1][1], dcd, keep2[2][1], keep2[3][1], n_steps, len(case["dec_blks"]), len(case["dec_tbs"]), 15)
-    b.record()
-    ctx.sync()
-    times3.append(a.elapsed_time(b))
-ms3 = float(np.median(times3))
-print(json.dumps({"workload": "all-intra reconstruction by wavefronts (intra_pred / MIP / CCLM + residual)", "width": w, "height": h, "pictures": batch,
+# the same pictures in ONE launch, dependencies resolved on the device; the steps in three legal orders
+one = {}
+for how in ("decode", "ctu_wavefront", "block_wave"):
+    arrs = synth.intra_step_order(case, how)
+    keep2 = [device.to_device(a) for a in arrs]
+    n_steps = len(arrs[1])
+    args = (keep2[0][1], keep2[1][1], dcd, keep2[2][1], keep2[3][1], n_steps, len(arrs[0]), len(arrs[2]), 15)
+    fr3 = device.DeviceFrames(geom, planes=planes)
+    ctx.intra_recon_frame_ordered(fr3.desc, *args)
+    got3 = fr3.to_numpy()
+    equal3 = all(np.array_equal(got3[c][:, :, :geom.plane_wh(c)[0]], want[c][:, :, :geom.plane_wh(c)[0]]) for c in range(3))
+    times3 = []
+    for _ in range(5):
+        fr4 = device.DeviceFrames(geom, planes=planes)
+        ctx.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ctx.intra_recon_frame_ordered(fr4.desc, *args)
+        b.record()
+        ctx.sync()
+        times3.append(a.elapsed_time(b))
+    ms3 = float(np.median(times3))
+    one[how] = {"steps": n_steps, "ms_per_ring": ms3, "ms_per_picture": ms3 / batch, "mpix_per_s": w * h * batch / (ms3 * 1e-3) / 1e6,
+                "parity_equal": bool(equal3)}
+print(json.dumps({"workload": "all-intra reconstruction (intra_pred / MIP / CCLM + residual)", "width": w, "height": h, "pictures": batch,
                   "blocks": int(len(case["blks"])), "transform_blocks": int(len(case["tbs"])), "waves": int(case["n_waves"]),
-                  "ms_per_ring": ms, "ms_per_picture": ms / batch, "mpix_per_s": w * h * batch / (ms * 1e-3) / 1e6, "us_per_wave": ms * 1e3 / case["n_waves"],
-                  "one_launch": {"steps": n_steps, "ms_per_ring": ms3, "ms_per_picture": ms3 / batch, "mpix_per_s": w * h * batch / (ms3 * 1e-3) / 1e6,
-                                 "parity_equal": bool(equal3)},
-                  "cpu_oracle_one_thread_mpix_per_s": w * h * batch / t_cpu / 1e6, "parity": {"pictures": batch, "equal": bool(equal), "against": "oracle"},
-                  "synth_s": t_synth}))
+                  "launch_per_wave": {"ms_per_ring": ms, "ms_per_picture": ms / batch, "mpix_per_s": w * h * batch / (ms * 1e-3) / 1e6,
+                                      "us_per_wave": ms * 1e3 / case["n_waves"], "parity_equal": bool(equal)},
+                  "one_launch": one,
+                  "cpu_oracle_one_thread_mpix_per_s": w * h * batch / t_cpu / 1e6, "against": "oracle", "synth_s": t_synth}))
