@@ -149,6 +149,33 @@ int vvc_cuda_sync(VVCCudaCtx *ctx)
     return ctx->err;
 }
 
+namespace {
+struct Notify { vvc_cuda_notify_fn fn; void *opaque; const VVCCudaCtx *ctx; };
+void CUDART_CB notify_trampoline(void *p)
+{
+    Notify *n = (Notify *)p;
+    n->fn(n->opaque, n->ctx->err);
+    free(n);
+}
+}  // namespace
+
+int vvc_cuda_notify(VVCCudaCtx *ctx, vvc_cuda_notify_fn fn, void *opaque)
+{
+    if (!ctx || !fn)
+        return VVC_CUDA_ERR_ARG;
+    if (ctx->err)
+        return ctx->err;
+    Notify *n = (Notify *)malloc(sizeof(*n));
+    if (!n)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_NOMEM, "notify: out of memory");
+    n->fn = fn; n->opaque = opaque; n->ctx = ctx;
+    if (vvc_ctx_check(ctx, cudaLaunchHostFunc(ctx->stream, notify_trampoline, n), "cudaLaunchHostFunc")) {
+        free(n);
+        return ctx->err;
+    }
+    return VVC_CUDA_OK;
+}
+
 int         vvc_cuda_last_error(const VVCCudaCtx *ctx)   { return ctx->err; }
 const char *vvc_cuda_error_string(const VVCCudaCtx *ctx) { return ctx->err ? ctx->msg : "ok"; }
 void       *vvc_cuda_stream(const VVCCudaCtx *ctx)       { return (void *)ctx->stream; }

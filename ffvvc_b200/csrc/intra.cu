@@ -20,7 +20,10 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+#ifndef INTRA_THREADS
+#define INTRA_THREADS 128
+#endif
+constexpr int kThreads = INTRA_THREADS;
 
 #include "itx_generic.cuh"        // process_tb: the residual step of the dependency-driven kernel below
 

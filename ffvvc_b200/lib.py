@@ -19,6 +19,7 @@ TABLE_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vvcdsp_tabl
 
 FP = C.POINTER(abi.VVCCudaFrame)
 CTX = C.c_void_p
+NOTIFY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
 
 _lib = None
 
@@ -55,6 +56,7 @@ def load():
     lib.vvc_cuda_error_string.restype = C.c_char_p
     lib.vvc_cuda_stream.argtypes = [CTX]
     lib.vvc_cuda_stream.restype = C.c_void_p
+    lib.vvc_cuda_notify.argtypes = [CTX, NOTIFY_FN, C.c_void_p]
     lib.vvc_cuda_launch_count.argtypes = [CTX]
     lib.vvc_cuda_launch_count.restype = C.c_uint64
     for name in ("vvc_cuda_alf_frame", "vvc_cuda_alf_frame_host"):
@@ -118,6 +120,7 @@ class Context:
         must then do so on `torch_stream()`, the legacy default stream does not order with it."""
         self.lib = load()
         self.handle = CTX()
+        self._callbacks = []
         self.device = device
         rc = self.lib.vvc_cuda_ctx_create(C.byref(self.handle), device, stream)
         if rc != 0:
@@ -140,6 +143,13 @@ class Context:
 
     def sync(self):
         self.check(self.lib.vvc_cuda_sync(self.handle))
+
+    def notify(self, fn):
+        """fn(status) is called from a driver thread once everything submitted so far has finished on the GPU
+        (vvc_cuda_notify: the decoder's progress report for a submitted stage).  fn must not touch CUDA."""
+        cb = NOTIFY_FN(lambda _opaque, status: fn(status))
+        self._callbacks.append(cb)               # ctypes thunks must outlive the call
+        self.check(self.lib.vvc_cuda_notify(self.handle, cb, None))
 
     @property
     def stream_ptr(self):

@@ -54,6 +54,14 @@ int         vvc_cuda_sync(VVCCudaCtx *ctx);            /* waits for the stream; 
 int         vvc_cuda_last_error(const VVCCudaCtx *ctx);
 const char *vvc_cuda_error_string(const VVCCudaCtx *ctx);
 void       *vvc_cuda_stream(const VVCCudaCtx *ctx);    /* the cudaStream_t in use */
+/* Stream-ordered completion report.  fn(opaque, status) runs on a driver thread once everything submitted through the
+ * context before this call has finished on the GPU (status = the context's error state then); work submitted afterwards
+ * does not wait for it.  This is where a decoder wired to the batched entries calls ff_vvc_report_progress /
+ * ff_vvc_report_frame_finished (report_frame_progress, libavcodec/vvc/vvc_thread.c:390-410; vvc_refs.c:532-565) for the
+ * stage it has just submitted, instead of blocking a worker thread in vvc_cuda_sync.  fn must not call into CUDA or
+ * into this library. */
+typedef void (*vvc_cuda_notify_fn)(void *opaque, int status);
+int         vvc_cuda_notify(VVCCudaCtx *ctx, vvc_cuda_notify_fn fn, void *opaque);
 /* number of kernel launches issued through this context since creation (bench bookkeeping) */
 uint64_t    vvc_cuda_launch_count(const VVCCudaCtx *ctx);
 const char *vvc_cuda_version(void);
