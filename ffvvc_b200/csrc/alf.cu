@@ -158,7 +158,18 @@ alf_frame_kernel(const AlfK p)
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const int ctb = 1 << p.ctb_log2;
     const int cx = tx0 >> p.ctb_log2, cy = ty0 >> p.ctb_log2;
-    const VVCCudaALFCtb a = p.ctbs[((long long)k * p.ctb_rows + cy) * p.ctb_cols + cx];
+    VVCCudaALFCtb a;                     // 12 bytes of byte fields: three word loads where the table is word aligned
+    {
+        const VVCCudaALFCtb *ap = p.ctbs + ((long long)k * p.ctb_rows + cy) * p.ctb_cols + cx;
+        static_assert(sizeof(VVCCudaALFCtb) == 12, "VVCCudaALFCtb is three words");
+        if (((uintptr_t)p.ctbs & 3) == 0) {
+            const uint32_t *aw = reinterpret_cast<const uint32_t *>(ap);
+            const uint32_t wv[3] = { __ldg(aw), __ldg(aw + 1), __ldg(aw + 2) };
+            memcpy(&a, wv, 12);
+        } else {
+            a = *ap;
+        }
+    }
     const VVCCudaALFSets *sets = p.sets + (p.sets_per_frame ? k : 0);
     const int bd = p.bd;
 

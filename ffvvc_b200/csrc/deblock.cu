@@ -31,6 +31,7 @@ struct DbkK {
     long long  msize[3];
     int        bd, ctb_log2, planes;
     int        tiles_x[3], tiles_y[3], tile_base[3];   // flattened tile index ranges per plane
+    unsigned   tiles_x_rcp[3];                         // ceil(2^32 / tiles_x): t / tiles_x = umulhi(t, rcp) for t < 2^16
 };
 
 constexpr int kThreads = 256;
@@ -272,7 +273,8 @@ deblock_kernel(const DbkK p)
     }
     t -= p.tile_base[c];
     const int k = blockIdx.y;
-    const int tx0 = (t % p.tiles_x[c]) * TW, ty0 = (t / p.tiles_x[c]) * TH;
+    const int trow = p.tiles_x[c] == 1 ? t : (int)__umulhi((unsigned)t, p.tiles_x_rcp[c]);
+    const int tx0 = (t - trow * p.tiles_x[c]) * TW, ty0 = trow * TH;
     const int pw = p.pw[c], ph = p.ph[c];
     const pel *src = p.src[c] + k * p.sb[c];
     pel *dst = p.dst[c] + k * p.db[c];
@@ -306,13 +308,13 @@ deblock_kernel(const DbkK p)
 
     // ---- filter: one thread per edge segment (4 luma lines; 2 or 4 chroma lines) ----
     const bool chroma = c != 0;
-    const int grid = chroma ? 8 : 4;
+    const int lgrid = chroma ? 3 : 2, grid = 1 << lgrid;
     const int shift = chroma ? (VERT ? p.vs[c] : p.hs[c]) : 0;
-    const int seg = chroma ? 4 >> shift : 4;                 // lines per segment
+    const int lseg = chroma ? 2 - shift : 2, seg = 1 << lseg;   // lines per segment
     constexpr int ALONG = VERT ? TH : TW;                    // tile extent along the edges
     constexpr int ACROSS = VERT ? TW : TH;
-    const int n_edges = ACROSS / grid + 1;                   // both tile borders included
-    const int n_segs = ALONG / seg;
+    const int n_edges = (ACROSS >> lgrid) + 1;               // both tile borders included
+    const int n_segs = ALONG >> lseg;
     const VVCCudaDbkEdge *map = p.map[c] + k * p.msize[c];
     const int ctb_mask = (1 << p.ctb_log2) - 1;
     constexpr int xs = VERT ? 1 : PITCH, ys = VERT ? PITCH : 1;
@@ -320,14 +322,18 @@ deblock_kernel(const DbkK p)
     // VERT: consecutive lanes take consecutive edges of one row of segments (their samples are 4 or 8 columns apart: the
     // 32 lanes of a load touch 32 different banks); !VERT: consecutive lanes take consecutive segments of one edge
     for (int it = tid; it < n_edges * n_segs; it += kThreads) {
-        const int e = VERT ? it % n_edges : it / n_segs, sg = VERT ? it / n_edges : it - e * n_segs;
+        // it / n_edges (17 or 9 edges) as a multiply: exact for it < 256
+        const int qv = (int)(((unsigned)it * (chroma ? 7282u : 3856u)) >> 16);
+        const int e = VERT ? it - qv * n_edges : it >> (7 - lseg), sg = VERT ? qv : it - e * n_segs;
+        static_assert(!VERT || (TW == 64 && TH == 32), "the reciprocals above are those of 64 / 4 + 1 and 64 / 8 + 1");
+        static_assert(VERT || TW == 128, "n_segs = 128 >> lseg");
         const int pos = (VERT ? tx0 : ty0) + e * grid;       // edge coordinate in the plane
         const int a0 = sg * seg, along = (VERT ? ty0 : tx0) + a0;
         if (pos == 0 || pos >= (VERT ? pw : ph) || along >= (VERT ? ph : pw))
             continue;
-        const int sidx = along / seg;
-        const VVCCudaDbkEdge ed = VERT ? map[(long long)sidx * p.mpitch[c] + pos / grid]
-                                       : map[(long long)(pos / grid) * p.mpitch[c] + sidx];
+        const int sidx = along >> lseg;
+        const VVCCudaDbkEdge ed = VERT ? map[(long long)sidx * p.mpitch[c] + (pos >> lgrid)]
+                                       : map[(long long)(pos >> lgrid) * p.mpitch[c] + sidx];
         if (!ed.tc)
             continue;
         // Q0 of line 0 of this segment inside the tile
@@ -396,6 +402,9 @@ int launch(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src, co
         p.pw[c] = src->width >> p.hs[c];       p.ph[c] = src->height >> p.vs[c];
         p.map[c] = maps->edge[dir][c];         p.mpitch[c] = maps->pitch[dir][c];  p.msize[c] = maps->size[dir][c];
         p.tiles_x[c] = ceil_div(p.pw[c], T::TW);  p.tiles_y[c] = ceil_div(p.ph[c], T::TH);
+        p.tiles_x_rcp[c] = (unsigned)((0x100000000ull + p.tiles_x[c] - 1) / p.tiles_x[c]);
+        if ((long long)p.tiles_x[c] * p.tiles_y[c] >= 65536)
+            return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "deblock: plane of %d x %d exceeds the tile index range", p.pw[c], p.ph[c]);
         p.tile_base[c] = total;
         if (c < p.planes)
             total += p.tiles_x[c] * p.tiles_y[c];
