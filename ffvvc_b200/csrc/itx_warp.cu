@@ -553,12 +553,14 @@ __global__ void __launch_bounds__(kThreads, ITX_WARP_MB) itx_warp_kernel(const I
         }
         // columns nzw .. of the mid stage are zero (scale_clip's memset); pad to the rounded reduction length
         if (rdh_e > nzw) {
-            const int pad = rdh_e - nzw;                    // < 32
-            for (int idx = lane; idx < h * 32; idx += 32) {
-                const int y = idx >> 5, k = idx & 31;
-                if (k < pad)
+            // lane = (column of the pad, row group): h * pad stores take ceil(h * pad' / 32) rounds, pad' = pad rounded up
+            // to a power of two (most blocks: a pad of 1 - 3 columns, one or two rounds)
+            const int pad = rdh_e - nzw;                    // 1 .. 31
+            const int lp = 32 - __clz(pad - 1);
+            const int k = lane & ((1 << lp) - 1);
+            if (k < pad)
+                for (int y = lane >> lp; y < h; y += 32 >> lp)
                     s.mid[y * P2 + nzw + k] = 0;
-            }
         }
         __syncwarp();
 

@@ -129,12 +129,12 @@ __device__ __forceinline__ void edge_row(uint32_t o[4], const Row &above, const 
 __global__ void __launch_bounds__(32 * WARPS, SAO_MIN_CTAS) sao_kernel(const SaoK p)
 {
     const int lane = threadIdx.x, warp = threadIdx.y;
-    const int per_pic = p.cta_start[3];
-    const int k = blockIdx.x / per_pic;
-    int r = blockIdx.x - k * per_pic;
+    // grid: x = CTB column, y = the row chunks of plane 0, then 1, then 2, z = picture (no index arithmetic to undo)
+    const int k = blockIdx.z, cx = blockIdx.x;
+    int r = blockIdx.y;
     const int c = r >= p.cta_start[2] ? 2 : r >= p.cta_start[1] ? 1 : 0;
     r -= p.cta_start[c];
-    const int cx = r % p.ctb_cols, chunk = (r / p.ctb_cols) * WARPS + warp;
+    const int chunk = r * WARPS + warp;
 
     const int pw = p.pw[c], ph = p.ph[c];
     const int ctb_w = (1 << p.ctb_log2) >> p.hs[c], ctb_h = (1 << p.ctb_log2) >> p.vs[c];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(32 * WARPS, SAO_MIN_CTAS) sao_kernel(const Sao
     const int y0 = wy0 + g * RPT;
     const bool live = g < groups && 8 * lx < bw && y0 < ph;    // dead lanes still take part in the shuffles
     const int xs = live ? x : bx0, ys = live ? y0 : wy0;
-    const int cy = wy0 / ctb_h;
+    const int cy = wy0 >> (p.ctb_log2 - p.vs[c]);
     const int by0 = cy * ctb_h, bh = min(ctb_h, ph - by0);
 
     const pel *src = p.src[c] + k * p.sb[c];
@@ -296,18 +296,20 @@ extern "C" int vvc_cuda_sao_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, cons
     p.ctb_cols = ceil_div(src->width, 1 << src->ctb_log2);
     p.ctb_rows = ceil_div(src->height, 1 << src->ctb_log2);
     p.ctbs = ctbs;
-    // a flat grid: per picture, the CTAs of plane 0, then 1, then 2; a CTA is one CTB column x WARPS warps of rows
+    // grid.y: the row chunks of plane 0, then 1, then 2; a CTA is one CTB column x WARPS warps of rows
     int total = 0;
     for (int c = 0; c < p.planes; c++) {
         const int ctb_h = (1 << p.ctb_log2) >> p.vs[c], lxl = p.ctb_log2 - p.hs[c] - 3;
         const int groups = (32 >> lxl) < ctb_h / RPT ? (32 >> lxl) : ctb_h / RPT;
         p.cta_start[c] = total;
-        total += ceil_div(ceil_div(p.ph[c], RPT * groups), WARPS) * p.ctb_cols;
+        total += ceil_div(ceil_div(p.ph[c], RPT * groups), WARPS);
     }
     for (int c = p.planes; c < 4; c++)
         p.cta_start[c] = total;
     p.cta_start[3] = total;
-    sao_kernel<<<(unsigned)total * src->batch, dim3(32, WARPS), 0, ctx->stream>>>(p);
+    if (total > 65535 || src->batch > 65535)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "sao: picture ring exceeds the grid");
+    sao_kernel<<<dim3(p.ctb_cols, total, src->batch), dim3(32, WARPS), 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Per-source-line executed-instruction and stall-sample totals of one kernel in an .ncu-rep.
 Joins `ncu --page source --print-source sass` (per SASS address) with `nvdisasm --print-line-info`
-of the object the kernel was built from.  Usage: ncu_lines.py rep.ncu-rep build/x.o [top [kernel-filter]]"""
+of the object the kernel was built from.  Usage: ncu_lines.py rep.ncu-rep build/x.o [top [kernel-filter [section-substring]]]
+An object that holds several kernels (template instantiations) needs the section substring - part of the mangled name, e.g.
+itx_warp_kernelILi2E - or the sections' addresses, which all start at 0, are merged and the attribution is wrong."""
 import collections
 import csv
 import glob
@@ -12,7 +14,7 @@ import sys
 import tempfile
 
 
-def main(rep, obj, top=40, kernel=None):
+def main(rep, obj, top=40, kernel=None, fsub=None):
     # kernel: optional name filter (ncu --kernel-name syntax, e.g. regex:itx_warp) for reports holding several kernels
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + (["--kernel-name", kernel] if kernel else []),
                          capture_output=True, text=True, check=True).stdout
@@ -35,7 +37,7 @@ def main(rep, obj, top=40, kernel=None):
     line_at, cur, in_text = {}, None, False
     for ln in dis.splitlines():
         if ln.lstrip().startswith(".section"):
-            in_text = ".text." in ln
+            in_text = ".text." in ln and (fsub is None or fsub in ln)
             continue
         if not in_text:
             continue
