@@ -30,8 +30,7 @@ struct DbkK {
     int        mpitch[3];
     long long  msize[3];
     int        bd, ctb_log2, planes;
-    int        tiles_x[3], tiles_y[3], tile_base[3];   // flattened tile index ranges per plane
-    unsigned   tiles_x_rcp[3];                         // ceil(2^32 / tiles_x): t / tiles_x = umulhi(t, rcp) for t < 2^16
+    int        tiles_x[3], tiles_y[3];                 // tiles per plane
 };
 
 constexpr int kThreads = 256;
@@ -46,7 +45,7 @@ constexpr int kThreads = 256;
 // the lines are filtered from registers.  in / out: Q0 of line 0 in the unfiltered / output tile; XS / YS: sample strides
 // across / along the edge.
 template <int XS, int YS>
-__device__ __forceinline__ void luma_segment(const pel *__restrict__ in, pel *__restrict__ out, int tc_in, int beta_in,
+__device__ __forceinline__ void luma_segment(const pel *in, pel *out, int tc_in, int beta_in,
                                              int lp, int lq, int hor_ctu_edge, int bd)
 {
     const int tc = tc_in << (bd - 10), beta = beta_in << (bd - 8);
@@ -183,7 +182,7 @@ __device__ __forceinline__ void luma_segment(const pel *__restrict__ in, pel *__
 
 // One chroma segment of `lines` lines (2 when the edge direction is subsampled, else 4) by one thread.
 template <int XS, int YS>
-__device__ __forceinline__ void chroma_segment(const pel *__restrict__ in, pel *__restrict__ out, int lines,
+__device__ __forceinline__ void chroma_segment(const pel *in, pel *out, int lines,
                                                int tc_in, int beta_in, int lp, int lq, int bd)
 {
     const int tc = tc_in << (bd - 10), beta = beta_in << (bd - 8);
@@ -237,12 +236,27 @@ __device__ __forceinline__ void chroma_segment(const pel *__restrict__ in, pel *
 #undef AT
 
 // VERT: vertical edges (filtering runs along rows).  Tile geometry:
-//   VERT : TW = 64, TH = 32, apron of 8 columns left and right, row pitch TW + 16 + 2 (odd word count
+//   VERT : TW = 128, TH = 64, apron of 8 columns left and right, row pitch TW + 16 + 2 (odd word count
 //          so the 32 lanes of a warp, which walk consecutive rows of one edge, hit distinct banks)
-//   !VERT: TW = 128, TH = 16, apron of 8 rows above and below, lanes walk consecutive columns
+//   !VERT: TW = 128, TH = 64, apron of 8 rows above and below, lanes walk consecutive columns
+// Tile shapes by tools/sweep_dbk_tile.sh (ms per 16 4K pictures, V / H): 64x32 / 128x16 0.364 / 0.323, 128x32 / 128x32
+// 0.293 / 0.285, 128x64 / 128x64 0.269 / 0.244, 128x128 0.318 / 0.273, 256x64 V 0.312, 256x32 H 0.263: the apron and the
+// per-CTA set-up are amortised over more samples until the shared memory costs resident CTAs.
+#ifndef DBK_TW_V
+#define DBK_TW_V 128
+#endif
+#ifndef DBK_TH_H
+#define DBK_TH_H 64
+#endif
+#ifndef DBK_TH_V
+#define DBK_TH_V 64
+#endif
+#ifndef DBK_TW_H
+#define DBK_TW_H 128
+#endif
 template <bool VERT>
 struct DbkTile {
-    static constexpr int TW = VERT ? 64 : 128, TH = VERT ? 32 : 16;
+    static constexpr int TW = VERT ? DBK_TW_V : DBK_TW_H, TH = VERT ? DBK_TH_V : DBK_TH_H;
     static constexpr int AX = VERT ? 8 : 0, AY = VERT ? 0 : 8;
     static constexpr int PITCH = TW + 2 * AX + (VERT ? 2 : 0);
     static constexpr int ROWS = TH + 2 * AY;
@@ -262,19 +276,23 @@ deblock_kernel(const DbkK p)
 {
     using T = DbkTile<VERT>;
     constexpr int TW = T::TW, TH = T::TH, AX = T::AX, AY = T::AY, PITCH = T::PITCH, ROWS = T::ROWS;
-    __shared__ alignas(16) pel s_in[ROWS * PITCH];
-    __shared__ alignas(16) pel s_out[ROWS * PITCH];
+    // ONE tile, filtered in place: no edge reads a sample another edge of the same direction modifies (the filter lengths
+    // are derived so - it is what lets the reference filter in place edge after edge, and lets the threads here take the
+    // edges concurrently); every line's samples are in registers before its first store
+    __shared__ alignas(16) pel s_t[ROWS * PITCH];
 
-    // which plane / tile
-    int c = 0, t = blockIdx.x;
-    if (p.planes == 3) {
-        if (t >= p.tile_base[2])      c = 2;
-        else if (t >= p.tile_base[1]) c = 1;
+    // which plane / tile.  grid: x = tile column (the two chroma planes side by side), y = the tile rows of luma, then
+    // those of chroma, z = picture
+    int c = 0, tcol = blockIdx.x, trow = blockIdx.y;
+    if (trow >= p.tiles_y[0]) {
+        trow -= p.tiles_y[0];
+        c = 1;
+        if (tcol >= p.tiles_x[1]) { tcol -= p.tiles_x[1]; c = 2; }
     }
-    t -= p.tile_base[c];
-    const int k = blockIdx.y;
-    const int trow = p.tiles_x[c] == 1 ? t : (int)__umulhi((unsigned)t, p.tiles_x_rcp[c]);
-    const int tx0 = (t - trow * p.tiles_x[c]) * TW, ty0 = trow * TH;
+    if (tcol >= p.tiles_x[c])
+        return;
+    const int k = blockIdx.z;
+    const int tx0 = tcol * TW, ty0 = trow * TH;
     const int pw = p.pw[c], ph = p.ph[c];
     const pel *src = p.src[c] + k * p.sb[c];
     pel *dst = p.dst[c] + k * p.db[c];
@@ -299,10 +317,9 @@ deblock_kernel(const DbkK p)
                 v[e] = lo | (hi << 16);
             }
         }
-        unsigned *o_in  = reinterpret_cast<unsigned *>(&s_in[i * PITCH + 8 * q]);
-        unsigned *o_out = reinterpret_cast<unsigned *>(&s_out[i * PITCH + 8 * q]);
+        unsigned *o = reinterpret_cast<unsigned *>(&s_t[i * PITCH + 8 * q]);
 #pragma unroll
-        for (int e = 0; e < 4; e++) { o_in[e] = v[e]; o_out[e] = v[e]; }
+        for (int e = 0; e < 4; e++) o[e] = v[e];
     }
     __syncthreads();
 
@@ -322,11 +339,11 @@ deblock_kernel(const DbkK p)
     // VERT: consecutive lanes take consecutive edges of one row of segments (their samples are 4 or 8 columns apart: the
     // 32 lanes of a load touch 32 different banks); !VERT: consecutive lanes take consecutive segments of one edge
     for (int it = tid; it < n_edges * n_segs; it += kThreads) {
-        // it / n_edges (17 or 9 edges) as a multiply: exact for it < 256
-        const int qv = (int)(((unsigned)it * (chroma ? 7282u : 3856u)) >> 16);
-        const int e = VERT ? it - qv * n_edges : it >> (7 - lseg), sg = VERT ? qv : it - e * n_segs;
-        static_assert(!VERT || (TW == 64 && TH == 32), "the reciprocals above are those of 64 / 4 + 1 and 64 / 8 + 1");
-        static_assert(VERT || TW == 128, "n_segs = 128 >> lseg");
+        // it / n_edges as a multiply by ceil(65536 / n_edges): exact for it < 65536 / n_edges
+        constexpr unsigned NE_L = ACROSS / 4 + 1, NE_C = ACROSS / 8 + 1;
+        const int qv = (int)(((unsigned)it * (chroma ? (65536u + NE_C - 1) / NE_C : (65536u + NE_L - 1) / NE_L)) >> 16);
+        const int e = VERT ? it - qv * n_edges : it >> ((TW == 256 ? 8 : 7) - lseg), sg = VERT ? qv : it - e * n_segs;
+        static_assert(VERT || TW == 128 || TW == 256, "n_segs = TW >> lseg as a shift");
         const int pos = (VERT ? tx0 : ty0) + e * grid;       // edge coordinate in the plane
         const int a0 = sg * seg, along = (VERT ? ty0 : tx0) + a0;
         if (pos == 0 || pos >= (VERT ? pw : ph) || along >= (VERT ? ph : pw))
@@ -340,9 +357,9 @@ deblock_kernel(const DbkK p)
         const int off = VERT ? (a0 + AY) * PITCH + (e * grid + AX) : (e * grid + AY) * PITCH + (a0 + AX);
         if (!chroma) {
             const int ctu_edge = !VERT && !(pos & ctb_mask);
-            luma_segment<xs, ys>(s_in + off, s_out + off, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, ctu_edge, p.bd);
+            luma_segment<xs, ys>(s_t + off, s_t + off, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, ctu_edge, p.bd);
         } else {
-            chroma_segment<xs, ys>(s_in + off, s_out + off, seg, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, p.bd);
+            chroma_segment<xs, ys>(s_t + off, s_t + off, seg, ed.tc, ed.beta, ed.max_len & 15, ed.max_len >> 4, p.bd);
         }
     }
     __syncthreads();
@@ -354,7 +371,7 @@ deblock_kernel(const DbkK p)
         const int y = ty0 + i, x = tx0 + 8 * q;
         if (y >= ph || x >= pw)
             continue;
-        const pel *sp = &s_out[(i + AY) * PITCH + AX + 8 * q];
+        const pel *sp = &s_t[(i + AY) * PITCH + AX + 8 * q];
         pel *drow = dst + (long long)y * p.dp[c] + x;
         if (x + 7 < pw) {
             const unsigned *s32 = reinterpret_cast<const unsigned *>(sp);
@@ -393,7 +410,6 @@ int launch(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src, co
     using T = DbkTile<VERT>;
     DbkK p;
     p.planes = src->chroma_format_idc ? 3 : 1;
-    int total = 0;
     for (int c = 0; c < 3; c++) {
         p.src[c] = (const pel *)src->data[c];  p.dst[c] = (pel *)dst->data[c];
         p.sp[c] = (int)(src->stride[c] / 2);   p.dp[c] = (int)(dst->stride[c] / 2);
@@ -402,15 +418,13 @@ int launch(VVCCudaCtx *ctx, const VVCCudaFrame *dst, const VVCCudaFrame *src, co
         p.pw[c] = src->width >> p.hs[c];       p.ph[c] = src->height >> p.vs[c];
         p.map[c] = maps->edge[dir][c];         p.mpitch[c] = maps->pitch[dir][c];  p.msize[c] = maps->size[dir][c];
         p.tiles_x[c] = ceil_div(p.pw[c], T::TW);  p.tiles_y[c] = ceil_div(p.ph[c], T::TH);
-        p.tiles_x_rcp[c] = (unsigned)((0x100000000ull + p.tiles_x[c] - 1) / p.tiles_x[c]);
-        if ((long long)p.tiles_x[c] * p.tiles_y[c] >= 65536)
-            return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "deblock: plane of %d x %d exceeds the tile index range", p.pw[c], p.ph[c]);
-        p.tile_base[c] = total;
-        if (c < p.planes)
-            total += p.tiles_x[c] * p.tiles_y[c];
     }
     p.bd = src->bit_depth; p.ctb_log2 = src->ctb_log2;
-    deblock_kernel<VERT><<<dim3(total, src->batch), kThreads, 0, ctx->stream>>>(p);
+    const dim3 grid(p.planes == 3 ? max(p.tiles_x[0], 2 * p.tiles_x[1]) : p.tiles_x[0],
+                    p.tiles_y[0] + (p.planes == 3 ? p.tiles_y[1] : 0), src->batch);
+    if (grid.y > 65535 || grid.z > 65535)
+        return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "deblock: picture ring exceeds the grid");
+    deblock_kernel<VERT><<<grid, kThreads, 0, ctx->stream>>>(p);
     VVC_LAUNCHED(ctx);
     return VVC_CUDA_OK;
 }
