@@ -135,6 +135,9 @@ __device__ __noinline__ uint2 alf_strip_wide(const pel *p0, int d1, int d2, int 
     return make_uint2(res[0] | (res[1] << 16), res[2] | (res[3] << 16));
 }
 
+#ifndef ALF_TH
+#define ALF_TH 32                    // tile height of the 64-wide tiles
+#endif
 #ifndef ALF_MIN_CTAS
 #define ALF_MIN_CTAS 0               // resident CTAs per SM the kernel is compiled for (0: the compiler's choice; tools/sweep_alf_occ.sh)
 #endif
@@ -567,8 +570,8 @@ extern "C" int vvc_cuda_alf_frame(VVCCudaCtx *ctx, const VVCCudaFrame *dst, cons
     p.wide_multiply = ctx->alf_wide_multiply;
 
     if (p.ctb_log2 >= 6) {
-        dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, 32), src->batch);
-        alf_frame_kernel<64, 32><<<grid, kThreads, 0, ctx->stream>>>(p);
+        dim3 grid(ceil_div(p.w, 64), ceil_div(p.h, ALF_TH), src->batch);
+        alf_frame_kernel<64, ALF_TH><<<grid, kThreads, 0, ctx->stream>>>(p);
     } else {
         dim3 grid(ceil_div(p.w, 32), ceil_div(p.h, 32), src->batch);
         alf_frame_kernel<32, 32><<<grid, kThreads, 0, ctx->stream>>>(p);

@@ -33,7 +33,10 @@ struct SaoK {
     const VVCCudaSAOCtb *ctbs;
 };
 
-constexpr int RPT = 4;          // rows per lane
+#ifndef SAO_RPT
+#define SAO_RPT 4
+#endif
+constexpr int RPT = SAO_RPT;    // rows per lane
 constexpr int WARPS = 8;        // warps per CTA, each on its own rows
 
 struct Row { uint32_t w[4]; uint32_t left, right; };     // 8 samples as 4 pairs; left = (., x-1) in the high half, right = (x+8, .) in the low half

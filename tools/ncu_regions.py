@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Executed warp-instructions of inter_warp_kernel grouped by code region (marker strings in the source).
-Usage: ncu_regions.py rep.ncu-rep obj.o source.cu n_records"""
+Usage: ncu_regions.py rep.ncu-rep obj.o source.cu n_records [kernel-filter [section-substring [nth]]]
+section-substring: part of the mangled name of the instantiation (an object with several kernels has several .text sections
+that all start at address 0); nth: which table of the report's source page to take (each launch appears twice)."""
 import collections
 import csv
 import glob
@@ -11,11 +13,14 @@ import sys
 import tempfile
 
 rep, obj, srcpath, nrec = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
-kernel = sys.argv[5] if len(sys.argv) > 5 else None      # optional ncu --kernel-name filter for reports with several kernels
+kernel = sys.argv[5] if len(sys.argv) > 5 and sys.argv[5] != "-" else None      # optional ncu --kernel-name filter for reports with several kernels
+fsub = sys.argv[6] if len(sys.argv) > 6 else None
+nth = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"] + (["--kernel-name", kernel] if kernel else []),
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
+hdr = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][nth]
+print("kernel:", rows[hdr - 1][1][:110])
 h = rows[hdr]
 ii = h.index("Instructions Executed")
 recs = []
@@ -31,7 +36,7 @@ base_name = os.path.basename(srcpath)
 line_at, cur, last_own, in_text = {}, None, None, False
 for ln in dis.splitlines():
     if ln.lstrip().startswith(".section"):
-        in_text = ".text." in ln
+        in_text = ".text." in ln and (fsub is None or fsub in ln)
         continue
     if not in_text:
         continue
