@@ -21,12 +21,15 @@ struct InterK {
 // launch in the context's scratch slot 2.  A patch task = record << 3 | patch.  The uni lists grow from the
 // front of their array, the bi lists from the back (a record is one or the other, so they never meet).
 struct InterLists {
-    uint32_t *luma;    int cap_luma;     // 8 tasks per record at most: patches of 4 columns x 8 rows
+    uint32_t *luma[3]; int cap_luma[3];  // patches of 4 columns x 8 rows, one list per record width 4 / 8 / 16 (at most 2 / 4 / 8 tasks per
+                                         // record): the tasks of one row of patches are consecutive and aligned, they share a staged window
     uint32_t *chroma;  int cap_chroma;   // 4 tasks per record at most: (plane, patch column)
     uint32_t *luma_b, *chroma_b;         // the same for records whose reference windows may leave the picture (clamped loads)
     uint32_t *coop;                      // records of the warp-per-record kernels: DMVR / BDOF from the front, PROF from the back
-    uint32_t *count;                     // [0] luma uni, [1] luma bi, [2] chroma uni, [3] chroma bi, [4] DMVR / BDOF, [5] PROF,
-                                         // [8], [9] work counters of the two warp kernels, [10..13] = [0..3] of the border lists
+    uint32_t *count;                     // [2] chroma uni, [3] chroma bi, [4] DMVR / BDOF, [5] PROF, [8], [9], [14] work counters of the warp
+                                         // kernels, [10..13] border lists (luma uni, bi, chroma uni, bi), [16..18] luma uni by width class,
+                                         // [20..22] luma bi by width class
+    uint32_t *tail;                      // first word behind the lists (refined vectors of the split DMVR kernels)
 };
 
 // 10-bit path (bd == 10, 4:2:0 or 4:0:0, 16-byte aligned planes / pitches): classify + patch kernel

@@ -944,7 +944,7 @@ int vvc_inter_launch_warp(VVCCudaCtx *ctx, const InterK &p, const InterLists &li
     const int ctas = ceil_div(p.n, kWarps);
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    VVCCudaDmvrOut *refined = reinterpret_cast<VVCCudaDmvrOut *>(lists.count + 16 + 25 * (size_t)p.n);      // behind the lists
+    VVCCudaDmvrOut *refined = reinterpret_cast<VVCCudaDmvrOut *>(lists.tail);      // behind the lists
     if (ctx->inter_tma) {
         if (make_window_map(ctx, p, &map))
             return ctx->err;
