@@ -73,6 +73,9 @@ __device__ __forceinline__ void tma_box_3d(void *dst, const CUtensorMap *map, in
 #define INTER_STAGE_UNROLL 4             // window rows a lane requests before it stores the first one
 #endif
 constexpr int kStageUnroll = INTER_STAGE_UNROLL;
+#ifndef INTER_STAGE_ASYNC
+#define INTER_STAGE_ASYNC 1              // window rows by cp.async instead of load + store (tools/sweep_stage_async.sh)
+#endif
 #ifndef INTER_WARP_PREFETCH
 #define INTER_WARP_PREFETCH 0            // measured slower (tools/sweep_prefetch2.sh: inter 2.285 -> 2.381 ms per 16 pictures)
 #endif
@@ -148,9 +151,19 @@ __device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const p
         if (inside) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(plane + (long long)(wy0 + rsub) * pitch + bx) + k;
             const int sstep = rstep * (pitch >> 1);
+#if INTER_STAGE_ASYNC
+            // cp.async: no destination register and no wait between the rows - every row of the lane is in flight before the
+            // single wait below (the register form paid a round trip per kStageUnroll rows: a quarter of the kernel's stall samples)
+            uint32_t sd = smem_u32(dst);
+#pragma unroll 4
+            for (int r = rsub; r < rows; r += rstep, src += sstep, sd += dstep * 4)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sd), "l"(src) : "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+#else
 #pragma unroll kStageUnroll
             for (int r = rsub; r < rows; r += rstep, src += sstep, dst += dstep)
                 *dst = __ldg(src);
+#endif
         } else {
             const int xa = d_clip3(bx + 2 * k, 0, W - 1), xb = d_clip3(bx + 2 * k + 1, 0, W - 1);
 #pragma unroll 2
