@@ -72,7 +72,6 @@ __device__ __forceinline__ void tma_box_3d(void *dst, const CUtensorMap *map, in
 #ifndef INTER_STAGE_UNROLL
 #define INTER_STAGE_UNROLL 4             // window rows a lane requests before it stores the first one
 #endif
-constexpr int kStageUnroll = INTER_STAGE_UNROLL;
 #ifndef INTER_STAGE_ASYNC
 #define INTER_STAGE_ASYNC 1              // window rows by cp.async instead of load + store (tools/sweep_stage_async.sh)
 #endif
@@ -153,14 +152,14 @@ __device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const p
             const int sstep = rstep * (pitch >> 1);
 #if INTER_STAGE_ASYNC
             // cp.async: no destination register and no wait between the rows - every row of the lane is in flight before the
-            // single wait below (the register form paid a round trip per kStageUnroll rows: a quarter of the kernel's stall samples)
+            // single wait below (the register form paid a round trip per INTER_STAGE_UNROLL rows: a quarter of the kernel's stall samples)
             uint32_t sd = smem_u32(dst);
 #pragma unroll 4
             for (int r = rsub; r < rows; r += rstep, src += sstep, sd += dstep * 4)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sd), "l"(src) : "memory");
             asm volatile("cp.async.wait_all;" ::: "memory");
 #else
-#pragma unroll kStageUnroll
+#pragma unroll INTER_STAGE_UNROLL
             for (int r = rsub; r < rows; r += rstep, src += sstep, dst += dstep)
                 *dst = __ldg(src);
 #endif
