@@ -23,12 +23,12 @@ struct InterK {
 struct InterLists {
     uint32_t *luma[3]; int cap_luma[3];  // patches of 4 columns x 8 rows, one list per record width 4 / 8 / 16 (at most 2 / 4 / 8 tasks per
                                          // record): the tasks of one row of patches are consecutive and aligned, they share a staged window
-    uint32_t *chroma[2]; int cap_chroma[2];   // (plane, patch column) tasks: records up to 8 wide (2 tasks), 16-wide records (4 tasks)
+    uint32_t *chroma;  int cap_chroma;   // 4 tasks per record at most: (plane, patch column)
     uint32_t *luma_b, *chroma_b;         // the same for records whose reference windows may leave the picture (clamped loads)
     uint32_t *coop;                      // records of the warp-per-record kernels: DMVR / BDOF from the front, PROF from the back
     uint32_t *count;                     // [2] chroma uni, [3] chroma bi, [4] DMVR / BDOF, [5] PROF, [8], [9], [14] work counters of the warp
                                          // kernels, [10..13] border lists (luma uni, bi, chroma uni, bi), [16..18] luma uni by width class,
-                                         // [20..22] luma bi by width class, [24], [25] chroma uni / bi of 16-wide records ([2], [3]: narrower ones)
+                                         // [20..22] luma bi by width class
     uint32_t *tail;                      // first word behind the lists (refined vectors of the split DMVR kernels)
 };
 

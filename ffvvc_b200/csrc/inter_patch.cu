@@ -49,7 +49,7 @@ constexpr int kThreads = 128;
 #define PATCH_MB_LB 3
 #endif
 #ifndef PATCH_MB_CU
-#define PATCH_MB_CU 6
+#define PATCH_MB_CU 7
 #endif
 #ifndef PATCH_MB_CB
 #define PATCH_MB_CB 6
@@ -90,13 +90,11 @@ __device__ __noinline__ uint2 gpm_row(uint32_t k0, uint32_t k1, int o0, int o1, 
 // word (row r, i) of lane t at word [(r * NW + i) * 32 + t] of the area (4-byte requests).  MODE 2 / 3: a region per group of 2 / 4 lanes = one row of patches
 // of a record 8 / 16 wide, rows of 40 / 64 bytes starting at the 8 / 16-byte aligned sample gx <= x - 3; lane k of the
 // group requests chunks k, k + 2, k + 4 (8 bytes each) / chunk k (16 bytes) of every row.
-// MODE 4 (chroma of 16-wide records): the two patch columns of a plane, rows of 48 bytes from the 16-byte aligned
-// sample gx <= x - 1; lane 0 requests chunks 0 and 2, lane 1 chunk 1.
-__host__ __device__ constexpr int mode_lanes(int m)  { return m == 3 ? 4 : m == 2 || m == 4 ? 2 : 1; }
-__host__ __device__ constexpr int mode_chunk(int m)  { return m == 3 || m == 4 ? 8 : m == 2 ? 4 : 2; }      // samples per request
-__host__ __device__ constexpr int mode_pitch(int m)  { return m == 3 ? 64 : m == 4 ? 48 : 40; }             // bytes per window row in a region
-__host__ __device__ constexpr int mode_region(int m) { return m == 3 ? 992 : m == 4 ? 528 : 616; }          // bytes per region (15 / 11 rows; the stride spreads the groups of a warp over the banks)
-__host__ __device__ constexpr int area_bytes(bool luma) { return luma ? 32 * 15 * 6 * 4 : 16 * 528; }       // per warp: 32 private luma slots (the group modes need less) / 16 chroma pair regions
+__host__ __device__ constexpr int mode_lanes(int m)  { return m == 3 ? 4 : m == 2 ? 2 : 1; }
+__host__ __device__ constexpr int mode_chunk(int m)  { return m == 3 ? 8 : m == 2 ? 4 : 2; }      // samples per request
+__host__ __device__ constexpr int mode_pitch(int m)  { return m == 3 ? 64 : 40; }                 // bytes per window row in a region
+__host__ __device__ constexpr int mode_region(int m) { return m == 3 ? 992 : 616; }               // bytes per region: 15 rows, and a stride that spreads the groups of a warp over the banks
+constexpr int kSlotBytes = 15 * 6 * 4;                                        // per lane, all modes
 
 struct Win { const char *src; int pitch, nr, nch; };    // the lane's first request of row 0, bytes per plane row, rows to stage (0: none), requests per row (MODE 2)
 
@@ -118,7 +116,7 @@ __device__ __forceinline__ Win win_of(const pel *plane, int pitch, int x, int y,
     w.src = reinterpret_cast<const char *>(plane + (long long)(y - B) * pitch + gx + k * CS);
     w.pitch = pitch * 2;
     w.nr = nrows + TAPS - 1;
-    w.nch = MODE == 2 ? 3 - k : MODE == 4 ? 2 - k : 1;
+    w.nch = MODE == 2 ? 3 - k : 1;
     return w;
 }
 
@@ -138,11 +136,6 @@ __device__ __forceinline__ void stage_row(uint32_t sm, const Win &w, int r)
             for (int j = 0; j < 3; j++)
                 if (j < w.nch)
                     cp_async8(sm + r * mode_pitch(2) + j * 16, g + j * 16);
-        } else if (MODE == 4) {
-#pragma unroll
-            for (int j = 0; j < 2; j++)
-                if (j < w.nch)
-                    cp_async16(sm + r * mode_pitch(4) + j * 32, g + j * 32);
         } else {
             cp_async16(sm + r * mode_pitch(3), g);
         }
@@ -327,10 +320,10 @@ __device__ __forceinline__ Blend blend_of(const Rec &pb, const VVCCudaWP *wp, bo
 }
 
 // ---- work lists -------------------------------------------------------------------------------------------
-// scan slots of the classifier -> ls.count[] entries: luma uni by width class, luma bi by width class, chroma uni / bi of
-// records up to 8 wide, DMVR-BDOF / PROF, luma border uni / bi, chroma border uni / bi, chroma uni / bi of 16-wide records
-constexpr int kSlots = 16;
-__constant__ int kCountOf[kSlots] = { 16, 17, 18, 20, 21, 22, 2, 3, 4, 5, 10, 11, 12, 13, 24, 25 };
+// scan slots of the classifier -> ls.count[] entries: luma uni by width class, luma bi by width class, chroma uni / bi,
+// DMVR-BDOF / PROF, luma border uni / bi, chroma border uni / bi
+constexpr int kSlots = 14;
+__constant__ int kCountOf[kSlots] = { 16, 17, 18, 20, 21, 22, 2, 3, 4, 5, 10, 11, 12, 13 };
 
 __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, const InterLists ls)
 {
@@ -352,7 +345,7 @@ __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, con
             if ((planes & VVC_CUDA_PB_CHROMA) && p.planes == 3) { cls_c = bi; n_c = w > 8 ? 4 : 2; }   // 2 planes x patch columns
             // Records whose windows may leave the picture (a conservative test; mc_patch decides per patch) go to lists
             // of their own: their clamped loads cost ten times a plain patch, and one such lane stalls its whole warp.
-            // 8 samples more on either side: the reach of the staged windows' aligned 8 / 16-byte requests.
+            // Luma: 8 samples more on either side, the reach of the staged windows' aligned 8 / 16-byte requests.
             const int x0 = r0 & 0xffff, y0 = r0 >> 16;
             for (int l = 0; l < 2; l++) {
                 if (!bi && l != pred - 1)
@@ -362,13 +355,13 @@ __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, con
                 const int m = p.margin, mc = p.margin >> 1;
                 border |= xx - 12 < -m || xx + w + 13 > p.w + m || yy - 3 < -m || yy + h + 4 > p.h + m;
                 const int xc = (x0 >> 1) + (mx >> 5), yc = (y0 >> 1) + (my >> 5);
-                border |= xc - 10 < -mc || xc + (w >> 1) + 15 > (p.w >> 1) + mc || yc - 1 < -mc || yc + (h >> 1) + 2 > (p.h >> 1) + mc;
+                border |= xc - 2 < -mc || xc + (w >> 1) + 6 > (p.w >> 1) + mc || yc - 1 < -mc || yc + (h >> 1) + 2 > (p.h >> 1) + mc;
             }
         }
     }
     // this record's slots
     const int sl = cls_l < 0 ? -1 : border ? 10 + cls_l : cls_l * 3 + wc;
-    const int sc = cls_c < 0 ? -1 : border ? 12 + cls_c : (wc == 2 ? 14 : 6) + cls_c;
+    const int sc = cls_c < 0 ? -1 : border ? 12 + cls_c : 6 + cls_c;
     const int sk = coop < 0 ? -1 : 8 + coop;
     uint32_t excl[kSlots];
 #pragma unroll
@@ -408,11 +401,9 @@ __global__ void __launch_bounds__(256) inter_classify_kernel(const InterK p, con
     }
     if (cls_c >= 0) {
         const int base = at(sc);
-        // 16-wide records: four tasks, the two patch columns of a plane side by side (a pair of lanes shares their window)
-        uint32_t *list = border ? ls.chroma_b : wc == 2 ? ls.chroma[1] : ls.chroma[0];
-        const int cap = border || wc == 2 ? ls.cap_chroma[1] : ls.cap_chroma[0];
+        uint32_t *list = border ? ls.chroma_b : ls.chroma;
         for (int k = 0; k < n_c; k++)
-            list[cls_c ? cap - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
+            list[cls_c ? ls.cap_chroma - 1 - (base + k) : base + k] = ((uint32_t)ri << 3) | k;
     }
 }
 
@@ -426,15 +417,15 @@ struct Lane { uint32_t sm_st, region; int k; };
 template <int TAPS, int MODE>
 __device__ __forceinline__ Lane lane_of(uint32_t smem)
 {
-    constexpr int G = mode_lanes(MODE);
+    constexpr int G = mode_lanes(MODE), NW = TAPS == 8 ? 6 : 4, NR = 8 + TAPS - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Lane l;
     l.k = lane & (G - 1);
     if (MODE == 1) {
-        l.region = smem + warp * area_bytes(TAPS == 8) + lane * 4;
+        l.region = smem + warp * (32 * NR * NW * 4) + lane * 4;
         l.sm_st = l.region;
     } else {
-        l.region = smem + warp * area_bytes(TAPS == 8) + (lane / G) * mode_region(MODE);
+        l.region = smem + warp * (32 * kSlotBytes) + (lane / G) * mode_region(MODE);
         l.sm_st = l.region + l.k * mode_chunk(MODE) * 2;
     }
     return l;
@@ -497,14 +488,13 @@ __device__ __forceinline__ void luma_task(const InterK &p, const Rec &pb, int pi
 }
 
 // ---- chroma (4:2:0): task pi = (plane, patch column) ----------------------------------------------------------
-// window `l` of a chroma task: MODE 1 the patch's own, MODE 4 the lane's share of the window of its plane's two patch columns
-template <int MODE>
-__device__ __forceinline__ Win chroma_win(const InterK &p, const Rec &pb, int pi, int l, int k)
+// window `l` of a chroma task (private slots only)
+__device__ __forceinline__ Win chroma_win(const InterK &p, const Rec &pb, int pi, int l)
 {
     const int bw = pb.w >> 1, bh = pb.h >> 1, ncx = bw > 4 ? 2 : 1;
-    const int pc = pi >> (ncx >> 1), ox = MODE == 1 ? (pi & (ncx - 1)) << 2 : 0;
-    return win_of<4, MODE>((pc ? p.ref[2] : p.ref[1]) + REF(l) * (pc ? p.rb[2] : p.rb[1]), pc ? p.rp[2] : p.rp[1],
-                           (pb.x0 >> 1) + ox + (MV0(l, 0) >> 5), (pb.y0 >> 1) + (MV0(l, 1) >> 5), bh, k);
+    const int pc = pi >> (ncx >> 1), ox = (pi & (ncx - 1)) << 2;
+    return win_of<4, 1>((pc ? p.ref[2] : p.ref[1]) + REF(l) * (pc ? p.rb[2] : p.rb[1]), pc ? p.rp[2] : p.rp[1],
+                        (pb.x0 >> 1) + ox + (MV0(l, 0) >> 5), (pb.y0 >> 1) + (MV0(l, 1) >> 5), bh, 0);
 }
 
 template <bool BI, int MODE = 0>
@@ -531,21 +521,19 @@ __device__ __forceinline__ void chroma_task(const InterK &p, const Rec &pb, int 
         (MV0(l, 0) & 31) ? chromaf[MV0(l, 0) & 31] : 0x00000100u, 0u, \
         (MV0(l, 1) & 31) ? chromaf[MV0(l, 1) & 31] : ((MV0(l, 0) & 31) ? 0x00000100u : 0x00001000u), 0u, \
         (MV0(l, 0) & 31) ? 2 : 0, (MV0(l, 1) & 31) ? ((MV0(l, 0) & 31) ? 6 : 2) : 0
-#define CHROMA_RD(l) ln.region + read_offset<4, MODE>(x0 + (MV0(l, 0) >> 5), x0 + ox + (MV0(l, 0) >> 5))
     if (BI) {
         Win second = Win();
         if (MODE)
-            second = chroma_win<MODE ? MODE : 1>(p, pb, pi, 1, ln.k);
+            second = chroma_win(p, pb, pi, 1);
         if (!live)
             second.nr = 0;
 #pragma unroll 1
         for (int l = 0; l < 2; l++)
-            mc_patch<4, true, MODE>(CHROMA_ARGS(l), l == 0, keep, k, gw, 2 * pb.gsx, 2 * pb.gsy, cmax, d, dpitch, bw > 2, CHROMA_RD(l), ln.sm_st, l == 0 ? second : next);
+            mc_patch<4, true, MODE>(CHROMA_ARGS(l), l == 0, keep, k, gw, 2 * pb.gsx, 2 * pb.gsy, cmax, d, dpitch, bw > 2, ln.region, ln.sm_st, l == 0 ? second : next);
     } else {
-        mc_patch<4, false, MODE>(CHROMA_ARGS(lx), false, keep, k, nullptr, 0, 0, cmax, d, dpitch, bw > 2, CHROMA_RD(lx), ln.sm_st, next);
+        mc_patch<4, false, MODE>(CHROMA_ARGS(lx), false, keep, k, nullptr, 0, 0, cmax, d, dpitch, bw > 2, ln.region, ln.sm_st, next);
     }
 #undef CHROMA_ARGS
-#undef CHROMA_RD
 }
 #undef MV0
 #undef REF
@@ -565,7 +553,7 @@ __device__ __forceinline__ void run_list(const InterK &p, const uint32_t *list, 
     auto first_win = [&](uint32_t t, bool live) {
         const Rec r = load_rec(p.pbs + (t >> 3));
         const int l = BI ? 0 : r.pred - 1;
-        Win w = LUMA ? luma_win<LUMA ? MODE : 1>(p, r, t & 7, l, ln.k) : chroma_win<LUMA ? 1 : MODE>(p, r, t & 7, l, ln.k);
+        Win w = LUMA ? luma_win<MODE>(p, r, t & 7, l, ln.k) : chroma_win(p, r, t & 7, l);
         if (!live)
             w.nr = 0;
         return w;
@@ -598,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_ke
     // that run the clamped path are full of such tasks instead of dragging plain patches through it, and they start first
     const int nb = (int)ls.count[10 + (LUMA ? 0 : 2) + (BI ? 1 : 0)];
     const uint32_t *blist = LUMA ? ls.luma_b : ls.chroma_b;
-    const int bcap = LUMA ? ls.cap_luma[2] : ls.cap_chroma[1];
+    const int bcap = LUMA ? ls.cap_luma[2] : ls.cap_chroma;
     const int stride = gridDim.x * kThreads;
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < nb; i += stride) {
         const uint32_t t = __ldg(blist + (BI ? bcap - 1 - i : i));
@@ -611,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_ke
 #if PATCH_STAGED
     // then the plain tasks through staged windows: the classifier sends every record with a window outside the plane (or its
     // margin, with room for the aligned requests of the group modes) to the border list, so these need no clamp
-    __shared__ __align__(16) uint32_t slots[area_bytes(LUMA) / 4 * (kThreads / 32)];
+    __shared__ __align__(16) uint32_t slots[(LUMA ? kSlotBytes / 4 : 11 * 4) * kThreads];
     const uint32_t smem = (uint32_t)__cvta_generic_to_shared(slots);
     if (LUMA) {
         // the lists lay the warp's area out differently: the whole warp leaves one before any lane enters the next
@@ -621,14 +609,12 @@ __global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_ke
         __syncwarp();
         run_list<true, BI, 1>(p, ls.luma[0], ls.cap_luma[0], (int)ls.count[(BI ? 20 : 16) + 0], smem);
     } else {
-        run_list<false, BI, 4>(p, ls.chroma[1], ls.cap_chroma[1], (int)ls.count[24 + (BI ? 1 : 0)], smem);
-        __syncwarp();
-        run_list<false, BI, 1>(p, ls.chroma[0], ls.cap_chroma[0], (int)ls.count[2 + (BI ? 1 : 0)], smem);
+        run_list<false, BI, 1>(p, ls.chroma, ls.cap_chroma, (int)ls.count[2 + (BI ? 1 : 0)], smem);
     }
 #else
-    for (int c = LUMA ? 2 : 1; c >= 0; c--) {
-        const uint32_t *list = LUMA ? ls.luma[c] : ls.chroma[c];
-        const int cap = LUMA ? ls.cap_luma[c] : ls.cap_chroma[c], n = (int)ls.count[LUMA ? (BI ? 20 : 16) + c : (c ? 24 : 2) + (BI ? 1 : 0)];
+    for (int c = LUMA ? 2 : 0; c >= 0; c--) {
+        const uint32_t *list = LUMA ? ls.luma[c] : ls.chroma;
+        const int cap = LUMA ? ls.cap_luma[c] : ls.cap_chroma, n = (int)ls.count[LUMA ? (BI ? 20 : 16) + c : 2 + (BI ? 1 : 0)];
         for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
             const uint32_t t = __ldg(list + (BI ? cap - 1 - i : i));
             const Rec pb = load_rec(p.pbs + (t >> 3));
@@ -645,19 +631,18 @@ __global__ void __launch_bounds__(kThreads, patch_ctas(LUMA, BI)) inter_patch_ke
 
 int vvc_inter_launch_classify(VVCCudaCtx *ctx, const InterK &p, InterLists *ls)
 {
-    // scratch: [count: 128 bytes][luma by width class: 2 n, 4 n, 8 n][chroma: 2 n, 4 n][coop: n][luma border: 8 n][chroma border: 4 n] words,
+    // scratch: [count: 128 bytes][luma by width class: 2 n, 4 n, 8 n][chroma: 4 n][coop: n][luma border: 8 n][chroma border: 4 n] words,
     // then the refined vectors of the split DMVR kernels
     const size_t n = (size_t)p.n;
-    uint32_t *base = (uint32_t *)vvc_ctx_scratch(ctx, 2, 128 + 33 * n * sizeof(uint32_t) + n * sizeof(VVCCudaDmvrOut));
+    uint32_t *base = (uint32_t *)vvc_ctx_scratch(ctx, 2, 128 + 31 * n * sizeof(uint32_t) + n * sizeof(VVCCudaDmvrOut));
     if (!base)
         return ctx->err;
     ls->count = base;
     ls->luma[0] = base + 32;             ls->cap_luma[0] = (int)(2 * n);
     ls->luma[1] = ls->luma[0] + 2 * n;   ls->cap_luma[1] = (int)(4 * n);
     ls->luma[2] = ls->luma[1] + 4 * n;   ls->cap_luma[2] = (int)(8 * n);
-    ls->chroma[0] = ls->luma[2] + 8 * n; ls->cap_chroma[0] = (int)(2 * n);
-    ls->chroma[1] = ls->chroma[0] + 2 * n; ls->cap_chroma[1] = (int)(4 * n);
-    ls->coop = ls->chroma[1] + 4 * n;
+    ls->chroma = ls->luma[2] + 8 * n;    ls->cap_chroma = (int)(4 * n);
+    ls->coop = ls->chroma + 4 * n;
     ls->luma_b = ls->coop + n;
     ls->chroma_b = ls->luma_b + 8 * n;
     ls->tail = ls->chroma_b + 4 * n;
