@@ -49,10 +49,10 @@ constexpr int kThreads = 128;
 #define PATCH_MB_LB 3
 #endif
 #ifndef PATCH_MB_CU
-#define PATCH_MB_CU 7
+#define PATCH_MB_CU 4
 #endif
 #ifndef PATCH_MB_CB
-#define PATCH_MB_CB 6
+#define PATCH_MB_CB 4
 #endif
 #ifndef PATCH_STAGED
 #define PATCH_STAGED 1
