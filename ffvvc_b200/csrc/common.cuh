@@ -29,6 +29,13 @@ struct VVCCudaCtx {
     cudaStream_t  side[3];                           // lazily created: independent kernels of one stage run beside the context stream
     cudaEvent_t   fork_ev, join_ev[3];
     cudaEvent_t   ev[8];
+    cudaEvent_t   ev_desc[3][4];                      // reconstruction host entry, per descriptor slot: uploaded, kernels done, refined vectors downloaded
+    cudaEvent_t   ev_out[16], ev_refs[2];             // reconstruction host entry: copy-out of an output slot finished, kernels of the call that used a reference area finished
+    // vvc_cuda_recon_frame_host(_async): pictures issued so far (slot and event rotation continue across calls), the staging
+    // layout of the calls in flight, and whether copies of an earlier call may still be running on the copy streams
+    uint64_t      host_seq, host_calls;
+    size_t        host_layout[4];
+    bool          host_pending, host_owner;
 };
 
 int  vvc_ctx_fail(VVCCudaCtx *ctx, int code, const char *fmt, ...);
@@ -41,6 +48,8 @@ void *vvc_ctx_scratch(VVCCudaCtx *ctx, int slot, size_t bytes);
 // ctx->stream so far; vvc_ctx_join makes ctx->stream wait for what was issued on them since.  The kernels of one stage
 // that touch disjoint samples (task classes of the inter stage, the two residual kernels) are issued this way so that
 // the tail of one fills with the next instead of draining the machine between launches.
+// the copy streams and events of the *_host pipelines, created on first use
+int   vvc_ctx_copy_streams(VVCCudaCtx *ctx);
 int   vvc_ctx_fork(VVCCudaCtx *ctx, int n);
 int   vvc_ctx_join(VVCCudaCtx *ctx, int n);
 

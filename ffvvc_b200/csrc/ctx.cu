@@ -25,8 +25,23 @@ int vvc_ctx_check(VVCCudaCtx *ctx, cudaError_t e, const char *what)
     return 1;
 }
 
+// the copy streams of the host entries: an asynchronous call may have left copies running on them
+static void drain_copy_streams(VVCCudaCtx *ctx)
+{
+    if (ctx->host_pending) {
+        vvc_ctx_check(ctx, cudaStreamSynchronize(ctx->copy_in), "cudaStreamSynchronize(copy_in)");
+        vvc_ctx_check(ctx, cudaStreamSynchronize(ctx->copy_out), "cudaStreamSynchronize(copy_out)");
+        ctx->host_pending = false;
+    }
+}
+
 void *vvc_ctx_dev_stage(VVCCudaCtx *ctx, size_t bytes)
 {
+    // the staging area may still be the source / destination of an asynchronous host entry's copies: any other user waits
+    if (ctx->host_pending && !ctx->host_owner) {
+        cudaStreamSynchronize(ctx->stream);
+        drain_copy_streams(ctx);
+    }
     if (bytes > ctx->d_stage_size) {
         if (ctx->d_stage) {
             cudaStreamSynchronize(ctx->stream);
@@ -70,6 +85,23 @@ void *vvc_ctx_scratch(VVCCudaCtx *ctx, int slot, size_t bytes)
         ctx->d_scratch_size[slot] = bytes;
     }
     return ctx->d_scratch[slot];
+}
+
+int vvc_ctx_copy_streams(VVCCudaCtx *ctx)
+{
+    if (ctx->copy_in)
+        return 0;
+    VVC_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    VVC_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++)
+        VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 16; i++)
+        VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++)
+        VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_refs[i], cudaEventDisableTiming));
+    for (int i = 0; i < 12; i++)
+        VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_desc[i / 4][i % 4], cudaEventDisableTiming));
+    return 0;
 }
 
 int vvc_ctx_fork(VVCCudaCtx *ctx, int n)
@@ -139,6 +171,9 @@ void vvc_cuda_ctx_destroy(VVCCudaCtx *ctx)
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 16; i++) if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    for (int i = 0; i < 2; i++) if (ctx->ev_refs[i]) cudaEventDestroy(ctx->ev_refs[i]);
+    for (int i = 0; i < 12; i++) if (ctx->ev_desc[i / 4][i % 4]) cudaEventDestroy(ctx->ev_desc[i / 4][i % 4]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -146,6 +181,7 @@ void vvc_cuda_ctx_destroy(VVCCudaCtx *ctx)
 int vvc_cuda_sync(VVCCudaCtx *ctx)
 {
     vvc_ctx_check(ctx, cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    drain_copy_streams(ctx);
     return ctx->err;
 }
 
@@ -169,6 +205,13 @@ int vvc_cuda_notify(VVCCudaCtx *ctx, vvc_cuda_notify_fn fn, void *opaque)
     if (!n)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_NOMEM, "notify: out of memory");
     n->fn = fn; n->opaque = opaque; n->ctx = ctx;
+    // "everything submitted so far" includes the copy-out of an asynchronous host entry: the report waits for it
+    if (ctx->host_pending &&
+        (vvc_ctx_check(ctx, cudaEventRecord(ctx->ev[7], ctx->copy_out), "cudaEventRecord") ||
+         vvc_ctx_check(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[7], 0), "cudaStreamWaitEvent"))) {
+        free(n);
+        return ctx->err;
+    }
     if (vvc_ctx_check(ctx, cudaLaunchHostFunc(ctx->stream, notify_trampoline, n), "cudaLaunchHostFunc")) {
         free(n);
         return ctx->err;

@@ -84,12 +84,8 @@ extern "C" int vvc_cuda_inloop_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *d
         return ctx->err;
     if (!dst || !src || !desc || !desc->deblock || !desc->sao || !desc->alf || !desc->alf_sets)
         return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "inloop_host: null argument");
-    if (!ctx->copy_in) {
-        VVC_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
-        VVC_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; i++)
-            VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
-    }
+    if (vvc_ctx_copy_streams(ctx))
+        return ctx->err;
     const int planes = src->chroma_format_idc ? 3 : 1;
     const int n_ctb = ceil_div(src->width, 1 << src->ctb_log2) * ceil_div(src->height, 1 << src->ctb_log2);
     const VVCCudaDeblockMaps *hm = desc->deblock;

@@ -157,11 +157,17 @@ extern "C" int vvc_cuda_recon_arena_bind(const VVCCudaFrame *frame, VVCCudaRecon
     return VVC_CUDA_OK;
 }
 
-// Host entry.  Three streams: copy_in (H2D of picture k's descriptors), the context stream (kernels)
-// and copy_out (D2H of finished pictures); two descriptor slots and two picture slots rotate, events
-// order reuse.  Host buffers should be pinned for the copies to overlap.
-extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
-                                         const VVCCudaReconDesc *descs)
+// Host entry.  Three streams: copy_in (H2D of picture k's references and descriptors), the context stream (kernels)
+// and copy_out (D2H of finished pictures); kDescSlots descriptor slots (uploads run ahead of the kernels), two working
+// pictures and kOutSlots output pictures rotate, events order reuse.  Host buffers should be pinned for the copies to overlap.
+// The two copy directions are not busy at the same time by themselves: the first pictures of a call bring their reference
+// pictures with them (upload bound), the later ones only their descriptors (copy-out bound).  With sixteen output slots
+// the copy-out may lag behind the kernels by a whole call, and the asynchronous form returns once everything is queued:
+// slots and events keep rotating across calls (ctx->host_seq) and host reference pictures alternate between two areas,
+// so the next call's uploads run under this call's copy-out instead of the pipeline draining at every call.
+constexpr int kOutSlots = 16, kDescSlots = 4;
+extern "C" int vvc_cuda_recon_frame_host_async(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
+                                               const VVCCudaReconDesc *descs)
 {
     if (ctx->err)
         return ctx->err;
@@ -170,12 +176,8 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
     for (int k = 0; k < out->batch; k++)
         if (!descs[k].inloop.deblock || !descs[k].inloop.sao || !descs[k].inloop.alf || !descs[k].inloop.alf_sets)
             return vvc_ctx_fail(ctx, VVC_CUDA_ERR_ARG, "recon_host: in-loop descriptors missing");
-    if (!ctx->copy_in) {
-        VVC_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
-        VVC_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; i++)
-            VVC_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
-    }
+    if (vvc_ctx_copy_streams(ctx))
+        return ctx->err;
     const int planes = out->chroma_format_idc ? 3 : 1;
     const int n_ctb = ceil_div(out->width, 1 << out->ctb_log2) * ceil_div(out->height, 1 << out->ctb_log2);
     const VVCCudaFrame out1 = one_picture(out, 0);
@@ -187,11 +189,27 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
         const size_t n = layout(out, &descs[k], it, &dm);
         dsz = n > dsz ? n : dsz;
     }
-    // layout: [refs][cur x2][out x2][desc slot x2]
-    uint8_t *base = (uint8_t *)vvc_ctx_dev_stage(ctx, rsz + 4 * psz + 2 * dsz);
+    cudaStream_t cin = ctx->copy_in, cout = ctx->copy_out, run = ctx->stream;
+    // layout: [refs x2][cur x2][out x kOutSlots][desc slot x kDescSlots].  A call whose layout differs from that of the calls in flight waits for them
+    // (its slots would lie elsewhere in the staging area) and starts the rotation again.
+    const size_t lay[4] = { rsz, psz, dsz, 2 * rsz + (2 + kOutSlots) * psz + kDescSlots * dsz };
+    if (ctx->host_pending && (memcmp(lay, ctx->host_layout, sizeof(lay)) || lay[3] > ctx->d_stage_size)) {
+        if (vvc_cuda_sync(ctx))
+            return ctx->err;
+    }
+    const bool continuing = ctx->host_pending;
+    if (!continuing)
+        ctx->host_seq = ctx->host_calls = 0;
+    memcpy(ctx->host_layout, lay, sizeof(lay));
+    ctx->host_owner = true;
+    uint8_t *base = (uint8_t *)vvc_ctx_dev_stage(ctx, lay[3]);
+    ctx->host_owner = false;
     if (!base)
         return ctx->err;
-    cudaStream_t cin = ctx->copy_in, cout = ctx->copy_out, run = ctx->stream;
+    ctx->host_pending = true;
+    const uint64_t seq0 = ctx->host_seq;
+    const int area = (int)(ctx->host_calls & 1);                   // host reference pictures: the area the previous call did not use
+    uint8_t *pics = base + 2 * rsz;                                // cur x2, out x kOutSlots, desc slot x kDescSlots
     // The DPB may already live in HBM (earlier output pictures of this context): device pointers are used in place,
     // host pictures are staged once per call.
     cudaPointerAttributes attr;
@@ -203,10 +221,14 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
     if (refs_on_device)
         drefs = *refs;
     else
-        vvc_stage_frame_layout(refs, base, &drefs);
-    VVC_TRY(ctx, cudaEventRecord(ctx->ev[0], run));           // earlier work on the context stream owns the staging area
-    VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev[0], 0));
-    VVC_TRY(ctx, cudaStreamWaitEvent(cout, ctx->ev[0], 0));
+        vvc_stage_frame_layout(refs, base + area * rsz, &drefs);
+    if (!continuing) {
+        VVC_TRY(ctx, cudaEventRecord(ctx->ev[0], run));       // earlier work on the context stream owns the staging area
+        VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev[0], 0));
+        VVC_TRY(ctx, cudaStreamWaitEvent(cout, ctx->ev[0], 0));
+    } else if (!refs_on_device && ctx->host_calls >= 2) {
+        VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev_refs[area], 0));     // the kernels of the call before the previous one read this area
+    }
     // Host reference pictures: slot s goes up (on the copy-in stream) right before the descriptors of the first
     // picture whose ref_slots names it, so the upload of later references overlaps the kernels of earlier pictures;
     // a picture with ref_slots == 0 (unknown) waits for the whole ring.
@@ -226,25 +248,30 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
         }
         return 0;
     };
-    // events: ev[1+s] descriptors of slot s uploaded, ev[3+s] kernels of slot s done, ev[5+s] output of slot s downloaded
+    // events: ev_desc[0][s] descriptors of slot s uploaded, [1][s] kernels of slot s done, [2][s] refined vectors of slot s
+    // downloaded; ev_out[o] output slot o downloaded
     for (int k = 0; k < out->batch; k++) {
-        const int sl = k & 1;
+        const int sl = (int)((seq0 + k) & 1), ds = (int)((seq0 + k) % kDescSlots), os = (int)((seq0 + k) % kOutSlots);
         const VVCCudaReconDesc *h = &descs[k];
         VVCCudaFrame dcur, dout;
-        vvc_stage_frame_layout(&out1, base + rsz + sl * psz, &dcur);
+        vvc_stage_frame_layout(&out1, pics + sl * psz, &dcur);
         if (out_on_device)
             dout = one_picture(out, k);                    // the output ring lives in HBM (it is the DPB of later pictures)
         else
-            vvc_stage_frame_layout(&out1, base + rsz + (2 + sl) * psz, &dout);
-        uint8_t *slot = base + rsz + 4 * psz + sl * dsz;
+            vvc_stage_frame_layout(&out1, pics + (2 + os) * psz, &dout);
+        uint8_t *slot = pics + (2 + kOutSlots) * psz + ds * dsz;
         VVCCudaReconDesc dd = *h;
         VVCCudaDeblockMaps dm = *h->inloop.deblock;
-        if (k >= 2) {
-            VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev[3 + sl], 0));     // slot's previous kernels finished reading descriptors
-            VVC_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev[5 + sl], 0));     // slot's previous output has left
-        }
+        // the picture's reference pictures first: they do not wait for a descriptor slot
         if (upload_refs(h->ref_slots && refs->batch <= 32 ? (uint64_t)h->ref_slots : ~0ull))
             return ctx->err;
+        if (seq0 + k >= (uint64_t)kDescSlots) {
+            VVC_TRY(ctx, cudaStreamWaitEvent(cin, ctx->ev_desc[1][ds], 0));     // slot's previous kernels finished reading descriptors
+            if (h->dmvr_out)
+                VVC_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev_desc[2][ds], 0)); // slot's previous refined vectors have left
+        }
+        if (!out_on_device && seq0 + k >= (uint64_t)kOutSlots)
+            VVC_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev_out[os], 0));     // the output slot's previous picture has left
         Item it[IT_COUNT];
         size_t dmvr_off;
         layout(out, h, it, &dmvr_off);
@@ -278,15 +305,15 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
         dd.dmvr_out = h->dmvr_out ? ddm : NULL;
         dd.inloop.deblock = &dm;
         dd.inloop.alf_sets_per_frame = 0;
-        VVC_TRY(ctx, cudaEventRecord(ctx->ev[1 + sl], cin));
-        VVC_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev[1 + sl], 0));
+        VVC_TRY(ctx, cudaEventRecord(ctx->ev_desc[0][ds], cin));
+        VVC_TRY(ctx, cudaStreamWaitEvent(run, ctx->ev_desc[0][ds], 0));
         // samples no record covers keep a defined value
         for (int c = 0; c < planes; c++)
             VVC_TRY(ctx, cudaMemsetAsync(dcur.data[c], 0, (size_t)dcur.batch_stride[c], run));
         if (vvc_cuda_recon_frame(ctx, &dout, &dcur, &drefs, &dd))
             return ctx->err;
-        VVC_TRY(ctx, cudaEventRecord(ctx->ev[3 + sl], run));
-        VVC_TRY(ctx, cudaStreamWaitEvent(cout, ctx->ev[3 + sl], 0));
+        VVC_TRY(ctx, cudaEventRecord(ctx->ev_desc[1][ds], run));
+        VVC_TRY(ctx, cudaStreamWaitEvent(cout, ctx->ev_desc[1][ds], 0));
         if (!out_on_device) {
             const VVCCudaFrame hk = one_picture(out, k);
             cudaStream_t saved = ctx->stream;
@@ -296,10 +323,21 @@ extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *ou
             if (rc)
                 return ctx->err;
         }
+        VVC_TRY(ctx, cudaEventRecord(ctx->ev_out[os], cout));
         if (h->dmvr_out && h->n_pbs > 0)
             VVC_TRY(ctx, cudaMemcpyAsync(h->dmvr_out, ddm, (size_t)h->n_pbs * sizeof(VVCCudaDmvrOut), cudaMemcpyDeviceToHost, cout));
-        VVC_TRY(ctx, cudaEventRecord(ctx->ev[5 + sl], cout));
+        VVC_TRY(ctx, cudaEventRecord(ctx->ev_desc[2][ds], cout));
     }
-    VVC_TRY(ctx, cudaStreamSynchronize(cout));
-    return vvc_cuda_sync(ctx);
+    VVC_TRY(ctx, cudaEventRecord(ctx->ev_refs[area], run));
+    ctx->host_seq = seq0 + out->batch;
+    ctx->host_calls++;
+    return VVC_CUDA_OK;
+}
+
+extern "C" int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
+                                         const VVCCudaReconDesc *descs)
+{
+    if (vvc_cuda_recon_frame_host_async(ctx, out, refs, descs))
+        return ctx->err;
+    return vvc_cuda_sync(ctx);                  // the context stream and both copy streams
 }

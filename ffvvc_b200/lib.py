@@ -86,6 +86,7 @@ def load():
     RP = C.POINTER(abi.VVCCudaReconDesc)
     lib.vvc_cuda_recon_frame.argtypes = [CTX, FP, FP, FP, RP]
     lib.vvc_cuda_recon_frame_host.argtypes = [CTX, FP, FP, RP]
+    lib.vvc_cuda_recon_frame_host_async.argtypes = [CTX, FP, FP, RP]
     lib.vvc_cuda_recon_arena_size.argtypes = [FP, RP]
     lib.vvc_cuda_recon_arena_size.restype = C.c_size_t
     lib.vvc_cuda_recon_arena_bind.argtypes = [FP, RP, C.POINTER(abi.VVCCudaDeblockMaps), C.c_void_p]
@@ -242,6 +243,10 @@ class Context:
     def recon_frame_host(self, out, refs, descs):
         """descs: ctypes array of VVCCudaReconDesc, one per picture of `out` (host pointers everywhere)."""
         self.check(self.lib.vvc_cuda_recon_frame_host(self.handle, C.byref(out), C.byref(refs), descs))
+
+    def recon_frame_host_async(self, out, refs, descs):
+        """The same, returning once everything is queued: every host buffer stays valid and untouched until sync()."""
+        self.check(self.lib.vvc_cuda_recon_frame_host_async(self.handle, C.byref(out), C.byref(refs), descs))
 
     def intra_leaf_frame(self, frame, pbs_ptr, n_pbs, edges_ptr):
         """Intra leaf predictors (planar / DC / V / H / angular / MIP) of a list of independent blocks."""

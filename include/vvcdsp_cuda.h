@@ -719,6 +719,14 @@ size_t vvc_cuda_recon_arena_size(const VVCCudaFrame *frame, const VVCCudaReconDe
 int    vvc_cuda_recon_arena_bind(const VVCCudaFrame *frame, VVCCudaReconDesc *desc, VVCCudaDeblockMaps *maps, void *arena);
 int vvc_cuda_recon_frame_host(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
                               const VVCCudaReconDesc *descs);
+/* The same, returning as soon as everything is queued: the pictures, arenas and dmvr_out arrays must stay valid and
+ * untouched until vvc_cuda_sync() (or vvc_cuda_notify()'s report).  Consecutive calls keep the three-stage pipeline
+ * full across the call boundary - the copy-out of one call's last pictures runs under the next call's uploads and
+ * kernels - which is how a decoder that delivers pictures continuously should drive it (ff_vvc_frame_submit per frame,
+ * libavcodec/vvc/vvc_thread.c:432-566, no wait between frames).  Calls must share one geometry and descriptor layout to
+ * overlap; a call with a different layout first waits for the earlier ones. */
+int vvc_cuda_recon_frame_host_async(VVCCudaCtx *ctx, const VVCCudaFrame *out, const VVCCudaFrame *refs,
+                              const VVCCudaReconDesc *descs);
 
 #ifdef __cplusplus
 }

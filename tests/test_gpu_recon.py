@@ -179,6 +179,22 @@ def test_recon_entries_bit_exact(ctx, w, h, batch, seed, coeff_mode, lmcs_chroma
     ctx.recon_frame_host(f_out, refs.desc, descs)
     got = [t.numpy().view(np.uint16) for t in h_out]
     util.assert_planes_equal(gr, got, want, "recon_frame_host with a device-resident DPB vs oracle chain")
+    # the asynchronous form, three calls back to back (slots and events rotate across the calls, the second and third
+    # calls' uploads run under the copy-out of the one before); the completion report arrives after the last copy-out
+    for t in h_out:
+        t.zero_()
+    import threading
+    done = threading.Event()
+    status = []
+    for _ in range(3):
+        ctx.recon_frame_host_async(f_out, f_refs, descs)
+    keep = ctx.notify(lambda st: (status.append(st), done.set()))
+    assert done.wait(60), "no completion report"
+    assert status == [0]
+    got = [t.numpy().view(np.uint16).copy() for t in h_out]
+    ctx.sync()
+    util.assert_planes_equal(gr, got, want, "recon_frame_host_async x3 + notify vs oracle chain")
+    del keep
 
 
 def test_recon_4k_bit_exact(ctx):
