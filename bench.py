@@ -598,7 +598,7 @@ def main():
             descs[k].inloop.deblock = C.pointer(m)
             arena_bytes += int(d.arena_bytes)
         h2d = sum(t.numel() * 2 for t in h_refs) + arena_bytes
-        e_steps = max(2, min(args.steps, 4))
+        e_steps = max(2, min(args.steps, 8))
         ctx.recon_frame_host(f_out, f_refs, descs)
 
         def timed_host_steps(call, sync_each):
@@ -632,9 +632,12 @@ def main():
                                      "what": "vvc_cuda_recon_frame_host: every step waits for its own last copy-out"}}
         # the same call with the DPB already in HBM (reference pictures are earlier outputs in a decoder): only the
         # per-picture records / coefficients / filter parameters go up, the output pictures come back
+        ctx.recon_frame_host(f_out, refs.desc, descs)
+        barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            ctx.recon_frame_host(f_out, refs.desc, descs)
+            ctx.recon_frame_host_async(f_out, refs.desc, descs)
+        ctx.sync()
         barrier()
         r_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
@@ -650,7 +653,8 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            ctx.recon_frame_host(out.desc, refs.desc, descs)
+            ctx.recon_frame_host_async(out.desc, refs.desc, descs)
+        ctx.sync()
         barrier()
         o_ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
