@@ -45,6 +45,9 @@ struct AlfSmem {
     alignas(16) uint32_t coef[(TH / 4) * (TW / 4)][25];
 };
 
+#ifndef ALF_STAGE_ASYNC
+#define ALF_STAGE_ASYNC 1           // tile staging by cp.async (tools/sweep_alf_stage.sh)
+#endif
 struct ClampWin { int xlo, xhi, ylo, yhi; };
 
 __device__ __forceinline__ ClampWin make_win(int x0, int y0, int w, int h, int pw, int ph, unsigned edges)
@@ -70,7 +73,13 @@ __device__ __forceinline__ void stage_tile(pel *sm, const pel *__restrict__ plan
         const pel *row = plane + (long long)y * pitch;
         pel *out = sm + i * PITCH + 8 * q;
         if (xs >= cw.xlo && xs + 7 <= cw.xhi) {
+#if ALF_STAGE_ASYNC
+            // cp.async: the chunk goes to shared memory without a destination register, so a thread's chunks of all three planes
+            // are in flight together; one wait in front of the tile's barrier (the load -> store form paid a round trip per chunk)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(out)), "l"(row + xs) : "memory");
+#else
             *reinterpret_cast<uint4 *>(out) = __ldg(reinterpret_cast<const uint4 *>(row + xs));
+#endif
         } else {
 #pragma unroll
             for (int e = 0; e < 8; e++)
@@ -196,6 +205,9 @@ alf_frame_kernel(const AlfK p)
             stage_tile<CP>(&sm.chroma[c][0][0], p.src[c + 1] + k * p.sb[c + 1], p.sp[c + 1],
                            (tx0 >> 1) - 8, (ty0 >> 1) - 2, CH + 4, CP / 8, cw);
     }
+#if ALF_STAGE_ASYNC
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
     __syncthreads();
 
     const int vb = ctb - 4;               // luma virtual boundary, CTB relative (:1304)

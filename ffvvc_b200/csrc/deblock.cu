@@ -262,6 +262,9 @@ struct DbkTile {
     static constexpr int ROWS = TH + 2 * AY;
 };
 
+#ifndef DBK_STAGE_ASYNC
+#define DBK_STAGE_ASYNC 1            // tile staging by cp.async (tools/sweep_alf_stage.sh)
+#endif
 #ifndef DBK_MIN_CTAS
 #define DBK_MIN_CTAS 8               // resident CTAs per SM the kernel is compiled for: full occupancy at 32 registers (tools/sweep_dbk2.sh: 4 / 5 / 6 / 7-8 -> V 0.62 / 0.53 / 0.47 / 0.40 ms per 16 pictures; the pass is latency bound)
 #endif
@@ -307,6 +310,13 @@ deblock_kernel(const DbkK p)
         const pel *row = src + (long long)y * p.sp[c];
         unsigned v[4];
         if (xs0 >= 0 && xs0 + 7 < pw) {
+            // cp.async where the tile's pitch keeps the chunks 16-byte aligned (the horizontal-edge tile): every chunk of the thread is
+            // in flight before the one wait in front of the barrier, H pass 0.245 -> 0.208 ms per 16 4K pictures.  The odd pitch of
+            // the vertical-edge tile would need 4-byte requests, which cost more than they save (0.270 -> 0.277): it keeps load + store.
+            if (DBK_STAGE_ASYNC && (PITCH * 2) % 16 == 0) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_t[i * PITCH + 8 * q])), "l"(row + xs0) : "memory");
+                continue;
+            }
             const uint4 u = __ldg(reinterpret_cast<const uint4 *>(row + xs0));
             v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
         } else {
@@ -321,6 +331,8 @@ deblock_kernel(const DbkK p)
 #pragma unroll
         for (int e = 0; e < 4; e++) o[e] = v[e];
     }
+    if (DBK_STAGE_ASYNC && (PITCH * 2) % 16 == 0)
+        asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
     // ---- filter: one thread per edge segment (4 luma lines; 2 or 4 chroma lines) ----
