@@ -159,7 +159,8 @@ __device__ __noinline__ void stage_units(uint32_t *win, int pw, int pad, const p
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sd), "l"(src) : "memory");
             asm volatile("cp.async.wait_all;" ::: "memory");
 #else
-#pragma unroll INTER_STAGE_UNROLL
+            constexpr int kStageUnroll = INTER_STAGE_UNROLL;
+#pragma unroll kStageUnroll
             for (int r = rsub; r < rows; r += rstep, src += sstep, dst += dstep)
                 *dst = __ldg(src);
 #endif
