@@ -489,16 +489,20 @@ def main():
                      "frac": ALGO_BYTES_PER_LUMA_PX[n] * px_per_launch / (v * 1e-3) / 1e9 / peak}
                  for n, v in zip(STAGES, stage_ms)}
     chain_gbs = CHAIN_ALGO_BYTES_PER_LUMA_PX * luma_px_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9 * (1.0 if world == 1 else 1.0)
-    # measured DRAM traffic of the dominant stage (ncu --set full capture, profiles/r01_traffic.json), per launch like `achieved`
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["per_stage"][STAGES[dom]]
-        traffic = (tr["dram_read_mb_per_picture"] + tr["dram_write_mb_per_picture"]) * 1e6 * group * (args.width * args.height) / (3840 * 2160)
-    except Exception:
-        pass
+    # measured DRAM traffic of the dominant stage, per launch like `achieved`: dram__bytes_read + dram__bytes_write of its kernels in
+    # one `ncu --set full` capture at the bench's 16 pictures per launch (profiles/r02_traffic.json, from r02_recon16_ncu_full.csv)
+    traffic, traffic_src = None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", name)))["per_stage"][STAGES[dom]]
+            traffic = (tr["dram_read_mb_per_picture"] + tr["dram_write_mb_per_picture"]) * 1e6 * group * (args.width * args.height) / (3840 * 2160)
+            traffic_src = "profiles/" + name
+            break
+        except Exception:
+            pass
     roofline = {
         "bound": "hbm", "kernel": STAGES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": algo_bytes, "stages": per_stage,
         "chain": {"algorithmic_bytes_per_luma_px": CHAIN_ALGO_BYTES_PER_LUMA_PX, "achieved_gbs": chain_gbs, "frac": chain_gbs / peak},
     }
