@@ -6,11 +6,10 @@
 // (libavcodec/h26x/h2656_inter_template.c:29-577), avg, w_avg, put_gpm (libavcodec/vvc/vvc_inter_template.c
 // :25-98).
 //
-// B200 design: 8 lanes per record, one lane per patch of 4 columns x 8 rows.  A lane runs the whole separable
-// filter in registers: per window row six 32-bit loads (12 samples, L1/L2 resident: neighbouring patches
-// share them), the horizontal 8-tap sums as IDP.2A on sample pairs, and a streaming vertical pass that keeps
-// only the last 7 row-pairs per column.  No synchronisation, no per-record scalar work replicated over a warp --
-// about 25 thread-instructions per predicted sample.
+// B200 design: at most 8 lanes per record, one lane per patch of 4 columns x 8 rows.  A lane runs the whole separable
+// filter in registers: per window row 12 samples (six words), the horizontal 8-tap sums as IDP.2A on sample pairs, and a
+// streaming vertical pass that keeps only the last 7 row-pairs per column.  No per-record scalar work replicated over a
+// warp -- about 25 thread-instructions per predicted sample.
 //
 // Window staging (PATCH_STAGED): what bounds the register-staged form is not arithmetic but the L1: every lane fetched its
 // own 12 x 15 window with 90 scattered 4-byte loads (3.5 L1 wavefronts and 11 sectors per request, ncu).  Now the lanes
@@ -41,7 +40,8 @@ constexpr int kThreads = 128;
 #ifndef PATCH_DEPTH
 #define PATCH_DEPTH 2
 #endif
-// resident CTAs per SM the class kernels are compiled for (register budget = 65536 / (128 * n)); measured sweep in profiles/README.md
+// resident CTAs per SM the class kernels are compiled for (register budget = 65536 / (128 * n)): profiles/r02_sweep_patch_staged.txt.
+// The chroma kernels run on a side stream beside the luma and warp kernels: more of their CTAs only take room from those.
 #ifndef PATCH_MB_LU
 #define PATCH_MB_LU 3
 #endif
