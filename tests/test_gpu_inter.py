@@ -94,6 +94,57 @@ def test_inter_pre_padded_reference_planes_bit_exact(ctx, w, h, seed, uniform, p
     assert np.array_equal(keep[3][0].cpu().numpy().view(abi.DMVR_OUT_DTYPE)[dm], oo[dm])
 
 
+@pytest.mark.parametrize("pad", [0, 16])
+def test_inter_patch_window_alignment_sweep(ctx, pad):
+    """The staged windows of the patch kernels: every record shape (4 / 8 / 16 wide and high), uni and bi, with the integer
+    part of the horizontal vector walking through every alignment of a window against the 8 / 16-byte requests and across the
+    left / right picture border (records that stay inside take the cp.async regions, the others the clamped path), every
+    fractional phase; without and with a pre-padded DPB.  Against the oracle, every sample."""
+    from ffvvc_b200 import device
+    W, H = 256, 128
+    gd, gr, refs, _, wp, prof = make_case(W, H, 77)
+    shapes = [(w, h) for w in (4, 8, 16) for h in (4, 8, 16) if (w, h) != (4, 4)]
+    recs = []
+    n = 0
+    for cy in range(H // 16):
+        for cx in range(W // 16):
+            w, h = shapes[(cx + 3 * cy) % len(shapes)]
+            bi = w >= 8 and h >= 8 and (cx + cy) % 3 != 0
+            for y in range(0, 16, h):
+                for x in range(0, 16, w):
+                    r = np.zeros(1, dtype=abi.PB_DTYPE)
+                    r["x0"], r["y0"], r["w"], r["h"] = cx * 16 + x, cy * 16 + y, w, h
+                    r["planes"] = abi.PB_LUMA | abi.PB_CHROMA
+                    r["pred_flag"] = abi.PF_BI if bi else (abi.PF_L0 if n % 2 else abi.PF_L1)
+                    r["ref"] = [(n // 3) % gr.batch, (n // 5 + 1) % gr.batch]
+                    for l in range(2):
+                        ix = (n * (3 + 4 * l) + 5 * l) % 23 - 11            # -11 .. 11 samples: every residue of the window start
+                        iy = (n * (5 - 2 * l) + l) % 9 - 4
+                        r["mv"][0, l, 0] = ix * 16 + (n * (7 + l)) % 16
+                        r["mv"][0, l, 1] = iy * 16 + (n * (11 + 2 * l) + 3) % 16
+                    if n % 7 == 0:
+                        r["mv"][0, :, 0] &= ~15                             # integer columns
+                    if n % 11 == 0:
+                        r["mv"][0, :, 1] &= ~15                             # integer rows
+                    r["filt"] = 1 if n % 13 == 0 else 0
+                    recs.append(r)
+                    n += 1
+    pbs = np.concatenate(recs)
+    dst = device.DeviceFrames(gd, planes=abi.alloc_planes(gd, fill=77))
+    ref = device.DeviceFrames(gr, planes=refs, pad=pad)
+    if pad:
+        ctx.pad_frame(ref.desc, pad)
+    keep = [device.to_device(a) for a in (pbs, wp, prof, np.zeros(len(pbs), dtype=abi.DMVR_OUT_DTYPE))]
+    ctx.set_option(abi.OPT_REF_PAD, pad)
+    try:
+        ctx.inter_frame(dst.desc, ref.desc, keep[0][1], len(pbs), keep[1][1], keep[2][1], keep[3][1])
+        ctx.sync()
+    finally:
+        ctx.set_option(abi.OPT_REF_PAD, 0)
+    od, _ = run_inter(util.oracle().vvco_inter_frame, gd, gr, refs, pbs, wp, prof)
+    util.assert_planes_equal(gd, dst.to_numpy(), od, "patch kernels, window alignment sweep (margin %d) vs oracle" % pad)
+
+
 def test_inter_generic_kernel_matches(ctx):
     """The generic CTA-per-record kernel (any bit depth / alignment) and the 10-bit warp-per-record kernel agree."""
     gd, gr, refs, pbs, wp, prof = make_case(416, 240, 11, mix=STRESS_MIX)
