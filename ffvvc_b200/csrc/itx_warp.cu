@@ -324,17 +324,24 @@ __global__ void __launch_bounds__(256) itx_sort_kernel(const ItxW p)
         else if (l2w <= 2 && l2h <= 2 && !lfnst && !(flags & VVC_CUDA_TB_STORE_RESIDUAL) && !(__ldg(q + 5) >> 16)) cls = 5;   // (not with LMCS chroma scaling)
         else cls = l2w + l2h >= 12 ? 0 : l2w + l2h == 11 ? 1 : l2w + l2h == 10 ? 2 : 3;
     }
+    // one reservation per class and warp, all six requested before the first answer is awaited (one after the other, a warp
+    // paid a round trip to the counters per class it holds)
+    unsigned m[6];
+    uint32_t base[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) {
-        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
-        if (!m)
+        m[c] = __ballot_sync(0xffffffffu, cls == c);
+        base[c] = 0;
+        if (m[c] && lane == __ffs(m[c]) - 1)
+            base[c] = atomicAdd(p.counts + c, (uint32_t)__popc(m[c]));
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        if (!m[c])
             continue;
-        uint32_t base = 0;
-        if (lane == __ffs(m) - 1)
-            base = atomicAdd(p.counts + c, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        const uint32_t b = __shfl_sync(0xffffffffu, base[c], __ffs(m[c]) - 1);
         if (cls == c)
-            p.lists[(size_t)c * p.n_tbs + base + __popc(m & ((1u << lane) - 1))] = ti;
+            p.lists[(size_t)c * p.n_tbs + b + __popc(m[c] & ((1u << lane) - 1))] = ti;
     }
 }
 
